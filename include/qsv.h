@@ -1,0 +1,184 @@
+/*
+ * qsv.h — C-ABI of the B200-native state-vector engine (libqsv.so).
+ *
+ * This is the drop-in boundary underneath the reference's Python API
+ * (MatejVitek/Quantum-Circuits, main/circuit.py + main/matrix.py).  The reference has no
+ * FFI of its own: its hot path is Circuit.run_method2 (main/circuit.py:279-337) plus the
+ * sampling in Circuit.run (main/circuit.py:341-366).  Every entry point below replaces one
+ * step of that path and cites it.  The Python mirror of the reference API
+ * (quantum-circuits_b200/main/circuit.py) binds these symbols with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - All pointers named *_dev are CUDA device pointers; everything else is host memory.
+ *   - `state_dev` is an array of 2^n_local complex128 amplitudes (re, im interleaved, 16 B each).
+ *   - Bit positions are PHYSICAL index bits: position 0 = least-significant bit of the amplitude
+ *     index.  The reference is big-endian (wire 0 = MSB, main/circuit.py:290-299), so for an
+ *     unsharded n-qubit state wire w lives at position n-1-w.  Positions >= n_local are "global"
+ *     qubits held in `rank_bits` (multi-GPU sharding by the top log2(P) qubits).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Every function returns 0 on success, non-zero on error; qsv_last_error() then returns a
+ *     thread-local message.  Nothing here ever falls back to the CPU.
+ */
+#ifndef QSV_H
+#define QSV_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSV_ABI_VERSION 1
+
+/* ---- in-tile op program (consumed by qsv_run_pass) -------------------------------------- */
+
+#define QSV_MAX_TILE_K   5   /* widest dense / diagonal gate applied inside a shared-memory tile */
+#define QSV_MAX_TILE_T  13   /* largest tile: 2^13 amplitudes = 128 KiB of shared memory        */
+#define QSV_OP_HEADER_BYTES 96
+
+enum qsv_op_kind {
+    QSV_OP_DENSE = 1,   /* k-qubit dense matrix on tile-local targets, optional controls        */
+    QSV_OP_MCX   = 2,   /* (multi-)controlled X: exact pair swap (X, CNot, Toffoli)             */
+    QSV_OP_PHASE = 3,   /* multiply amplitudes whose control bits match by one complex scalar   */
+    QSV_OP_DIAG  = 4,   /* k-qubit diagonal table; bits may be tile-local or external           */
+    QSV_OP_SWAP  = 5    /* exchange two tile-local qubits (exact data movement)                 */
+};
+
+/* One op of a pass program.  Laid out for direct device consumption; ops are variable-size:
+ * header (96 B) followed by `payload` (dense matrix row-major 2^k x 2^k complex128, or diagonal
+ * table 2^k complex128).  All positions in `ins`/`tgt` are TILE-LOCAL bit positions unless the
+ * 0x80 flag marks them as external physical positions (DIAG only). */
+typedef struct qsv_op {
+    uint32_t kind;          /* enum qsv_op_kind                                                   */
+    uint32_t k;             /* number of target qubits (DENSE, DIAG); 1 for MCX; 2 for SWAP        */
+    uint32_t n_ins;         /* number of entries of ins[]                                          */
+    uint32_t flags;         /* QSV_OPF_*                                                           */
+    uint64_t ext_ctrl_mask; /* physical-index bits OUTSIDE the tile that gate the whole op         */
+    uint64_t ext_ctrl_val;  /* required value of those bits                                        */
+    uint32_t loc_ctrl_val;  /* tile-local control bits that must be 1 (OR-ed into the local index) */
+    uint32_t payload_off;   /* byte offset of the payload from the start of this op (16-aligned)   */
+    uint32_t op_bytes;      /* total bytes of this op including payload (multiple of 16)           */
+    uint32_t reserved;
+    uint8_t  ins[16];       /* sorted ascending: tile-local bits fixed by the op (targets+controls) */
+    uint8_t  tgt[8];        /* tgt[0] = most-significant bit of the gate index (= gate port 0)     */
+    double   scalar[2];     /* PHASE: (re, im)                                                     */
+} qsv_op_t;
+
+#define QSV_OPF_REAL_MATRIX 1u   /* DENSE: all imaginary parts are exactly zero                   */
+
+/* Geometry of one pass over the state: which physical bits form the shared-memory tile. */
+typedef struct qsv_pass {
+    int32_t  n_local;       /* log2(number of amplitudes on this device)                           */
+    int32_t  tile_bits;     /* T: tile holds 2^T amplitudes (T <= QSV_MAX_TILE_T, T <= n_local)    */
+    int32_t  low_bits;      /* L: physical bits 0..L-1 are always in the tile (contiguous runs)    */
+    int32_t  n_hi;          /* T - L                                                              */
+    uint8_t  hi_pos[16];    /* ascending physical positions (>= L) of the remaining tile bits      */
+    uint64_t rank_bits;     /* value of the global index bits, pre-shifted by n_local              */
+    int32_t  max_dense_k;   /* widest DENSE op in the program (selects the register-heavy variant)  */
+    int32_t  reserved;
+} qsv_pass_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+
+int         qsv_abi_version(void);
+const char *qsv_last_error(void);
+/* Number of kernels this library has launched since load / last reset (bench.py's gpu_launches). */
+uint64_t    qsv_launch_count(void);
+void        qsv_reset_launch_count(void);
+
+/* ---- state preparation ------------------------------------------------------------------ */
+
+/* |in_v> basis state: replaces the tensor product of e0/e1 columns, main/circuit.py:290-301 and
+ * main/matrix.py:6-11.  `index` is the global basis index; only the shard that owns it (top bits
+ * == rank) writes the 1. */
+int qsv_init_basis(void *state_dev, int n_local, uint64_t index, uint64_t rank, void *stream);
+
+/* ---- gate application: replaces P2*psi; M*psi; P1*psi, main/circuit.py:303-327 ----------- */
+
+/* Apply `n_ops` ops to every tile of one pass.  `op_offsets_dev[i]` is the byte offset of op i
+ * from `prog_dev`.  One read + one write of every tile that has at least one active op; tiles whose
+ * external controls switch every op off are skipped entirely. */
+int qsv_run_pass(void *state_dev, const qsv_pass_t *pass, const void *prog_dev,
+                 const uint32_t *op_offsets_dev, int n_ops, void *stream);
+
+/* Single-gate conveniences (host arguments only; each is one pass with a one-op program built by
+ * the library).  `targets[0]` is the gate's port 0 = most-significant bit of the matrix index
+ * (main/circuit.py:305-313).  Controls are physical positions that must be 1. */
+int qsv_apply_dense(void *state_dev, int n_local, int k, const int *targets,
+                    int n_ctrl, const int *controls, const double *matrix_re_im, /* 2*4^k doubles */
+                    uint64_t rank_bits, void *stream);
+int qsv_apply_diag(void *state_dev, int n_local, int k, const int *targets,
+                   const double *diag_re_im, /* 2*2^k doubles */ uint64_t rank_bits, void *stream);
+int qsv_apply_phase(void *state_dev, int n_local, int n_ctrl, const int *controls,
+                    double re, double im, uint64_t rank_bits, void *stream);
+int qsv_apply_cx(void *state_dev, int n_local, int n_ctrl, const int *controls, int target,
+                 uint64_t rank_bits, void *stream);
+
+/* Wide gates (k > QSV_MAX_TILE_K), used for the reference's full-width dense operators
+ * (main/Grover.py:14-31, main/Shor.py:54-83, main/matrix.py:212-219).  Out-of-place for dense and
+ * permutation, in-place for diagonal.  `perm_dev[c]` = row r with M[r][c] == 1. */
+int qsv_apply_dense_wide(const void *state_in_dev, void *state_out_dev, int n_local, int k,
+                         const int *targets, const void *matrix_dev, void *stream);
+int qsv_apply_perm_wide(const void *state_in_dev, void *state_out_dev, int n_local, int k,
+                        const int *targets, const uint32_t *perm_dev, void *stream);
+int qsv_apply_diag_wide(void *state_dev, int n_local, int k, const int *targets,
+                        const void *diag_dev, void *stream);
+
+/* ---- Grover: main/Grover.py:14-22 (oracle F) and :24-31,40-44 (H U0 H) -------------------- */
+
+/* Oracle for one marked item: exchanges the two amplitudes idx0 <-> idx1 (local indices). */
+int qsv_grover_oracle(void *state_dev, uint64_t idx0, uint64_t idx1, void *stream);
+/* Diffusion 2|s><s| - I on the search register = all physical bits >= anc_bits, independently for
+ * each value of the low `anc_bits` ancilla bits.  Three steps so that a multi-GPU caller can
+ * all-reduce the sums between them:
+ *   qsv_diffusion_sums   : sums_dev[2*a .. 2*a+1] = sum over the search register of psi[., a]
+ *   (all-reduce sums_dev across ranks)
+ *   qsv_diffusion_update : psi[i, a] = 2 * sums[a] / 2^n_search_total - psi[i, a]
+ * `scratch_dev` must hold qsv_diffusion_scratch_bytes(n_local, anc_bits) bytes. */
+size_t qsv_diffusion_scratch_bytes(int n_local, int anc_bits);
+int qsv_diffusion_sums(const void *state_dev, int n_local, int anc_bits, void *scratch_dev,
+                       void *sums_dev, void *stream);
+int qsv_diffusion_update(void *state_dev, int n_local, int anc_bits, const void *sums_dev,
+                         int n_search_total, void *stream);
+
+/* ---- Shor: modular-exponentiation involution, main/Shor.py:54-83 -------------------------- */
+
+/* For every x (bits at x_pos[0..nx), x_pos[0] = MSB) with f = a^x mod N:
+ *   (x, y=0) <-> (x, y=f)   and   (x, y=2^h-1) <-> (x, y=(2^h-1) & ~f),   y bits at y_pos[0..h).
+ * x bits at positions >= n_local are taken from rank_bits. */
+int qsv_modexp_involution(void *state_dev, int n_local, int nx, const int *x_pos, int h,
+                          const int *y_pos, uint64_t a, uint64_t N, uint64_t rank_bits,
+                          void *stream);
+
+/* ---- measurement: main/circuit.py:329-337 (relabel + |psi|^2) and :360-364 (sampling) ----- */
+
+/* out_dev[z] = |psi[y(z)]|^2 where bit b of z is taken from physical bit src_pos[b] of y
+ * (src_pos == NULL: identity).  Output relabel of main/circuit.py:329-332 folded into the read. */
+int qsv_probs(const void *state_dev, int n_local, const int *src_pos, void *out_dev, void *stream);
+/* sums_dev[j] = sum of |psi|^2 over output indices z in [j*2^block_bits, (j+1)*2^block_bits). */
+int qsv_block_sums(const void *state_dev, int n_local, const int *src_pos, int block_bits,
+                   void *sums_dev, void *stream);
+/* Sequential left-to-right accumulation from `prefix`, starting at output index z_start: writes the
+ * first z with cum > target to result_dev[0] (uint64), clamped to z_last, and the running sum at
+ * the point where the scan stopped to result_dev[1] (double) — with target = +inf that is the
+ * exact sequential total.  Reproduces bisect_right(accumulate(weights), u*total, 0, N-1) of
+ * random.choices (main/circuit.py:364).  result_dev holds 16 bytes. */
+int qsv_sample_scan(const void *state_dev, int n_local, const int *src_pos, uint64_t z_start,
+                    uint64_t z_last, double prefix, double target, void *result_dev, void *stream);
+
+/* ---- multi-GPU re-layout helpers ---------------------------------------------------------- */
+
+/* Pack / unpack between the state and a contiguous staging buffer for the chunked all-to-all
+ * qubit swap: copies n_chunks slices of `chunk_elems` amplitudes, slice j starting at
+ * state[j*stride_elems + offset_elems], to/from staging[j*chunk_elems]. */
+int qsv_pack_slices(const void *state_dev, void *staging_dev, uint64_t n_chunks,
+                    uint64_t stride_elems, uint64_t offset_elems, uint64_t chunk_elems, void *stream);
+int qsv_unpack_slices(void *state_dev, const void *staging_dev, uint64_t n_chunks,
+                      uint64_t stride_elems, uint64_t offset_elems, uint64_t chunk_elems, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSV_H */
