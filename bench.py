@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the state-vector hot path (BASELINE.json metric: gates/sec at 30 q on 1 GPU and at
+30+log2(N) q sharded over N GPUs; fraction of the HBM roofline per gate pass).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--qubits Q] [--depth D]
+    python bench.py --impl reference ...      # CPU arm: the oracle port timed on the host cores
+
+One "step" = one complete run of the config-3 circuit (random H / X / T8 / phase layers with CNot / CZ
+matchings, depth 20 -> 45 gates per layer at 30 q) on a fresh |0...0> state: state preparation, every
+gate pass, and one measurement sample.  `value` times that with the packed program already in HBM;
+`e2e` times Circuit.run(in_v, 2) through the public API (host scheduling, H2D of the program, D2H of
+the sampled index inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "quantum-circuits_b200"),):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "gates/sec"
+SEED = 20261019
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--qubits", type=int, default=0, help="total qubits (default 30 + log2(gpus))")
+    ap.add_argument("--depth", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-qubits", type=int, default=22, help="register size of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gate-pass", action="store_true", help="skip the single-gate-pass roofline sweep")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on the host cores (bounded sample of the same workload)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_baseline(n_cpu, depth=1, budget_s=25.0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import statevec_oracle as so
+    steps = so.random_layered_steps(n_cpu, depth, seed=SEED)
+    psi = so.initial_state([0] * n_cpu)
+    done = 0
+    t0 = time.perf_counter()
+    for M, wires, _ in steps:
+        psi = so.apply_gate(psi, n_cpu, wires, M)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    w = so.weights(psi)
+    so.sample_index(w[: 1 << min(n_cpu, 16)], 0.5)
+    try:
+        import threadpoolctl
+        threads = max([p["num_threads"] for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        threads = 1
+    return {"value": done / dt, "unit": METRIC, "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle port (numpy restatement of Circuit.run_method2): config-3 generator, %d qubits, "
+                      "first %d gates of layer 1 (the reference itself needs 86 s/gate at 10 qubits)" % (n_cpu, done)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself is not
+    present on the GPU box) on the host cores, same metric/unit.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(args.cpu_qubits, 1, budget_s=20.0)
+        if i >= args.warmup:
+            vals.append(base["value"])
+        if i == 0 and args.warmup > 0:
+            continue
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": METRIC, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+            "config": {"workload": "config-3 random H/X/T8/phase + CNot/CZ layered circuit, CPU sample at %d qubits"
+                                   % args.cpu_qubits, "seed": SEED},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from qsv.dist import Comm
+        comm = Comm(dist.group.WORLD)
+    g = (world - 1).bit_length()
+    assert world == 1 << g, "number of GPUs must be a power of two"
+    n = args.qubits if args.qubits else 30 + g
+
+    from qsv import _cabi, engine, lowering, workloads, schedule
+    lib = _cabi.load()
+
+    # ---- build + lower the workload once (host), upload the packed programs (resident in HBM)
+    t_host0 = time.perf_counter()
+    circ = workloads.random_layered_circuit(n, args.depth, seed=SEED)
+    circ.sort()
+    n_gates = len(circ.gates)
+    if comm is None:
+        ops, src_pos = lowering.lower(circ)
+    else:
+        ops, src_pos = lowering.lower(circ, n_global=g)
+    t_host = time.perf_counter() - t_host0
+
+    sv = engine.StateVector(n, comm=comm)
+    plan = sv.prepare(ops)
+    in_index = 0
+
+    def step(u=0.37):
+        sv.init_basis(in_index)
+        sv.execute(plan)
+        return sv.sample(u, src_pos)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events, max over ranks
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.qsv_reset_launch_count()
+    passes0 = sv.passes_run
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = int(lib.qsv_launch_count())
+    passes_per_step = (sv.passes_run - passes0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = n_gates / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_pass): per-launch CUDA-event timing of every pass
+    peak, peak_src = measured_peak_gbs()
+    pass_ms = sv.time_passes(plan, repeats=2)
+    n_local = sv.n_local
+    alg_bytes = [32.0 * (1 << n_local) * f for f in sv.pass_active_fractions(plan)]
+    tot_ms = sum(pass_ms)
+    achieved = sum(alg_bytes) / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "qsv::k_pass (tiled TMA gate pass)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "launches_timed": len(pass_ms), "avg_launch_ms": tot_ms / max(1, len(pass_ms)),
+                "algorithmic_bytes_per_launch": sum(alg_bytes) / max(1, len(alg_bytes)),
+                "share_of_step": tot_ms / ms_per_step if ms_per_step else None,
+                "gates_per_pass": n_gates / max(1, passes_per_step)}
+
+    gate_pass = None
+    if not args.no_gate_pass and rank == 0 and world == 1:
+        gate_pass = single_gate_sweep(sv, peak)
+
+    # ---- end to end through the public API: Circuit.run(in_v, 2) with host inputs
+    in_v = [0] * n
+    e2e = None
+    if world == 1:
+        import io
+        import contextlib
+        import random
+        random.seed(1)
+        del sv
+        torch.cuda.empty_cache()
+        for _ in range(2):
+            with contextlib.redirect_stdout(io.StringIO()):
+                circ.run(in_v, 2)
+        torch.cuda.synchronize()
+        k_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            with contextlib.redirect_stdout(io.StringIO()):
+                out = circ.run(in_v, 2)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / k_e2e
+        st = lowering.last_run_stats()
+        e2e = {"value": n_gates / dt, "unit": METRIC, "h2d_bytes_per_step": st["h2d_bytes"],
+               "d2h_bytes_per_step": st["d2h_bytes"], "ms_per_step": dt * 1e3,
+               "api": "main.circuit.Circuit.run(in_v, 2)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex128 (f64 pairs)", "data": "synthetic",
+        "config": {"workload": "config-3: random H/X/T8/phase layers + CNot/CZ matchings, %d qubits, depth %d, "
+                               "%d gates, complex128, input |0...0>, one sample per step" % (n, args.depth, n_gates),
+                   "qubits": n, "depth": args.depth, "gates": n_gates, "seed": SEED,
+                   "state_bytes_per_gpu": 16 << n_local, "passes_per_step": passes_per_step,
+                   "cache": "state (%.1f GB/GPU) is far larger than the 126 MB L2; no flush needed"
+                            % ((16 << n_local) / 1e9),
+                   "sharding": "top %d qubits across %d GPUs" % (g, world) if world > 1 else "none",
+                   "host_lowering_s": t_host},
+        "roofline": roofline, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+    }
+    if gate_pass is not None:
+        line["gate_pass"] = gate_pass
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_qubits)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def single_gate_sweep(sv, peak):
+    """One gate per pass, the figure the north star's '>= 70 % of HBM roofline per gate pass' refers to:
+    algorithmic bytes / CUDA-event time of that single launch."""
+    import numpy as np
+    import torch
+    from qsv.schedule import Op
+    s = 2 ** -0.5
+    Hm = np.array([[s, s], [s, -s]], dtype=np.complex128)
+    n = sv.n_local
+    N = 1 << n
+    cases = [("H q0 (lsb)", Op("dense", (0,), (), matrix=Hm), 32 * N),
+             ("H q%d (mid)" % (n // 2), Op("dense", (n // 2,), (), matrix=Hm), 32 * N),
+             ("H q%d (msb)" % (n - 1), Op("dense", (n - 1,), (), matrix=Hm), 32 * N),
+             ("X q%d" % (n - 2), Op("mcx", (n - 2,), ()), 32 * N),
+             ("CNot c%d t%d" % (n - 1, 3), Op("mcx", (3,), (n - 1,)), 16 * N),
+             ("CZ %d,%d" % (n - 1, n - 2), Op("phase", (), (n - 1, n - 2), scalar=-1 + 0j), 8 * N),
+             ("phase q%d" % (n - 1), Op("phase", (), (n - 1,), scalar=complex(s, s)), 16 * N)]
+    out = []
+    for label, op, nbytes in cases:
+        plan = sv.prepare([op])
+        for _ in range(2):
+            sv.execute(plan)
+        ms = sv.time_passes(plan, repeats=5)
+        t = sum(ms) / len(ms)
+        gbs = nbytes / (t * 1e-3) / 1e9
+        out.append({"gate": label, "ms": t, "algorithmic_GBps": gbs, "frac_of_peak": gbs / peak})
+    return out
+
+
+if __name__ == "__main__":
+    main()

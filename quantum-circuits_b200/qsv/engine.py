@@ -1,0 +1,297 @@
+"""Device-side execution: owns the complex128 state in HBM and drives libqsv through the C-ABI.
+
+torch is used for plumbing only (device memory, the current CUDA stream, torch.distributed); every
+amplitude is touched by the hand-written kernels of csrc/.  There is no CPU path: constructing a
+StateVector without CUDA raises RuntimeError.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _cabi
+from .schedule import Op, TILED_KINDS, plan_passes, pack_passes
+
+SCAN_BITS_EXACT = 20     # up to 2^20 outcomes: one fully sequential scan (bit-exact with random.choices)
+SAMPLE_BLOCK_BITS = 12   # larger states: block sums of 2^12 outcomes, then a sequential scan inside one block
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("qsv: no CUDA device available - the state-vector engine has no CPU fallback")
+
+
+class StateVector:
+    """2^n_local complex128 amplitudes of one shard, plus the operations of the hot path.
+
+    n        total qubits of the register
+    comm     optional qsv.dist.Comm (rank, world size 2^g); the shard holds the amplitudes whose top g
+             index bits equal the rank
+    """
+
+    def __init__(self, n, device=None, comm=None):
+        _require_cuda()
+        self.lib = _cabi.load()
+        self.n = int(n)
+        self.comm = comm
+        self.g = comm.global_bits if comm is not None else 0
+        self.rank = comm.rank if comm is not None else 0
+        self.n_local = self.n - self.g
+        if self.n_local < 1:
+            raise RuntimeError("qsv: need at least one local qubit per shard")
+        self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+        self.state = torch.empty(1 << self.n_local, dtype=torch.complex128, device=self.device)
+        self._scratch = None
+        self._keep = []       # host/device buffers that must outlive the async launches
+        self.passes_run = 0
+        self.d2h_bytes = 0
+        self.tile_bits = None
+        self.low_bits = None
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def rank_bits(self):
+        return self.rank << self.n_local
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ptr(self, t):
+        return C.c_void_p(t.data_ptr())
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        self._keep.clear()
+
+    # ------------------------------------------------------------------ state preparation
+    def init_basis(self, index):
+        """|index>: main/circuit.py:290-301."""
+        _cabi.check(self.lib.qsv_init_basis(self._ptr(self.state), self.n_local, int(index), self.rank,
+                                            self._stream()), "qsv_init_basis")
+
+    # ------------------------------------------------------------------ gate application
+    def upload_program(self, ops):
+        """Plan + pack a run of tiled ops and copy the image to the device.  Returns a handle for
+        run_program (so benchmarks can separate host scheduling from device time)."""
+        passes = plan_passes(ops, self.n_local, self.tile_bits, self.low_bits)
+        packed = pack_passes(passes)
+        host = torch.from_numpy(packed.blob)
+        dev = host.to(self.device, non_blocking=False)
+        return (packed, dev)
+
+    def run_program(self, handle):
+        packed, dev = handle
+        for meta in packed.passes:
+            self._launch_pass(meta, dev)
+            self.passes_run += 1
+        self._keep.append(dev)
+
+    def _scratch_state(self):
+        if self._scratch is None:
+            self._scratch = torch.empty_like(self.state)
+        return self._scratch
+
+    def _run_whole_state_op(self, op):
+        st = self._stream()
+        if op.kind == "wide_dense":
+            M = torch.from_numpy(np.ascontiguousarray(op.matrix, dtype=np.complex128)).to(self.device)
+            out = self._scratch_state()
+            _cabi.check(self.lib.qsv_apply_dense_wide(self._ptr(self.state), self._ptr(out), self.n_local,
+                                                      len(op.targets), _cabi.int_array(op.targets), self._ptr(M),
+                                                      st), "qsv_apply_dense_wide")
+            self.state, self._scratch = out, self.state
+            self._keep.append(M)
+        elif op.kind == "wide_perm":
+            P = torch.from_numpy(np.ascontiguousarray(op.perm, dtype=np.uint32).view(np.int32)).to(self.device)
+            out = self._scratch_state()
+            _cabi.check(self.lib.qsv_apply_perm_wide(self._ptr(self.state), self._ptr(out), self.n_local,
+                                                     len(op.targets), _cabi.int_array(op.targets), self._ptr(P),
+                                                     st), "qsv_apply_perm_wide")
+            self.state, self._scratch = out, self.state
+            self._keep.append(P)
+        elif op.kind == "wide_diag":
+            D = torch.from_numpy(np.ascontiguousarray(op.matrix, dtype=np.complex128)).to(self.device)
+            _cabi.check(self.lib.qsv_apply_diag_wide(self._ptr(self.state), self.n_local, len(op.targets),
+                                                     _cabi.int_array(op.targets), self._ptr(D), st),
+                        "qsv_apply_diag_wide")
+            self._keep.append(D)
+        elif op.kind == "modexp":
+            p = op.params
+            _cabi.check(self.lib.qsv_modexp_involution(self._ptr(self.state), self.n_local, len(p["x_pos"]),
+                                                       _cabi.int_array(p["x_pos"]), len(p["y_pos"]),
+                                                       _cabi.int_array(p["y_pos"]), int(p["a"]), int(p["N"]),
+                                                       self.rank_bits, st), "qsv_modexp_involution")
+        elif op.kind == "oracle":
+            self._oracle(op)
+        elif op.kind == "diffusion":
+            self._diffusion(op)
+        elif op.kind == "global_swap":
+            if self.comm is None:
+                raise RuntimeError("qsv: global_swap op without a communicator")
+            self.comm.swap_global_local(self, op.params["n_swap"])
+        else:
+            raise RuntimeError("qsv: unknown op kind %r" % op.kind)
+
+    def _oracle(self, op):
+        """Grover oracle for one marked item (main/Grover.py:14-22): exchange the two amplitudes whose
+        search-register bits equal x.  params: idx0, idx1 = global indices of the pair."""
+        i0, i1 = int(op.params["idx0"]), int(op.params["idx1"])
+        if (i0 >> self.n_local) != (i1 >> self.n_local):
+            raise RuntimeError("qsv: oracle pair straddles shards; the target qubit must be local")
+        if (i0 >> self.n_local) != self.rank:
+            return
+        m = (1 << self.n_local) - 1
+        _cabi.check(self.lib.qsv_grover_oracle(self._ptr(self.state), i0 & m, i1 & m, self._stream()),
+                    "qsv_grover_oracle")
+
+    def _diffusion(self, op):
+        """2|s><s| - I on all positions >= anc_bits (main/Grover.py:24-31,40-44)."""
+        anc = int(op.params["anc_bits"])
+        need = self.lib.qsv_diffusion_scratch_bytes(self.n_local, anc)
+        scratch = torch.empty(max(16, need), dtype=torch.uint8, device=self.device)
+        sums = torch.empty(1 << anc, dtype=torch.complex128, device=self.device)
+        st = self._stream()
+        _cabi.check(self.lib.qsv_diffusion_sums(self._ptr(self.state), self.n_local, anc, self._ptr(scratch),
+                                                self._ptr(sums), st), "qsv_diffusion_sums")
+        if self.comm is not None and self.comm.world > 1:
+            self.comm.all_reduce_sum(sums)
+        _cabi.check(self.lib.qsv_diffusion_update(self._ptr(self.state), self.n_local, anc, self._ptr(sums),
+                                                  self.n - anc, st), "qsv_diffusion_update")
+        self._keep += [scratch, sums]
+
+    def prepare(self, ops):
+        """Host scheduling + upload: split ops into tiled programs (planned, packed, copied to HBM) and
+        whole-state ops.  The returned plan can be executed any number of times."""
+        segments = []
+        batch = []
+        h2d = 0
+        for op in ops:
+            if op.kind in TILED_KINDS:
+                batch.append(op)
+                continue
+            if batch:
+                segments.append(("program", self.upload_program(batch)))
+                batch = []
+            segments.append(("op", op))
+        if batch:
+            segments.append(("program", self.upload_program(batch)))
+        for kind, seg in segments:
+            if kind == "program":
+                h2d += int(seg[0].blob.size)
+        return {"segments": segments, "h2d_bytes": h2d}
+
+    def execute(self, plan):
+        for kind, seg in plan["segments"]:
+            if kind == "program":
+                self.run_program(seg)
+            else:
+                self._run_whole_state_op(seg)
+
+    def run_ops(self, ops):
+        """Apply ops (physical positions) in order; consecutive tiled ops share passes."""
+        plan = self.prepare(ops)
+        self.execute(plan)
+        return plan
+
+    # ------------------------------------------------------------------ instrumentation (bench.py)
+    def _launch_pass(self, packed_meta, dev):
+        ps, table_off, n_ops, maxk = packed_meta
+        base = dev.data_ptr()
+        cp = _cabi.QsvPass()
+        cp.n_local, cp.tile_bits, cp.low_bits = ps.n_local, ps.tile_bits, ps.low_bits
+        cp.n_hi = ps.tile_bits - ps.low_bits
+        for j, p in enumerate(ps.hi_pos):
+            cp.hi_pos[j] = p
+        cp.rank_bits = self.rank_bits
+        cp.max_dense_k = maxk
+        _cabi.check(self.lib.qsv_run_pass(self._ptr(self.state), C.byref(cp), C.c_void_p(base),
+                                          C.c_void_p(base + table_off), n_ops, self._stream()), "qsv_run_pass")
+
+    def time_passes(self, plan, repeats=1):
+        """CUDA-event duration (ms) of every k_pass launch of the plan, on the launching stream."""
+        stream = torch.cuda.current_stream(self.device)
+        out = []
+        for kind, seg in plan["segments"]:
+            if kind != "program":
+                continue
+            packed, dev = seg
+            for meta in packed.passes:
+                best = []
+                for _ in range(repeats):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    self._launch_pass(meta, dev)
+                    e1.record(stream)
+                    e1.synchronize()
+                    best.append(e0.elapsed_time(e1))
+                out.append(sum(best) / len(best))
+        return out
+
+    def pass_active_fractions(self, plan):
+        """Fraction of tiles each pass actually loads (tiles switched off by external controls are
+        skipped): 1.0 if any op is unconditional, else the union bound over the ops' control masks."""
+        out = []
+        for kind, seg in plan["segments"]:
+            if kind != "program":
+                continue
+            packed, _ = seg
+            for ps, _, _, _ in packed.passes:
+                frac = 0.0
+                for op in ps.ops:
+                    ext = [c for c in op.controls if c >= ps.n_local or ps.loc(c) < 0]
+                    frac += 2.0 ** (-len(ext))
+                out.append(min(1.0, frac))
+        return out
+
+    # ------------------------------------------------------------------ measurement
+    def probs(self, src_pos=None):
+        """float64 tensor of the local probabilities in OUTPUT order (main/circuit.py:329-337)."""
+        out = torch.empty(1 << self.n_local, dtype=torch.float64, device=self.device)
+        sp = _cabi.int_array(src_pos) if src_pos is not None else None
+        _cabi.check(self.lib.qsv_probs(self._ptr(self.state), self.n_local, sp, self._ptr(out), self._stream()),
+                    "qsv_probs")
+        return out
+
+    def _scan(self, sp, z0, z1, prefix, target):
+        res = torch.empty(2, dtype=torch.int64, device=self.device)
+        _cabi.check(self.lib.qsv_sample_scan(self._ptr(self.state), self.n_local, sp, z0, z1, float(prefix),
+                                             float(target), self._ptr(res), self._stream()), "qsv_sample_scan")
+        host = res.cpu().numpy()
+        self.d2h_bytes += 16
+        return int(host[0]), float(host.view(np.float64)[1])
+
+    def sample(self, u, src_pos=None):
+        """Outcome index of random.choices(states, weights) for the uniform draw u
+        (main/circuit.py:360-364): bisect_right(accumulate(weights), u*total, 0, N-1)."""
+        if self.comm is not None and self.comm.world > 1:
+            return self.comm.sample(self, u, src_pos)
+        sp = _cabi.int_array(src_pos) if src_pos is not None else None
+        last = (1 << self.n_local) - 1
+        if self.n_local <= SCAN_BITS_EXACT:
+            _, total = self._scan(sp, 0, last, 0.0, float("inf"))
+            if not total > 0.0:
+                raise ValueError("Total of weights must be greater than zero")
+            z, _ = self._scan(sp, 0, last, 0.0, u * total)
+            return z
+        sums = self.block_sums(src_pos, SAMPLE_BLOCK_BITS).cpu().numpy()
+        self.d2h_bytes += 8 * sums.size
+        cum = np.cumsum(sums)
+        total = float(cum[-1])
+        if not total > 0.0:
+            raise ValueError("Total of weights must be greater than zero")
+        target = u * total
+        blk = min(int(np.searchsorted(cum, target, side="right")), len(cum) - 1)
+        prefix = float(cum[blk - 1]) if blk > 0 else 0.0
+        z, _ = self._scan(sp, blk << SAMPLE_BLOCK_BITS, last, prefix, target)
+        return z
+
+    def block_sums(self, src_pos=None, block_bits=SAMPLE_BLOCK_BITS):
+        block_bits = min(block_bits, self.n_local)
+        out = torch.empty(1 << (self.n_local - block_bits), dtype=torch.float64, device=self.device)
+        sp = _cabi.int_array(src_pos) if src_pos is not None else None
+        _cabi.check(self.lib.qsv_block_sums(self._ptr(self.state), self.n_local, sp, block_bits, self._ptr(out),
+                                            self._stream()), "qsv_block_sums")
+        return out
+
+    def amplitudes(self):
+        """Local amplitudes as a numpy array (tests / small states only)."""
+        return self.state.cpu().numpy()

@@ -1,0 +1,234 @@
+"""Circuit -> op list: the host half of run_method2 (reference main/circuit.py:279-337).
+
+The reference resolves, per gate, which input-wire qubits its ports act on (startqbit,
+main/circuit.py:380-389), builds permutation matrices to bring them to the front, and multiplies.
+Here the same target resolution is done once for the whole circuit in O(gates), each gate is
+classified (qsv.schedule.classify_matrix) into index-arithmetic ops on PHYSICAL bit positions, and
+the final output relabel (main/circuit.py:329-332) becomes a bit map applied when measuring.
+"""
+import math
+import numpy as np
+
+from .schedule import Op, classify_matrix
+from . import engine as _engine
+
+LIST_WEIGHTS_MAX_QUBITS = 22   # run_method2 returns a plain list up to here, a lazy sequence above
+QFT_DENSE_MAX = 8              # QFT(size) gates up to this size use the reference's dense matrix entries
+
+
+def topological_gates(circuit):
+    """Gates in a dependency-respecting order without mutating the circuit (method 1 of the reference
+    never reorders circuit.gates)."""
+    if not circuit.check():
+        raise RuntimeError("Cannot sort - please finish building the circuit first.")
+    indeg = {}
+    for g in circuit.gates:
+        indeg[g] = sum(1 for w in g.in_wires if w.left is not circuit)
+    ready = [g for g in circuit.gates if indeg[g] == 0]
+    order = []
+    while ready:
+        g = ready.pop(0)
+        order.append(g)
+        for w in g.out_wires:
+            if w.right is not circuit:
+                indeg[w.right] -= 1
+                if indeg[w.right] == 0:
+                    ready.append(w.right)
+    return order
+
+
+def gate_targets(circuit, gates):
+    """For every gate (in the given topological order) the input-wire qubit each port acts on —
+    startqbit() of main/circuit.py:380-389 for all gates at once."""
+    qubit_of = {}
+    table = []
+    for g in gates:
+        tg = []
+        for j, w in enumerate(g.in_wires):
+            q = w.lind if w.left is circuit else qubit_of[(w.left, w.lind)]
+            qubit_of[(g, j)] = q
+            tg.append(q)
+        table.append(tg)
+    out = []
+    for i in range(len(circuit)):
+        w = circuit.output[i]
+        out.append(w.lind if w.left is circuit else qubit_of[(w.left, w.lind)])
+    return table, out
+
+
+class Layout:
+    """wire (logical qubit) -> physical bit position.  Big-endian start: wire w at position n-1-w."""
+
+    def __init__(self, n):
+        self.n = n
+        self.pos = [n - 1 - w for w in range(n)]
+
+    def positions(self, wires):
+        return tuple(self.pos[w] for w in wires)
+
+    def relabel(self, wires, new_wires):
+        """The qubit currently known as wires[i] is henceforth called new_wires[i]."""
+        old = [self.pos[w] for w in wires]
+        for w, p in zip(new_wires, old):
+            self.pos[w] = p
+
+
+def _qft_ladder(wires, layout):
+    """QFT with +i exponent on `wires` (wires[0] = MSB), equal to Matrix.QFT (main/matrix.py:212-219):
+    H + controlled-phase ladder; the closing bit reversal is a relabel of the layout, not a data pass."""
+    k = len(wires)
+    s = 2 ** (-0.5)
+    Hm = np.array([[s, s], [s, -s]], dtype=np.complex128)
+    ops = []
+    for i in range(k):
+        ops.append(Op("dense", (layout.pos[wires[i]],), (), matrix=Hm, name="QFT.H"))
+        for j in range(i + 1, k):
+            theta = 2.0 * math.pi / (1 << (j - i + 1))
+            ops.append(Op("phase", (), (layout.pos[wires[j]], layout.pos[wires[i]]),
+                          scalar=complex(math.cos(theta), math.sin(theta)), name="QFT.CP"))
+    layout.relabel(list(wires), list(reversed(wires)))
+    return ops
+
+
+def lower_gate(gate, wires, layout, transposed=False):
+    """Ops (physical positions) for one gate acting on logical qubits `wires` (wires[p] = port p)."""
+    hook = getattr(gate, "_qsv_lower", None)
+    if hook is not None:
+        return hook(wires, layout, transposed)
+    m = gate.matrix
+    spec = m.structure() if hasattr(m, "structure") else None
+    name = getattr(gate, "name", "")
+    if spec is not None and spec[0] == "power":
+        base = np.array(spec[1], dtype=np.complex128)
+        if transposed:
+            base = base.T
+        ops = []
+        for w in wires:
+            ops += classify_matrix(base, (layout.pos[w],), name)
+        return ops
+    if spec is not None and spec[0] == "qft" and spec[1] > QFT_DENSE_MAX:
+        return _qft_ladder(wires, layout)          # symmetric matrix: transposition changes nothing
+    M = np.array(m.rows, dtype=np.complex128)
+    dim = 1 << len(wires)
+    if M.shape != (dim, dim):
+        raise RuntimeError("Gates should be represented by square matrices.")
+    if transposed:
+        M = M.T
+    return classify_matrix(M, layout.positions(wires), name)
+
+
+def lower(circuit, transposed=False, presorted=True):
+    """(ops, src_pos): ops in application order; src_pos[b] = physical position feeding bit b of the
+    OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map."""
+    n = len(circuit)
+    gates = circuit.gates if presorted else topological_gates(circuit)
+    table, out_qubits = gate_targets(circuit, gates)
+    layout = Layout(n)
+    ops = []
+    for g, wires in zip(gates, table):
+        ops += lower_gate(g, wires, layout, transposed)
+    src_pos = [0] * n
+    for i in range(n):
+        src_pos[n - 1 - i] = layout.pos[out_qubits[i]]
+    if sorted(src_pos) != list(range(n)):
+        raise RuntimeError("circuit outputs do not carry every qubit exactly once")
+    return ops, src_pos
+
+
+def basis_index(in_v):
+    idx = 0
+    for b in in_v:
+        idx = (idx << 1) | int(b)
+    return idx
+
+
+_last_stats = {"h2d_bytes": 0, "d2h_bytes": 0, "passes": 0}
+
+
+def last_run_stats():
+    """Host<->device traffic of the most recent simulate_* call (bench.py's e2e accounting)."""
+    return dict(_last_stats)
+
+
+def evolve(circuit, in_v, transposed=False, presorted=True, comm=None):
+    ops, src_pos = lower(circuit, transposed, presorted)
+    sv = _engine.StateVector(len(circuit), comm=comm)
+    sv.init_basis(basis_index(in_v))
+    plan = sv.run_ops(ops)
+    _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=0, passes=sv.passes_run)
+    return sv, src_pos
+
+
+class LazyWeights:
+    """Sequence view of 2^n probabilities kept in device/host tensor form (large registers)."""
+
+    def __init__(self, tensor):
+        self._t = tensor
+
+    def __len__(self):
+        return self._t.numel()
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self._t[i].cpu().tolist()
+        return float(self._t[i])
+
+    def __iter__(self):
+        step = 1 << 20
+        for s in range(0, len(self), step):
+            yield from self._t[s:s + step].cpu().tolist()
+
+    def tensor(self):
+        return self._t
+
+
+def simulate_weights(circuit, in_v, transposed=False, presorted=True):
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted)
+    w = sv.probs(src_pos)
+    sv.synchronize()
+    if len(circuit) <= LIST_WEIGHTS_MAX_QUBITS:
+        _last_stats["d2h_bytes"] = 8 * w.numel()
+        return w.cpu().tolist()
+    return LazyWeights(w)
+
+
+def simulate_sample(circuit, in_v, rand_fn, transposed=False, presorted=True):
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted)
+    u = rand_fn()                       # exactly one uniform draw per run, after the weights exist
+    z = sv.sample(u, src_pos)
+    sv.synchronize()
+    _last_stats["d2h_bytes"] = sv.d2h_bytes
+    return z
+
+
+def simulate_amplitudes(circuit, in_v, transposed=False, presorted=True):
+    """Final amplitudes in OUTPUT order as numpy complex128 (tests; the reference only exposes weights)."""
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted)
+    amp = sv.amplitudes()
+    n = len(circuit)
+    z = np.arange(1 << n, dtype=np.int64)
+    y = np.zeros_like(z)
+    for b in range(n):
+        y |= ((z >> b) & 1) << src_pos[b]
+    return amp[y]
+
+
+def circuit_unitary_rows(circuit):
+    """Rows of the whole-circuit unitary (get_subcircuit, main/circuit.py:122-157)."""
+    circuit.sort()
+    n = len(circuit)
+    ops, src_pos = lower(circuit, False, True)
+    dim = 1 << n
+    z = np.arange(dim, dtype=np.int64)
+    y = np.zeros_like(z)
+    for b in range(n):
+        y |= ((z >> b) & 1) << src_pos[b]
+    cols = []
+    sv = _engine.StateVector(n)
+    handle = None
+    for c in range(dim):
+        sv.init_basis(c)
+        sv.run_ops(ops)
+        cols.append(sv.amplitudes()[y])
+    U = np.stack(cols, axis=1)
+    return [[complex(v) for v in row] for row in U]

@@ -1,0 +1,185 @@
+"""Shared test helpers: rebuild fixture circuits with the mirror API, emulate packed tile programs."""
+import numpy as np
+
+
+def to_complex_rows(m):
+    out = []
+    for row in m:
+        r = []
+        for re, im in row:
+            r.append(complex(re, im) if im != 0 else (int(re) if float(re).is_integer() else re))
+        out.append(r)
+    return out
+
+
+def perm_to_rows(perm):
+    D = len(perm)
+    rows = [[0] * D for _ in range(D)]
+    for col, r in enumerate(perm):
+        rows[int(r)][col] = 1
+    return rows
+
+
+def build_circuit(case, arrays=None):
+    """Re-create a serialised fixture circuit with quantum-circuits_b200/main (the mirror API)."""
+    import main.circuit as mc
+    from main.matrix import Matrix
+    c = mc.Circuit(case["n"])
+    gates = []
+    for g in case["gates"]:
+        cls = g["cls"]
+        if cls == "Gate":
+            if "perm_matrix" in g:
+                rows = perm_to_rows(arrays["modexp_perm/" + g["perm_matrix"]])
+            elif "matrix_key" in g:
+                rows = [[complex(v) for v in row] for row in arrays[g["matrix_key"]]]
+            else:
+                rows = to_complex_rows(g["matrix"])
+            obj = mc.Gate(Matrix(rows), g["name"], True)
+        elif cls in ("CNot", "T"):
+            obj = getattr(mc, cls)(g["name"])
+        else:
+            obj = getattr(mc, cls)(g["size"], g["name"])
+        gates.append(c.add(obj))
+    for src, sp, dst, dp in case["wires"]:
+        c.add_wire(c if src < 0 else gates[src], sp, c if dst < 0 else gates[dst], dp)
+    return c
+
+
+def circuit_from_steps(steps, n):
+    """Mirror-API circuit from oracle-style (matrix, wires[, label]) steps."""
+    import main.circuit as mc
+    from main.matrix import Matrix
+    c = mc.Circuit(n)
+    last = [(c, i) for i in range(n)]
+    for k, st in enumerate(steps):
+        M, wires = st[0], st[1]
+        label = st[2] if len(st) > 2 else "G"
+        rows = [[complex(v) for v in row] for row in np.asarray(M)]
+        g = c.add(mc.Gate(Matrix(rows), "%s_%d" % (label, k), True))
+        for p, w in enumerate(wires):
+            c.add_wire(last[w][0], last[w][1], g, p)
+            last[w] = (g, p)
+    for w in range(n):
+        c.add_wire(last[w][0], last[w][1], c, w)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy emulation of k_pass (csrc/qsv_tile.cu) working directly on the packed device image: checks
+# plan_passes + encode_op + the tile index arithmetic on the CPU, where no GPU is available.
+# ------------------------------------------------------------------------------------------------
+
+def _insert_zero(v, p):
+    return ((v >> p) << (p + 1)) | (v & ((1 << p) - 1))
+
+
+def emulate_program(packed, psi, rank_bits=0):
+    from qsv.schedule import OP_DTYPE
+    from qsv import _cabi
+    blob = packed.blob.tobytes()
+    psi = psi.copy()
+    for ps, table_off, n_ops, maxk in packed.passes:
+        T, L = ps.tile_bits, ps.low_bits
+        hi = list(ps.hi_pos)
+        offs = np.frombuffer(blob, dtype="<u4", count=n_ops, offset=table_off)
+        loc = np.arange(1 << T)
+        gl_off = loc & ((1 << L) - 1)
+        for j, p in enumerate(hi):
+            gl_off = gl_off | (((loc >> (L + j)) & 1) << p)
+        for t in range(1 << (ps.n_local - T)):
+            base = t << L
+            for p in hi:
+                base = _insert_zero(base, p)
+            gbase = base | rank_bits
+            tile = psi[base + gl_off].copy()
+            for o in offs:
+                hdr = np.frombuffer(blob, dtype=OP_DTYPE, count=1, offset=int(o))[0]
+                if (gbase & int(hdr["ext_ctrl_mask"])) != int(hdr["ext_ctrl_val"]):
+                    continue
+                k, n_ins = int(hdr["k"]), int(hdr["n_ins"])
+                ins = [int(x) for x in hdr["ins"][:n_ins]]
+                tgt = [int(x) for x in hdr["tgt"]]
+                j = np.arange(1 << (T - n_ins))
+                for p in ins:
+                    j = _insert_zero(j, p)
+                bidx = j | int(hdr["loc_ctrl_val"])
+                pay = int(o) + int(hdr["payload_off"])
+                kind = int(hdr["kind"])
+                if kind == _cabi.QSV_OP_DENSE:
+                    D = 1 << k
+                    M = np.frombuffer(blob, dtype=np.complex128, count=D * D, offset=pay).reshape(D, D)
+                    off = [sum(((c >> (k - 1 - p)) & 1) << tgt[p] for p in range(k)) for c in range(D)]
+                    x = np.stack([tile[bidx | off[c]] for c in range(D)])
+                    y = M @ x
+                    for r in range(D):
+                        tile[bidx | off[r]] = y[r]
+                elif kind == _cabi.QSV_OP_MCX:
+                    b = 1 << tgt[0]
+                    a0, a1 = tile[bidx].copy(), tile[bidx | b].copy()
+                    tile[bidx], tile[bidx | b] = a1, a0
+                elif kind == _cabi.QSV_OP_SWAP:
+                    ba, bb = 1 << tgt[0], 1 << tgt[1]
+                    a0, a1 = tile[bidx | ba].copy(), tile[bidx | bb].copy()
+                    tile[bidx | ba], tile[bidx | bb] = a1, a0
+                elif kind == _cabi.QSV_OP_PHASE:
+                    tile[bidx] = tile[bidx] * complex(hdr["scalar"][0], hdr["scalar"][1])
+                elif kind == _cabi.QSV_OP_DIAG:
+                    d = np.frombuffer(blob, dtype=np.complex128, count=1 << k, offset=pay)
+                    di = np.zeros_like(bidx)
+                    for p in range(k):
+                        tb = tgt[p]
+                        if tb & 0x80:
+                            di |= ((gbase >> (tb & 0x7F)) & 1) << (k - 1 - p)
+                        else:
+                            di |= ((bidx >> tb) & 1) << (k - 1 - p)
+                    tile[bidx] = tile[bidx] * d[di]
+                else:
+                    raise AssertionError("bad op kind %d" % kind)
+            psi[base + gl_off] = tile
+    return psi
+
+
+def emulate_ops(ops, psi, n_local, tile_bits=None, low_bits=None, rank_bits=0):
+    """Run a list of qsv.schedule.Op on a numpy state the way engine.run_ops would (tiled ops through
+    the packed-program emulator, whole-state ops through direct numpy restatements)."""
+    from qsv.schedule import TILED_KINDS, plan_passes, pack_passes
+    batch = []
+
+    def flush(psi):
+        if batch:
+            psi = emulate_program(pack_passes(plan_passes(batch, n_local, tile_bits, low_bits)), psi, rank_bits)
+            batch.clear()
+        return psi
+
+    for op in ops:
+        if op.kind in TILED_KINDS:
+            batch.append(op)
+            continue
+        psi = flush(psi)
+        idx = np.arange(psi.size)
+        k = len(op.targets)
+        c = np.zeros_like(idx)
+        for p, pos in enumerate(op.targets):
+            c |= ((idx >> pos) & 1) << (k - 1 - p)
+        tmask = sum(1 << p for p in op.targets)
+
+        def scatter(v):
+            o = np.zeros_like(idx)
+            for p, pos in enumerate(op.targets):
+                o |= ((v >> (k - 1 - p)) & 1) << pos
+            return o
+        if op.kind == "wide_perm":
+            out = np.empty_like(psi)
+            out[(idx & ~tmask) | scatter(op.perm[c].astype(np.int64))] = psi
+            psi = out
+        elif op.kind == "wide_diag":
+            psi = psi * op.matrix[c]
+        elif op.kind == "wide_dense":
+            out = np.zeros_like(psi)
+            for col in range(1 << k):
+                out += op.matrix[c, col] * psi[(idx & ~tmask) | scatter(np.full_like(idx, col))]
+            psi = out
+        else:
+            raise AssertionError("emulate_ops: unsupported op kind %s" % op.kind)
+    return flush(psi)

@@ -1,0 +1,64 @@
+"""The C-ABI library builds, loads and exports every symbol include/qsv.h declares (no compute
+calls: there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from qsv import _cabi
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "qsv.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(qsv_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in include/qsv.h"
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.qsv_abi_version() == 1
+    assert lib.qsv_launch_count() == 0
+
+
+def test_struct_layouts_match_header():
+    from qsv import _cabi, schedule
+    assert ctypes.sizeof(_cabi.QsvPass) == 48
+    assert schedule.OP_DTYPE.itemsize == 88 and schedule.OP_DTYPE.itemsize <= _cabi.QSV_OP_HEADER_BYTES
+    offs = {n: schedule.OP_DTYPE.fields[n][1] for n in schedule.OP_DTYPE.names}
+    assert offs == {"kind": 0, "k": 4, "n_ins": 8, "flags": 12, "ext_ctrl_mask": 16, "ext_ctrl_val": 24,
+                    "loc_ctrl_val": 32, "payload_off": 36, "op_bytes": 40, "reserved": 44, "ins": 48, "tgt": 64,
+                    "scalar": 72}
+
+
+def test_argument_validation_without_gpu():
+    """Host-side validation runs before any CUDA call, so error paths are testable on the CPU."""
+    from qsv import _cabi
+    lib = _cabi.load()
+    rc = lib.qsv_apply_cx(None, 4, 0, None, 1, 0, None)
+    assert rc != 0 and b"NULL" in lib.qsv_last_error()
+    buf = ctypes.c_void_p(16)
+    rc = lib.qsv_apply_cx(buf, 4, 0, None, 9, 0, None)
+    assert rc != 0 and b"not a local qubit" in lib.qsv_last_error()
+    rc = lib.qsv_apply_dense(buf, 4, 6, _cabi.int_array([0, 1, 2, 3, 4, 5]), 0, None,
+                             (ctypes.c_double * 2)(), 0, None)
+    assert rc != 0 and b"qsv_apply_dense_wide" in lib.qsv_last_error()
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        return
+    import pytest
+    from qsv import engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.StateVector(3)
+    import main.circuit as mc
+    c = mc.Circuit(1)
+    x = c.add_gate(mc.X)
+    c.add_wire(c, 0, x, 0)
+    c.add_wire(x, 0, c, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.run([0], 2)

@@ -1,0 +1,187 @@
+"""Host logic of the drop-in mirror (quantum-circuits_b200/main) against reference fixtures.  CPU only."""
+import inspect
+import pickle
+import random
+import sys
+
+import numpy as np
+import pytest
+
+import main.circuit as mc
+import main.matrix as mm
+from main.matrix import Matrix, MatrixError, tensor, matrix_product
+from helpers import build_circuit
+
+
+def _rows(m):
+    return [[complex(re, im) for re, im in row] for row in m]
+
+
+def test_matrix_factories_bit_identical_to_reference(golden):
+    meta = golden[0]
+    built = {
+        "H1": Matrix.H(), "H3": Matrix.H(3), "X2": Matrix.X(2), "Y2": Matrix.Y(2), "Z2": Matrix.Z(2),
+        "SqrtNot2": Matrix.SqrtNot(2), "Phase0.3_2": Matrix.PhaseShift(0.3, 2), "QFT1": Matrix.QFT(1),
+        "QFT3": Matrix.QFT(3), "QFT4": Matrix.QFT(4), "Cnot": Matrix.Cnot(), "T": Matrix.T(),
+        "Perm201": Matrix.Permutation([2, 0, 1]), "Id4": Matrix.Id(4), "Zero2x3": Matrix.Zero(2, 3),
+    }
+    A, B = Matrix.QFT(2), Matrix.SqrtNot(2)
+    built["QFT2*SqrtNot2"] = A * B
+    built["QFT2.conj"] = A.getConjugate()
+    built["QFT2.round3"] = A.Round(3)
+    built["tensor3"] = tensor([Matrix.H(), Matrix.Y(), Matrix.PhaseShift(1.1)])
+    built["matrix_product"] = matrix_product([Matrix.H(), Matrix.Y(), Matrix.SqrtNot()])
+    built["apply"] = Matrix.vector([1, 0, 0, 0]).apply([Matrix.H(2), Matrix.Cnot()])
+    for name, m in built.items():
+        ref = _rows(meta["matrices"][name])
+        got = [[complex(v) for v in row] for row in m.rows]
+        assert got == ref, name
+        ints = all(isinstance(v, int) for row in m.rows for v in row)
+        assert ints == meta["matrix_int_entries"][name], name
+    assert Matrix.QFT(3).isUnitary() is meta["isUnitary"]["QFT3"]
+    assert Matrix.T().isUnitary() is meta["isUnitary"]["T"]
+    assert Matrix([[1, 1], [0, 1]]).isUnitary() is meta["isUnitary"]["nonunitary"]
+    assert str(Matrix.Cnot()) == meta["str_Cnot"]
+    assert repr(Matrix.X()) == meta["repr_X"]
+
+
+def test_matrix_errors_and_symbolic_powers():
+    with pytest.raises(MatrixError, match="Please specify the rows of the matrix."):
+        Matrix([])
+    with pytest.raises(MatrixError, match="Row dimensions are not consistent."):
+        Matrix([[1, 2], [3]])
+    with pytest.raises(MatrixError, match="Matrix dimensions must agree."):
+        Matrix.Id(2) * Matrix.Id(4)
+    with pytest.raises(MatrixError, match="This method is reserved for vectors."):
+        Matrix.Id(2).apply([Matrix.Id(2)])
+    big = Matrix.H(30)                       # symbolic: no 2^30 x 2^30 list is ever built
+    assert len(big) == 2 ** 30 and big.structure()[0] == "power"
+    with pytest.raises(MatrixError):
+        big.rows
+    h2 = Matrix.H(2)
+    assert h2.structure() is not None
+    assert h2[3][3] == (2 ** -0.5) * (2 ** -0.5)     # materialises on demand
+    assert h2.structure() is None
+    m = Matrix.X(2)
+    m.rows[0] = [1, 0, 0, 0]                            # callers write into .rows (main/Grover.py:18)
+    assert m.structure() is None
+    t = Matrix([[1, 2], [3, 4]])
+    assert t.transpose() is None and t.rows == [[1, 3], [2, 4]]
+    assert pickle.loads(pickle.dumps(Matrix.H(2))).rows == Matrix.H(2).rows
+
+
+def test_star_import_surface():
+    ns = {}
+    exec("from main.circuit import *", ns)
+    for name in ("Matrix", "tensor", "Counter", "product", "choices", "choice", "randint", "log", "modf", "uuid4",
+                 "Wire", "Circuit", "Gate", "X", "Y", "Z", "H", "SqrtNot", "QFT", "CNot", "T"):
+        assert name in ns, name
+    check = lambda t: inspect.isclass(t) and issubclass(t, mc.Gate) and t is not mc.Gate   # gui/main_window.py:269
+    palette = sorted(n for n, _ in inspect.getmembers(sys.modules["main.circuit"], check))
+    assert palette == ["CNot", "H", "QFT", "SqrtNot", "T", "X", "Y", "Z"]
+    assert (mc.Gate.SIZE, mc.CNot.SIZE, mc.T.SIZE) == (1, 2, 3)
+    for cls in (mc.X, mc.Y, mc.Z, mc.H, mc.SqrtNot, mc.QFT, mc.CNot, mc.T):
+        g = cls()                                   # gui/scene.py:197 instantiates with defaults
+        assert pickle.loads(pickle.dumps(cls)) is cls
+        assert len(g) == cls.SIZE
+
+
+def test_graph_logic_matches_reference(golden):
+    meta, cases, arrays = golden
+    for name, case in cases.items():
+        c = build_circuit(case, arrays)
+        assert c.check() and not c.contains_cycle()
+        before = {g: i for i, g in enumerate(c.gates)}
+        c.sort()
+        assert [before[g] for g in c.gates] == case["sorted_order"], name     # same DFS order as the reference
+        assert [str(g) for g in c.gates] == case["sorted_gate_names"], name
+        assert [[c.startqbit(i, p) for p in range(len(g))] for i, g in enumerate(c.gates)] == case["targets"], name
+        assert c.startqbits() == case["startqbits"], name
+        from qsv.lowering import gate_targets, topological_gates
+        table, outq = gate_targets(c, c.gates)
+        assert table == case["targets"] and outq == case["startqbits"]
+        order = topological_gates(c)
+        seen = set()
+        for g in order:
+            for w in g.in_wires:
+                assert w.left is c or w.left in seen
+            seen.add(g)
+
+
+def test_random_circuit_consumes_rng_like_reference(golden):
+    meta, cases, arrays = golden
+    for seed in range(1, 13):
+        case = cases["random_seed%d" % seed]
+        random.seed(seed)
+        c = mc.Circuit.random_circuit()
+        assert len(c) == case["n"]
+        c.sort()
+        assert [str(g) for g in c.gates] == case["sorted_gate_names"]
+        assert [type(g).__name__ for g in c.gates] == [case["gates"][i]["cls"] for i in case["sorted_order"]]
+        assert c.startqbits() == case["startqbits"]
+
+
+def test_error_messages():
+    c = mc.Circuit(2)
+    h = c.add_gate(mc.H)
+    with pytest.raises(RuntimeError, match="Component is already added to a circuit."):
+        c.add(h)
+    other = mc.H()
+    with pytest.raises(RuntimeError, match="Cannot add wire: Start point is not a valid component."):
+        c.add_wire(other, 0, h, 0)
+    with pytest.raises(RuntimeError, match="Cannot add wire: End point is not a valid component."):
+        c.add_wire(h, 0, other, 0)
+    with pytest.raises(RuntimeError, match="Cannot add wire: H does not have 2 output ports."):
+        c.add_wire(h, 1, c, 0)
+    with pytest.raises(RuntimeError, match="Cannot add wire: H does not have 3 input ports."):
+        c.add_wire(c, 0, h, 2)
+    with pytest.raises(RuntimeError, match="Number of output ports does not match number of input ports."):
+        c.add_wires(c, (0, 1), h, ())
+    with pytest.raises(RuntimeError, match="Cannot sort - please finish building the circuit first."):
+        c.sort()
+    with pytest.raises(RuntimeError, match="Cannot sort - please finish building the circuit first."):
+        c.run_method2([0, 0])
+    with pytest.raises(RuntimeError, match="Gates should be represented by square matrices."):
+        mc.Gate(Matrix([[1, 0, 0], [0, 1, 0]]), "bad")
+    with pytest.raises(RuntimeError, match="Gates should be represented by unitary matrices."):
+        mc.Gate(Matrix([[1, 1], [0, 1]]), "bad")
+    with pytest.raises(RuntimeError, match="Invalid gate dimension."):
+        mc.Gate(Matrix.Id(3), "bad")
+    c2 = mc.Circuit(1)
+    x = c2.add_gate(mc.X)
+    c2.add_wire(c2, 0, x, 0)
+    c2.add_wire(x, 0, c2, 0)
+    with pytest.raises(RuntimeError, match="Input length does not match the size of the circuit."):
+        c2.run_method2([0, 1])
+    with pytest.raises(RuntimeError, match="Invalid input - values must be 0 or 1."):
+        c2.run_method2([2])
+    with pytest.raises(RuntimeError, match="Please choose one of the avalible methods: 1 or 2"):
+        c2.run([0], 3)
+
+
+def test_cycle_detection_and_removal():
+    c = mc.Circuit(1)
+    a, b = c.add_gate(mc.CNot), c.add_gate(mc.CNot)
+    c.add_wire(c, 0, a, 0)
+    c.add_wire(a, 0, b, 0)
+    c.add_wire(b, 0, a, 1)
+    c.add_wire(a, 1, b, 1)
+    c.add_wire(b, 1, c, 0)
+    assert c.contains_cycle() and not c.check()
+    w = b.out_wires[0]
+    c.remove_wire(w)
+    assert b.out_wires[0] is None and a.in_wires[1] is None and w not in c.wires
+    assert not c.contains_cycle()
+    c.remove_gate(b)
+    assert b not in c.gates and c.output[0] is None and a.out_wires[0] is None
+    assert str(a) == "CNot1"          # two gates named CNot were registered: ids are shown
+
+
+def test_circuit_pickle_roundtrip(golden):
+    meta, cases, arrays = golden
+    c = build_circuit(cases["paper5"], arrays)
+    d = pickle.loads(pickle.dumps(c))
+    d.sort()
+    assert [str(g) for g in d.gates] == cases["paper5"]["sorted_gate_names"]
+    assert d.startqbits() == cases["paper5"]["startqbits"]
+    assert {g: 1 for g in d}                      # gates hashable (gui/scene.py:81)

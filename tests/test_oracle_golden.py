@@ -1,0 +1,152 @@
+"""Pin the CPU oracle (oracle/statevec_oracle.py) against vectors produced by the reference itself
+(tests/golden/, written by oracle/gen_golden.py).  CPU only."""
+import random
+
+import numpy as np
+import pytest
+
+import statevec_oracle as so
+from helpers import build_circuit
+
+TOL = 1e-12   # north_star: max-abs per amplitude for floating-point gates
+
+
+def _cases(golden):
+    return golden[1]
+
+
+@pytest.mark.parametrize("name", [
+    "paper5", "grover7", "shor15_a2", "shor15_a7", "shor15_a13", "layered_n5_d3", "layered_n6_d2",
+    "layered_n7_d2", "builtin_mix"] + ["random_seed%d" % s for s in range(1, 13)])
+def test_oracle_matches_reference_weights_and_amplitudes(golden, name):
+    meta, cases, arrays = golden
+    case = cases[name]
+    c = build_circuit(case, arrays)
+    for i, in_v in enumerate(case["inputs"]):
+        steps, sq = so.trace(c)
+        psi = so.evolve(steps, sq, in_v)
+        ref_amps = arrays[name + "/amps"][i]
+        ref_w = arrays[name + "/weights_m2"][i]
+        assert np.max(np.abs(psi - ref_amps)) <= TOL
+        assert np.max(np.abs(so.weights(psi) - ref_w)) <= TOL
+        if name + "/weights_m1" in arrays:
+            w1 = so.run_method1(c, in_v)
+            assert np.max(np.abs(w1 - arrays[name + "/weights_m1"][i])) <= TOL
+
+
+def test_oracle_permutation_circuits_are_bit_exact(golden):
+    """Index work (X / CNot / Toffoli only) must be exact, not merely within tolerance."""
+    meta, cases, arrays = golden
+    case = cases["paper5"]
+    c = build_circuit(case, arrays)
+    for i, in_v in enumerate(case["inputs"]):
+        w = so.run_method2(c, in_v)
+        assert np.array_equal(w, arrays["paper5/weights_m2"][i])
+        idx = int(np.argmax(w))
+        a, b = in_v[0], in_v[1]
+        assert so.index_bits(idx, 6) == [a, b, 1 - a, 1 - b, (1 - a) & (1 - b), a | b]
+    assert [int(np.argmax(arrays["paper5/weights_m2"][i])) for i in range(4)] == [14, 25, 37, 49]
+
+
+def test_modexp_closed_form_matches_reference_matrices(golden):
+    meta, cases, arrays = golden
+    for key in [k for k in arrays.files if k.startswith("modexp_perm/")]:
+        N, a = (int(x) for x in key.split("/")[1].split("_"))
+        q = (len(bin(N)) - 2) * 2
+        ref = arrays[key]
+        assert np.array_equal(so.modexp_permutation(q, a, N), ref)
+        assert np.array_equal(ref[ref], np.arange(1 << q))          # involution
+    # the O(4^q) loop restatement agrees with the closed form (q = 8)
+    U = so.modexp_matrix_reference_loops(8, 7, 15)
+    assert np.array_equal(np.argmax(U, axis=0), arrays["modexp_perm/15_7"])
+    assert (U.sum(axis=0) == 1).all() and (U.sum(axis=1) == 1).all()
+
+
+def test_shor21_weights_from_closed_form_steps(golden):
+    meta, cases, arrays = golden
+    steps, q = so.shor_steps(21, 17)
+    psi = so.evolve(steps, list(range(q)), meta["shor21"]["input"])
+    assert np.max(np.abs(so.weights(psi) - arrays["shor21_a17/weights_m1"][0])) <= TOL
+
+
+def test_grover_steps_match_reference_circuit(golden):
+    meta, cases, arrays = golden
+    steps = so.grover_steps(6, cases["grover7"]["marked"])
+    psi = so.evolve(steps, list(range(7)), [0] * 6 + [1])
+    assert np.max(np.abs(psi - arrays["grover7/amps"][0])) <= TOL
+    w = so.weights(psi)
+    assert abs(w[26] - 0.4982928403934023) < 1e-12 and abs(w[27] - 0.4982928403934023) < 1e-12
+    # closed-form iteration (used for large registers) equals the matrix form
+    phi = so.apply_gate(so.initial_state([0] * 6 + [1]), 7, list(range(7)), steps[0][0])
+    for _ in range(6):
+        phi = so.grover_iteration_closed_form(phi, 6, 13)
+    assert np.max(np.abs(phi - psi)) <= TOL
+
+
+def test_sampling_rule_reproduces_reference_outcomes(golden):
+    """random.seed(s); Shor(15): the reference drew a = randint(2,14) and then one random() per run.
+    Replaying the same stream through the oracle's sampler must give the same outcome bits."""
+    meta, cases, arrays = golden
+    from math import gcd
+    for seed, rec in meta["shor15_sequences"].items():
+        random.seed(int(seed))
+        runs = list(rec["runs"])
+        N = 15
+        a = random.randint(2, N - 1)
+        assert gcd(a, N) == 1, "fixture seeds were chosen so that the first a is coprime"
+        steps, q = so.shor_steps(N, a)
+        w = so.weights(so.evolve(steps, list(range(q)), [0] * (q // 2) + [1] * (q // 2)))
+        got = []
+        while True:
+            out = so.index_bits(so.sample_index(w, random.random()), q)
+            got.append(out)
+            if int("".join(map(str, out[: q // 2])), 2) != 0:
+                break
+        assert got == runs[: len(got)]
+
+
+def test_sample_index_matches_random_choices():
+    rng = random.Random(7)
+    for n in (1, 3, 6):
+        w = [rng.random() for _ in range(1 << n)]
+        states = list(range(1 << n))
+        for _ in range(50):
+            st = rng.getstate()
+            expect = rng.choices(states, w)[0]
+            rng.setstate(st)
+            assert so.sample_index(w, rng.random()) == expect
+
+
+def test_cost_model(golden):
+    meta = golden[0]
+    assert meta["method_choice"] == {"grover7": 2, "shor21": 1}
+    assert so.choose_method(25, 7, 168) == 2
+
+
+def test_gate_constants_match_reference(golden):
+    mats = golden[0]["matrices"]
+
+    def ref(name):
+        return np.array([[complex(re, im) for re, im in row] for row in mats[name]])
+    assert np.array_equal(so.mat_H(), ref("H1"))
+    assert np.array_equal(so.kron_power(so.mat_H(), 3), ref("H3"))
+    assert np.array_equal(so.kron_power(so.mat_Y(), 2), ref("Y2"))
+    assert np.array_equal(so.kron_power(so.mat_SqrtNot(), 2), ref("SqrtNot2"))
+    assert np.array_equal(so.kron_power(so.mat_PhaseShift(0.3), 2), ref("Phase0.3_2"))
+    assert np.array_equal(so.mat_QFT(3), ref("QFT3"))
+    assert np.array_equal(so.mat_QFT(4), ref("QFT4"))
+    assert np.array_equal(so.mat_Cnot(), ref("Cnot"))
+    assert np.array_equal(so.mat_Toffoli(), ref("T"))
+
+
+def test_qft_ladder_equals_dense_qft_up_to_bit_reversal():
+    for n in (1, 2, 3, 5, 7):
+        steps = so.qft_ladder_steps(n)
+        rng = np.random.default_rng(n)
+        psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        psi /= np.linalg.norm(psi)
+        out = psi.copy()
+        for M, wires, _ in steps:
+            out = so.apply_gate(out, n, wires, M)
+        out = so.output_relabel(out, n, list(reversed(range(n))))
+        assert np.max(np.abs(out - so.mat_QFT(n) @ psi)) < 1e-13

@@ -1,0 +1,176 @@
+"""Lowering + pass planning + program packing, executed by a numpy emulation of the tile kernel that
+decodes the packed device image (tests/helpers.py).  Checks all index arithmetic on the CPU."""
+import numpy as np
+import pytest
+
+import statevec_oracle as so
+from helpers import build_circuit, circuit_from_steps, emulate_ops
+from qsv import schedule
+from qsv.lowering import lower, basis_index
+
+TOL = 1e-12
+
+
+def _final_output_order(psi, src_pos):
+    n = len(src_pos)
+    z = np.arange(1 << n)
+    y = np.zeros_like(z)
+    for b in range(n):
+        y |= ((z >> b) & 1) << src_pos[b]
+    return psi[y]
+
+
+def _run_emulated(c, in_v, transposed=False, tile_bits=None, low_bits=None):
+    c.sort()
+    ops, src_pos = lower(c, transposed, True)
+    n = len(c)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[basis_index(in_v)] = 1
+    psi = emulate_ops(ops, psi, n, tile_bits, low_bits)
+    return _final_output_order(psi, src_pos), ops
+
+
+@pytest.mark.parametrize("name", [
+    "paper5", "grover7", "shor15_a7", "layered_n5_d3", "layered_n6_d2", "layered_n7_d2", "builtin_mix"]
+    + ["random_seed%d" % s for s in range(1, 13)])
+@pytest.mark.parametrize("geom", [(None, None), (4, 2), (3, 0)])
+def test_emulated_engine_matches_reference(golden, name, geom):
+    meta, cases, arrays = golden
+    case = cases[name]
+    if name in ("grover7", "shor15_a7") and geom != (None, None):
+        pytest.skip("large fixtures only with the default tile")
+    c = build_circuit(case, arrays)
+    for i, in_v in enumerate(case["inputs"]):
+        psi, ops = _run_emulated(c, in_v, tile_bits=geom[0], low_bits=geom[1])
+        assert np.max(np.abs(psi - arrays[name + "/amps"][i])) <= TOL
+        if name + "/weights_m1" in arrays:
+            psi1, _ = _run_emulated(c, in_v, transposed=True, tile_bits=geom[0], low_bits=geom[1])
+            assert np.max(np.abs(np.abs(psi1) ** 2 - arrays[name + "/weights_m1"][i])) <= TOL
+
+
+def test_permutation_circuit_is_bit_exact(golden):
+    meta, cases, arrays = golden
+    c = build_circuit(cases["paper5"], arrays)
+    for i, in_v in enumerate(cases["paper5"]["inputs"]):
+        psi, ops = _run_emulated(c, in_v, tile_bits=4, low_bits=1)
+        assert all(op.kind == "mcx" for op in ops)
+        assert np.array_equal(psi, arrays["paper5/amps"][i])
+
+
+def test_classification_of_reference_operators():
+    # Grover oracle F (main/Grover.py:14-22): one multi-controlled X with 0/1 control values
+    F = so.grover_oracle_matrix(6, 13)
+    ops = schedule.classify_matrix(F, tuple(range(6, -1, -1)))
+    assert len(ops) == 1 and ops[0].kind == "mcx" and ops[0].targets == (0,)
+    assert sorted(zip(ops[0].controls, ops[0].cvals)) == [(1 + b, (13 >> b) & 1) for b in range(6)]
+    # U0 (x) I: phase -1 on "search register != 0" is not a single controlled phase -> diag table on 6 bits
+    U = so.grover_u0_matrix(6)
+    ops = schedule.classify_matrix(U, tuple(range(6, -1, -1)))
+    assert [o.kind for o in ops] == ["diag"] and ops[0].targets == (6, 5, 4, 3, 2, 1)
+    # H^6 (x) I: six 1-qubit dense ops, no op on the ancilla
+    HI = np.kron(so.kron_power(so.mat_H(), 6), np.eye(2))
+    ops = schedule.classify_matrix(HI, tuple(range(6, -1, -1)))
+    assert [o.kind for o in ops] == ["dense"] * 6 and sorted(o.targets[0] for o in ops) == [1, 2, 3, 4, 5, 6]
+    prod = np.eye(1)
+    for o in sorted(ops, key=lambda o: -o.targets[0]):
+        prod = np.kron(prod, o.matrix)
+    assert np.max(np.abs(np.kron(prod, np.eye(2)) - HI)) < 1e-15
+    # CNot / Toffoli / CZ / Z / phase
+    assert [(o.kind, o.targets, o.controls) for o in schedule.classify_matrix(so.mat_Cnot(), (5, 2))] == [("mcx", (2,), (5,))]
+    t = schedule.classify_matrix(so.mat_Toffoli(), (7, 3, 1))[0]
+    assert t.kind == "mcx" and t.targets == (1,) and sorted(t.controls) == [3, 7] and set(t.cvals) == {1}
+    z = schedule.classify_matrix(so.mat_Z(), (4,))[0]
+    assert z.kind == "phase" and z.controls == (4,) and z.scalar == -1
+    cz = schedule.classify_matrix(so.mat_CZ(), (4, 9))[0]
+    assert cz.kind == "phase" and sorted(cz.controls) == [4, 9]
+    # Shor U (1024 x 1024 permutation) -> exact wide permutation; QFT(5) -> dense 5-qubit tile op
+    perm = so.modexp_permutation(10, 17, 21)
+    Umat = np.zeros((1024, 1024))
+    Umat[perm, np.arange(1024)] = 1
+    ops = schedule.classify_matrix(Umat, tuple(range(9, -1, -1)))
+    assert [o.kind for o in ops] == ["wide_perm"] and np.array_equal(ops[0].perm, perm)
+    ops = schedule.classify_matrix(so.mat_QFT(5), (9, 8, 7, 6, 5))
+    assert [o.kind for o in ops] == ["dense"] and ops[0].matrix.shape == (32, 32)
+    assert schedule.classify_matrix(np.eye(8), (2, 1, 0)) == []
+
+
+def test_pass_planner_respects_dependencies_and_tile_capacity():
+    n = 16
+    steps = so.random_layered_steps(n, 4, seed=3)
+    c = circuit_from_steps(steps, n)
+    c.sort()
+    ops, src_pos = lower(c)
+    for T, L in ((12, 6), (8, 3), (13, 5)):
+        passes = schedule.plan_passes(ops, n, T, L)
+        assert sum(len(p.ops) for p in passes) == len(ops)
+        for p in passes:
+            assert len(p.hi_pos) == p.tile_bits - p.low_bits and list(p.hi_pos) == sorted(set(p.hi_pos))
+            for op in p.ops:
+                assert all(p.loc(b) >= 0 for b in op.nondiag_bits())
+        # order preserved for every pair of ops that do not commute structurally
+        flat = [id(o) for p in passes for o in p.ops]
+        rank = {o: i for i, o in enumerate(flat)}
+        for i, a in enumerate(ops):
+            for b in ops[i + 1:]:
+                a_nd, b_nd = set(a.nondiag_bits()), set(b.nondiag_bits())
+                a_all, b_all = a_nd | set(a.diag_bits()), b_nd | set(b.diag_bits())
+                if (a_nd & b_all) or (b_nd & a_all):
+                    assert rank[id(a)] < rank[id(b)]
+    # and the result is still right
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    got = emulate_ops(ops, psi, n, 8, 3)
+    ref = so.initial_state([0] * n)
+    for M, wires, _ in steps:
+        ref = so.apply_gate(ref, n, wires, M)
+    assert np.max(np.abs(_final_output_order(got, src_pos) - ref)) <= TOL
+
+
+def test_single_gate_pass_keeps_controls_external():
+    """A lone CNot / CZ on high qubits must leave its control outside the tile so that the kernel skips
+    the tiles the control switches off (half / quarter traffic)."""
+    n = 20
+    cn = schedule.classify_matrix(so.mat_Cnot(), (19, 17))
+    p = schedule.plan_passes(cn, n)[0]
+    assert p.loc(17) >= 0 and p.loc(19) < 0
+    cz = schedule.classify_matrix(so.mat_CZ(), (19, 18))
+    p = schedule.plan_passes(cz, n)[0]
+    assert p.loc(19) < 0 and p.loc(18) < 0
+    packed = schedule.pack_passes([p])
+    hdr = np.frombuffer(packed.blob.tobytes(), dtype=schedule.OP_DTYPE, count=1, offset=16)[0]
+    assert int(hdr["ext_ctrl_mask"]) == (1 << 19) | (1 << 18) and int(hdr["n_ins"]) == 0
+
+
+def test_symbolic_gates_lower_without_materialising():
+    import main.circuit as mc
+    n = 30
+    c = mc.Circuit(n)
+    h = c.add_gate(mc.H, n)
+    x = c.add_gate(mc.X, n)
+    c.add_wires(c, (), h, ())
+    c.add_wires(h, (), x, ())
+    c.add_wires(x, (), c, ())
+    c.sort()
+    ops, src_pos = lower(c)
+    assert len(ops) == 2 * n and src_pos == list(range(n))
+    assert h.matrix.structure() is not None          # still symbolic: nothing built a 2^30 x 2^30 list
+    passes = schedule.plan_passes(ops, n)
+    assert len(passes) <= 2 * 4 + 1
+
+
+def test_large_qft_gate_uses_ladder_and_relabel():
+    import main.circuit as mc
+    n = 10
+    c = mc.Circuit(n)
+    q = c.add_gate(mc.QFT, 9)
+    c.add_wires(c, tuple(range(1, 10)), q, ())
+    c.add_wire(c, 0, c, 0)
+    c.add_wires(q, (), c, tuple(range(1, 10)))
+    c.sort()
+    ops, src_pos = lower(c)
+    assert all(o.kind in ("dense", "phase") for o in ops) and len(ops) == 9 + 36
+    rng = np.random.default_rng(1)
+    psi0 = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    got = _final_output_order(emulate_ops(ops, psi0, n), src_pos)
+    ref = so.apply_gate(psi0, n, list(range(1, 10)), so.mat_QFT(9))
+    assert np.max(np.abs(got - ref)) < 1e-12
