@@ -126,7 +126,7 @@ def cpu_baseline(n_cpu, depth=1, budget_s=25.0):
             break
     dt = time.perf_counter() - t0
     w = so.weights(psi)
-    so.sample_index(w[: 1 << min(n_cpu, 16)], 0.5)
+    so.sample_index_np(w, 0.5)
     try:
         import threadpoolctl
         threads = max([p["num_threads"] for p in threadpoolctl.threadpool_info()] or [1])

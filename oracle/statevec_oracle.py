@@ -162,6 +162,16 @@ def sample_index(w, u):
     return bisect.bisect_right(cum, u * total, 0, len(cum) - 1)
 
 
+def sample_index_np(w, u):
+    """Same rule as sample_index with numpy primitives (np.cumsum adds strictly left to right, so the
+    prefix sums are bit-identical to itertools.accumulate); for registers too large for Python loops."""
+    cum = np.cumsum(np.asarray(w, dtype=np.float64))
+    total = float(cum[-1])
+    if total <= 0.0:
+        raise ValueError("Total of weights must be greater than zero")
+    return int(np.searchsorted(cum[:-1], u * total, side="right"))
+
+
 def index_bits(index, n):
     """Outcome as the bit list run() returns (wire 0 first) — main/circuit.py:360-364."""
     return [(index >> (n - 1 - i)) & 1 for i in range(n)]

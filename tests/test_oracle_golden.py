@@ -114,7 +114,8 @@ def test_sample_index_matches_random_choices():
             st = rng.getstate()
             expect = rng.choices(states, w)[0]
             rng.setstate(st)
-            assert so.sample_index(w, rng.random()) == expect
+            u = rng.random()
+            assert so.sample_index(w, u) == expect == so.sample_index_np(w, u)
 
 
 def test_cost_model(golden):
