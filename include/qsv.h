@@ -80,6 +80,59 @@ typedef struct qsv_pass {
     int32_t  reserved;
 } qsv_pass_t;
 
+/* ---- register-resident pass program (consumed by qsv_run_pass_rounds) --------------------- */
+/* The tile (2^T amplitudes, T >= 4) is held in REGISTERS: 2^(T-4) threads x 16 amplitudes.  A pass is a
+ * sequence of ROUNDS; a round fixes 4 tile-local "register bits" rb[0..3] (ascending): thread t owns the
+ * 16 amplitudes that differ only in those bits, so every op whose non-diagonal target is a register bit
+ * runs without touching shared memory.  Between rounds the tile is re-distributed through shared memory.
+ * Host image: [qsv_rprog_hdr_t][qsv_round_t x n_rounds][qsv_rop_t x n_ops]; it is passed to the kernel
+ * BY VALUE (constant bank), so op fields and matrix entries are read through the uniform datapath.
+ * Diagonal tables (rare) stay in a device buffer; qsv_rop_t.table_off is a byte offset into it. */
+
+#define QSV_RPROG_MAX_ROUNDS 32
+#define QSV_RPROG_MAX_OPS    120
+/* kind byte of qsv_rop_t: straight-line specialisations first, generic predicated forms last */
+#define QSV_ROP_DENSE1      0x10  /* +J        complex 1-qubit matrix on register bit J               */
+#define QSV_ROP_DENSE1_REAL 0x14  /* +J        real matrix                                            */
+#define QSV_ROP_PHASE_T     0x60  /*           phase independent of the register bits                 */
+#define QSV_ROP_PHASE1      0x70  /* +2J+V     phase on the slots with register bit J == V            */
+#define QSV_ROP_PERM        0x80  /* (multi-)controlled X as an address permutation at a round boundary:
+                                     if ((addr & tmask) == tval) addr ^= table_off   (tile-local bits)    */
+#define QSV_ROP_GEN_PHASE   0xF3  /* generic form: any (rmask, rval) condition on the register index    */
+#define QSV_ROP_DIAG        0xF4
+#define QSV_ROPF_REAL  1u   /* matrix entries are real                                               */
+#define QSV_ROPF_NEG   2u   /* PHASE: scalar is exactly -1                                            */
+
+typedef struct qsv_rprog_hdr {
+    uint32_t n_rounds, total_bytes, n_ops, reserved;
+} qsv_rprog_hdr_t;
+
+typedef struct qsv_round {
+    uint8_t  rb[4];         /* ascending tile-local positions held in registers this round             */
+    uint32_t n_ops;         /* register ops of the round                                               */
+    uint32_t first_op;      /* index of the round's first op: [n_pre PERM][n_ops register][n_post PERM] */
+    uint16_t n_pre;         /* permutation ops applied to the addresses the round LOADS from           */
+    uint16_t n_post;        /* permutation ops applied to the addresses the round STORES to            */
+} qsv_round_t;
+
+typedef struct qsv_rop {
+    uint8_t  kind;          /* QSV_ROP_*                                                               */
+    uint8_t  j;             /* DENSE1 / MCX: target register bit 0..3                                  */
+    uint8_t  rmask, rval;   /* condition on the register index r (controls that are register bits)     */
+    uint32_t tmask, tval;   /* condition on the thread's tile-local base index (register bits are 0)   */
+    uint32_t reserved0;
+    uint64_t ext_mask;      /* condition on physical index bits outside the tile                       */
+    uint64_t ext_val;
+    uint32_t flags;         /* QSV_ROPF_*                                                              */
+    uint32_t table_off;     /* DIAG: byte offset of the 2^k complex128 table inside tables_dev         */
+    uint8_t  dsrc[8];       /* DIAG table bit p (p=0 most significant): 0x00..0x3f thread-held local
+                               position, 0x80|pos external physical position, 0xff = register bit      */
+    uint8_t  rc[4];         /* DIAG: table-index bits contributed by register bit 0..3                 */
+    uint32_t k;             /* DIAG: number of table bits                                              */
+    double   m[8];          /* DENSE1: m00,m01,m10,m11 as (re,im); PHASE: m[0..1] = scalar             */
+    uint8_t  pad[8];
+} qsv_rop_t;                /* 128 bytes                                                               */
+
 /* ---- library ---------------------------------------------------------------------------- */
 
 int         qsv_abi_version(void);
@@ -102,6 +155,12 @@ int qsv_init_basis(void *state_dev, int n_local, uint64_t index, uint64_t rank, 
  * external controls switch every op off are skipped entirely. */
 int qsv_run_pass(void *state_dev, const qsv_pass_t *pass, const void *prog_dev,
                  const uint32_t *op_offsets_dev, int n_ops, void *stream);
+
+/* Same contract as qsv_run_pass for a register-resident program (see qsv_rop_t).  `prog_host` is HOST
+ * memory (at most QSV_RPROG_MAX_ROUNDS rounds / QSV_RPROG_MAX_OPS ops); `tables_dev` is the device
+ * buffer diagonal ops index with table_off (may be NULL if the program has none).  tile_bits >= 4. */
+int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                        const void *tables_dev, void *stream);
 
 /* Single-gate conveniences (host arguments only; each is one pass with a one-op program built by
  * the library).  `targets[0]` is the gate's port 0 = most-significant bit of the matrix index

@@ -239,8 +239,9 @@ k_pass(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P, const 
         if (!__syncthreads_or(act)) continue;
 
         if (tid == 0) mbar_arrive_expect_tx(&mbar, 16u << T);
-        for (uint32_t r = tid; r < n_runs; r += kThreads)
-            bulk_g2s(tile + ((size_t)r << L), state + base + s_hi_off[r], run_bytes, &mbar);
+        if ((tid & 31) == 0)        // one lane per warp issues the bulk copies: operands stay warp-uniform
+            for (uint32_t r = tid >> 5; r < n_runs; r += kThreads / 32)
+                bulk_g2s(tile + ((size_t)r << L), state + base + s_hi_off[r], run_bytes, &mbar);
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
@@ -268,8 +269,9 @@ k_pass(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P, const 
 
         fence_proxy_async();   // generic-proxy writes to the tile -> visible to the bulk-copy engine
         __syncthreads();
-        for (uint32_t r = tid; r < n_runs; r += kThreads)
-            bulk_s2g(state + base + s_hi_off[r], tile + ((size_t)r << L), run_bytes);
+        if ((tid & 31) == 0)
+            for (uint32_t r = tid >> 5; r < n_runs; r += kThreads / 32)
+                bulk_s2g(state + base + s_hi_off[r], tile + ((size_t)r << L), run_bytes);
         bulk_commit();
         bulk_wait_read0();     // the tile may be overwritten / the CTA may exit once the reads are done
     }

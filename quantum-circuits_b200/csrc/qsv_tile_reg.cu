@@ -1,0 +1,358 @@
+// Register-resident tiled gate pass (k_pass_reg): the fused-circuit workhorse.
+//
+// Same tile geometry and TMA bulk load/store as k_pass (qsv_tile.cu), but between load and store the
+// tile lives in REGISTERS: 256 threads x 16 complex128.  A pass is split by the host into rounds; in a
+// round, four tile bits are "register bits" (each thread owns the 16 amplitudes that differ in them), so
+// 1-qubit dense gates, (multi-)controlled X and phases whose target is a register bit are straight-line
+// register arithmetic: no shared-memory traffic, no barrier.  Between rounds the tile is re-distributed
+// through shared memory (one store + one load per amplitude).  In the shared-memory kernel every op costs
+// a full tile read+write of shared memory and a barrier, which made 30-gate passes 6x slower than the HBM
+// time of the pass; here the cost is per round, not per op.
+#include "qsv_common.cuh"
+#include <string.h>
+
+namespace qsv {
+
+constexpr int kRThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32r(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_r(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32r(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_r(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32r(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_r(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done) : "r"(smem_u32r(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s_r(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32r(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32r(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_r(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32r(smem_src)), "r"(bytes) : "memory");
+}
+
+// ---- register ops: everything is unrolled over the 16 register slots, r is a compile-time constant.
+// The common cases are STRAIGHT-LINE code selected by the op's kind byte (no per-slot predicates, no
+// selects): the first profile of this kernel showed the ALU pipe saturated by FSEL/ISETP/LOP3 that the
+// compiler generated for dynamic per-slot conditions.  Encodings (see qsv/schedule.py encode_rounds):
+//   0x10+J        dense 1-qubit, complex matrix, target register bit J, no register-bit condition
+//   0x14+J        same, real matrix
+//   0x80          (multi-)controlled X: NOT a register op.  It is an index permutation, applied to the
+//                 shared-memory addresses when a round loads / stores its registers (zero data movement;
+//                 register swaps cost ~100 MOV per op and thread in the first version of this kernel)
+//   0x60          phase with no register-bit dependence: folded into the thread's pending scalar
+//   0x70+2J+V     phase on the slots whose register bit J == V
+//   0xF3/0xF4     generic predicated phase / diagonal table (any rmask/rval)
+
+// In-place complex scale x <- x * s (5 FP64 instructions, one temporary, no register moves).
+__device__ __forceinline__ void cscale_inplace(double2 &x, const double2 s) {
+    const double t = s.y * x.x;
+    x.x = x.x * s.x;
+    x.x = fma(-s.y, x.y, x.x);
+    x.y = x.y * s.x;
+    x.y = x.y + t;
+}
+
+// 2x2 update written so that every result lands in the register that held its last operand: the
+// interpreter's switch forces x[] into fixed registers at every merge point, and the natural
+// "compute y0,y1 then assign" form cost 6-8 MOV per pair (60 % of all issued instructions in the first
+// profile).   y0 = a x0 + b x1,  y1 = c x0 + d x1.
+template <int J, bool REAL>
+__device__ __forceinline__ void f_dense1(double2 (&x)[16], const qsv_rop_t *op) {
+    const double2 a = make_double2(op->m[0], op->m[1]), b = make_double2(op->m[2], op->m[3]);
+    const double2 c = make_double2(op->m[4], op->m[5]), d = make_double2(op->m[6], op->m[7]);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if ((r >> J) & 1) continue;
+        double2 &x0 = x[r], &x1 = x[r | (1 << J)];
+        if (REAL) {
+            const double tr = b.x * x1.x, ti = b.x * x1.y;     // b*x1 before x1 is overwritten
+            x1.x = d.x * x1.x;
+            x1.y = d.x * x1.y;
+            x1.x = fma(c.x, x0.x, x1.x);
+            x1.y = fma(c.x, x0.y, x1.y);
+            x0.x = fma(a.x, x0.x, tr);
+            x0.y = fma(a.x, x0.y, ti);
+        } else {
+            double tr = b.x * x1.x, ti = b.x * x1.y;
+            tr = fma(-b.y, x1.y, tr);
+            ti = fma(b.y, x1.x, ti);
+            cscale_inplace(x1, d);
+            x1.x = fma(c.x, x0.x, x1.x);
+            x1.x = fma(-c.y, x0.y, x1.x);
+            x1.y = fma(c.x, x0.y, x1.y);
+            x1.y = fma(c.y, x0.x, x1.y);
+            const double w = a.y * x0.x;
+            x0.x = fma(a.x, x0.x, tr);
+            x0.x = fma(-a.y, x0.y, x0.x);
+            x0.y = fma(a.x, x0.y, ti);
+            x0.y = x0.y + w;
+        }
+    }
+}
+
+template <int J, int V>
+__device__ __forceinline__ void f_phase1(double2 (&x)[16], const qsv_rop_t *op) {
+    const double2 s = make_double2(op->m[0], op->m[1]);
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+        if (((r >> J) & 1) == V) cscale_inplace(x[r], s);
+}
+
+// generic predicated forms (register-bit conditions of any shape)
+__device__ __forceinline__ void r_phase(double2 (&x)[16], const qsv_rop_t *op) {
+    const uint32_t rmask = op->rmask, rval = op->rval;
+    const double2 s = make_double2(op->m[0], op->m[1]);
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+        if ((r & rmask) == rval) x[r] = cmul(x[r], s);
+}
+
+__device__ __forceinline__ void r_diag(double2 (&x)[16], const qsv_rop_t *op, const uint8_t *sprog, uint32_t tb,
+                                       uint64_t gbase) {
+    const int k = (int)op->k;
+    uint32_t di = 0;
+    for (int p = 0; p < k; ++p) {
+        const uint32_t s = op->dsrc[p];
+        if (s == 0xffu) continue;
+        const uint32_t bit = (s & 0x80u) ? (uint32_t)((gbase >> (s & 0x7fu)) & 1ull) : ((tb >> s) & 1u);
+        di |= bit << (k - 1 - p);
+    }
+    const double2 *tab = reinterpret_cast<const double2 *>(sprog + op->table_off);
+    const uint32_t c0 = op->rc[0], c1 = op->rc[1], c2 = op->rc[2], c3 = op->rc[3];
+    const uint32_t rmask = op->rmask, rval = op->rval;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if ((r & rmask) != rval) continue;
+        const uint32_t d = di | ((r & 1) ? c0 : 0u) | ((r & 2) ? c1 : 0u) | ((r & 4) ? c2 : 0u) | ((r & 8) ? c3 : 0u);
+        cscale_inplace(x[r], __ldg(tab + d));
+    }
+}
+
+#define QSV_CASE_J4(base, CALL) \
+    case (base) + 0: { constexpr int J = 0; CALL; } break; \
+    case (base) + 1: { constexpr int J = 1; CALL; } break; \
+    case (base) + 2: { constexpr int J = 2; CALL; } break; \
+    case (base) + 3: { constexpr int J = 3; CALL; } break;
+#define QSV_CASE_PH1(J_) \
+    case 0x70 + 2 * (J_) + 0: f_phase1<J_, 0>(x, op); break; \
+    case 0x70 + 2 * (J_) + 1: f_phase1<J_, 1>(x, op); break;
+
+__device__ __forceinline__ void apply_rop(double2 (&x)[16], double2 &S, const qsv_rop_t *op, uint32_t kind,
+                                          const uint8_t *sprog, uint32_t tb, uint64_t gbase) {
+    switch (kind) {
+        QSV_CASE_J4(0x10, (f_dense1<J, false>(x, op)))
+        QSV_CASE_J4(0x14, (f_dense1<J, true>(x, op)))
+        case 0x60: S = cmul(S, make_double2(op->m[0], op->m[1])); break;
+        QSV_CASE_PH1(0) QSV_CASE_PH1(1) QSV_CASE_PH1(2) QSV_CASE_PH1(3)
+        case 0xF3: r_phase(x, op); break;
+        case 0xF4: r_diag(x, op, sprog, tb, gbase); break;
+        default: break;
+    }
+}
+
+// The pass program travels as a __grid_constant__ kernel parameter: it lives in the constant bank, op
+// fields and matrix entries are fetched through the uniform datapath (LDCU/ULDC -> uniform registers or
+// direct constant operands), which takes ~25 vector registers out of the interpreter's hot loop.
+struct RProgParam {
+    qsv_rprog_hdr_t hdr;
+    qsv_round_t rounds[QSV_RPROG_MAX_ROUNDS];
+    qsv_rop_t ops[QSV_RPROG_MAX_OPS];
+};
+
+__global__ void __launch_bounds__(kRThreads, 2)
+k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
+           const __grid_constant__ RProgParam prog, const uint8_t *__restrict__ tables, uint64_t n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *tile = reinterpret_cast<double2 *>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint64_t s_hi_off[256];
+
+    const int tid = threadIdx.x;
+    const int T = P.tile_bits, L = P.low_bits, n_hi = P.n_hi;
+    const uint8_t *sprog = tables;      // diagonal tables stay in global memory (read-only path)
+    const uint32_t n_runs = 1u << n_hi;
+    const uint32_t run_bytes = 16u << L;
+    const uint32_t n_active = 1u << (T - 4);       // threads that own amplitudes
+
+    for (uint32_t r = tid; r < n_runs; r += kRThreads) {
+        uint64_t o = 0;
+        for (int j = 0; j < n_hi; ++j)
+            if ((r >> j) & 1u) o |= 1ull << P.hi_pos[j];
+        s_hi_off[r] = o;
+    }
+    if (tid == 0) {
+        mbar_init_r(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_rounds = (int)prog.hdr.n_rounds, n_ops = (int)prog.hdr.n_ops;
+    const qsv_round_t *rounds = prog.rounds;
+    const qsv_rop_t *ops = prog.ops;
+
+    uint32_t parity = 0;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint64_t base = t << L;
+        for (int j = 0; j < n_hi; ++j) base = insert_zero(base, P.hi_pos[j]);
+        const uint64_t gbase = base | P.rank_bits;
+
+        int act = 0;
+        for (int i = tid; i < n_ops; i += kRThreads) act |= ((gbase & ops[i].ext_mask) == ops[i].ext_val);
+        if (!__syncthreads_or(act)) continue;
+
+        if (tid == 0) mbar_arrive_expect_tx_r(&mbar, 16u << T);
+        if ((tid & 31) == 0)        // one lane per warp issues the bulk copies: operands stay warp-uniform
+            for (uint32_t r = tid >> 5; r < n_runs; r += kRThreads / 32)
+                bulk_g2s_r(tile + ((size_t)r << L), state + base + s_hi_off[r], run_bytes, &mbar);
+        mbar_wait_r(&mbar, parity);
+        parity ^= 1u;
+
+        for (int rd = 0; rd < n_rounds; ++rd) {
+            const qsv_round_t R = rounds[rd];
+            const uint32_t b0 = 1u << R.rb[0], b1 = 1u << R.rb[1], b2 = 1u << R.rb[2], b3 = 1u << R.rb[3];
+            uint32_t tb = (uint32_t)tid;
+            tb = insert_zero32(tb, R.rb[0]);
+            tb = insert_zero32(tb, R.rb[1]);
+            tb = insert_zero32(tb, R.rb[2]);
+            tb = insert_zero32(tb, R.rb[3]);
+            const uint32_t n_pre = R.n_pre, n_post = R.n_post;
+            if (rd > 0) __syncthreads();           // the previous round's stores are visible
+            double2 x[16];
+            const bool owner = (uint32_t)tid < n_active;
+            if (owner) {
+                if (n_pre == 0) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        x[r] = tile[tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u)];
+                } else {
+                    // leading X / CNot / Toffoli ops: new[a] = old[p_1(p_2(...p_k(a)))]
+                    uint32_t a[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        a[r] = tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u);
+                    for (int i = (int)n_pre - 1; i >= 0; --i) {
+                        const qsv_rop_t *op = ops + R.first_op + i;
+                        if ((gbase & op->ext_mask) != op->ext_val) continue;
+                        const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) a[r] ^= ((a[r] & cm) == cv) ? xm : 0u;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) x[r] = tile[a[r]];
+                }
+                double2 S = make_double2(1.0, 0.0);       // pending thread-uniform phase (commutes with all ops)
+                bool hasS = false;
+                for (uint32_t i = 0; i < R.n_ops; ++i) {
+                    const qsv_rop_t *op = ops + R.first_op + n_pre + i;
+                    if ((gbase & op->ext_mask) != op->ext_val) continue;
+                    if ((tb & op->tmask) != op->tval) continue;
+                    const uint32_t kind = op->kind;
+                    hasS |= (kind == 0x60u);
+                    apply_rop(x, S, op, kind, sprog, tb, gbase);
+                }
+                if (hasS) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) cscale_inplace(x[r], S);
+                }
+            }
+            if (n_pre + n_post) __syncthreads();   // permuted stores land in other threads' slots: all loads first
+            if (owner) {
+                if (n_post == 0) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        tile[tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u)] = x[r];
+                } else {
+                    // trailing permutation ops: new[p_k(...p_1(a))] = old[a]
+                    uint32_t a[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        a[r] = tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u);
+                    for (uint32_t i = 0; i < n_post; ++i) {
+                        const qsv_rop_t *op = ops + R.first_op + n_pre + R.n_ops + i;
+                        if ((gbase & op->ext_mask) != op->ext_val) continue;
+                        const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) a[r] ^= ((a[r] & cm) == cv) ? xm : 0u;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) tile[a[r]] = x[r];
+                }
+            }
+        }
+
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if ((tid & 31) == 0)
+            for (uint32_t r = tid >> 5; r < n_runs; r += kRThreads / 32)
+                bulk_s2g_r(state + base + s_hi_off[r], tile + ((size_t)r << L), run_bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+}  // namespace qsv
+
+using namespace qsv;
+
+static_assert(sizeof(qsv_rop_t) == 128, "qsv_rop_t must be 128 bytes");
+static_assert(sizeof(qsv_round_t) == 16 && sizeof(qsv_rprog_hdr_t) == 16, "round/program headers are 16 bytes");
+static_assert(sizeof(qsv_op_t) == 88 && sizeof(qsv_pass_t) == 48, "struct layout mirrored in qsv/schedule.py");
+
+extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
+                                   const void *tables_dev, void *stream) {
+    QSV_CHECK_ARG(state_dev && P && prog_host, "qsv_run_pass_rounds: NULL pointer");
+    QSV_CHECK_ARG(P->n_local >= 1 && P->n_local <= 40, "qsv_run_pass_rounds: n_local=%d out of range", P->n_local);
+    QSV_CHECK_ARG(P->tile_bits >= 4 && P->tile_bits <= 12 && P->tile_bits <= P->n_local,
+                  "qsv_run_pass_rounds: tile_bits=%d must be in [4, 12] and <= n_local", P->tile_bits);
+    QSV_CHECK_ARG(P->low_bits >= 0 && P->low_bits <= P->tile_bits && P->n_hi == P->tile_bits - P->low_bits &&
+                      P->n_hi <= 8, "qsv_run_pass_rounds: bad tile geometry");
+    int prev = P->low_bits - 1;
+    for (int j = 0; j < P->n_hi; ++j) {
+        QSV_CHECK_ARG((int)P->hi_pos[j] > prev && (int)P->hi_pos[j] < P->n_local,
+                      "qsv_run_pass_rounds: hi_pos[%d]=%d not ascending in [low_bits, n_local)", j, (int)P->hi_pos[j]);
+        prev = P->hi_pos[j];
+    }
+    QSV_CHECK_ARG(prog_bytes >= sizeof(qsv_rprog_hdr_t), "qsv_run_pass_rounds: program too short");
+    const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
+    QSV_CHECK_ARG(hdr->n_rounds >= 1 && hdr->n_rounds <= QSV_RPROG_MAX_ROUNDS && hdr->n_ops <= QSV_RPROG_MAX_OPS,
+                  "qsv_run_pass_rounds: %u rounds / %u ops exceed the limits (%d / %d)", hdr->n_rounds, hdr->n_ops,
+                  QSV_RPROG_MAX_ROUNDS, QSV_RPROG_MAX_OPS);
+    const size_t need = sizeof(qsv_rprog_hdr_t) + sizeof(qsv_round_t) * hdr->n_rounds + sizeof(qsv_rop_t) * hdr->n_ops;
+    QSV_CHECK_ARG(prog_bytes >= need, "qsv_run_pass_rounds: prog_bytes=%u smaller than the %zu bytes the header implies",
+                  prog_bytes, need);
+    static RProgParam param;       // repacked: fixed-capacity arrays inside the kernel parameter
+    memset(&param, 0, sizeof(param));
+    param.hdr = *hdr;
+    const uint8_t *src = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);
+    memcpy(param.rounds, src, sizeof(qsv_round_t) * hdr->n_rounds);
+    memcpy(param.ops, src + sizeof(qsv_round_t) * hdr->n_rounds, sizeof(qsv_rop_t) * hdr->n_ops);
+    bool has_diag = false;
+    for (uint32_t i = 0; i < hdr->n_ops; ++i) {
+        has_diag = has_diag || param.ops[i].kind == QSV_ROP_DIAG;
+        for (int q = 0; q < 4; ++q) (void)q;
+    }
+    for (uint32_t r = 0; r < hdr->n_rounds; ++r) {
+        const qsv_round_t &R = param.rounds[r];
+        QSV_CHECK_ARG(R.rb[0] < R.rb[1] && R.rb[1] < R.rb[2] && R.rb[2] < R.rb[3] && R.rb[3] < P->tile_bits,
+                      "qsv_run_pass_rounds: round %u register bits not ascending inside the tile", r);
+        QSV_CHECK_ARG((uint64_t)R.first_op + R.n_ops <= hdr->n_ops, "qsv_run_pass_rounds: round %u op range", r);
+    }
+    QSV_CHECK_ARG(!has_diag || tables_dev, "qsv_run_pass_rounds: diagonal op without a table buffer");
+    const uint64_t n_tiles = 1ull << (P->n_local - P->tile_bits);
+    const size_t smem = (size_t)16 << P->tile_bits;
+    const unsigned grid = (unsigned)(n_tiles < (1ull << 30) ? n_tiles : (1ull << 30));
+    QSV_CUDA(cudaFuncSetAttribute(k_pass_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
+    k_pass_reg<<<grid, kRThreads, smem, (cudaStream_t)stream>>>((double2 *)state_dev, *P, param,
+                                                                (const uint8_t *)tables_dev, n_tiles);
+    QSV_LAUNCH_CHECK();
+    return 0;
+}

@@ -177,6 +177,7 @@ class StateVector:
         for kind, seg in segments:
             if kind == "program":
                 h2d += int(seg[0].blob.size)
+                h2d += sum(int(m[3][0].size) for m in seg[0].passes if m[2] < 0)   # by-value round programs
         return {"segments": segments, "h2d_bytes": h2d}
 
     def execute(self, plan):
@@ -202,6 +203,14 @@ class StateVector:
         for j, p in enumerate(ps.hi_pos):
             cp.hi_pos[j] = p
         cp.rank_bits = self.rank_bits
+        if n_ops < 0:       # register-resident round program (host image, passed to the kernel by value)
+            prog = maxk[0]
+            cp.max_dense_k = 1
+            _cabi.check(self.lib.qsv_run_pass_rounds(self._ptr(self.state), C.byref(cp),
+                                                     C.c_void_p(prog.ctypes.data), int(prog.size),
+                                                     C.c_void_p(base + table_off), self._stream()),
+                        "qsv_run_pass_rounds")
+            return
         cp.max_dense_k = maxk
         _cabi.check(self.lib.qsv_run_pass(self._ptr(self.state), C.byref(cp), C.c_void_p(base),
                                           C.c_void_p(base + table_off), n_ops, self._stream()), "qsv_run_pass")

@@ -381,19 +381,42 @@ def encode_op(op, ps):
 @dataclass
 class PackedProgram:
     blob: np.ndarray        # uint8, the whole device image
-    passes: list            # [(Pass, offsets_byte_offset, n_ops, max_dense_k)]
+    passes: list            # [(Pass, offsets_byte_offset, n_ops, max_dense_k)] or [(Pass, byte_offset, -n_bytes, n_rounds)]
 
 
-def pack_passes(passes):
-    """Lay out [offset tables of every pass | ops of every pass] in one buffer; op offsets are
-    relative to the start of the buffer."""
+def use_register_kernel():
+    return os.environ.get("QSV_REGISTER_KERNEL", "1") != "0"
+
+
+def pack_passes(passes, register_kernel=None):
+    """Device image [offset tables | ops] for the passes that run on the shared-memory kernel (op
+    offsets relative to the start of the buffer).  Passes the register-resident kernel can run carry a
+    HOST round program instead (it is passed to the kernel by value) plus, if they use diagonal tables,
+    a slice of the device image: meta = (Pass, table_byte_offset, -1, (program_bytes, n_rounds))."""
+    if register_kernel is None:
+        register_kernel = use_register_kernel()
+    round_progs = {}
+    if register_kernel:
+        for i, ps in enumerate(passes):
+            rounds = plan_rounds(ps)
+            if rounds is not None:
+                enc = encode_rounds(ps, rounds)
+                if enc is not None:
+                    round_progs[i] = (enc[0], enc[1], len(rounds))
     tables = 0
-    for ps in passes:
-        tables += (4 * len(ps.ops) + 15) // 16 * 16
+    for i, ps in enumerate(passes):
+        if i not in round_progs:
+            tables += (4 * len(ps.ops) + 15) // 16 * 16
     chunks, meta, table_words = [], [], []
     cursor = tables
     tcur = 0
-    for ps in passes:
+    for i, ps in enumerate(passes):
+        if i in round_progs:
+            prog, tab, n_rounds = round_progs[i]
+            meta.append((ps, cursor, -1, (prog, n_rounds)))
+            chunks.append(tab)
+            cursor += len(tab)
+            continue
         offs = []
         maxk = 0
         for op in ps.ops:
@@ -409,9 +432,248 @@ def pack_passes(passes):
         table_words.append(tw)
         meta.append((ps, tcur, len(offs), maxk))
         tcur += tbytes
-    blob = np.frombuffer(b"".join([t.tobytes() for t in table_words] + chunks), dtype=np.uint8).copy()
-    assert blob.size == cursor and cursor < 2 ** 32
+    raw = b"".join([t.tobytes() for t in table_words] + chunks)
+    if not raw:
+        raw = b"\0" * 16
+    blob = np.frombuffer(raw, dtype=np.uint8).copy()
+    assert cursor < 2 ** 32
     return PackedProgram(blob, meta)
+
+
+# ------------------------------------------------------------------------------------------------
+# register-resident rounds (must mirror qsv_rop_t / qsv_round_t / qsv_rprog_hdr_t in include/qsv.h)
+# ------------------------------------------------------------------------------------------------
+
+ROP_DTYPE = np.dtype([
+    ("kind", "u1"), ("j", "u1"), ("rmask", "u1"), ("rval", "u1"), ("tmask", "<u4"), ("tval", "<u4"),
+    ("reserved0", "<u4"), ("ext_mask", "<u8"), ("ext_val", "<u8"), ("flags", "<u4"), ("table_off", "<u4"),
+    ("dsrc", "u1", (8,)), ("rc", "u1", (4,)), ("k", "<u4"), ("m", "<f8", (8,)), ("pad", "u1", (8,)),
+])
+assert ROP_DTYPE.itemsize == 128
+ROUND_DTYPE = np.dtype([("rb", "u1", (4,)), ("n_ops", "<u4"), ("first_op", "<u4"), ("n_pre", "<u2"), ("n_post", "<u2")])
+assert ROUND_DTYPE.itemsize == 16
+RPROG_MAX_ROUNDS, RPROG_MAX_OPS = 32, 120
+ROP_DENSE1, ROP_DENSE1_REAL, ROP_PHASE_T, ROP_PHASE1, ROP_PERM = 0x10, 0x14, 0x60, 0x70, 0x80
+ROP_GEN_PHASE, ROP_DIAG = 0xF3, 0xF4
+ROPF_REAL, ROPF_NEG = 1, 2
+REG_BITS = 4
+
+
+def _single_bit(mask):
+    return mask != 0 and (mask & (mask - 1)) == 0
+
+
+def _round_eligible(op):
+    if op.kind == "dense":
+        return len(op.targets) == 1
+    if op.kind in ("mcx", "phase"):
+        return True
+    if op.kind == "diag":
+        return len(op.targets) <= _cabi.QSV_MAX_DIAG_K
+    return False
+
+
+@dataclass
+class Round:
+    rb: list                # 4 ascending tile-local register bits
+    pre: list               # mcx ops applied as an address permutation when the round loads its registers
+    reg: list               # dense1 / phase / diag ops executed in registers
+    post: list              # mcx ops applied as an address permutation when the round stores
+
+
+def plan_rounds(ps):
+    """Split the ops of one pass into rounds of the register-resident kernel.
+
+    A round fixes 4 tile-local register bits.  Its ops are ordered [pre | reg | post]: `reg` ops (1-qubit
+    dense with the target on a register bit, phases, diagonal tables) run on registers; X / CNot /
+    Toffoli are pure index permutations and ride for free on the shared-memory addresses used when the
+    round loads (`pre`) or stores (`post`) its registers.  Ops are taken in program order and may slide
+    past each other only when they commute structurally (same rule as plan_passes).  Returns a list of
+    Round, or None if the pass holds an op the register kernel does not implement."""
+    T = ps.tile_bits
+    if T < REG_BITS or T > 12 or not all(_round_eligible(op) for op in ps.ops):
+        return None
+    remaining = list(ps.ops)
+    rounds = []
+    while remaining:
+        rb, pre, reg, post = [], [], [], []
+        blocked_nd = blocked_d = 0          # bits touched by ops deferred to a later round
+        reg_nd = reg_d = post_nd = post_d = 0
+        rest = []
+        for op in remaining:
+            nd_m, dg_m = _mask(op.nondiag_bits()), _mask(op.diag_bits())
+            free = not (nd_m & (blocked_nd | blocked_d)) and not (dg_m & blocked_nd)
+            placed = False
+            if free and op.kind == "mcx":
+                before_reg = not (nd_m & (reg_nd | reg_d)) and not (dg_m & reg_nd)
+                before_post = not (nd_m & (post_nd | post_d)) and not (dg_m & post_nd)
+                if before_reg and before_post:      # commutes with everything queued: ride on the loads
+                    pre.append(op)
+                else:
+                    post.append(op)
+                    post_nd |= nd_m
+                    post_d |= dg_m
+                placed = True
+            elif free:
+                # must commute with every permutation already queued behind the register phase
+                commutes = not (nd_m & (post_nd | post_d)) and not (dg_m & post_nd)
+                # a controlled dense op needs its controls on thread bits (no register-bit predicates)
+                ctrl_loc = [ps.loc(c) for c in op.controls if c < ps.n_local and ps.loc(c) >= 0] \
+                    if op.kind == "dense" else []
+                if commutes:
+                    nd = op.nondiag_bits()
+                    l = ps.loc(nd[0]) if nd else None
+                    fits = l is None or l in rb or len(rb) < REG_BITS
+                    if fits and not (set(ctrl_loc) & set(rb)) and not (l is not None and l in
+                                                                      _dense_ctrl_bits(reg, ps)):
+                        if l is not None and l not in rb:
+                            rb.append(l)
+                        reg.append(op)
+                        reg_nd |= nd_m
+                        reg_d |= dg_m
+                        placed = True
+            if not placed:
+                blocked_nd |= nd_m
+                blocked_d |= dg_m
+                rest.append(op)
+        avoid = _dense_ctrl_bits(reg, ps)
+        for l in list(range(T - 1, -1, -1)):       # pad with the highest free tile bits (bank friendly)
+            if len(rb) == REG_BITS:
+                break
+            if l not in rb and l not in avoid:
+                rb.append(l)
+        for l in range(T - 1, -1, -1):
+            if len(rb) == REG_BITS:
+                break
+            if l not in rb:
+                return None                        # cannot keep a dense control off the register bits
+        rounds.append(Round(sorted(rb), pre, reg, post))
+        remaining = rest
+    return rounds
+
+
+def _dense_ctrl_bits(reg_ops, ps):
+    out = set()
+    for op in reg_ops:
+        if op.kind == "dense":
+            for c in op.controls:
+                if c < ps.n_local and ps.loc(c) >= 0:
+                    out.add(ps.loc(c))
+    return out
+
+
+def _perm_fields(op, ps):
+    """(local control mask, local control values, local xor mask, ext mask, ext values) of an mcx op."""
+    cm = cv = em = ev = 0
+    ctrls = tuple(op.controls)
+    cvals = tuple(op.cvals) if op.cvals is not None else (1,) * len(ctrls)
+    for c, v in zip(ctrls, cvals):
+        l = ps.loc(c) if c < ps.n_local else -1
+        if l < 0:
+            em |= 1 << c
+            ev |= (1 << c) if v else 0
+        else:
+            cm |= 1 << l
+            cv |= (1 << l) if v else 0
+    return cm, cv, 1 << ps.loc(op.targets[0]), em, ev
+
+
+def _merge_perms(ops, ps):
+    """Adjacent permutation ops with the same condition fold into one (their xor masks combine)."""
+    out = []
+    for op in ops:
+        f = list(_perm_fields(op, ps))
+        if out and out[-1][0] == f[0] and out[-1][1] == f[1] and out[-1][3] == f[3] and out[-1][4] == f[4]:
+            out[-1][2] ^= f[2]
+        else:
+            out.append(f)
+    return [f for f in out if f[2]]
+
+
+def encode_rounds(ps, rounds):
+    """Host image of a register-resident pass program -> (program bytes, diagonal-table bytes), or None
+    if it exceeds the kernel-parameter capacity (RPROG_MAX_ROUNDS / RPROG_MAX_OPS)."""
+    if len(rounds) > RPROG_MAX_ROUNDS:
+        return None
+    rnd = np.zeros(len(rounds), dtype=ROUND_DTYPE)
+    rops = []
+    tables = []
+    table_cursor = 0
+    for r, R in enumerate(rounds):
+        rb = R.rb
+        rnd[r]["rb"] = rb
+        rnd[r]["first_op"] = len(rops)
+        pre, post = _merge_perms(R.pre, ps), _merge_perms(R.post, ps)
+        rnd[r]["n_pre"], rnd[r]["n_ops"], rnd[r]["n_post"] = len(pre), len(R.reg), len(post)
+
+        def perm_rop(f):
+            h = np.zeros((), dtype=ROP_DTYPE)
+            h["kind"] = ROP_PERM
+            h["tmask"], h["tval"], h["table_off"], h["ext_mask"], h["ext_val"] = f
+            return h
+
+        rops += [perm_rop(f) for f in pre]
+        for op in R.reg:
+            h = np.zeros((), dtype=ROP_DTYPE)
+            ctrls = tuple(op.controls)
+            cvals = tuple(op.cvals) if op.cvals is not None else (1,) * len(ctrls)
+            rmask = rval = tmask = tval = ext_mask = ext_val = 0
+            for c, v in zip(ctrls, cvals):
+                l = ps.loc(c) if c < ps.n_local else -1
+                if l < 0:
+                    ext_mask |= 1 << c
+                    ext_val |= (1 << c) if v else 0
+                elif l in rb:
+                    rmask |= 1 << rb.index(l)
+                    rval |= (1 << rb.index(l)) if v else 0
+                else:
+                    tmask |= 1 << l
+                    tval |= (1 << l) if v else 0
+            if op.kind == "dense":
+                assert rmask == 0, "round planner must keep dense controls off the register bits"
+                M = np.asarray(op.matrix, dtype=np.complex128)
+                j = rb.index(ps.loc(op.targets[0]))
+                real = not np.any(M.imag)
+                h["j"] = j
+                h["m"] = M.reshape(-1).view(np.float64)
+                h["flags"] = ROPF_REAL if real else 0
+                h["kind"] = (ROP_DENSE1_REAL if real else ROP_DENSE1) + j
+            elif op.kind == "phase":
+                h["m"][0], h["m"][1] = op.scalar.real, op.scalar.imag
+                if op.scalar == -1:
+                    h["flags"] = ROPF_NEG
+                if rmask == 0:
+                    h["kind"] = ROP_PHASE_T
+                elif _single_bit(rmask):
+                    h["kind"] = ROP_PHASE1 + 2 * (rmask.bit_length() - 1) + (1 if rval else 0)
+                else:
+                    h["kind"] = ROP_GEN_PHASE
+            else:
+                k = len(op.targets)
+                h["kind"], h["k"] = ROP_DIAG, k
+                for p, t in enumerate(op.targets):
+                    l = ps.loc(t) if t < ps.n_local else -1
+                    if l < 0:
+                        h["dsrc"][p] = 0x80 | t
+                    elif l in rb:
+                        h["dsrc"][p] = 0xFF
+                        h["rc"][rb.index(l)] |= 1 << (k - 1 - p)
+                    else:
+                        h["dsrc"][p] = l
+                h["table_off"] = table_cursor
+                tb = np.ascontiguousarray(op.matrix, dtype=np.complex128).tobytes()
+                tables.append(tb)
+                table_cursor += len(tb)
+            h["rmask"], h["rval"], h["tmask"], h["tval"] = rmask, rval, tmask, tval
+            h["ext_mask"], h["ext_val"] = ext_mask, ext_val
+            rops.append(h)
+        rops += [perm_rop(f) for f in post]
+    if len(rops) > RPROG_MAX_OPS:
+        return None
+    hdr = np.array([len(rounds), 16 + 16 * len(rounds) + 128 * len(rops), len(rops), 0], dtype="<u4")
+    blob = hdr.tobytes() + rnd.tobytes() + b"".join(h.tobytes() for h in rops)
+    assert len(blob) == int(hdr[1])
+    return np.frombuffer(blob, dtype=np.uint8).copy(), b"".join(tables)
 
 
 # ------------------------------------------------------------------------------------------------

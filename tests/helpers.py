@@ -80,6 +80,9 @@ def emulate_program(packed, psi, rank_bits=0):
     blob = packed.blob.tobytes()
     psi = psi.copy()
     for ps, table_off, n_ops, maxk in packed.passes:
+        if n_ops < 0:
+            psi = emulate_round_program(maxk[0], blob[table_off:], ps, psi, rank_bits)
+            continue
         T, L = ps.tile_bits, ps.low_bits
         hi = list(ps.hi_pos)
         offs = np.frombuffer(blob, dtype="<u4", count=n_ops, offset=table_off)
@@ -137,6 +140,103 @@ def emulate_program(packed, psi, rank_bits=0):
                 else:
                     raise AssertionError("bad op kind %d" % kind)
             psi[base + gl_off] = tile
+    return psi
+
+
+def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
+    """numpy emulation of k_pass_reg (csrc/qsv_tile_reg.cu) on the host round program."""
+    from qsv.schedule import ROP_DTYPE, ROUND_DTYPE
+    prog = bytes(prog)
+    n_rounds, total, n_ops, _ = np.frombuffer(prog, dtype="<u4", count=4)
+    assert total == len(prog)
+    rounds = np.frombuffer(prog, dtype=ROUND_DTYPE, count=n_rounds, offset=16)
+    rops = np.frombuffer(prog, dtype=ROP_DTYPE, count=n_ops, offset=16 + 16 * int(n_rounds))
+    T, L = ps.tile_bits, ps.low_bits
+    hi = list(ps.hi_pos)
+    loc = np.arange(1 << T)
+    gl_off = loc & ((1 << L) - 1)
+    for j, p in enumerate(hi):
+        gl_off = gl_off | (((loc >> (L + j)) & 1) << p)
+    psi = psi.copy()
+    tid = np.arange(1 << (T - 4))
+
+    def permute(a, ops, gbase):
+        for o in ops:
+            assert int(o["kind"]) == 0x80
+            if (gbase & int(o["ext_mask"])) != int(o["ext_val"]):
+                continue
+            cm, cv, xm = int(o["tmask"]), int(o["tval"]), int(o["table_off"])
+            assert xm and not (xm & cm)
+            a = np.where((a & cm) == cv, a ^ xm, a)
+        return a
+
+    for t in range(1 << (ps.n_local - T)):
+        base = t << L
+        for p in hi:
+            base = _insert_zero(base, p)
+        gbase = base | rank_bits
+        if not any((gbase & int(o["ext_mask"])) == int(o["ext_val"]) for o in rops):
+            continue
+        tile = psi[base + gl_off].copy()
+        for R in rounds:
+            rb = [int(b) for b in R["rb"]]
+            assert rb == sorted(rb) and len(set(rb)) == 4
+            tb = tid.copy()
+            for b in rb:
+                tb = _insert_zero(tb, b)
+            roff = [sum((1 << rb[q]) for q in range(4) if (r >> q) & 1) for r in range(16)]
+            f0, npre, nreg, npost = int(R["first_op"]), int(R["n_pre"]), int(R["n_ops"]), int(R["n_post"])
+            addr = np.stack([tb | roff[r] for r in range(16)])
+            x = tile[permute(addr, rops[f0: f0 + npre][::-1], gbase)]           # [16, threads]
+            for o in rops[f0 + npre: f0 + npre + nreg]:
+                if (gbase & int(o["ext_mask"])) != int(o["ext_val"]):
+                    continue
+                tp = (tb & int(o["tmask"])) == int(o["tval"])
+                kind, J = int(o["kind"]), int(o["j"])
+                rm, rv = int(o["rmask"]), int(o["rval"])
+                rsel = [r for r in range(16) if (r & rm) == rv]
+                # decode the kind byte exactly like apply_rop() in csrc/qsv_tile_reg.cu and cross-check
+                # the specialisation against the generic (j, rmask, rval) fields
+                if 0x10 <= kind < 0x18:
+                    assert J == (kind & 3) and rm == 0 and bool(int(o["flags"]) & 1) == (kind >= 0x14)
+                    m = o["m"].view(np.complex128)
+                    for r in range(16):
+                        if (r >> J) & 1:
+                            continue
+                        x0, x1 = x[r].copy(), x[r | (1 << J)].copy()
+                        x[r] = np.where(tp, m[0] * x0 + m[1] * x1, x0)
+                        x[r | (1 << J)] = np.where(tp, m[2] * x0 + m[3] * x1, x1)
+                elif kind == 0x60 or 0x70 <= kind < 0x78 or kind == 0xF3:
+                    if kind == 0x60:
+                        assert rm == 0
+                    elif kind != 0xF3:
+                        jj, vv = (kind - 0x70) >> 1, (kind - 0x70) & 1
+                        assert rm == 1 << jj and rv == vv << jj
+                    sc = complex(o["m"][0], o["m"][1])
+                    for r in rsel:
+                        x[r] = np.where(tp, x[r] * sc, x[r])
+                elif kind == 0xF4:
+                    k = int(o["k"])
+                    tab = np.frombuffer(tables, dtype=np.complex128, count=1 << k, offset=int(o["table_off"]))
+                    di = np.zeros_like(tb)
+                    for p in range(k):
+                        s_ = int(o["dsrc"][p])
+                        if s_ == 0xFF:
+                            continue
+                        bit = ((gbase >> (s_ & 0x7F)) & 1) if (s_ & 0x80) else ((tb >> s_) & 1)
+                        di |= bit << (k - 1 - p)
+                    for r in rsel:
+                        d = di.copy()
+                        for q in range(4):
+                            if (r >> q) & 1:
+                                d |= int(o["rc"][q])
+                        x[r] = np.where(tp, x[r] * tab[d], x[r])
+                else:
+                    raise AssertionError("bad rop kind 0x%x" % kind)
+            new_tile = tile.copy()
+            new_tile[permute(addr, rops[f0 + npre + nreg: f0 + npre + nreg + npost], gbase)] = x
+            tile = new_tile
+        psi[base + gl_off] = tile
     return psi
 
 

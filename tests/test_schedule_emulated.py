@@ -136,9 +136,51 @@ def test_single_gate_pass_keeps_controls_external():
     cz = schedule.classify_matrix(so.mat_CZ(), (19, 18))
     p = schedule.plan_passes(cz, n)[0]
     assert p.loc(19) < 0 and p.loc(18) < 0
-    packed = schedule.pack_passes([p])
+    packed = schedule.pack_passes([p], register_kernel=False)
     hdr = np.frombuffer(packed.blob.tobytes(), dtype=schedule.OP_DTYPE, count=1, offset=16)[0]
     assert int(hdr["ext_ctrl_mask"]) == (1 << 19) | (1 << 18) and int(hdr["n_ins"]) == 0
+    packed = schedule.pack_passes([p], register_kernel=True)
+    ps, off, marker, (prog, n_rounds) = packed.passes[0]
+    assert marker < 0 and n_rounds == 1
+    rop = np.frombuffer(prog.tobytes(), dtype=schedule.ROP_DTYPE, count=1, offset=32)[0]
+    assert int(rop["ext_mask"]) == (1 << 19) | (1 << 18) and int(rop["kind"]) == schedule.ROP_PHASE_T
+    assert int(rop["flags"]) & schedule.ROPF_NEG
+
+
+def test_round_planner_groups_ops_by_register_bits():
+    n = 16
+    steps = so.random_layered_steps(n, 6, seed=9)
+    c = circuit_from_steps(steps, n)
+    c.sort()
+    ops, src_pos = lower(c)
+    passes = schedule.plan_passes(ops, n, 12, 6)
+    total_rounds = 0
+    for p in passes:
+        rounds = schedule.plan_rounds(p)
+        assert rounds is not None
+        assert sum(len(R.pre) + len(R.reg) + len(R.post) for R in rounds) == len(p.ops)
+        for R in rounds:
+            rb = R.rb
+            assert len(rb) == 4 and rb == sorted(set(rb)) and all(0 <= b < 12 for b in rb)
+            assert all(op.kind == "mcx" for op in R.pre + R.post)
+            for op in R.reg:
+                assert op.kind != "mcx"
+                for b in op.nondiag_bits():
+                    assert p.loc(b) in rb
+        total_rounds += len(rounds)
+    assert total_rounds < len(ops) / 3          # the point of rounds: several ops per shared-memory trip
+    both = []
+    for reg in (False, True):
+        psi = np.zeros(1 << n, dtype=np.complex128)
+        psi[5] = 1
+        from helpers import emulate_program
+        both.append(emulate_program(schedule.pack_passes(passes, register_kernel=reg), psi))
+    assert np.max(np.abs(both[0] - both[1])) < 1e-14
+    ref = np.zeros(1 << n, dtype=np.complex128)
+    ref[5] = 1
+    for M, wires, _ in steps:
+        ref = so.apply_gate(ref, n, wires, M)
+    assert np.max(np.abs(both[1] - ref)) <= TOL
 
 
 def test_symbolic_gates_lower_without_materialising():
