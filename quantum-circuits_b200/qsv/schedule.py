@@ -398,7 +398,9 @@ def pack_passes(passes, register_kernel=None):
     round_progs = {}
     if register_kernel:
         for i, ps in enumerate(passes):
-            rounds = plan_rounds(ps)
+            # one- and two-op passes stay on the shared-memory kernel: it is HBM-bound there (3 CTAs/SM,
+            # 104-106 % of the measured copy peak) while the register kernel pays its round overhead
+            rounds = plan_rounds(ps) if len(ps.ops) > int(os.environ.get("QSV_REG_MIN_OPS", "2")) else None
             if rounds is not None:
                 enc = encode_rounds(ps, rounds)
                 if enc is not None:

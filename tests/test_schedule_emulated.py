@@ -139,7 +139,12 @@ def test_single_gate_pass_keeps_controls_external():
     packed = schedule.pack_passes([p], register_kernel=False)
     hdr = np.frombuffer(packed.blob.tobytes(), dtype=schedule.OP_DTYPE, count=1, offset=16)[0]
     assert int(hdr["ext_ctrl_mask"]) == (1 << 19) | (1 << 18) and int(hdr["n_ins"]) == 0
-    packed = schedule.pack_passes([p], register_kernel=True)
+    import os
+    os.environ["QSV_REG_MIN_OPS"] = "0"          # force the register kernel even for a one-op pass
+    try:
+        packed = schedule.pack_passes([p], register_kernel=True)
+    finally:
+        del os.environ["QSV_REG_MIN_OPS"]
     ps, off, marker, (prog, n_rounds) = packed.passes[0]
     assert marker < 0 and n_rounds == 1
     rop = np.frombuffer(prog.tobytes(), dtype=schedule.ROP_DTYPE, count=1, offset=32)[0]
