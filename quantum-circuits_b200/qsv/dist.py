@@ -1,0 +1,144 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).
+
+The register of n qubits is sharded by its top g = log2(P) physical positions: rank r holds the
+2^(n-g) amplitudes whose top g index bits equal r.  Everything local, diagonal, or merely
+controlled by a global qubit runs without communication (the rank index supplies the bit).  The only
+exchange step is the global<->local qubit swap: the g global positions trade places with the top g
+local positions, which is exactly an all-to-all of equal blocks — rank r sends its block j to rank j
+and stores rank j's block r in slot j.  At 36 qubits on 8 GPUs a shard is 137 GB of 180 GB, so the
+exchange is done in place in column chunks through a small staging buffer.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+DEFAULT_STAGING_BYTES = 1 << 30      # per direction
+
+
+def plan_exchange(n_local, g, staging_bytes=DEFAULT_STAGING_BYTES):
+    """Chunk plan of one global<->local swap.  The shard is a [P, S] matrix of amplitudes (P = 2^g
+    blocks of S = 2^(n_local-g)); chunk k covers columns [k*C, (k+1)*C) of every block and is
+    exchanged with one all-to-all of P*C amplitudes.  Returns (P, S, C, n_chunks)."""
+    P = 1 << g
+    S = 1 << (n_local - g)
+    C_ = max(1, min(S, staging_bytes // (16 * P)))
+    C_ = 1 << (C_.bit_length() - 1)               # power of two: divides S
+    return P, S, C_, S // C_
+
+
+class Comm:
+    """Thin wrapper over a torch.distributed process group of size 2^g."""
+
+    def __init__(self, group=None, staging_bytes=DEFAULT_STAGING_BYTES):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.global_bits = (self.world - 1).bit_length()
+        if self.world != 1 << self.global_bits:
+            raise RuntimeError("qsv.dist: world size must be a power of two")
+        self.staging_bytes = staging_bytes
+        self._staging = None
+        self.bytes_sent = 0
+        self.swaps = 0
+
+    # ------------------------------------------------------------------ collectives
+    def all_reduce_sum(self, t):
+        """In-place sum of a complex128 / float64 tensor over all ranks (NCCL has no complex type)."""
+        v = torch.view_as_real(t) if t.is_complex() else t
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_to_all(self, out, inp):
+        """Equal-split all-to-all on float64 views; gloo (CPU tests) has no all_to_all -> send/recv."""
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_to_all_single(out, inp, group=self.group)
+            return
+        P = self.world
+        ins, outs = inp.chunk(P), out.chunk(P)
+        outs[self.rank].copy_(ins[self.rank])
+        reqs = []
+        for peer in range(P):
+            if peer == self.rank:
+                continue
+            reqs.append(dist.isend(ins[peer].contiguous(), dist.get_global_rank(self.group, peer), group=self.group))
+            reqs.append(dist.irecv(outs[peer], dist.get_global_rank(self.group, peer), group=self.group))
+        for r in reqs:
+            r.wait()
+
+    # ------------------------------------------------------------------ qubit swap
+    def exchange(self, state, n_local, pack, unpack):
+        """Swap the g global positions with the top g local positions of `state` (complex128 tensor of
+        2^n_local amplitudes), in place, chunk by chunk.  pack(staging, offset, C) gathers column chunk
+        [offset, offset+C) of every block into the contiguous staging tensor; unpack scatters it back."""
+        g = self.global_bits
+        P, S, C_, n_chunks = plan_exchange(n_local, g, self.staging_bytes)
+        need = P * C_
+        if self._staging is None or self._staging[0].numel() < need or self._staging[0].device != state.device:
+            self._staging = (torch.empty(need, dtype=torch.complex128, device=state.device),
+                             torch.empty(need, dtype=torch.complex128, device=state.device))
+        s_in, s_out = self._staging[0][:need], self._staging[1][:need]
+        for k in range(n_chunks):
+            pack(s_in, k * C_, C_)
+            self.all_to_all(torch.view_as_real(s_out).view(-1), torch.view_as_real(s_in).view(-1))
+            unpack(s_out, k * C_, C_)
+        self.bytes_sent += 16 * (P - 1) * S
+        self.swaps += 1
+
+    def swap_global_local(self, sv, n_swap):
+        """Engine hook for a 'global_swap' op (CUDA pack/unpack kernels of libqsv)."""
+        if n_swap != self.global_bits:
+            raise RuntimeError("qsv.dist: only full swaps of all %d global qubits are planned" % self.global_bits)
+        lib = sv.lib
+        P = 1 << self.global_bits
+        S = 1 << (sv.n_local - self.global_bits)
+
+        def pack(staging, offset, C_):
+            _cabi.check(lib.qsv_pack_slices(sv._ptr(sv.state), C.c_void_p(staging.data_ptr()), P, S, offset, C_,
+                                            sv._stream()), "qsv_pack_slices")
+
+        def unpack(staging, offset, C_):
+            _cabi.check(lib.qsv_unpack_slices(sv._ptr(sv.state), C.c_void_p(staging.data_ptr()), P, S, offset, C_,
+                                              sv._stream()), "qsv_unpack_slices")
+
+        self.exchange(sv.state, sv.n_local, pack, unpack)
+
+    # ------------------------------------------------------------------ measurement
+    def sample(self, sv, u, src_pos=None):
+        """One outcome for the uniform draw u on a sharded register.  Shard totals are all-gathered
+        (P doubles), the owning rank runs the block search + sequential scan of the single-GPU path, and
+        the index is broadcast.  Accumulation runs in PHYSICAL index order; the outcome is mapped to the
+        output order through src_pos, so it is a sample of the same distribution (bit-exact agreement
+        with random.choices is only defined for the unsharded order)."""
+        from . import engine as E
+        import numpy as np
+        bb = min(E.SAMPLE_BLOCK_BITS, sv.n_local)
+        sums = sv.block_sums(None, bb)
+        local_total = sums.sum().reshape(1)
+        totals = torch.empty(self.world, dtype=torch.float64, device=sums.device)
+        dist.all_gather_into_tensor(totals, local_total, group=self.group)
+        totals = totals.cpu().numpy()
+        cum = np.cumsum(totals)
+        total = float(cum[-1])
+        if not total > 0.0:
+            raise ValueError("Total of weights must be greater than zero")
+        target = u * total
+        owner = min(int(np.searchsorted(cum, target, side="right")), self.world - 1)
+        res = torch.zeros(1, dtype=torch.int64, device=sums.device)
+        if owner == self.rank:
+            prefix_rank = float(cum[owner - 1]) if owner > 0 else 0.0
+            lc = np.cumsum(sums.cpu().numpy()) + prefix_rank
+            blk = min(int(np.searchsorted(lc, target, side="right")), len(lc) - 1)
+            prefix = float(lc[blk - 1]) if blk > 0 else prefix_rank
+            z, _ = sv._scan(None, blk << bb, (1 << sv.n_local) - 1, prefix, target)
+            res[0] = (self.rank << sv.n_local) | z
+        dist.broadcast(res, dist.get_global_rank(self.group, owner), group=self.group)
+        y = int(res.item())
+        if src_pos is None:
+            return y
+        z = 0
+        for b, p in enumerate(src_pos):
+            z |= ((y >> p) & 1) << b
+        return z

@@ -115,10 +115,10 @@ class StateVector:
                         "qsv_apply_diag_wide")
             self._keep.append(D)
         elif op.kind == "modexp":
-            p = op.params
-            _cabi.check(self.lib.qsv_modexp_involution(self._ptr(self.state), self.n_local, len(p["x_pos"]),
-                                                       _cabi.int_array(p["x_pos"]), len(p["y_pos"]),
-                                                       _cabi.int_array(p["y_pos"]), int(p["a"]), int(p["N"]),
+            p = op.params          # controls = x register (MSB first, may be global), targets = y register
+            _cabi.check(self.lib.qsv_modexp_involution(self._ptr(self.state), self.n_local, len(op.controls),
+                                                       _cabi.int_array(op.controls), len(op.targets),
+                                                       _cabi.int_array(op.targets), int(p["a"]), int(p["N"]),
                                                        self.rank_bits, st), "qsv_modexp_involution")
         elif op.kind == "oracle":
             self._oracle(op)
@@ -134,9 +134,14 @@ class StateVector:
     def _oracle(self, op):
         """Grover oracle for one marked item (main/Grover.py:14-22): exchange the two amplitudes whose
         search-register bits equal x.  params: idx0, idx1 = global indices of the pair."""
-        i0, i1 = int(op.params["idx0"]), int(op.params["idx1"])
-        if (i0 >> self.n_local) != (i1 >> self.n_local):
+        cvals = op.cvals if op.cvals is not None else (1,) * len(op.controls)
+        i0 = 0
+        for c, v in zip(op.controls, cvals):
+            i0 |= (1 if v else 0) << c
+        anc = op.targets[0]
+        if anc >= self.n_local:
             raise RuntimeError("qsv: oracle pair straddles shards; the target qubit must be local")
+        i1 = i0 | (1 << anc)
         if (i0 >> self.n_local) != self.rank:
             return
         m = (1 << self.n_local) - 1
@@ -154,6 +159,8 @@ class StateVector:
                                                 self._ptr(sums), st), "qsv_diffusion_sums")
         if self.comm is not None and self.comm.world > 1:
             self.comm.all_reduce_sum(sums)
+        if sorted(op.targets) != list(range(anc, self.n)):
+            raise RuntimeError("qsv: diffusion needs the search register on positions [%d, %d)" % (anc, self.n))
         _cabi.check(self.lib.qsv_diffusion_update(self._ptr(self.state), self.n_local, anc, self._ptr(sums),
                                                   self.n - anc, st), "qsv_diffusion_update")
         self._keep += [scratch, sums]

@@ -69,13 +69,8 @@ class GroverOracle(Gate):
 
     def _qsv_lower(self, wires, layout, transposed):
         n = self.n_search
-        idx0 = 0
-        for p in range(n):
-            idx0 |= ((self.x >> (n - 1 - p)) & 1) << layout.pos[wires[p]]
-        anc = layout.pos[wires[n]]
-        return [Op("oracle", (anc,), tuple(layout.pos[w] for w in wires[:n]),
-                   cvals=tuple((self.x >> (n - 1 - p)) & 1 for p in range(n)),
-                   params={"idx0": idx0, "idx1": idx0 | (1 << anc)}, name=self.name)]
+        return [Op("oracle", (layout.pos[wires[n]],), tuple(layout.pos[w] for w in wires[:n]),
+                   cvals=tuple((self.x >> (n - 1 - p)) & 1 for p in range(n)), name=self.name)]
 
 
 class GroverDiffusion(Gate):
@@ -96,7 +91,8 @@ class GroverDiffusion(Gate):
         pos = sorted(layout.pos[w] for w in wires)
         anc_bits = n_total - self.n_search
         if pos == list(range(anc_bits, n_total)) and anc_bits <= 3:
-            return [Op("diffusion", tuple(pos), (), params={"anc_bits": anc_bits}, name=self.name)]
+            return [Op("diffusion", tuple(pos), (), params={"anc_bits": anc_bits, "n_search": self.n_search},
+                       name=self.name)]
         # general placement: H, reflection about |0..0>, H
         s = 2 ** (-0.5)
         Hm = np.array([[s, s], [s, -s]], dtype=np.complex128)
@@ -139,7 +135,5 @@ class ModExp(Gate):
 
     def _qsv_lower(self, wires, layout, transposed):
         h = self.q // 2
-        return [Op("modexp", tuple(layout.pos[w] for w in wires), (),
-                   params={"x_pos": [layout.pos[w] for w in wires[:h]],
-                           "y_pos": [layout.pos[w] for w in wires[h:]], "a": self.a, "N": self.N},
-                   name=self.name)]
+        return [Op("modexp", tuple(layout.pos[w] for w in wires[h:]), tuple(layout.pos[w] for w in wires[:h]),
+                   params={"a": self.a, "N": self.N}, name=self.name)]

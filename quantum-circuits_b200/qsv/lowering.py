@@ -117,9 +117,11 @@ def lower_gate(gate, wires, layout, transposed=False):
     return classify_matrix(M, layout.positions(wires), name)
 
 
-def lower(circuit, transposed=False, presorted=True):
+def lower(circuit, transposed=False, presorted=True, n_global=0):
     """(ops, src_pos): ops in application order; src_pos[b] = physical position feeding bit b of the
-    OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map."""
+    OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map.  With
+    n_global > 0 the ops are placed on a register sharded by its top n_global positions
+    (qsv.schedule.place inserts the global<->local qubit swaps)."""
     n = len(circuit)
     gates = circuit.gates if presorted else topological_gates(circuit)
     table, out_qubits = gate_targets(circuit, gates)
@@ -132,6 +134,9 @@ def lower(circuit, transposed=False, presorted=True):
         src_pos[n - 1 - i] = layout.pos[out_qubits[i]]
     if sorted(src_pos) != list(range(n)):
         raise RuntimeError("circuit outputs do not carry every qubit exactly once")
+    if n_global:
+        from .schedule import place
+        ops, src_pos = place(ops, n, n_global, src_pos)
     return ops, src_pos
 
 

@@ -31,18 +31,28 @@ class Op:
     name: str = ""
 
     def nondiag_bits(self):
-        if self.kind in ("dense", "mcx", "swap"):
-            return tuple(self.targets)
-        if self.kind in ("phase", "diag"):
+        """Positions whose amplitudes the op mixes or moves (they must be local / inside the tile)."""
+        if self.kind in ("dense", "mcx", "swap", "oracle", "modexp"):
+            return tuple(self.targets)          # oracle: the ancilla; modexp: the y register
+        if self.kind in ("phase", "diag", "wide_diag", "diffusion"):
             return ()
         return tuple(self.targets) + tuple(self.controls)
 
     def diag_bits(self):
-        if self.kind in ("dense", "mcx", "swap"):
-            return tuple(self.controls)
-        if self.kind in ("phase", "diag"):
+        """Positions the op only reads (controls, diagonal factors): they may be anywhere."""
+        if self.kind in ("dense", "mcx", "swap", "oracle", "modexp"):
+            return tuple(self.controls)         # oracle: search register; modexp: the x register
+        if self.kind in ("phase", "diag", "wide_diag", "diffusion"):
             return tuple(self.targets) + tuple(self.controls)
         return ()
+
+    def remapped(self, phys):
+        """Copy of the op with every position v replaced by phys[v]."""
+        import copy
+        o = copy.copy(self)
+        o.targets = tuple(phys[v] for v in self.targets)
+        o.controls = tuple(phys[v] for v in self.controls)
+        return o
 
 
 # ------------------------------------------------------------------------------------------------
@@ -192,6 +202,64 @@ def classify_matrix(M, pos, name=""):
     if k <= _cabi.QSV_MAX_TILE_K:
         return [Op("dense", pos, (), matrix=M, name=name)]
     return [Op("wide_dense", pos, (), matrix=M, name=name)]
+
+
+# ------------------------------------------------------------------------------------------------
+# placement on a sharded register: virtual positions -> physical positions, global<->local swaps
+# ------------------------------------------------------------------------------------------------
+
+def place(ops, n, n_global, src_pos=None, lookahead=400):
+    """Map ops written on VIRTUAL positions (single-device numbering, 0 = least significant) onto a
+    register whose top `n_global` physical positions are the rank index.
+
+    An op whose non-diagonal target sits on a global position triggers a re-layout: `n_global` local
+    qubits that are not needed for the longest time are moved to the top local positions (local 'swap'
+    ops, fused into the surrounding passes) and one 'global_swap' op exchanges them with the global
+    qubits (an all-to-all over NVLink).  Diagonal ops and controls on global qubits need no
+    communication.  Returns (physical ops, physical src_pos)."""
+    phys = list(range(n))                       # virtual position -> physical position
+    if n_global == 0:
+        return list(ops), (list(src_pos) if src_pos is not None else None)
+    n_local = n - n_global
+    # qubits a diffusion op treats as ancillas must stay on the low positions its kernel assumes
+    pinned = set()
+    for op in ops:
+        if op.kind == "diffusion":
+            pinned |= set(range(n)) - set(op.targets)
+    out = []
+    for idx, op in enumerate(ops):
+        need = set(op.nondiag_bits())
+        if any(phys[v] >= n_local for v in need):
+            # next non-diagonal use of every virtual qubit
+            nxt = {}
+            for d, later in enumerate(ops[idx: idx + lookahead]):
+                for v in later.nondiag_bits():
+                    nxt.setdefault(v, d)
+            local_virtual = [v for v in range(n) if phys[v] < n_local and v not in need and v not in pinned]
+            if len(local_virtual) < n_global:
+                raise RuntimeError("op %r needs more local qubits than one shard holds" % (op.name,))
+            local_virtual.sort(key=lambda v: (-nxt.get(v, lookahead + 1), -phys[v]))
+            victims = local_virtual[:n_global]
+            tops = list(range(n_local - n_global, n_local))
+            # victims already sitting on a top position keep it; the others are swapped in
+            free_tops = [t for t in tops if t not in [phys[v] for v in victims]]
+            at = {phys[v]: v for v in range(n)}
+            for v in victims:
+                if phys[v] in tops:
+                    continue
+                t = free_tops.pop(0)
+                u = at[t]
+                out.append(Op("swap", (phys[v], t), (), name="relayout"))
+                at[t], at[phys[v]] = v, u
+                phys[u], phys[v] = phys[v], t
+            out.append(Op("global_swap", (), (), params={"n_swap": n_global}, name="relayout"))
+            at = {phys[v]: v for v in range(n)}
+            for i in range(n_global):
+                a, b = at[n_local - n_global + i], at[n_local + i]
+                phys[a], phys[b] = n_local + i, n_local - n_global + i
+        out.append(op.remapped(phys))
+    new_src = [phys[v] for v in src_pos] if src_pos is not None else None
+    return out, new_src
 
 
 # ------------------------------------------------------------------------------------------------
@@ -684,6 +752,8 @@ def encode_rounds(ps, rounds):
 
 def algorithmic_bytes(op, n_local):
     N = 1 << n_local
+    if op.kind == "global_swap":
+        return 0
     if op.kind in ("dense", "wide_dense", "wide_perm", "swap"):
         return 32 * N >> len([c for c in op.controls if c < n_local])
     if op.kind == "mcx":

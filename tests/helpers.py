@@ -283,3 +283,30 @@ def emulate_ops(ops, psi, n_local, tile_bits=None, low_bits=None, rank_bits=0):
         else:
             raise AssertionError("emulate_ops: unsupported op kind %s" % op.kind)
     return flush(psi)
+
+
+def emulate_sharded(ops, psi, n, g, tile_bits=None, low_bits=None):
+    """Run PLACED ops (qsv.schedule.place) on P = 2^g virtual ranks held as rows of one numpy array:
+    tiled ops go through the packed-program emulator with each rank's rank_bits, 'global_swap' is the
+    all-to-all written as an axis swap.  Returns the full state in physical order."""
+    n_local = n - g
+    P = 1 << g
+    shards = psi.reshape(P, 1 << n_local).copy()
+    batch = []
+
+    def flush():
+        nonlocal shards
+        if batch:
+            for r in range(P):
+                shards[r] = emulate_ops(batch, shards[r], n_local, tile_bits, low_bits, rank_bits=r << n_local)
+            batch.clear()
+
+    for op in ops:
+        if op.kind == "global_swap":
+            flush()
+            t = shards.reshape(P, P, -1)            # [rank, top local field, rest]
+            shards = np.ascontiguousarray(t.transpose(1, 0, 2)).reshape(P, -1)
+        else:
+            batch.append(op)
+    flush()
+    return shards.reshape(-1)

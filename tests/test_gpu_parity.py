@@ -120,8 +120,8 @@ def test_shor21_example_weights_and_modexp_kernel(golden, qsv_gpu):
         sv.state.copy_(torch.from_numpy(psi))
         h = q // 2
         from qsv.schedule import Op
-        sv.run_ops([Op("modexp", (), (), params={"x_pos": list(range(q - 1, h - 1, -1)),
-                                                 "y_pos": list(range(h - 1, -1, -1)), "a": a, "N": N})])
+        sv.run_ops([Op("modexp", tuple(range(h - 1, -1, -1)), tuple(range(q - 1, h - 1, -1)),
+                       params={"a": a, "N": N})])
         out = sv.amplitudes()
         expect = np.empty_like(psi)
         expect[arrays[key]] = psi
