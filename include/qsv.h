@@ -91,15 +91,19 @@ typedef struct qsv_pass {
 
 #define QSV_RPROG_MAX_ROUNDS 32
 #define QSV_RPROG_MAX_OPS    120
-/* kind byte of qsv_rop_t: straight-line specialisations first, generic predicated forms last */
-#define QSV_ROP_DENSE1      0x10  /* +J        complex 1-qubit matrix on register bit J               */
-#define QSV_ROP_DENSE1_REAL 0x14  /* +J        real matrix                                            */
-#define QSV_ROP_PHASE_T     0x60  /*           phase independent of the register bits                 */
-#define QSV_ROP_PHASE1      0x70  /* +2J+V     phase on the slots with register bit J == V            */
-#define QSV_ROP_PERM        0x80  /* (multi-)controlled X as an address permutation at a round boundary:
-                                     if ((addr & tmask) == tval) addr ^= table_off   (tile-local bits)    */
-#define QSV_ROP_GEN_PHASE   0xF3  /* generic form: any (rmask, rval) condition on the register index    */
-#define QSV_ROP_DIAG        0xF4
+/* kind byte of qsv_rop_t.  0..17 are contiguous (one jump table in the kernel). */
+#define QSV_ROP_DENSE1       0   /* +J      complex 1-qubit matrix on register bit J                    */
+#define QSV_ROP_DENSE1_REAL  4   /* +J      real matrix                                                 */
+#define QSV_ROP_PHASE1       8   /* +2J+V   phase on the slots with register bit J == V                 */
+#define QSV_ROP_GEN_PHASE   16   /*         phase with any (rmask, rval) condition on the register index */
+#define QSV_ROP_DIAG        17   /*         diagonal table (k <= 8 bits: thread, register or external)  */
+#define QSV_ROP_PHASE_T     18   /*         phase independent of the register bits: kept in a separate
+                                            list per round and folded into one scalar per thread       */
+#define QSV_ROP_PERM        19   /* (multi-)controlled X as an address permutation at a round boundary:
+                                    if ((addr & tmask) == tval) addr ^= table_off   (tile-local bits).
+                                    Linear lists: j = 0xff if the condition is slot-independent, else
+                                    j = register index q and rval = position of the one condition bit
+                                    that varies with r_q                                                */
 #define QSV_ROPF_REAL  1u   /* matrix entries are real                                               */
 #define QSV_ROPF_NEG   2u   /* PHASE: scalar is exactly -1                                            */
 
@@ -109,10 +113,11 @@ typedef struct qsv_rprog_hdr {
 
 typedef struct qsv_round {
     uint8_t  rb[4];         /* ascending tile-local positions held in registers this round             */
-    uint32_t n_ops;         /* register ops of the round                                               */
-    uint32_t first_op;      /* index of the round's first op: [n_pre PERM][n_ops register][n_post PERM] */
-    uint16_t n_pre;         /* permutation ops applied to the addresses the round LOADS from           */
-    uint16_t n_post;        /* permutation ops applied to the addresses the round STORES to            */
+    uint32_t n_ops;         /* bits 0-15: ordered register ops; bits 16-29: QSV_ROP_PHASE_T ops        */
+    uint32_t first_op;      /* index of the round's first op: [PERM pre][PHASE_T][register ops][PERM post] */
+    uint16_t n_pre;         /* permutation ops applied to the addresses the round LOADS from;
+                               bit 15: the list is not XOR-linear, use the per-slot general form       */
+    uint16_t n_post;        /* same for the addresses the round STORES to                              */
 } qsv_round_t;
 
 typedef struct qsv_rop {
@@ -120,7 +125,7 @@ typedef struct qsv_rop {
     uint8_t  j;             /* DENSE1 / MCX: target register bit 0..3                                  */
     uint8_t  rmask, rval;   /* condition on the register index r (controls that are register bits)     */
     uint32_t tmask, tval;   /* condition on the thread's tile-local base index (register bits are 0)   */
-    uint32_t reserved0;
+    uint32_t flags2;        /* bit 0: ext_mask != 0 (the external condition has to be evaluated)       */
     uint64_t ext_mask;      /* condition on physical index bits outside the tile                       */
     uint64_t ext_val;
     uint32_t flags;         /* QSV_ROPF_*                                                              */

@@ -143,20 +143,63 @@ __device__ __forceinline__ void r_diag(double2 (&x)[16], const qsv_rop_t *op, co
     case (base) + 2: { constexpr int J = 2; CALL; } break; \
     case (base) + 3: { constexpr int J = 3; CALL; } break;
 #define QSV_CASE_PH1(J_) \
-    case 0x70 + 2 * (J_) + 0: f_phase1<J_, 0>(x, op); break; \
-    case 0x70 + 2 * (J_) + 1: f_phase1<J_, 1>(x, op); break;
+    case QSV_ROP_PHASE1 + 2 * (J_) + 0: f_phase1<J_, 0>(x, op); break; \
+    case QSV_ROP_PHASE1 + 2 * (J_) + 1: f_phase1<J_, 1>(x, op); break;
 
-__device__ __forceinline__ void apply_rop(double2 (&x)[16], double2 &S, const qsv_rop_t *op, uint32_t kind,
+// kinds 0..17 are contiguous so that the dispatch is one jump table (BRX), not a compare tree
+__device__ __forceinline__ void apply_rop(double2 (&x)[16], const qsv_rop_t *op, uint32_t kind,
                                           const uint8_t *sprog, uint32_t tb, uint64_t gbase) {
     switch (kind) {
-        QSV_CASE_J4(0x10, (f_dense1<J, false>(x, op)))
-        QSV_CASE_J4(0x14, (f_dense1<J, true>(x, op)))
-        case 0x60: S = cmul(S, make_double2(op->m[0], op->m[1])); break;
+        QSV_CASE_J4(QSV_ROP_DENSE1, (f_dense1<J, false>(x, op)))
+        QSV_CASE_J4(QSV_ROP_DENSE1_REAL, (f_dense1<J, true>(x, op)))
         QSV_CASE_PH1(0) QSV_CASE_PH1(1) QSV_CASE_PH1(2) QSV_CASE_PH1(3)
-        case 0xF3: r_phase(x, op); break;
-        case 0xF4: r_diag(x, op, sprog, tb, gbase); break;
+        case QSV_ROP_GEN_PHASE: r_phase(x, op); break;
+        case QSV_ROP_DIAG: r_diag(x, op, sprog, tb, gbase); break;
         default: break;
     }
+}
+
+// ---- address permutations at round boundaries -----------------------------------------------------
+// The 16 slot addresses of a thread are kept in XOR-linear form  address(r) = base ^ XOR_{q in r} d_q.
+// A (multi-)controlled X whose condition does not depend on the slot flips `base`; one whose condition
+// reads a single register-dependent bit flips d_q (and maybe base): 4-10 instructions per op and thread
+// instead of 3 per op and SLOT.  The host proves linearity (qsv/schedule.py linearize_perms); anything
+// else runs the per-slot general form.
+struct AddrState { uint32_t base, d0, d1, d2, d3; };
+
+__device__ __forceinline__ void perm_linear(AddrState &A, const qsv_rop_t *op, uint64_t gbase) {
+    if ((gbase & op->ext_mask) != op->ext_val) return;
+    const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off, q = op->j;
+    if (q == 0xffu) {                                   // condition is the same for all 16 slots
+        A.base ^= ((A.base & cm) == cv) ? xm : 0u;
+        return;
+    }
+    const uint32_t pbit = 1u << op->rval;               // the one condition bit that may vary with r_q
+    const uint32_t cmu = cm & ~pbit;
+    const uint32_t f = ((A.base & cmu) == (cv & cmu)) ? xm : 0u;
+    const uint32_t dq = (q == 0u) ? A.d0 : (q == 1u) ? A.d1 : (q == 2u) ? A.d2 : A.d3;
+    const uint32_t fd = (dq & pbit) ? f : 0u;           // slots with r_q = 1 see the bit toggled
+    A.base ^= (((A.base ^ cv) & pbit) == 0u) ? f : 0u;  // the r_q = 0 slots satisfy the condition
+    A.d0 ^= (q == 0u) ? fd : 0u;
+    A.d1 ^= (q == 1u) ? fd : 0u;
+    A.d2 ^= (q == 2u) ? fd : 0u;
+    A.d3 ^= (q == 3u) ? fd : 0u;
+}
+
+__device__ __forceinline__ void slot_addresses(uint32_t (&a)[16], const AddrState &A) {
+    a[0] = A.base;
+#pragma unroll
+    for (int r = 1; r < 16; ++r) {
+        const int low = r & -r;                          // lowest set bit of r
+        a[r] = a[r & (r - 1)] ^ (low == 1 ? A.d0 : low == 2 ? A.d1 : low == 4 ? A.d2 : A.d3);
+    }
+}
+
+__device__ __forceinline__ void perm_general(uint32_t (&a)[16], const qsv_rop_t *op, uint64_t gbase) {
+    if ((gbase & op->ext_mask) != op->ext_val) return;
+    const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) a[r] ^= ((a[r] & cm) == cv) ? xm : 0u;
 }
 
 // The pass program travels as a __grid_constant__ kernel parameter: it lives in the constant bank, op
@@ -179,6 +222,9 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
     const int tid = threadIdx.x;
     const int T = P.tile_bits, L = P.low_bits, n_hi = P.n_hi;
     const uint8_t *sprog = tables;      // diagonal tables stay in global memory (read-only path)
+    // The program arrives in the constant bank (kernel parameter); every CTA copies the used part to
+    // shared memory once: indexed constant loads (LDC c[0x0][R+imm]) cost a dependent ~100+ cycle round
+    // trip per field, three to four of them per op, which made every op cost ~600 cycles per tile.
     const uint32_t n_runs = 1u << n_hi;
     const uint32_t run_bytes = 16u << L;
     const uint32_t n_active = 1u << (T - 4);       // threads that own amplitudes
@@ -218,71 +264,71 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
 
         for (int rd = 0; rd < n_rounds; ++rd) {
             const qsv_round_t R = rounds[rd];
-            const uint32_t b0 = 1u << R.rb[0], b1 = 1u << R.rb[1], b2 = 1u << R.rb[2], b3 = 1u << R.rb[3];
             uint32_t tb = (uint32_t)tid;
             tb = insert_zero32(tb, R.rb[0]);
             tb = insert_zero32(tb, R.rb[1]);
             tb = insert_zero32(tb, R.rb[2]);
             tb = insert_zero32(tb, R.rb[3]);
-            const uint32_t n_pre = R.n_pre, n_post = R.n_post;
+            const uint32_t n_pre = R.n_pre & 0x7fffu, n_post = R.n_post & 0x7fffu;
+            const uint32_t n_reg = R.n_ops & 0xffffu;            // ordered register ops
+            const uint32_t n_pt = (R.n_ops >> 16) & 0x3fffu;     // thread-level phases (commute with everything)
             if (rd > 0) __syncthreads();           // the previous round's stores are visible
             double2 x[16];
+            // Threads beyond 2^(T-4) own no amplitudes (tiles smaller than 4096): they run the same
+            // UNIFORM control flow on zeros and only their loads/stores are predicated off.  Keeping the
+            // op loop out of any thread-dependent branch lets the compiler keep the loop counter, the op
+            // pointer and the op fields in uniform registers (ULDC) instead of chains of indexed LDC.
             const bool owner = (uint32_t)tid < n_active;
-            if (owner) {
-                if (n_pre == 0) {
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)
-                        x[r] = tile[tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u)];
+            {
+                // ---- load: slot r <- tile[address(r)], address(r) = base ^ XOR_{q in r} d_q.  Leading
+                // X / CNot / Toffoli ops permute the addresses: new[a] = old[p_1(p_2(...p_k(a)))].
+                uint32_t a[16];
+                AddrState A = {tb, 1u << R.rb[0], 1u << R.rb[1], 1u << R.rb[2], 1u << R.rb[3]};
+                if (!(R.n_pre & 0x8000u)) {
+                    for (int i = (int)n_pre - 1; i >= 0; --i) perm_linear(A, ops + R.first_op + i, gbase);
+                    slot_addresses(a, A);
                 } else {
-                    // leading X / CNot / Toffoli ops: new[a] = old[p_1(p_2(...p_k(a)))]
-                    uint32_t a[16];
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)
-                        a[r] = tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u);
-                    for (int i = (int)n_pre - 1; i >= 0; --i) {
-                        const qsv_rop_t *op = ops + R.first_op + i;
-                        if ((gbase & op->ext_mask) != op->ext_val) continue;
-                        const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off;
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) a[r] ^= ((a[r] & cm) == cv) ? xm : 0u;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) x[r] = tile[a[r]];
+                    slot_addresses(a, A);
+                    for (int i = (int)n_pre - 1; i >= 0; --i) perm_general(a, ops + R.first_op + i, gbase);
                 }
-                double2 S = make_double2(1.0, 0.0);       // pending thread-uniform phase (commutes with all ops)
-                bool hasS = false;
-                for (uint32_t i = 0; i < R.n_ops; ++i) {
-                    const qsv_rop_t *op = ops + R.first_op + n_pre + i;
-                    if ((gbase & op->ext_mask) != op->ext_val) continue;
-                    if ((tb & op->tmask) != op->tval) continue;
-                    const uint32_t kind = op->kind;
-                    hasS |= (kind == 0x60u);
-                    apply_rop(x, S, op, kind, sprog, tb, gbase);
-                }
-                if (hasS) {
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) cscale_inplace(x[r], S);
+                for (int r = 0; r < 16; ++r) x[r] = owner ? tile[a[r]] : make_double2(0.0, 0.0);
+            }
+            if (n_pt) {
+                // thread-level phases: one pending scalar per thread, applied once to all 16 slots
+                double2 S = make_double2(1.0, 0.0);
+                const qsv_rop_t *pt = ops + R.first_op + n_pre;
+                for (uint32_t i = 0; i < n_pt; ++i) {
+                    const uint4 h = *reinterpret_cast<const uint4 *>(pt + i);     // kind.. | tmask | tval | flags2
+                    if ((h.w & 1u) && (gbase & pt[i].ext_mask) != pt[i].ext_val) continue;
+                    const double2 m = make_double2(pt[i].m[0], pt[i].m[1]);     // m is 8-byte aligned only
+                    if ((tb & h.y) == h.z) S = cmul(S, m);
+                }
+#pragma unroll
+                for (int r = 0; r < 16; ++r) cscale_inplace(x[r], S);
+            }
+            {
+                const qsv_rop_t *rg = ops + R.first_op + n_pre + n_pt;
+                for (uint32_t i = 0; i < n_reg; ++i) {
+                    const uint4 h = *reinterpret_cast<const uint4 *>(rg + i);
+                    if ((h.w & 1u) && (gbase & rg[i].ext_mask) != rg[i].ext_val) continue;     // uniform
+                    if ((tb & h.y) == h.z) apply_rop(x, rg + i, h.x & 0xffu, sprog, tb, gbase);
                 }
             }
             if (n_pre + n_post) __syncthreads();   // permuted stores land in other threads' slots: all loads first
-            if (owner) {
-                if (n_post == 0) {
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)
-                        tile[tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u)] = x[r];
+            {
+                // ---- store: tile[p_k(...p_1(address(r)))] <- slot r
+                uint32_t a[16];
+                AddrState A = {tb, 1u << R.rb[0], 1u << R.rb[1], 1u << R.rb[2], 1u << R.rb[3]};
+                const qsv_rop_t *post = ops + R.first_op + n_pre + n_pt + n_reg;
+                if (!(R.n_post & 0x8000u)) {
+                    for (uint32_t i = 0; i < n_post; ++i) perm_linear(A, post + i, gbase);
+                    slot_addresses(a, A);
                 } else {
-                    // trailing permutation ops: new[p_k(...p_1(a))] = old[a]
-                    uint32_t a[16];
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)
-                        a[r] = tb | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u) | ((r & 4) ? b2 : 0u) | ((r & 8) ? b3 : 0u);
-                    for (uint32_t i = 0; i < n_post; ++i) {
-                        const qsv_rop_t *op = ops + R.first_op + n_pre + R.n_ops + i;
-                        if ((gbase & op->ext_mask) != op->ext_val) continue;
-                        const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off;
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) a[r] ^= ((a[r] & cm) == cv) ? xm : 0u;
-                    }
+                    slot_addresses(a, A);
+                    for (uint32_t i = 0; i < n_post; ++i) perm_general(a, post + i, gbase);
+                }
+                if (owner) {
 #pragma unroll
                     for (int r = 0; r < 16; ++r) tile[a[r]] = x[r];
                 }
@@ -306,6 +352,17 @@ using namespace qsv;
 static_assert(sizeof(qsv_rop_t) == 128, "qsv_rop_t must be 128 bytes");
 static_assert(sizeof(qsv_round_t) == 16 && sizeof(qsv_rprog_hdr_t) == 16, "round/program headers are 16 bytes");
 static_assert(sizeof(qsv_op_t) == 88 && sizeof(qsv_pass_t) == 48, "struct layout mirrored in qsv/schedule.py");
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
 
 extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
                                    const void *tables_dev, void *stream) {
@@ -344,12 +401,16 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
         const qsv_round_t &R = param.rounds[r];
         QSV_CHECK_ARG(R.rb[0] < R.rb[1] && R.rb[1] < R.rb[2] && R.rb[2] < R.rb[3] && R.rb[3] < P->tile_bits,
                       "qsv_run_pass_rounds: round %u register bits not ascending inside the tile", r);
-        QSV_CHECK_ARG((uint64_t)R.first_op + R.n_ops <= hdr->n_ops, "qsv_run_pass_rounds: round %u op range", r);
+        QSV_CHECK_ARG((uint64_t)R.first_op + (R.n_pre & 0x7fffu) + (R.n_ops & 0xffffu) + ((R.n_ops >> 16) & 0x3fffu) +
+                              (R.n_post & 0x7fffu) <= hdr->n_ops, "qsv_run_pass_rounds: round %u op range", r);
     }
     QSV_CHECK_ARG(!has_diag || tables_dev, "qsv_run_pass_rounds: diagonal op without a table buffer");
     const uint64_t n_tiles = 1ull << (P->n_local - P->tile_bits);
     const size_t smem = (size_t)16 << P->tile_bits;
-    const unsigned grid = (unsigned)(n_tiles < (1ull << 30) ? n_tiles : (1ull << 30));
+    // persistent CTAs: 2 resident per SM, 4x oversubscribed so that skipped tiles do not unbalance the
+    // SMs; the per-CTA prologue (program copy, tables, mbarrier) is paid once per ~50+ tiles, not per tile
+    const uint64_t resident = (uint64_t)sm_count() * 2ull * 4ull;
+    const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
     QSV_CUDA(cudaFuncSetAttribute(k_pass_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
     k_pass_reg<<<grid, kRThreads, smem, (cudaStream_t)stream>>>((double2 *)state_dev, *P, param,
                                                                 (const uint8_t *)tables_dev, n_tiles);

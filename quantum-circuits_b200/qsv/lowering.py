@@ -7,6 +7,7 @@ classified (qsv.schedule.classify_matrix) into index-arithmetic ops on PHYSICAL 
 the final output relabel (main/circuit.py:329-332) becomes a bit map applied when measuring.
 """
 import math
+import os
 import numpy as np
 
 from .schedule import Op, classify_matrix
@@ -134,6 +135,9 @@ def lower(circuit, transposed=False, presorted=True, n_global=0):
         src_pos[n - 1 - i] = layout.pos[out_qubits[i]]
     if sorted(src_pos) != list(range(n)):
         raise RuntimeError("circuit outputs do not carry every qubit exactly once")
+    if os.environ.get("QSV_FUSE_1Q", "1") != "0":
+        from .schedule import fuse_1q
+        ops = fuse_1q(ops)
     if n_global:
         from .schedule import place
         ops, src_pos = place(ops, n, n_global, src_pos)

@@ -205,6 +205,99 @@ def classify_matrix(M, pos, name=""):
 
 
 # ------------------------------------------------------------------------------------------------
+# host-side fusion of 1-qubit gates
+# ------------------------------------------------------------------------------------------------
+
+def _as_1q_matrix(op):
+    """2x2 matrix of an UNCONTROLLED 1-qubit op and its position, or None."""
+    if op.kind == "dense" and len(op.targets) == 1 and not op.controls:
+        return op.targets[0], np.asarray(op.matrix, dtype=np.complex128)
+    if op.kind == "mcx" and not op.controls:
+        return op.targets[0], np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    if op.kind == "phase" and len(op.controls) == 1 and not op.targets:
+        v = 1 if op.cvals is None else op.cvals[0]
+        d = [1.0, op.scalar] if v else [op.scalar, 1.0]
+        return op.controls[0], np.diag(np.array(d, dtype=np.complex128))
+    if op.kind == "diag" and len(op.targets) == 1 and not op.controls:
+        return op.targets[0], np.diag(np.asarray(op.matrix, dtype=np.complex128))
+    return None
+
+
+def _emit_1q(b, P, name="fused"):
+    if np.array_equal(P, np.eye(2)):
+        return []
+    if P[0, 1] == 0 and P[1, 0] == 0:
+        out = []
+        if P[0, 0] != 1:
+            out.append(Op("phase", (), (b,), cvals=(0,), scalar=complex(P[0, 0]), name=name))
+        if P[1, 1] != 1:
+            out.append(Op("phase", (), (b,), cvals=(1,), scalar=complex(P[1, 1]), name=name))
+        return out
+    if P[0, 0] == 0 and P[1, 1] == 0 and P[0, 1] == 1 and P[1, 0] == 1:
+        return [Op("mcx", (b,), (), name=name)]
+    return [Op("dense", (b,), (), matrix=P, name=name)]
+
+
+def _is_diag2(M):
+    return M[0, 1] == 0 and M[1, 0] == 0
+
+
+def _cheap_product(P, M):
+    """Fuse two 1-qubit matrices only if the product is no more expensive than its most expensive
+    factor: diagonal.diagonal stays a phase (free when the qubit is a thread bit), real.real stays on the
+    4-instruction-per-amplitude path, dense.dense saves a whole gate.  A phase is NOT folded into a real
+    matrix: the complex 2x2 update costs 9 FP64 instructions per amplitude, a real one 4."""
+    dP, dM = _is_diag2(P), _is_diag2(M)
+    if dP and dM:
+        return True
+    if not np.any(P.imag) and not np.any(M.imag):
+        return True
+    return not dP and not dM
+
+
+def fuse_1q(ops):
+    """Multiply runs of uncontrolled 1-qubit gates on the same qubit into one 2x2 matrix.  A pending
+    matrix is carried past every op that does not touch its qubit, and — while it is diagonal — past
+    ops that use the qubit only as a control / diagonal factor (they commute).  Exact 0/1 matrices stay
+    exact (X.X = I is dropped, X stays a permutation), so index work remains bit-exact."""
+    pending = {}
+    out = []
+
+    def flush(b):
+        P = pending.pop(b, None)
+        if P is not None:
+            out.extend(_emit_1q(b, P))
+
+    for op in ops:
+        one = _as_1q_matrix(op)
+        if one is not None:
+            b, M = one
+            P = pending.get(b)
+            if P is None:
+                pending[b] = M
+            elif _cheap_product(P, M):
+                pending[b] = M @ P
+            else:                       # a complex 2x2 costs more FP64 work than a real one plus a phase
+                flush(b)
+                pending[b] = M
+            continue
+        if op.kind in ("diffusion", "wide_dense", "wide_perm", "wide_diag", "global_swap"):
+            for b in sorted(set(op.targets) | set(op.controls) if op.kind != "global_swap" else set(pending)):
+                flush(b)
+        else:
+            for b in op.nondiag_bits():
+                flush(b)
+            for b in op.diag_bits():
+                P = pending.get(b)
+                if P is not None and (P[0, 1] != 0 or P[1, 0] != 0):
+                    flush(b)
+        out.append(op)
+    for b in sorted(pending):
+        flush(b)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # placement on a sharded register: virtual positions -> physical positions, global<->local swaps
 # ------------------------------------------------------------------------------------------------
 
@@ -516,15 +609,14 @@ def pack_passes(passes, register_kernel=None):
 
 ROP_DTYPE = np.dtype([
     ("kind", "u1"), ("j", "u1"), ("rmask", "u1"), ("rval", "u1"), ("tmask", "<u4"), ("tval", "<u4"),
-    ("reserved0", "<u4"), ("ext_mask", "<u8"), ("ext_val", "<u8"), ("flags", "<u4"), ("table_off", "<u4"),
+    ("flags2", "<u4"), ("ext_mask", "<u8"), ("ext_val", "<u8"), ("flags", "<u4"), ("table_off", "<u4"),
     ("dsrc", "u1", (8,)), ("rc", "u1", (4,)), ("k", "<u4"), ("m", "<f8", (8,)), ("pad", "u1", (8,)),
 ])
 assert ROP_DTYPE.itemsize == 128
 ROUND_DTYPE = np.dtype([("rb", "u1", (4,)), ("n_ops", "<u4"), ("first_op", "<u4"), ("n_pre", "<u2"), ("n_post", "<u2")])
 assert ROUND_DTYPE.itemsize == 16
 RPROG_MAX_ROUNDS, RPROG_MAX_OPS = 32, 120
-ROP_DENSE1, ROP_DENSE1_REAL, ROP_PHASE_T, ROP_PHASE1, ROP_PERM = 0x10, 0x14, 0x60, 0x70, 0x80
-ROP_GEN_PHASE, ROP_DIAG = 0xF3, 0xF4
+ROP_DENSE1, ROP_DENSE1_REAL, ROP_PHASE1, ROP_GEN_PHASE, ROP_DIAG, ROP_PHASE_T, ROP_PERM = 0, 4, 8, 16, 17, 18, 19
 ROPF_REAL, ROPF_NEG = 1, 2
 REG_BITS = 4
 
@@ -660,6 +752,31 @@ def _merge_perms(ops, ps):
     return [f for f in out if f[2]]
 
 
+def linearize_perms(fields, rb):
+    """Decide whether a list of permutation ops (in APPLICATION order) can run in the kernel's XOR-linear
+    address form.  Tracks, per tile-local bit, which register indices may toggle it (initially bit rb[q]
+    depends on q).  An op is linear if its condition reads no register-dependent bit (slot-uniform), or
+    exactly one such bit that depends on exactly one register index q.  Returns [(q or 0xff, bitpos)] per
+    op, or None if some op is not linear (the kernel then uses the per-slot general form)."""
+    dep = {}
+    for q, b in enumerate(rb):
+        dep[b] = {q}
+    out = []
+    for cm, cv, xm, em, ev in fields:
+        bits = [p for p in range(32) if (cm >> p) & 1 and dep.get(p)]
+        if not bits:
+            out.append((0xFF, 0))
+            continue
+        if len(bits) != 1 or len(dep[bits[0]]) != 1:
+            return None
+        q = next(iter(dep[bits[0]]))
+        out.append((q, bits[0]))
+        for t in range(32):
+            if (xm >> t) & 1:
+                dep.setdefault(t, set()).add(q)      # conservative: the flip may or may not have fired
+    return out
+
+
 def encode_rounds(ps, rounds):
     """Host image of a register-resident pass program -> (program bytes, diagonal-table bytes), or None
     if it exceeds the kernel-parameter capacity (RPROG_MAX_ROUNDS / RPROG_MAX_OPS)."""
@@ -674,15 +791,21 @@ def encode_rounds(ps, rounds):
         rnd[r]["rb"] = rb
         rnd[r]["first_op"] = len(rops)
         pre, post = _merge_perms(R.pre, ps), _merge_perms(R.post, ps)
-        rnd[r]["n_pre"], rnd[r]["n_ops"], rnd[r]["n_post"] = len(pre), len(R.reg), len(post)
+        lin_pre = linearize_perms(pre[::-1], rb)      # the load side applies the list in reverse order
+        lin_post = linearize_perms(post, rb)
+        rnd[r]["n_pre"] = len(pre) | (0x8000 if lin_pre is None else 0)
+        rnd[r]["n_post"] = len(post) | (0x8000 if lin_post is None else 0)
+        pt_ops, reg_ops = [], []            # thread-level phases commute with every op of the round
 
-        def perm_rop(f):
+        def perm_rop(f, lin):
             h = np.zeros((), dtype=ROP_DTYPE)
             h["kind"] = ROP_PERM
             h["tmask"], h["tval"], h["table_off"], h["ext_mask"], h["ext_val"] = f
+            h["flags2"] = 1 if f[3] else 0
+            h["j"], h["rval"] = lin if lin is not None else (0xFF, 0)
             return h
 
-        rops += [perm_rop(f) for f in pre]
+        rops += [perm_rop(f, lin_pre[::-1][i] if lin_pre is not None else None) for i, f in enumerate(pre)]
         for op in R.reg:
             h = np.zeros((), dtype=ROP_DTYPE)
             ctrls = tuple(op.controls)
@@ -736,8 +859,11 @@ def encode_rounds(ps, rounds):
                 table_cursor += len(tb)
             h["rmask"], h["rval"], h["tmask"], h["tval"] = rmask, rval, tmask, tval
             h["ext_mask"], h["ext_val"] = ext_mask, ext_val
-            rops.append(h)
-        rops += [perm_rop(f) for f in post]
+            h["flags2"] = 1 if ext_mask else 0
+            (pt_ops if int(h["kind"]) == ROP_PHASE_T else reg_ops).append(h)
+        rnd[r]["n_ops"] = len(reg_ops) | (len(pt_ops) << 16)
+        rops += pt_ops + reg_ops
+        rops += [perm_rop(f, lin_post[i] if lin_post is not None else None) for i, f in enumerate(post)]
     if len(rops) > RPROG_MAX_OPS:
         return None
     hdr = np.array([len(rounds), 16 + 16 * len(rounds) + 128 * len(rops), len(rops), 0], dtype="<u4")

@@ -160,15 +160,43 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
     psi = psi.copy()
     tid = np.arange(1 << (T - 4))
 
-    def permute(a, ops, gbase):
+    def permute(tb, rb, ops, gbase, general):
+        """Addresses [16, threads] after the permutation ops, computed the way the kernel does: per slot
+        (general) or in XOR-linear form base ^ XOR d_q (perm_linear in csrc/qsv_tile_reg.cu)."""
+        roff = [sum((1 << rb[q]) for q in range(4) if (r >> q) & 1) for r in range(16)]
+        if general:
+            a = np.stack([tb | roff[r] for r in range(16)])
+            for o in ops:
+                assert int(o["kind"]) == 19 and bool(int(o["flags2"]) & 1) == bool(int(o["ext_mask"]))
+                if (gbase & int(o["ext_mask"])) != int(o["ext_val"]):
+                    continue
+                cm, cv, xm = int(o["tmask"]), int(o["tval"]), int(o["table_off"])
+                assert xm and not (xm & cm)
+                a = np.where((a & cm) == cv, a ^ xm, a)
+            return a
+        base = tb.copy()
+        d = [np.full_like(tb, 1 << rb[q]) for q in range(4)]
         for o in ops:
-            assert int(o["kind"]) == 0x80
+            assert int(o["kind"]) == 19 and bool(int(o["flags2"]) & 1) == bool(int(o["ext_mask"]))
             if (gbase & int(o["ext_mask"])) != int(o["ext_val"]):
                 continue
-            cm, cv, xm = int(o["tmask"]), int(o["tval"]), int(o["table_off"])
+            cm, cv, xm, q = int(o["tmask"]), int(o["tval"]), int(o["table_off"]), int(o["j"])
             assert xm and not (xm & cm)
-            a = np.where((a & cm) == cv, a ^ xm, a)
-        return a
+            if q == 0xFF:
+                base = np.where((base & cm) == cv, base ^ xm, base)
+                continue
+            pbit = 1 << int(o["rval"])
+            assert cm & pbit
+            cmu = cm & ~pbit
+            f = np.where((base & cmu) == (cv & cmu), xm, 0)
+            fd = np.where((d[q] & pbit) != 0, f, 0)
+            base = np.where(((base ^ cv) & pbit) == 0, base ^ f, base)
+            d[q] = d[q] ^ fd
+        a = [base]
+        for r in range(1, 16):
+            low = (r & -r).bit_length() - 1
+            a.append(a[r & (r - 1)] ^ d[low])
+        return np.stack(a)
 
     for t in range(1 << (ps.n_local - T)):
         base = t << L
@@ -185,10 +213,16 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
             for b in rb:
                 tb = _insert_zero(tb, b)
             roff = [sum((1 << rb[q]) for q in range(4) if (r >> q) & 1) for r in range(16)]
-            f0, npre, nreg, npost = int(R["first_op"]), int(R["n_pre"]), int(R["n_ops"]), int(R["n_post"])
-            addr = np.stack([tb | roff[r] for r in range(16)])
-            x = tile[permute(addr, rops[f0: f0 + npre][::-1], gbase)]           # [16, threads]
+            f0 = int(R["first_op"])
+            npre, gen_pre = int(R["n_pre"]) & 0x7FFF, bool(int(R["n_pre"]) & 0x8000)
+            npost, gen_post = int(R["n_post"]) & 0x7FFF, bool(int(R["n_post"]) & 0x8000)
+            n_pt, nreg0 = (int(R["n_ops"]) >> 16) & 0x3FFF, int(R["n_ops"]) & 0xFFFF
+            assert all(int(o["kind"]) == 18 for o in rops[f0 + npre: f0 + npre + n_pt])
+            assert all(int(o["kind"]) < 18 for o in rops[f0 + npre + n_pt: f0 + npre + n_pt + nreg0])
+            nreg = n_pt + nreg0          # the phase_t list commutes with the ordered list: emulate in sequence
+            x = tile[permute(tb, rb, rops[f0: f0 + npre][::-1], gbase, gen_pre)]           # [16, threads]
             for o in rops[f0 + npre: f0 + npre + nreg]:
+                assert bool(int(o["flags2"]) & 1) == bool(int(o["ext_mask"]))
                 if (gbase & int(o["ext_mask"])) != int(o["ext_val"]):
                     continue
                 tp = (tb & int(o["tmask"])) == int(o["tval"])
@@ -197,8 +231,8 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
                 rsel = [r for r in range(16) if (r & rm) == rv]
                 # decode the kind byte exactly like apply_rop() in csrc/qsv_tile_reg.cu and cross-check
                 # the specialisation against the generic (j, rmask, rval) fields
-                if 0x10 <= kind < 0x18:
-                    assert J == (kind & 3) and rm == 0 and bool(int(o["flags"]) & 1) == (kind >= 0x14)
+                if 0 <= kind < 8:
+                    assert J == (kind & 3) and rm == 0 and bool(int(o["flags"]) & 1) == (kind >= 4)
                     m = o["m"].view(np.complex128)
                     for r in range(16):
                         if (r >> J) & 1:
@@ -206,16 +240,16 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
                         x0, x1 = x[r].copy(), x[r | (1 << J)].copy()
                         x[r] = np.where(tp, m[0] * x0 + m[1] * x1, x0)
                         x[r | (1 << J)] = np.where(tp, m[2] * x0 + m[3] * x1, x1)
-                elif kind == 0x60 or 0x70 <= kind < 0x78 or kind == 0xF3:
-                    if kind == 0x60:
+                elif kind == 18 or 8 <= kind < 16 or kind == 16:
+                    if kind == 18:
                         assert rm == 0
-                    elif kind != 0xF3:
-                        jj, vv = (kind - 0x70) >> 1, (kind - 0x70) & 1
+                    elif kind != 16:
+                        jj, vv = (kind - 8) >> 1, (kind - 8) & 1
                         assert rm == 1 << jj and rv == vv << jj
                     sc = complex(o["m"][0], o["m"][1])
                     for r in rsel:
                         x[r] = np.where(tp, x[r] * sc, x[r])
-                elif kind == 0xF4:
+                elif kind == 17:
                     k = int(o["k"])
                     tab = np.frombuffer(tables, dtype=np.complex128, count=1 << k, offset=int(o["table_off"]))
                     di = np.zeros_like(tb)
@@ -234,7 +268,9 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
                 else:
                     raise AssertionError("bad rop kind 0x%x" % kind)
             new_tile = tile.copy()
-            new_tile[permute(addr, rops[f0 + npre + nreg: f0 + npre + nreg + npost], gbase)] = x
+            dst = permute(tb, rb, rops[f0 + npre + nreg: f0 + npre + nreg + npost], gbase, gen_post)
+            assert np.unique(dst).size == dst.size, "store addresses must be a permutation of the tile"
+            new_tile[dst] = x
             tile = new_tile
         psi[base + gl_off] = tile
     return psi

@@ -62,3 +62,37 @@ def test_engine_refuses_to_run_without_cuda():
     c.add_wire(x, 0, c, 0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         c.run([0], 2)
+
+
+def test_round_programs_pass_host_validation():
+    """Every round program the scheduler emits must get past qsv_run_pass_rounds' host-side checks; without
+    a GPU the call then fails inside the CUDA runtime, never in the argument validation."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    import ctypes as C
+    import statevec_oracle as so
+    from helpers import circuit_from_steps
+    from qsv import _cabi, schedule
+    from qsv.lowering import lower
+    lib = _cabi.load()
+    n = 14
+    c = circuit_from_steps(so.random_layered_steps(n, 6, seed=2), n)
+    c.sort()
+    ops, _ = lower(c)
+    packed = schedule.pack_passes(schedule.plan_passes(ops, n, 12, 6))
+    seen = 0
+    for ps, off, n_ops, extra in packed.passes:
+        if n_ops >= 0:
+            continue
+        prog = extra[0]
+        cp = _cabi.QsvPass()
+        cp.n_local, cp.tile_bits, cp.low_bits, cp.n_hi = ps.n_local, ps.tile_bits, ps.low_bits, ps.tile_bits - ps.low_bits
+        for j, p in enumerate(ps.hi_pos):
+            cp.hi_pos[j] = p
+        rc = lib.qsv_run_pass_rounds(C.c_void_p(16), C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size),
+                                     C.c_void_p(16), None)
+        msg = lib.qsv_last_error().decode()
+        assert rc != 0 and ("cuda" in msg.lower() or "kernel launch failed" in msg), msg
+        seen += 1
+    assert seen >= 1
