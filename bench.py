@@ -39,6 +39,10 @@ def parse():
     ap.add_argument("--cpu-qubits", type=int, default=22, help="register size of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gate-pass", action="store_true", help="skip the single-gate-pass roofline sweep")
+    ap.add_argument("--workload", default="layered", choices=["layered", "qft", "grover"],
+                    help="layered = BASELINE config 3 (headline); qft = config 4 (H + controlled-phase ladder); "
+                         "grover = config 5 (oracle + diffusion kernels)")
+    ap.add_argument("--iterations", type=int, default=32, help="Grover iterations (config 5)")
     return ap.parse_args()
 
 
@@ -96,6 +100,17 @@ class ClockSampler:
         sm.sort()
         med = sm[len(sm) // 2] if sm else None
         return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def traffic_from_profile(kind, n_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json: bytes per amplitude), scaled to this state size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            per_amp = json.load(f)[kind]["dram_bytes_per_amplitude"]
+        return per_amp * (1 << n_local)
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def measured_peak_gbs():
@@ -194,7 +209,21 @@ def main():
 
     # ---- build + lower the workload once (host), upload the packed programs (resident in HBM)
     t_host0 = time.perf_counter()
-    circ = workloads.random_layered_circuit(n, args.depth, seed=SEED)
+    check = None
+    if args.workload == "layered":
+        circ = workloads.random_layered_circuit(n, args.depth, seed=SEED)
+        in_bits = [0] * n
+        wl_name = ("config-3: random H/X/T8/phase layers + CNot/CZ matchings, %d qubits, depth %d" % (n, args.depth))
+    elif args.workload == "qft":
+        circ = workloads.qft_ladder_circuit(n)
+        in_bits = [(i + 1) % 2 for i in range(n)]
+        wl_name = "config-4: QFT as H + controlled-phase ladder (sign +i, bit reversal in the output map), %d qubits" % n
+    else:
+        x_marked = 0x5A5A5A5A5 & ((1 << (n - 1)) - 1)
+        circ = workloads.grover_circuit(n - 1, x_marked, args.iterations)
+        in_bits = [0] * (n - 1) + [1]
+        wl_name = ("config-5: Grover, %d search qubits + ancilla, H on all then %d x [oracle, diffusion]"
+                   % (n - 1, args.iterations))
     circ.sort()
     n_gates = len(circ.gates)
     if comm is None:
@@ -205,7 +234,7 @@ def main():
 
     sv = engine.StateVector(n, comm=comm)
     plan = sv.prepare(ops)
-    in_index = 0
+    in_index = lowering.basis_index(in_bits)
 
     def step(u=0.37):
         sv.init_basis(in_index)
@@ -227,6 +256,9 @@ def main():
         sampler.start()
     lib.qsv_reset_launch_count()
     passes0 = sv.passes_run
+    if comm is not None:
+        comm.swap_stats()
+        bytes0 = comm.bytes_sent
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -238,6 +270,16 @@ def main():
     launches = int(lib.qsv_launch_count())
     passes_per_step = (sv.passes_run - passes0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
+    swap = None
+    if comm is not None:
+        n_sw, sw_ms = comm.swap_stats()
+        out_bytes = comm.bytes_sent - bytes0
+        nv_peak = 770.0      # measured peer-copy GB/s per direction per GPU (B200_PROFILING.md); 900 nominal
+        gbs = out_bytes / (sw_ms * 1e-3) / 1e9 if sw_ms > 0 else 0.0
+        swap = {"swaps_per_step": n_sw / args.steps, "ms_per_step": sw_ms / args.steps,
+                "bytes_out_per_gpu_per_swap": out_bytes / max(1, n_sw), "achieved_GBps_out_per_gpu": gbs,
+                "nvlink_peak_GBps": nv_peak, "frac_of_nvlink": gbs / nv_peak,
+                "note": "time includes pack/unpack kernels around each chunked all_to_all"}
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -245,28 +287,54 @@ def main():
     ms_per_step = ms / args.steps
     value = n_gates / (ms_per_step * 1e-3)
 
+    if args.workload == "grover":
+        # closed form: amplitude of the marked pair after K iterations = +-sin((2K+1) theta)/sqrt(2)
+        import math
+        idx = (x_marked << 1)
+        owner = idx >> sv.n_local
+        val = torch.zeros(2, dtype=torch.complex128, device="cuda")
+        if owner == (comm.rank if comm else 0):
+            loc = idx & ((1 << sv.n_local) - 1)
+            val = sv.state[loc: loc + 2].clone()
+        if world > 1:
+            v = torch.view_as_real(val)
+            dist.all_reduce(v)
+        theta = math.asin(2.0 ** (-(n - 1) / 2))
+        expect = math.sin((2 * args.iterations + 1) * theta) / math.sqrt(2)
+        err = max(abs(complex(val[0]) - expect), abs(complex(val[1]) + expect))
+        check = {"marked_pair_amplitude_error": err, "expected": expect, "tolerance": 1e-12, "ok": bool(err < 1e-12)}
+
     # ---- roofline of the dominant kernel (k_pass): per-launch CUDA-event timing of every pass
     peak, peak_src = measured_peak_gbs()
-    pass_ms = sv.time_passes(plan, repeats=2)
     n_local = sv.n_local
-    alg_bytes = [32.0 * (1 << n_local) * f for f in sv.pass_active_fractions(plan)]
-    tot_ms = sum(pass_ms)
-    achieved = sum(alg_bytes) / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "qsv::k_pass (tiled TMA gate pass)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "launches_timed": len(pass_ms), "avg_launch_ms": tot_ms / max(1, len(pass_ms)),
-                "algorithmic_bytes_per_launch": sum(alg_bytes) / max(1, len(alg_bytes)),
-                "share_of_step": tot_ms / ms_per_step if ms_per_step else None,
-                "gates_per_pass": n_gates / max(1, passes_per_step)}
+    timed = sv.time_plan(plan, repeats=2)
+    by_kind = {}
+    for t in timed:
+        k = by_kind.setdefault(t["kind"], {"ms": 0.0, "bytes": 0.0, "launch_groups": 0, "ops": 0})
+        k["ms"] += t["ms"]; k["bytes"] += t["bytes"]; k["launch_groups"] += 1; k["ops"] += t["ops"]
+    dom = max(by_kind, key=lambda k: by_kind[k]["ms"]) if by_kind else "pass"
+    d = by_kind.get(dom, {"ms": 0.0, "bytes": 0.0, "launch_groups": 0, "ops": 0})
+    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    names = {"pass": "qsv::k_pass_reg / k_pass (tiled TMA gate pass)",
+             "diffusion": "qsv::k_diff_partial + k_diff_update (Grover diffusion)"}
+    roofline = {"bound": "hbm", "kernel": names.get(dom, dom), "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(dom, n_local),
+                "peak_source": peak_src, "launches_timed": d["launch_groups"],
+                "avg_launch_ms": d["ms"] / max(1, d["launch_groups"]),
+                "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launch_groups"]),
+                "share_of_step": d["ms"] / ms_per_step if ms_per_step else None,
+                "gates_per_launch": d["ops"] / max(1, d["launch_groups"]),
+                "other_kernels": {k: {"ms_per_step": v["ms"], "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else 0.0}
+                                  for k, v in by_kind.items() if k != dom}}
 
     gate_pass = None
     if not args.no_gate_pass and rank == 0 and world == 1:
         gate_pass = single_gate_sweep(sv, peak)
 
     # ---- end to end through the public API: Circuit.run(in_v, 2) with host inputs
-    in_v = [0] * n
+    in_v = in_bits
     e2e = None
-    if world == 1:
+    if world == 1 and (16 << n) * 2 < 170e9:
         import io
         import contextlib
         import random
@@ -298,8 +366,7 @@ def main():
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex128 (f64 pairs)", "data": "synthetic",
-        "config": {"workload": "config-3: random H/X/T8/phase layers + CNot/CZ matchings, %d qubits, depth %d, "
-                               "%d gates, complex128, input |0...0>, one sample per step" % (n, args.depth, n_gates),
+        "config": {"workload": wl_name + ", %d gates, complex128, one sample per step" % n_gates,
                    "qubits": n, "depth": args.depth, "gates": n_gates, "seed": SEED,
                    "state_bytes_per_gpu": 16 << n_local, "passes_per_step": passes_per_step,
                    "cache": "state (%.1f GB/GPU) is far larger than the 126 MB L2; no flush needed"
@@ -310,6 +377,10 @@ def main():
     }
     if gate_pass is not None:
         line["gate_pass"] = gate_pass
+    if swap is not None:
+        line["swap"] = swap
+    if check is not None:
+        line["check"] = check
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_qubits)
     print(json.dumps(line))

@@ -43,6 +43,7 @@ class Comm:
         self._staging = None
         self.bytes_sent = 0
         self.swaps = 0
+        self.swap_events = []            # (start, end) CUDA events of every swap, for bench.py
 
     # ------------------------------------------------------------------ collectives
     def all_reduce_sum(self, t):
@@ -80,12 +81,27 @@ class Comm:
             self._staging = (torch.empty(need, dtype=torch.complex128, device=state.device),
                              torch.empty(need, dtype=torch.complex128, device=state.device))
         s_in, s_out = self._staging[0][:need], self._staging[1][:need]
+        ev = None
+        if state.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         for k in range(n_chunks):
             pack(s_in, k * C_, C_)
             self.all_to_all(torch.view_as_real(s_out).view(-1), torch.view_as_real(s_in).view(-1))
             unpack(s_out, k * C_, C_)
+        if ev is not None:
+            ev[1].record()
+            self.swap_events.append(ev)
         self.bytes_sent += 16 * (P - 1) * S
         self.swaps += 1
+
+    def swap_stats(self):
+        """Total device time of the recorded swaps (ms) and bytes sent per GPU; clears the record."""
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self.swap_events)
+        n = len(self.swap_events)
+        self.swap_events = []
+        return n, ms
 
     def swap_global_local(self, sv, n_swap):
         """Engine hook for a 'global_swap' op (CUDA pack/unpack kernels of libqsv)."""

@@ -242,6 +242,41 @@ class StateVector:
                 out.append(sum(best) / len(best))
         return out
 
+    def time_plan(self, plan, repeats=1):
+        """CUDA-event duration of every launch group of the plan with its algorithmic bytes:
+        [{'kind': 'pass' | op kind, 'ms': .., 'bytes': ..}].  'global_swap' segments are skipped (they
+        are timed by the communicator)."""
+        from .schedule import algorithmic_bytes
+        stream = torch.cuda.current_stream(self.device)
+        out = []
+        fr = iter(self.pass_active_fractions(plan))
+        for kind, seg in plan["segments"]:
+            if kind == "program":
+                packed, dev = seg
+                for meta in packed.passes:
+                    ms = []
+                    for _ in range(repeats):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(stream)
+                        self._launch_pass(meta, dev)
+                        e1.record(stream)
+                        e1.synchronize()
+                        ms.append(e0.elapsed_time(e1))
+                    out.append({"kind": "pass", "ms": sum(ms) / len(ms),
+                                "bytes": 32.0 * (1 << self.n_local) * next(fr), "ops": len(meta[0].ops)})
+            elif seg.kind != "global_swap":
+                ms = []
+                for _ in range(repeats):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    self._run_whole_state_op(seg)
+                    e1.record(stream)
+                    e1.synchronize()
+                    ms.append(e0.elapsed_time(e1))
+                out.append({"kind": seg.kind, "ms": sum(ms) / len(ms), "bytes": float(algorithmic_bytes(seg, self.n_local)),
+                            "ops": 1})
+        return out
+
     def pass_active_fractions(self, plan):
         """Fraction of tiles each pass actually loads (tiles switched off by external controls are
         skipped): 1.0 if any op is unconditional, else the union bound over the ops' control masks."""

@@ -185,3 +185,29 @@ def test_circuit_pickle_roundtrip(golden):
     assert [str(g) for g in d.gates] == cases["paper5"]["sorted_gate_names"]
     assert d.startqbits() == cases["paper5"]["startqbits"]
     assert {g: 1 for g in d}                      # gates hashable (gui/scene.py:81)
+
+
+def test_reference_saved_circuits_unpickle_with_the_mirror(golden):
+    """Resources/Saved/*.cir start with a pickled Circuit (gui/scene.py:73-81).  With the mirror on the
+    path the reference's own files load into mirror objects (same module paths and attribute layout) and
+    lower to the same state as the fixture circuit.  Only where the reference checkout is mounted."""
+    import os
+    path = "/root/reference/Resources/Saved/5.cir"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    meta, cases, arrays = golden
+    with open(path, "rb") as f:
+        c = pickle.load(f)
+    assert type(c) is mc.Circuit and len(c) == 6 and c.check()
+    assert sorted(type(g).__name__ for g in c.gates) == ["CNot", "CNot", "CNot", "T", "X", "X", "X"]
+    import statevec_oracle as so
+    for i, in_v in enumerate(cases["paper5"]["inputs"]):
+        w = so.run_method2(c, in_v)
+        assert np.array_equal(w, arrays["paper5/weights_m2"][i])
+    with open("/root/reference/Resources/Saved/Grover.cir", "rb") as f:
+        g = pickle.load(f)
+    assert len(g) == 7 and len(g.gates) == 25 and isinstance(g.gates[1].matrix, Matrix)
+    from qsv.lowering import lower
+    g.sort()
+    ops, src = lower(g)
+    assert {o.kind for o in ops} <= {"dense", "mcx", "diag", "phase"}
