@@ -242,6 +242,15 @@ int qsv_pack_slices(const void *state_dev, void *staging_dev, uint64_t n_chunks,
 int qsv_unpack_slices(void *state_dev, const void *staging_dev, uint64_t n_chunks,
                       uint64_t stride_elems, uint64_t offset_elems, uint64_t chunk_elems, void *stream);
 
+/* In-place global<->local qubit swap over NVLink PEER MEMORY (no staging, no NCCL on the data path).
+ * `peer_state_ptrs[j]` is rank j's state pointer mapped into this process (CUDA VMM / symmetric memory);
+ * entry [rank] is ignored.  The shard is P = 2^g blocks of S = 2^(n_local-g) amplitudes; block j of rank r
+ * trades places with block r of rank j.  Every pair of ranks splits the work: in alternating granules one
+ * of the two ranks reads both sides and writes both sides (one remote read + one remote write per
+ * amplitude), so each amplitude crosses NVLink exactly once per direction and touches local HBM once.
+ * The caller must barrier all ranks before and after the call. */
+int qsv_swap_peer(void *state_dev, const uint64_t *peer_state_ptrs, int n_local, int g, int rank, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

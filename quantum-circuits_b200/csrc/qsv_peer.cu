@@ -1,0 +1,59 @@
+// Global<->local qubit swap as ONE kernel over NVLink peer memory (SURVEY 8e's exchange step without
+// NCCL, staging buffers or pack/unpack passes).  Each rank swaps, for every peer j, its block j with the
+// peer's block r; the two ranks of a pair alternate granules so that both NVLink directions and both
+// HBMs carry the same load.  16-byte vector accesses, fully coalesced on both sides.
+#include "qsv_common.cuh"
+
+namespace qsv {
+
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { double2 *p[kMaxPeers]; };
+
+__global__ void __launch_bounds__(256)
+k_swap_peer(double2 *__restrict__ local, const __grid_constant__ PeerPtrs peers, int P, int r, uint64_t S,
+            uint64_t G, uint64_t per_pair) {
+    const uint64_t total = (uint64_t)(P - 1) * per_pair;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const int pi = (int)(w / per_pair);
+        const uint64_t h = w - (uint64_t)pi * per_pair;
+        const int j = pi < r ? pi : pi + 1;
+        // granules alternate between the two ranks of the pair: the lower rank owns the even ones
+        const uint64_t e = S >= 2 ? ((h / G) * 2 + (r < j ? 0 : 1)) * G + (h % G) : 0;
+        if (S < 2 && r > j) continue;
+        double2 *mine = local + (uint64_t)j * S + e;
+        double2 *theirs = peers.p[j] + (uint64_t)r * S + e;
+        const double2 a = *mine;
+        const double2 b = *theirs;          // remote load over NVLink
+        *mine = b;
+        *theirs = a;                        // remote store over NVLink
+    }
+}
+
+}  // namespace qsv
+
+using namespace qsv;
+
+extern "C" int qsv_swap_peer(void *state_dev, const uint64_t *peer_state_ptrs, int n_local, int g, int rank,
+                             void *stream) {
+    QSV_CHECK_ARG(state_dev && peer_state_ptrs, "qsv_swap_peer: NULL pointer");
+    QSV_CHECK_ARG(g >= 1 && g <= 4 && g <= n_local, "qsv_swap_peer: g=%d out of range", g);
+    const int P = 1 << g;
+    QSV_CHECK_ARG(rank >= 0 && rank < P, "qsv_swap_peer: rank %d out of range", rank);
+    PeerPtrs pp;
+    for (int j = 0; j < kMaxPeers; ++j) pp.p[j] = nullptr;
+    for (int j = 0; j < P; ++j) {
+        QSV_CHECK_ARG(j == rank || peer_state_ptrs[j] != 0, "qsv_swap_peer: peer %d has no mapped pointer", j);
+        pp.p[j] = reinterpret_cast<double2 *>(peer_state_ptrs[j]);
+    }
+    const uint64_t S = 1ull << (n_local - g);
+    const uint64_t G = S >= 2 ? (S / 2 < 2048 ? S / 2 : 2048) : 1;
+    const uint64_t per_pair = S >= 2 ? S / 2 : 1;
+    const uint64_t total = (uint64_t)(P - 1) * per_pair;
+    uint64_t grid = (total + 255) / 256;
+    const uint64_t cap = 148ull * 16ull;
+    if (grid > cap) grid = cap;
+    k_swap_peer<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((double2 *)state_dev, pp, P, rank, S, G, per_pair);
+    QSV_LAUNCH_CHECK();
+    return 0;
+}

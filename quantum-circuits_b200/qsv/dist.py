@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 from . import _cabi
 
-DEFAULT_STAGING_BYTES = 1 << 30      # per direction
+DEFAULT_STAGING_BYTES = 1 << 29      # per staging buffer (two in flight per direction)
 
 
 def plan_exchange(n_local, g, staging_bytes=DEFAULT_STAGING_BYTES):
@@ -24,7 +24,7 @@ def plan_exchange(n_local, g, staging_bytes=DEFAULT_STAGING_BYTES):
     exchanged with one all-to-all of P*C amplitudes.  Returns (P, S, C, n_chunks)."""
     P = 1 << g
     S = 1 << (n_local - g)
-    C_ = max(1, min(S, staging_bytes // (16 * P)))
+    C_ = max(1, min(S, staging_bytes // (16 * max(1, P - 1))))
     C_ = 1 << (C_.bit_length() - 1)               # power of two: divides S
     return P, S, C_, S // C_
 
@@ -41,9 +41,51 @@ class Comm:
             raise RuntimeError("qsv.dist: world size must be a power of two")
         self.staging_bytes = staging_bytes
         self._staging = None
+        self._symm = None                # (tensor, handle) of the symmetric-memory state, if enabled
+        self.peer_swap = False
         self.bytes_sent = 0
         self.swaps = 0
         self.swap_events = []            # (start, end) CUDA events of every swap, for bench.py
+
+    # ------------------------------------------------------------------ peer memory
+    def alloc_state(self, n_amps, device):
+        """State buffer for a sharded register.  With QSV_SWAP=peer (default on NCCL) the buffer is
+        symmetric memory mapped into every rank of the node (torch.distributed._symmetric_memory), so the
+        qubit swap can run as one kernel over NVLink peer pointers; QSV_SWAP=nccl, or any failure to map,
+        falls back to a plain buffer + the chunked NCCL all-to-all."""
+        import os
+        want = os.environ.get("QSV_SWAP", "peer")
+        if want == "peer" and self.world > 1 and dist.get_backend(self.group) == "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                raw = symm_mem.empty(2 * n_amps, dtype=torch.float64, device=device)
+                hdl = symm_mem.rendezvous(raw, self.group)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+                    raise RuntimeError("incomplete peer mapping")
+                self._symm = (raw, hdl, ptrs)
+                self.peer_swap = True
+                return torch.view_as_complex(raw.view(-1, 2))
+            except Exception as e:                      # noqa: BLE001 - stay on the NCCL path, but say so
+                if self.rank == 0:
+                    print("qsv.dist: symmetric memory unavailable (%s); using the NCCL all-to-all" % (e,), flush=True)
+                self._symm = None
+                self.peer_swap = False
+        return torch.empty(n_amps, dtype=torch.complex128, device=device)
+
+    def _swap_peer(self, sv):
+        raw, hdl, ptrs = self._symm
+        arr = (C.c_uint64 * self.world)(*ptrs)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        hdl.barrier()                                   # every rank's earlier kernels are done
+        _cabi.check(sv.lib.qsv_swap_peer(sv._ptr(sv.state), arr, sv.n_local, self.global_bits, self.rank,
+                                         sv._stream()), "qsv_swap_peer")
+        hdl.barrier()                                   # nobody touches its shard before all swaps landed
+        ev[1].record()
+        self.swap_events.append(ev)
+        self.bytes_sent += 16 * (self.world - 1) * (1 << (sv.n_local - self.global_bits))
+        self.swaps += 1
 
     # ------------------------------------------------------------------ collectives
     def all_reduce_sum(self, t):
@@ -52,22 +94,26 @@ class Comm:
         dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
-    def all_to_all(self, out, inp):
-        """Equal-split all-to-all on float64 views; gloo (CPU tests) has no all_to_all -> send/recv."""
-        if dist.get_backend(self.group) == "nccl":
-            dist.all_to_all_single(out, inp, group=self.group)
-            return
+    def all_to_all(self, out, inp, async_op=False):
+        """All-to-all of P equal blocks where a rank's OWN block is not transferred (it never moves in a
+        qubit swap): `inp`/`out` hold P-1 blocks, one per peer in rank order.  gloo (CPU tests) has no
+        all_to_all -> send/recv.  With async_op the NCCL work handle is returned (wait() orders the
+        current stream after it)."""
         P = self.world
-        ins, outs = inp.chunk(P), out.chunk(P)
-        outs[self.rank].copy_(ins[self.rank])
+        blk = inp.numel() // (P - 1)
+        if dist.get_backend(self.group) == "nccl":
+            splits = [blk if j != self.rank else 0 for j in range(P)]
+            return dist.all_to_all_single(out, inp, output_split_sizes=splits, input_split_sizes=splits,
+                                          group=self.group, async_op=async_op)
+        ins, outs = inp.chunk(P - 1), out.chunk(P - 1)
+        peers = [j for j in range(P) if j != self.rank]
         reqs = []
-        for peer in range(P):
-            if peer == self.rank:
-                continue
-            reqs.append(dist.isend(ins[peer].contiguous(), dist.get_global_rank(self.group, peer), group=self.group))
-            reqs.append(dist.irecv(outs[peer], dist.get_global_rank(self.group, peer), group=self.group))
+        for i, peer in enumerate(peers):
+            reqs.append(dist.isend(ins[i].contiguous(), dist.get_global_rank(self.group, peer), group=self.group))
+            reqs.append(dist.irecv(outs[i], dist.get_global_rank(self.group, peer), group=self.group))
         for r in reqs:
             r.wait()
+        return None
 
     # ------------------------------------------------------------------ qubit swap
     def exchange(self, state, n_local, pack, unpack):
@@ -76,19 +122,30 @@ class Comm:
         [offset, offset+C) of every block into the contiguous staging tensor; unpack scatters it back."""
         g = self.global_bits
         P, S, C_, n_chunks = plan_exchange(n_local, g, self.staging_bytes)
-        need = P * C_
+        need = (P - 1) * C_              # the rank's own block stays where it is
         if self._staging is None or self._staging[0].numel() < need or self._staging[0].device != state.device:
-            self._staging = (torch.empty(need, dtype=torch.complex128, device=state.device),
-                             torch.empty(need, dtype=torch.complex128, device=state.device))
-        s_in, s_out = self._staging[0][:need], self._staging[1][:need]
+            self._staging = tuple(torch.empty(need, dtype=torch.complex128, device=state.device) for _ in range(4))
+        s_in = [self._staging[0][:need], self._staging[1][:need]]
+        s_out = [self._staging[2][:need], self._staging[3][:need]]
         ev = None
         if state.is_cuda:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        for k in range(n_chunks):
-            pack(s_in, k * C_, C_)
-            self.all_to_all(torch.view_as_real(s_out).view(-1), torch.view_as_real(s_in).view(-1))
-            unpack(s_out, k * C_, C_)
+        # two-deep pipeline: while chunk k is on the wire (NCCL stream), the compute stream unpacks chunk
+        # k-1 and packs chunk k+1.  Staging buffers alternate; a buffer is reused only after the collective
+        # that read / wrote it has been waited for.
+        handles = [None, None]
+        for k in range(n_chunks + 1):
+            if k < n_chunks:
+                b = k & 1
+                pack(s_in[b], k * C_, C_)
+                handles[b] = self.all_to_all(torch.view_as_real(s_out[b]).view(-1),
+                                             torch.view_as_real(s_in[b]).view(-1), async_op=True)
+            if k >= 1:
+                pb = (k - 1) & 1
+                if handles[pb] is not None:
+                    handles[pb].wait()
+                unpack(s_out[pb], (k - 1) * C_, C_)
         if ev is not None:
             ev[1].record()
             self.swap_events.append(ev)
@@ -107,17 +164,33 @@ class Comm:
         """Engine hook for a 'global_swap' op (CUDA pack/unpack kernels of libqsv)."""
         if n_swap != self.global_bits:
             raise RuntimeError("qsv.dist: only full swaps of all %d global qubits are planned" % self.global_bits)
+        if self.peer_swap and self._symm is not None and sv.state.data_ptr() == self._symm[2][self.rank]:
+            return self._swap_peer(sv)
         lib = sv.lib
         P = 1 << self.global_bits
         S = 1 << (sv.n_local - self.global_bits)
 
+        r = self.rank
+        base = sv.state.data_ptr()
+
+        # the blocks below / above the rank's own block are packed as two runs of slices
         def pack(staging, offset, C_):
-            _cabi.check(lib.qsv_pack_slices(sv._ptr(sv.state), C.c_void_p(staging.data_ptr()), P, S, offset, C_,
-                                            sv._stream()), "qsv_pack_slices")
+            sp = staging.data_ptr()
+            if r > 0:
+                _cabi.check(lib.qsv_pack_slices(C.c_void_p(base), C.c_void_p(sp), r, S, offset, C_, sv._stream()),
+                            "qsv_pack_slices")
+            if r < P - 1:
+                _cabi.check(lib.qsv_pack_slices(C.c_void_p(base + 16 * (r + 1) * S), C.c_void_p(sp + 16 * r * C_),
+                                                P - 1 - r, S, offset, C_, sv._stream()), "qsv_pack_slices")
 
         def unpack(staging, offset, C_):
-            _cabi.check(lib.qsv_unpack_slices(sv._ptr(sv.state), C.c_void_p(staging.data_ptr()), P, S, offset, C_,
-                                              sv._stream()), "qsv_unpack_slices")
+            sp = staging.data_ptr()
+            if r > 0:
+                _cabi.check(lib.qsv_unpack_slices(C.c_void_p(base), C.c_void_p(sp), r, S, offset, C_, sv._stream()),
+                            "qsv_unpack_slices")
+            if r < P - 1:
+                _cabi.check(lib.qsv_unpack_slices(C.c_void_p(base + 16 * (r + 1) * S), C.c_void_p(sp + 16 * r * C_),
+                                                  P - 1 - r, S, offset, C_, sv._stream()), "qsv_unpack_slices")
 
         self.exchange(sv.state, sv.n_local, pack, unpack)
 

@@ -39,7 +39,10 @@ class StateVector:
         if self.n_local < 1:
             raise RuntimeError("qsv: need at least one local qubit per shard")
         self.device = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
-        self.state = torch.empty(1 << self.n_local, dtype=torch.complex128, device=self.device)
+        if comm is not None and comm.world > 1:
+            self.state = comm.alloc_state(1 << self.n_local, self.device)
+        else:
+            self.state = torch.empty(1 << self.n_local, dtype=torch.complex128, device=self.device)
         self._scratch = None
         self._keep = []       # host/device buffers that must outlive the async launches
         self.passes_run = 0
@@ -85,6 +88,14 @@ class StateVector:
             self.passes_run += 1
         self._keep.append(dev)
 
+    def _adopt(self, out):
+        """Make `out` the state after an out-of-place op.  A symmetric-memory state keeps its buffer
+        (peers hold its address): the result is copied back instead of swapping references."""
+        if self.comm is not None and getattr(self.comm, "peer_swap", False):
+            self.state.copy_(out)
+        else:
+            self.state, self._scratch = out, self.state
+
     def _scratch_state(self):
         if self._scratch is None:
             self._scratch = torch.empty_like(self.state)
@@ -98,7 +109,7 @@ class StateVector:
             _cabi.check(self.lib.qsv_apply_dense_wide(self._ptr(self.state), self._ptr(out), self.n_local,
                                                       len(op.targets), _cabi.int_array(op.targets), self._ptr(M),
                                                       st), "qsv_apply_dense_wide")
-            self.state, self._scratch = out, self.state
+            self._adopt(out)
             self._keep.append(M)
         elif op.kind == "wide_perm":
             P = torch.from_numpy(np.ascontiguousarray(op.perm, dtype=np.uint32).view(np.int32)).to(self.device)
@@ -106,7 +117,7 @@ class StateVector:
             _cabi.check(self.lib.qsv_apply_perm_wide(self._ptr(self.state), self._ptr(out), self.n_local,
                                                      len(op.targets), _cabi.int_array(op.targets), self._ptr(P),
                                                      st), "qsv_apply_perm_wide")
-            self.state, self._scratch = out, self.state
+            self._adopt(out)
             self._keep.append(P)
         elif op.kind == "wide_diag":
             D = torch.from_numpy(np.ascontiguousarray(op.matrix, dtype=np.complex128)).to(self.device)

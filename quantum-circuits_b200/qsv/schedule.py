@@ -342,7 +342,11 @@ def place(ops, n, n_global, src_pos=None, lookahead=400):
                     continue
                 t = free_tops.pop(0)
                 u = at[t]
-                out.append(Op("swap", (phys[v], t), (), name="relayout"))
+                # SWAP(a, b) = CNot(a->b) CNot(b->a) CNot(a->b): three exact index permutations, which the
+                # register kernel applies as address permutations fused into the neighbouring passes
+                pa, pb = phys[v], t
+                out += [Op("mcx", (pb,), (pa,), name="relayout"), Op("mcx", (pa,), (pb,), name="relayout"),
+                        Op("mcx", (pb,), (pa,), name="relayout")]
                 at[t], at[phys[v]] = v, u
                 phys[u], phys[v] = phys[v], t
             out.append(Op("global_swap", (), (), params={"n_swap": n_global}, name="relayout"))

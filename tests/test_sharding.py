@@ -66,7 +66,7 @@ def test_diagonal_and_control_use_of_global_qubits_needs_no_swap():
 def test_exchange_plan():
     from qsv.dist import plan_exchange
     P, S, C, k = plan_exchange(33, 3, 1 << 30)
-    assert (P, S) == (8, 1 << 30) and C * k == S and 16 * P * C <= 1 << 30
+    assert (P, S) == (8, 1 << 30) and C * k == S and 16 * (P - 1) * C <= 1 << 30
     P, S, C, k = plan_exchange(10, 1, 1 << 30)
     assert (P, S, C, k) == (2, 512, 512, 1)
 
@@ -82,11 +82,13 @@ def _worker(rank, world, port, n, seed, out_dir):
     state = torch.from_numpy(full.reshape(world, -1)[rank].copy())
     P, S = world, 1 << (n_local - g)
 
+    peers = [j for j in range(P) if j != rank]
+
     def pack(staging, offset, C):
-        staging.view(P, C).copy_(state.view(P, S)[:, offset:offset + C])
+        staging.view(P - 1, C).copy_(state.view(P, S)[peers, offset:offset + C])
 
     def unpack(staging, offset, C):
-        state.view(P, S)[:, offset:offset + C].copy_(staging.view(P, C))
+        state.view(P, S)[peers, offset:offset + C] = staging.view(P - 1, C)
 
     comm.exchange(state, n_local, pack, unpack)
     expect = np.ascontiguousarray(full.reshape(world, world, -1).transpose(1, 0, 2)).reshape(world, -1)[rank]
@@ -106,3 +108,36 @@ def test_exchange_over_gloo(tmp_path, world):
     mp.spawn(_worker, args=(world, port, 9, 3, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / ("ok%d" % r)).read() == "1"
+
+
+@pytest.mark.parametrize("g,S", [(1, 1), (1, 2), (1, 8), (2, 4), (3, 16), (2, 8192), (1, 4096)])
+def test_peer_swap_kernel_index_logic(g, S):
+    """numpy restatement of k_swap_peer (csrc/qsv_peer.cu): every element of every block pair is swapped
+    exactly once, by exactly one of the two ranks, and the result equals the all-to-all transposition."""
+    P = 1 << g
+    G = (S // 2 if S // 2 < 2048 else 2048) if S >= 2 else 1
+    per_pair = S // 2 if S >= 2 else 1
+    rng = np.random.default_rng(S + g)
+    shards = rng.normal(size=(P, P * S))
+    expect = np.ascontiguousarray(shards.reshape(P, P, S).transpose(1, 0, 2)).reshape(P, P * S)
+    work = shards.copy()
+    touched = np.zeros((P, P * S), dtype=int)
+    for r in range(P):
+        for w in range((P - 1) * per_pair):
+            pi, h = divmod(w, per_pair)
+            j = pi if pi < r else pi + 1
+            if S >= 2:
+                e = ((h // G) * 2 + (0 if r < j else 1)) * G + (h % G)
+            else:
+                e = 0
+                if r > j:
+                    continue
+            a, b = work[r, j * S + e], work[j, r * S + e]
+            work[r, j * S + e], work[j, r * S + e] = b, a
+            touched[r, j * S + e] += 1
+            touched[j, r * S + e] += 1
+    off_diag = np.ones((P, P * S), dtype=bool)
+    for r in range(P):
+        off_diag[r, r * S:(r + 1) * S] = False
+    assert np.all(touched[off_diag] == 1) and np.all(touched[~off_diag] == 0)
+    assert np.array_equal(work, expect)
