@@ -786,6 +786,12 @@ def encode_rounds(ps, rounds):
     if it exceeds the kernel-parameter capacity (RPROG_MAX_ROUNDS / RPROG_MAX_OPS)."""
     if len(rounds) > RPROG_MAX_ROUNDS:
         return None
+    drop = os.environ.get("QSV_DEBUG_DROP", "")     # timing experiments only (results become wrong)
+    if drop:
+        rounds = [Round(R.rb, [] if "perm" in drop else R.pre,
+                        [op for op in R.reg if not (("reg" in drop) or ("dense" in drop and op.kind == "dense")
+                                                    or ("phase" in drop and op.kind == "phase"))],
+                        [] if "perm" in drop else R.post) for R in rounds]
     rnd = np.zeros(len(rounds), dtype=ROUND_DTYPE)
     rops = []
     tables = []
