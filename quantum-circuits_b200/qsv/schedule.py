@@ -137,7 +137,33 @@ def _is_identity(M):
     return np.array_equal(M, np.eye(M.shape[0], dtype=M.dtype))
 
 
+_CLASSIFY_CACHE = {}
+
+
 def classify_matrix(M, pos, name=""):
+    """Cached front end of _classify_matrix: circuits repeat a handful of small matrices hundreds of
+    times (H, X, phases, CNot, CZ), so the structural analysis is done once per distinct matrix on
+    placeholder positions 0..k-1 and re-targeted for every gate."""
+    M = np.ascontiguousarray(M, dtype=np.complex128)
+    k = len(pos)
+    if k > 4:
+        return _classify_matrix(M, pos, name)
+    key = (k, M.tobytes())
+    tmpl = _CLASSIFY_CACHE.get(key)
+    if tmpl is None:
+        tmpl = _classify_matrix(M, tuple(range(k)), "")
+        if len(_CLASSIFY_CACHE) < 4096:
+            _CLASSIFY_CACHE[key] = tmpl
+    pos = tuple(int(p) for p in pos)
+    out = []
+    for op in tmpl:
+        o = op.remapped(pos)
+        o.name = name
+        out.append(o)
+    return out
+
+
+def _classify_matrix(M, pos, name=""):
     """Turn one k-qubit gate matrix acting on physical positions pos (pos[0] = gate MSB) into ops.
 
     Follows the gate set of SURVEY §2a: diagonal -> phase/diag, permutation -> (multi-)controlled X or
@@ -161,7 +187,7 @@ def classify_matrix(M, pos, name=""):
             v = d.reshape(1 << (k - 1 - b), 2, 1 << b)
             if np.array_equal(v[:, 0, :], v[:, 1, :]):
                 keep = tuple(p for p in range(k) if p != k - 1 - b)
-                return classify_matrix(np.diag(v[:, 0, :].reshape(-1)), tuple(pos[p] for p in keep), name)
+                return _classify_matrix(np.diag(v[:, 0, :].reshape(-1)), tuple(pos[p] for p in keep), name)
         off = np.flatnonzero(d != 1)
         if off.size == 1:                             # Z, PhaseShift, CZ, controlled phase
             j = int(off[0])
@@ -194,9 +220,9 @@ def classify_matrix(M, pos, name=""):
             A, B = split
             ops = []
             if not _is_identity(A):
-                ops += classify_matrix(A, pos[:a], name)
+                ops += _classify_matrix(A, pos[:a], name)
             if not _is_identity(B):
-                ops += classify_matrix(B, pos[a:], name)
+                ops += _classify_matrix(B, pos[a:], name)
             return ops
 
     if k <= _cabi.QSV_MAX_TILE_K:
