@@ -279,7 +279,8 @@ def main():
         swap = {"swaps_per_step": n_sw / args.steps, "ms_per_step": sw_ms / args.steps,
                 "bytes_out_per_gpu_per_swap": out_bytes / max(1, n_sw), "achieved_GBps_out_per_gpu": gbs,
                 "nvlink_peak_GBps": nv_peak, "frac_of_nvlink": gbs / nv_peak,
-                "note": "time includes pack/unpack kernels around each chunked all_to_all"}
+                "path": "k_swap_peer over NVLink peer memory" if comm.peer_swap else "NCCL all_to_all_single, chunked in place",
+                "note": "device time between the barriers around each swap (peer kernel) / incl. pack+unpack (NCCL)"}
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

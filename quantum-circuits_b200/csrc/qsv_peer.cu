@@ -11,13 +11,18 @@ struct PeerPtrs { double2 *p[kMaxPeers]; };
 
 __global__ void __launch_bounds__(256)
 k_swap_peer(double2 *__restrict__ local, const __grid_constant__ PeerPtrs peers, int P, int r, uint64_t S,
-            uint64_t G, uint64_t per_pair) {
+            uint64_t G, uint64_t per_pair, uint64_t CH) {
+    // Work item w -> (chunk c, lane-in-chunk).  Consecutive chunks go to DIFFERENT peers (j = r ^ s,
+    // s = 1 + c mod (P-1)): at every moment each rank talks to all its peers at once and the traffic
+    // through the NVSwitch is a uniform all-to-all.  (Walking peer by peer made all ranks hit the same
+    // GPU at the same time: 305 GB/s at 8 GPUs against 680 GB/s at 2.)
     const uint64_t total = (uint64_t)(P - 1) * per_pair;
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total;
          w += (uint64_t)gridDim.x * blockDim.x) {
-        const int pi = (int)(w / per_pair);
-        const uint64_t h = w - (uint64_t)pi * per_pair;
-        const int j = pi < r ? pi : pi + 1;
+        const uint64_t c = w / CH;
+        const int s_ = 1 + (int)(c % (uint64_t)(P - 1));
+        const int j = r ^ s_;
+        const uint64_t h = (c / (uint64_t)(P - 1)) * CH + (w % CH);
         // granules alternate between the two ranks of the pair: the lower rank owns the even ones
         const uint64_t e = S >= 2 ? ((h / G) * 2 + (r < j ? 0 : 1)) * G + (h % G) : 0;
         if (S < 2 && r > j) continue;
@@ -49,11 +54,12 @@ extern "C" int qsv_swap_peer(void *state_dev, const uint64_t *peer_state_ptrs, i
     const uint64_t S = 1ull << (n_local - g);
     const uint64_t G = S >= 2 ? (S / 2 < 2048 ? S / 2 : 2048) : 1;
     const uint64_t per_pair = S >= 2 ? S / 2 : 1;
+    const uint64_t CH = per_pair < 512 ? per_pair : 512;      // contiguous elements per peer access (8 KiB)
     const uint64_t total = (uint64_t)(P - 1) * per_pair;
     uint64_t grid = (total + 255) / 256;
     const uint64_t cap = 148ull * 16ull;
     if (grid > cap) grid = cap;
-    k_swap_peer<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((double2 *)state_dev, pp, P, rank, S, G, per_pair);
+    k_swap_peer<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((double2 *)state_dev, pp, P, rank, S, G, per_pair, CH);
     QSV_LAUNCH_CHECK();
     return 0;
 }

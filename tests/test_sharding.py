@@ -117,6 +117,7 @@ def test_peer_swap_kernel_index_logic(g, S):
     P = 1 << g
     G = (S // 2 if S // 2 < 2048 else 2048) if S >= 2 else 1
     per_pair = S // 2 if S >= 2 else 1
+    CH = min(per_pair, 512)
     rng = np.random.default_rng(S + g)
     shards = rng.normal(size=(P, P * S))
     expect = np.ascontiguousarray(shards.reshape(P, P, S).transpose(1, 0, 2)).reshape(P, P * S)
@@ -124,8 +125,9 @@ def test_peer_swap_kernel_index_logic(g, S):
     touched = np.zeros((P, P * S), dtype=int)
     for r in range(P):
         for w in range((P - 1) * per_pair):
-            pi, h = divmod(w, per_pair)
-            j = pi if pi < r else pi + 1
+            c = w // CH
+            j = r ^ (1 + c % (P - 1))
+            h = (c // (P - 1)) * CH + (w % CH)
             if S >= 2:
                 e = ((h // G) * 2 + (0 if r < j else 1)) * G + (h % G)
             else:
