@@ -276,6 +276,21 @@ def main():
     cases.append(circuit_case(c, "builtin_mix", ins, with_m1=True, arrays=arrays))
     print("builtin mix done", time.time() - t0)
 
+    # --- J: get_subcircuit (main/circuit.py:122-157) on the small random circuits + a crossed-wire one
+    sub = {}
+    for seed in range(1, 13):
+        random.seed(seed)
+        c = rc.Circuit.random_circuit()
+        if len(c) <= 4:
+            try:
+                g = c.get_subcircuit("sub")
+            except RuntimeError as e:        # the reference's own unitarity check can reject its result
+                sub["random_seed%d" % seed] = {"n": len(c), "error": str(e)}
+                continue
+            arrays["subcircuit/random_seed%d" % seed] = np.array(g.matrix.rows, dtype=np.complex128)
+            sub["random_seed%d" % seed] = {"n": len(c), "error": None}
+    meta["subcircuit_cases"] = sub
+
     # --- H: Matrix factories / arithmetic (main/matrix.py)
     mats = {
         "H1": rm.Matrix.H(), "H3": rm.Matrix.H(3), "X2": rm.Matrix.X(2), "Y2": rm.Matrix.Y(2),

@@ -151,3 +151,15 @@ def test_qft_ladder_equals_dense_qft_up_to_bit_reversal():
             out = so.apply_gate(out, n, wires, M)
         out = so.output_relabel(out, n, list(reversed(range(n))))
         assert np.max(np.abs(out - so.mat_QFT(n) @ psi)) < 1e-13
+
+
+def test_oracle_unitary_matches_reference_get_subcircuit(golden):
+    meta, cases, arrays = golden
+    for name, info in meta["subcircuit_cases"].items():
+        if info["error"] is not None:
+            continue
+        c = build_circuit(cases[name], arrays)
+        steps, sq = so.trace(c)
+        n = info["n"]
+        U = np.stack([so.evolve(steps, sq, so.index_bits(col, n)) for col in range(1 << n)], axis=1)
+        assert np.max(np.abs(U - arrays["subcircuit/" + name])) <= TOL
