@@ -77,7 +77,7 @@ typedef struct qsv_pass {
     uint8_t  hi_pos[16];    /* ascending physical positions (>= L) of the remaining tile bits      */
     uint64_t rank_bits;     /* value of the global index bits, pre-shifted by n_local              */
     int32_t  max_dense_k;   /* widest DENSE op in the program (selects the register-heavy variant)  */
-    int32_t  reserved;
+    int32_t  reserved;      /* qsv_run_pass_rounds: register bits per round, 3 or 4 (0 = 4)         */
 } qsv_pass_t;
 
 /* ---- register-resident pass program (consumed by qsv_run_pass_rounds) --------------------- */
@@ -102,13 +102,13 @@ typedef struct qsv_pass {
 #define QSV_ROP_PERM        19   /* (multi-)controlled X as an address permutation at a round boundary:
                                     if ((addr & tmask) == tval) addr ^= table_off   (tile-local bits).
                                     Linear lists: j = 0xff if the condition is slot-independent, else
-                                    j = register index q and rval = position of the one condition bit
-                                    that varies with r_q                                                */
+                                    j = register index q, rval = position and flags = mask of the one
+                                    condition bit that varies with r_q (flags = 0 when j = 0xff)        */
 #define QSV_ROPF_REAL  1u   /* matrix entries are real                                               */
 #define QSV_ROPF_NEG   2u   /* PHASE: scalar is exactly -1                                            */
 
 typedef struct qsv_rprog_hdr {
-    uint32_t n_rounds, total_bytes, n_ops, reserved;
+    uint32_t n_rounds, total_bytes, n_ops, reserved;   /* reserved: register bits per round (informational) */
 } qsv_rprog_hdr_t;
 
 typedef struct qsv_round {

@@ -13,7 +13,9 @@
 
 namespace qsv {
 
-constexpr int kRThreads = 256;
+#ifndef QSV_REG_CTAS
+#define QSV_REG_CTAS 2
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32r(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init_r(uint64_t *bar, uint32_t count) {
@@ -65,12 +67,12 @@ __device__ __forceinline__ void cscale_inplace(double2 &x, const double2 s) {
 // interpreter's switch forces x[] into fixed registers at every merge point, and the natural
 // "compute y0,y1 then assign" form cost 6-8 MOV per pair (60 % of all issued instructions in the first
 // profile).   y0 = a x0 + b x1,  y1 = c x0 + d x1.
-template <int J, bool REAL>
-__device__ __forceinline__ void f_dense1(double2 (&x)[16], const qsv_rop_t *op) {
+template <int J, bool REAL, int NS>
+__device__ __forceinline__ void f_dense1(double2 (&x)[NS], const qsv_rop_t *op) {
     const double2 a = make_double2(op->m[0], op->m[1]), b = make_double2(op->m[2], op->m[3]);
     const double2 c = make_double2(op->m[4], op->m[5]), d = make_double2(op->m[6], op->m[7]);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < NS; ++r) {
         if ((r >> J) & 1) continue;
         double2 &x0 = x[r], &x1 = x[r | (1 << J)];
         if (REAL) {
@@ -99,24 +101,26 @@ __device__ __forceinline__ void f_dense1(double2 (&x)[16], const qsv_rop_t *op) 
     }
 }
 
-template <int J, int V>
-__device__ __forceinline__ void f_phase1(double2 (&x)[16], const qsv_rop_t *op) {
+template <int J, int V, int NS>
+__device__ __forceinline__ void f_phase1(double2 (&x)[NS], const qsv_rop_t *op) {
     const double2 s = make_double2(op->m[0], op->m[1]);
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
+    for (int r = 0; r < NS; ++r)
         if (((r >> J) & 1) == V) cscale_inplace(x[r], s);
 }
 
 // generic predicated forms (register-bit conditions of any shape)
-__device__ __forceinline__ void r_phase(double2 (&x)[16], const qsv_rop_t *op) {
+template <int NS>
+__device__ __forceinline__ void r_phase(double2 (&x)[NS], const qsv_rop_t *op) {
     const uint32_t rmask = op->rmask, rval = op->rval;
     const double2 s = make_double2(op->m[0], op->m[1]);
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
+    for (int r = 0; r < NS; ++r)
         if ((r & rmask) == rval) x[r] = cmul(x[r], s);
 }
 
-__device__ __forceinline__ void r_diag(double2 (&x)[16], const qsv_rop_t *op, const uint8_t *sprog, uint32_t tb,
+template <int NS>
+__device__ __forceinline__ void r_diag(double2 (&x)[NS], const qsv_rop_t *op, const uint8_t *sprog, uint32_t tb,
                                        uint64_t gbase) {
     const int k = (int)op->k;
     uint32_t di = 0;
@@ -130,31 +134,31 @@ __device__ __forceinline__ void r_diag(double2 (&x)[16], const qsv_rop_t *op, co
     const uint32_t c0 = op->rc[0], c1 = op->rc[1], c2 = op->rc[2], c3 = op->rc[3];
     const uint32_t rmask = op->rmask, rval = op->rval;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < NS; ++r) {
         if ((r & rmask) != rval) continue;
         const uint32_t d = di | ((r & 1) ? c0 : 0u) | ((r & 2) ? c1 : 0u) | ((r & 4) ? c2 : 0u) | ((r & 8) ? c3 : 0u);
         cscale_inplace(x[r], __ldg(tab + d));
     }
 }
 
+// kinds 0..17 are contiguous; register bits >= log2(NS) do not exist in the 8-slot variant
+#define QSV_CASE_J(base, J_, CALL) \
+    case (base) + (J_): if constexpr ((1 << (J_)) < NS) { constexpr int J = (J_); CALL; } break;
 #define QSV_CASE_J4(base, CALL) \
-    case (base) + 0: { constexpr int J = 0; CALL; } break; \
-    case (base) + 1: { constexpr int J = 1; CALL; } break; \
-    case (base) + 2: { constexpr int J = 2; CALL; } break; \
-    case (base) + 3: { constexpr int J = 3; CALL; } break;
+    QSV_CASE_J(base, 0, CALL) QSV_CASE_J(base, 1, CALL) QSV_CASE_J(base, 2, CALL) QSV_CASE_J(base, 3, CALL)
 #define QSV_CASE_PH1(J_) \
-    case QSV_ROP_PHASE1 + 2 * (J_) + 0: f_phase1<J_, 0>(x, op); break; \
-    case QSV_ROP_PHASE1 + 2 * (J_) + 1: f_phase1<J_, 1>(x, op); break;
+    case QSV_ROP_PHASE1 + 2 * (J_) + 0: if constexpr ((1 << (J_)) < NS) f_phase1<J_, 0, NS>(x, op); break; \
+    case QSV_ROP_PHASE1 + 2 * (J_) + 1: if constexpr ((1 << (J_)) < NS) f_phase1<J_, 1, NS>(x, op); break;
 
-// kinds 0..17 are contiguous so that the dispatch is one jump table (BRX), not a compare tree
-__device__ __forceinline__ void apply_rop(double2 (&x)[16], const qsv_rop_t *op, uint32_t kind,
+template <int NS>
+__device__ __forceinline__ void apply_rop(double2 (&x)[NS], const qsv_rop_t *op, uint32_t kind,
                                           const uint8_t *sprog, uint32_t tb, uint64_t gbase) {
     switch (kind) {
-        QSV_CASE_J4(QSV_ROP_DENSE1, (f_dense1<J, false>(x, op)))
-        QSV_CASE_J4(QSV_ROP_DENSE1_REAL, (f_dense1<J, true>(x, op)))
+        QSV_CASE_J4(QSV_ROP_DENSE1, (f_dense1<J, false, NS>(x, op)))
+        QSV_CASE_J4(QSV_ROP_DENSE1_REAL, (f_dense1<J, true, NS>(x, op)))
         QSV_CASE_PH1(0) QSV_CASE_PH1(1) QSV_CASE_PH1(2) QSV_CASE_PH1(3)
-        case QSV_ROP_GEN_PHASE: r_phase(x, op); break;
-        case QSV_ROP_DIAG: r_diag(x, op, sprog, tb, gbase); break;
+        case QSV_ROP_GEN_PHASE: r_phase<NS>(x, op); break;
+        case QSV_ROP_DIAG: r_diag<NS>(x, op, sprog, tb, gbase); break;
         default: break;
     }
 }
@@ -168,38 +172,37 @@ __device__ __forceinline__ void apply_rop(double2 (&x)[16], const qsv_rop_t *op,
 struct AddrState { uint32_t base, d0, d1, d2, d3; };
 
 __device__ __forceinline__ void perm_linear(AddrState &A, const qsv_rop_t *op, uint64_t gbase) {
-    if ((gbase & op->ext_mask) != op->ext_val) return;
+    // branch-free so that an unrolled list can issue the loads of several ops ahead of the (serial) updates
     const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off, q = op->j;
-    if (q == 0xffu) {                                   // condition is the same for all 16 slots
-        A.base ^= ((A.base & cm) == cv) ? xm : 0u;
-        return;
-    }
-    const uint32_t pbit = 1u << op->rval;               // the one condition bit that may vary with r_q
+    const uint32_t pbit = op->flags;                    // the one condition bit that may vary with r_q (0: none)
+    const bool ext_ok = !(op->flags2 & 1u) || (gbase & op->ext_mask) == op->ext_val;
     const uint32_t cmu = cm & ~pbit;
-    const uint32_t f = ((A.base & cmu) == (cv & cmu)) ? xm : 0u;
-    const uint32_t dq = (q == 0u) ? A.d0 : (q == 1u) ? A.d1 : (q == 2u) ? A.d2 : A.d3;
+    const uint32_t f = (ext_ok && (A.base & cmu) == (cv & cmu)) ? xm : 0u;
+    const uint32_t dq = (q == 0u) ? A.d0 : (q == 1u) ? A.d1 : (q == 2u) ? A.d2 : (q == 3u) ? A.d3 : 0u;
     const uint32_t fd = (dq & pbit) ? f : 0u;           // slots with r_q = 1 see the bit toggled
-    A.base ^= (((A.base ^ cv) & pbit) == 0u) ? f : 0u;  // the r_q = 0 slots satisfy the condition
+    A.base ^= (((A.base ^ cv) & pbit) == 0u) ? f : 0u;  // the r_q = 0 slots (or all slots) satisfy the condition
     A.d0 ^= (q == 0u) ? fd : 0u;
     A.d1 ^= (q == 1u) ? fd : 0u;
     A.d2 ^= (q == 2u) ? fd : 0u;
     A.d3 ^= (q == 3u) ? fd : 0u;
 }
 
-__device__ __forceinline__ void slot_addresses(uint32_t (&a)[16], const AddrState &A) {
+template <int NS>
+__device__ __forceinline__ void slot_addresses(uint32_t (&a)[NS], const AddrState &A) {
     a[0] = A.base;
 #pragma unroll
-    for (int r = 1; r < 16; ++r) {
+    for (int r = 1; r < NS; ++r) {
         const int low = r & -r;                          // lowest set bit of r
         a[r] = a[r & (r - 1)] ^ (low == 1 ? A.d0 : low == 2 ? A.d1 : low == 4 ? A.d2 : A.d3);
     }
 }
 
-__device__ __forceinline__ void perm_general(uint32_t (&a)[16], const qsv_rop_t *op, uint64_t gbase) {
+template <int NS>
+__device__ __forceinline__ void perm_general(uint32_t (&a)[NS], const qsv_rop_t *op, uint64_t gbase) {
     if ((gbase & op->ext_mask) != op->ext_val) return;
     const uint32_t cm = op->tmask, cv = op->tval, xm = op->table_off;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) a[r] ^= ((a[r] & cm) == cv) ? xm : 0u;
+    for (int r = 0; r < NS; ++r) a[r] ^= ((a[r] & cm) == cv) ? xm : 0u;
 }
 
 // The pass program travels as a __grid_constant__ kernel parameter: it lives in the constant bank, op
@@ -211,7 +214,8 @@ struct RProgParam {
     qsv_rop_t ops[QSV_RPROG_MAX_OPS];
 };
 
-__global__ void __launch_bounds__(kRThreads, 2)
+template <int RB>
+__global__ void __launch_bounds__(4096 >> RB, QSV_REG_CTAS)
 k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
            const __grid_constant__ RProgParam prog, const uint8_t *__restrict__ tables, uint64_t n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -219,6 +223,8 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint64_t s_hi_off[256];
 
+    constexpr int NS = 1 << RB;                    // amplitudes per thread
+    constexpr int kRThreads = 4096 >> RB;          // 256 threads x 16 slots, or 512 x 8
     const int tid = threadIdx.x;
     const int T = P.tile_bits, L = P.low_bits, n_hi = P.n_hi;
     const uint8_t *sprog = tables;      // diagonal tables stay in global memory (read-only path)
@@ -227,7 +233,7 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
     // trip per field, three to four of them per op, which made every op cost ~600 cycles per tile.
     const uint32_t n_runs = 1u << n_hi;
     const uint32_t run_bytes = 16u << L;
-    const uint32_t n_active = 1u << (T - 4);       // threads that own amplitudes
+    const uint32_t n_active = 1u << (T - RB);      // threads that own amplitudes
 
     for (uint32_t r = tid; r < n_runs; r += kRThreads) {
         uint64_t o = 0;
@@ -265,15 +271,13 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
         for (int rd = 0; rd < n_rounds; ++rd) {
             const qsv_round_t R = rounds[rd];
             uint32_t tb = (uint32_t)tid;
-            tb = insert_zero32(tb, R.rb[0]);
-            tb = insert_zero32(tb, R.rb[1]);
-            tb = insert_zero32(tb, R.rb[2]);
-            tb = insert_zero32(tb, R.rb[3]);
+#pragma unroll
+            for (int q = 0; q < RB; ++q) tb = insert_zero32(tb, R.rb[q]);
             const uint32_t n_pre = R.n_pre & 0x7fffu, n_post = R.n_post & 0x7fffu;
             const uint32_t n_reg = R.n_ops & 0xffffu;            // ordered register ops
             const uint32_t n_pt = (R.n_ops >> 16) & 0x3fffu;     // thread-level phases (commute with everything)
             if (rd > 0) __syncthreads();           // the previous round's stores are visible
-            double2 x[16];
+            double2 x[NS];
             // Threads beyond 2^(T-4) own no amplitudes (tiles smaller than 4096): they run the same
             // UNIFORM control flow on zeros and only their loads/stores are predicated off.  Keeping the
             // op loop out of any thread-dependent branch lets the compiler keep the loop counter, the op
@@ -282,17 +286,18 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
             {
                 // ---- load: slot r <- tile[address(r)], address(r) = base ^ XOR_{q in r} d_q.  Leading
                 // X / CNot / Toffoli ops permute the addresses: new[a] = old[p_1(p_2(...p_k(a)))].
-                uint32_t a[16];
-                AddrState A = {tb, 1u << R.rb[0], 1u << R.rb[1], 1u << R.rb[2], 1u << R.rb[3]};
+                uint32_t a[NS];
+                AddrState A = {tb, 1u << R.rb[0], 1u << R.rb[1], 1u << R.rb[2], RB > 3 ? 1u << R.rb[3] : 0u};
                 if (!(R.n_pre & 0x8000u)) {
+#pragma unroll 4
                     for (int i = (int)n_pre - 1; i >= 0; --i) perm_linear(A, ops + R.first_op + i, gbase);
-                    slot_addresses(a, A);
+                    slot_addresses<NS>(a, A);
                 } else {
-                    slot_addresses(a, A);
-                    for (int i = (int)n_pre - 1; i >= 0; --i) perm_general(a, ops + R.first_op + i, gbase);
+                    slot_addresses<NS>(a, A);
+                    for (int i = (int)n_pre - 1; i >= 0; --i) perm_general<NS>(a, ops + R.first_op + i, gbase);
                 }
 #pragma unroll
-                for (int r = 0; r < 16; ++r) x[r] = owner ? tile[a[r]] : make_double2(0.0, 0.0);
+                for (int r = 0; r < NS; ++r) x[r] = owner ? tile[a[r]] : make_double2(0.0, 0.0);
             }
             if (n_pt) {
                 // thread-level phases: one pending scalar per thread, applied once to all 16 slots
@@ -319,32 +324,33 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
                 }
                 S = cmul(S, S2);
 #pragma unroll
-                for (int r = 0; r < 16; ++r) cscale_inplace(x[r], S);
+                for (int r = 0; r < NS; ++r) cscale_inplace(x[r], S);
             }
             {
                 const qsv_rop_t *rg = ops + R.first_op + n_pre + n_pt;
                 for (uint32_t i = 0; i < n_reg; ++i) {
                     const uint4 h = *reinterpret_cast<const uint4 *>(rg + i);
                     if ((h.w & 1u) && (gbase & rg[i].ext_mask) != rg[i].ext_val) continue;     // uniform
-                    if ((tb & h.y) == h.z) apply_rop(x, rg + i, h.x & 0xffu, sprog, tb, gbase);
+                    if ((tb & h.y) == h.z) apply_rop<NS>(x, rg + i, h.x & 0xffu, sprog, tb, gbase);
                 }
             }
             if (n_pre + n_post) __syncthreads();   // permuted stores land in other threads' slots: all loads first
             {
                 // ---- store: tile[p_k(...p_1(address(r)))] <- slot r
-                uint32_t a[16];
-                AddrState A = {tb, 1u << R.rb[0], 1u << R.rb[1], 1u << R.rb[2], 1u << R.rb[3]};
+                uint32_t a[NS];
+                AddrState A = {tb, 1u << R.rb[0], 1u << R.rb[1], 1u << R.rb[2], RB > 3 ? 1u << R.rb[3] : 0u};
                 const qsv_rop_t *post = ops + R.first_op + n_pre + n_pt + n_reg;
                 if (!(R.n_post & 0x8000u)) {
+#pragma unroll 4
                     for (uint32_t i = 0; i < n_post; ++i) perm_linear(A, post + i, gbase);
-                    slot_addresses(a, A);
+                    slot_addresses<NS>(a, A);
                 } else {
-                    slot_addresses(a, A);
-                    for (uint32_t i = 0; i < n_post; ++i) perm_general(a, post + i, gbase);
+                    slot_addresses<NS>(a, A);
+                    for (uint32_t i = 0; i < n_post; ++i) perm_general<NS>(a, post + i, gbase);
                 }
                 if (owner) {
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) tile[a[r]] = x[r];
+                    for (int r = 0; r < NS; ++r) tile[a[r]] = x[r];
                 }
             }
         }
@@ -382,8 +388,10 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
                                    const void *tables_dev, void *stream) {
     QSV_CHECK_ARG(state_dev && P && prog_host, "qsv_run_pass_rounds: NULL pointer");
     QSV_CHECK_ARG(P->n_local >= 1 && P->n_local <= 40, "qsv_run_pass_rounds: n_local=%d out of range", P->n_local);
-    QSV_CHECK_ARG(P->tile_bits >= 4 && P->tile_bits <= 12 && P->tile_bits <= P->n_local,
-                  "qsv_run_pass_rounds: tile_bits=%d must be in [4, 12] and <= n_local", P->tile_bits);
+    const int RB = P->reserved ? P->reserved : 4;             // register bits per round (3 or 4)
+    QSV_CHECK_ARG(RB == 3 || RB == 4, "qsv_run_pass_rounds: register bits (pass->reserved) must be 3 or 4");
+    QSV_CHECK_ARG(P->tile_bits >= RB && P->tile_bits <= 12 && P->tile_bits <= P->n_local,
+                  "qsv_run_pass_rounds: tile_bits=%d must be in [%d, 12] and <= n_local", P->tile_bits, RB);
     QSV_CHECK_ARG(P->low_bits >= 0 && P->low_bits <= P->tile_bits && P->n_hi == P->tile_bits - P->low_bits &&
                       P->n_hi <= 8, "qsv_run_pass_rounds: bad tile geometry");
     int prev = P->low_bits - 1;
@@ -413,7 +421,8 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
     }
     for (uint32_t r = 0; r < hdr->n_rounds; ++r) {
         const qsv_round_t &R = param.rounds[r];
-        QSV_CHECK_ARG(R.rb[0] < R.rb[1] && R.rb[1] < R.rb[2] && R.rb[2] < R.rb[3] && R.rb[3] < P->tile_bits,
+        QSV_CHECK_ARG(R.rb[0] < R.rb[1] && R.rb[1] < R.rb[2] && (RB == 3 || R.rb[2] < R.rb[3]) &&
+                          R.rb[RB - 1] < P->tile_bits,
                       "qsv_run_pass_rounds: round %u register bits not ascending inside the tile", r);
         QSV_CHECK_ARG((uint64_t)R.first_op + (R.n_pre & 0x7fffu) + (R.n_ops & 0xffffu) + ((R.n_ops >> 16) & 0x3fffu) +
                               (R.n_post & 0x7fffu) <= hdr->n_ops, "qsv_run_pass_rounds: round %u op range", r);
@@ -425,9 +434,15 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
     // SMs; the per-CTA prologue (program copy, tables, mbarrier) is paid once per ~50+ tiles, not per tile
     const uint64_t resident = (uint64_t)sm_count() * 2ull * 4ull;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
-    QSV_CUDA(cudaFuncSetAttribute(k_pass_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
-    k_pass_reg<<<grid, kRThreads, smem, (cudaStream_t)stream>>>((double2 *)state_dev, *P, param,
-                                                                (const uint8_t *)tables_dev, n_tiles);
+    if (RB == 4) {
+        QSV_CUDA(cudaFuncSetAttribute(k_pass_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
+        k_pass_reg<4><<<grid, 256, smem, (cudaStream_t)stream>>>((double2 *)state_dev, *P, param,
+                                                                 (const uint8_t *)tables_dev, n_tiles);
+    } else {
+        QSV_CUDA(cudaFuncSetAttribute(k_pass_reg<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
+        k_pass_reg<3><<<grid, 512, smem, (cudaStream_t)stream>>>((double2 *)state_dev, *P, param,
+                                                                 (const uint8_t *)tables_dev, n_tiles);
+    }
     QSV_LAUNCH_CHECK();
     return 0;
 }

@@ -224,6 +224,7 @@ class StateVector:
         if n_ops < 0:       # register-resident round program (host image, passed to the kernel by value)
             prog = maxk[0]
             cp.max_dense_k = 1
+            cp.reserved = int(prog[12])          # register bits per round (program header word 3)
             _cabi.check(self.lib.qsv_run_pass_rounds(self._ptr(self.state), C.byref(cp),
                                                      C.c_void_p(prog.ctypes.data), int(prog.size),
                                                      C.c_void_p(base + table_off), self._stream()),

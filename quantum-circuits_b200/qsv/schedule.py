@@ -648,7 +648,12 @@ assert ROUND_DTYPE.itemsize == 16
 RPROG_MAX_ROUNDS, RPROG_MAX_OPS = 32, 120
 ROP_DENSE1, ROP_DENSE1_REAL, ROP_PHASE1, ROP_GEN_PHASE, ROP_DIAG, ROP_PHASE_T, ROP_PERM = 0, 4, 8, 16, 17, 18, 19
 ROPF_REAL, ROPF_NEG = 1, 2
-REG_BITS = 4
+
+
+def reg_bits():
+    """Register bits per round of k_pass_reg: 4 (256 threads x 16 amplitudes, 16 warps/SM) or 3 (512 threads x 8
+    amplitudes, 32 warps/SM)."""
+    return int(os.environ.get("QSV_REG_BITS", "4"))
 
 
 def _single_bit(mask):
@@ -683,6 +688,7 @@ def plan_rounds(ps):
     past each other only when they commute structurally (same rule as plan_passes).  Returns a list of
     Round, or None if the pass holds an op the register kernel does not implement."""
     T = ps.tile_bits
+    REG_BITS = reg_bits()
     if T < REG_BITS or T > 12 or not all(_round_eligible(op) for op in ps.ops):
         return None
     remaining = list(ps.ops)
@@ -819,12 +825,13 @@ def encode_rounds(ps, rounds):
                                                     or ("phase" in drop and op.kind == "phase"))],
                         [] if "perm" in drop else R.post) for R in rounds]
     rnd = np.zeros(len(rounds), dtype=ROUND_DTYPE)
+    n_rb = len(rounds[0].rb)
     rops = []
     tables = []
     table_cursor = 0
     for r, R in enumerate(rounds):
         rb = R.rb
-        rnd[r]["rb"] = rb
+        rnd[r]["rb"] = list(rb) + [0xFF] * (4 - len(rb))
         rnd[r]["first_op"] = len(rops)
         pre, post = _merge_perms(R.pre, ps), _merge_perms(R.post, ps)
         lin_pre = linearize_perms(pre[::-1], rb)      # the load side applies the list in reverse order
@@ -839,6 +846,7 @@ def encode_rounds(ps, rounds):
             h["tmask"], h["tval"], h["table_off"], h["ext_mask"], h["ext_val"] = f
             h["flags2"] = 1 if f[3] else 0
             h["j"], h["rval"] = lin if lin is not None else (0xFF, 0)
+            h["flags"] = (1 << int(lin[1])) if (lin is not None and lin[0] != 0xFF) else 0     # pbit mask
             return h
 
         rops += [perm_rop(f, lin_pre[::-1][i] if lin_pre is not None else None) for i, f in enumerate(pre)]
@@ -902,7 +910,7 @@ def encode_rounds(ps, rounds):
         rops += [perm_rop(f, lin_post[i] if lin_post is not None else None) for i, f in enumerate(post)]
     if len(rops) > RPROG_MAX_OPS:
         return None
-    hdr = np.array([len(rounds), 16 + 16 * len(rounds) + 128 * len(rops), len(rops), 0], dtype="<u4")
+    hdr = np.array([len(rounds), 16 + 16 * len(rounds) + 128 * len(rops), len(rops), n_rb], dtype="<u4")
     blob = hdr.tobytes() + rnd.tobytes() + b"".join(h.tobytes() for h in rops)
     assert len(blob) == int(hdr[1])
     return np.frombuffer(blob, dtype=np.uint8).copy(), b"".join(tables)

@@ -147,8 +147,9 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
     """numpy emulation of k_pass_reg (csrc/qsv_tile_reg.cu) on the host round program."""
     from qsv.schedule import ROP_DTYPE, ROUND_DTYPE
     prog = bytes(prog)
-    n_rounds, total, n_ops, _ = np.frombuffer(prog, dtype="<u4", count=4)
-    assert total == len(prog)
+    n_rounds, total, n_ops, RB = (int(v) for v in np.frombuffer(prog, dtype="<u4", count=4))
+    assert total == len(prog) and RB in (3, 4)
+    NS = 1 << RB
     rounds = np.frombuffer(prog, dtype=ROUND_DTYPE, count=n_rounds, offset=16)
     rops = np.frombuffer(prog, dtype=ROP_DTYPE, count=n_ops, offset=16 + 16 * int(n_rounds))
     T, L = ps.tile_bits, ps.low_bits
@@ -158,14 +159,14 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
     for j, p in enumerate(hi):
         gl_off = gl_off | (((loc >> (L + j)) & 1) << p)
     psi = psi.copy()
-    tid = np.arange(1 << (T - 4))
+    tid = np.arange(1 << (T - RB))
 
     def permute(tb, rb, ops, gbase, general):
         """Addresses [16, threads] after the permutation ops, computed the way the kernel does: per slot
         (general) or in XOR-linear form base ^ XOR d_q (perm_linear in csrc/qsv_tile_reg.cu)."""
-        roff = [sum((1 << rb[q]) for q in range(4) if (r >> q) & 1) for r in range(16)]
+        roff = [sum((1 << rb[q]) for q in range(len(rb)) if (r >> q) & 1) for r in range(1 << len(rb))]
         if general:
-            a = np.stack([tb | roff[r] for r in range(16)])
+            a = np.stack([tb | roff[r] for r in range(1 << len(rb))])
             for o in ops:
                 assert int(o["kind"]) == 19 and bool(int(o["flags2"]) & 1) == bool(int(o["ext_mask"]))
                 if (gbase & int(o["ext_mask"])) != int(o["ext_val"]):
@@ -175,7 +176,7 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
                 a = np.where((a & cm) == cv, a ^ xm, a)
             return a
         base = tb.copy()
-        d = [np.full_like(tb, 1 << rb[q]) for q in range(4)]
+        d = [np.full_like(tb, 1 << rb[q]) for q in range(len(rb))]
         for o in ops:
             assert int(o["kind"]) == 19 and bool(int(o["flags2"]) & 1) == bool(int(o["ext_mask"]))
             if (gbase & int(o["ext_mask"])) != int(o["ext_val"]):
@@ -183,17 +184,18 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
             cm, cv, xm, q = int(o["tmask"]), int(o["tval"]), int(o["table_off"]), int(o["j"])
             assert xm and not (xm & cm)
             if q == 0xFF:
+                assert int(o["flags"]) == 0
                 base = np.where((base & cm) == cv, base ^ xm, base)
                 continue
             pbit = 1 << int(o["rval"])
-            assert cm & pbit
+            assert cm & pbit and int(o["flags"]) == pbit
             cmu = cm & ~pbit
             f = np.where((base & cmu) == (cv & cmu), xm, 0)
             fd = np.where((d[q] & pbit) != 0, f, 0)
             base = np.where(((base ^ cv) & pbit) == 0, base ^ f, base)
             d[q] = d[q] ^ fd
         a = [base]
-        for r in range(1, 16):
+        for r in range(1, 1 << len(rb)):
             low = (r & -r).bit_length() - 1
             a.append(a[r & (r - 1)] ^ d[low])
         return np.stack(a)
@@ -207,12 +209,11 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
             continue
         tile = psi[base + gl_off].copy()
         for R in rounds:
-            rb = [int(b) for b in R["rb"]]
-            assert rb == sorted(rb) and len(set(rb)) == 4
+            rb = [int(b) for b in R["rb"]][:RB]
+            assert rb == sorted(rb) and len(set(rb)) == RB
             tb = tid.copy()
             for b in rb:
                 tb = _insert_zero(tb, b)
-            roff = [sum((1 << rb[q]) for q in range(4) if (r >> q) & 1) for r in range(16)]
             f0 = int(R["first_op"])
             npre, gen_pre = int(R["n_pre"]) & 0x7FFF, bool(int(R["n_pre"]) & 0x8000)
             npost, gen_post = int(R["n_post"]) & 0x7FFF, bool(int(R["n_post"]) & 0x8000)
@@ -228,13 +229,14 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
                 tp = (tb & int(o["tmask"])) == int(o["tval"])
                 kind, J = int(o["kind"]), int(o["j"])
                 rm, rv = int(o["rmask"]), int(o["rval"])
-                rsel = [r for r in range(16) if (r & rm) == rv]
+                rsel = [r for r in range(NS) if (r & rm) == rv]
                 # decode the kind byte exactly like apply_rop() in csrc/qsv_tile_reg.cu and cross-check
                 # the specialisation against the generic (j, rmask, rval) fields
                 if 0 <= kind < 8:
                     assert J == (kind & 3) and rm == 0 and bool(int(o["flags"]) & 1) == (kind >= 4)
                     m = o["m"].view(np.complex128)
-                    for r in range(16):
+                    assert J < RB
+                    for r in range(NS):
                         if (r >> J) & 1:
                             continue
                         x0, x1 = x[r].copy(), x[r | (1 << J)].copy()
@@ -261,7 +263,7 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
                         di |= bit << (k - 1 - p)
                     for r in rsel:
                         d = di.copy()
-                        for q in range(4):
+                        for q in range(RB):
                             if (r >> q) & 1:
                                 d |= int(o["rc"][q])
                         x[r] = np.where(tp, x[r] * tab[d], x[r])

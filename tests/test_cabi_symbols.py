@@ -90,6 +90,7 @@ def test_round_programs_pass_host_validation():
         cp.n_local, cp.tile_bits, cp.low_bits, cp.n_hi = ps.n_local, ps.tile_bits, ps.low_bits, ps.tile_bits - ps.low_bits
         for j, p in enumerate(ps.hi_pos):
             cp.hi_pos[j] = p
+        cp.reserved = int(prog[12])
         rc = lib.qsv_run_pass_rounds(C.c_void_p(16), C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size),
                                      C.c_void_p(16), None)
         msg = lib.qsv_last_error().decode()

@@ -166,7 +166,7 @@ def test_round_planner_groups_ops_by_register_bits():
         assert sum(len(R.pre) + len(R.reg) + len(R.post) for R in rounds) == len(p.ops)
         for R in rounds:
             rb = R.rb
-            assert len(rb) == 4 and rb == sorted(set(rb)) and all(0 <= b < 12 for b in rb)
+            assert len(rb) == schedule.reg_bits() and rb == sorted(set(rb)) and all(0 <= b < 12 for b in rb)
             assert all(op.kind == "mcx" for op in R.pre + R.post)
             for op in R.reg:
                 assert op.kind != "mcx"
