@@ -167,6 +167,24 @@ int qsv_run_pass(void *state_dev, const qsv_pass_t *pass, const void *prog_dev,
 int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
                         const void *tables_dev, void *stream);
 
+/* Pass-specialised form of qsv_run_pass_rounds.  For large states (n_local >= 28 by default; environment
+ * QSV_JIT=0 never, QSV_JIT=force always, QSV_JIT_MIN_QUBITS=n) qsv_run_pass_rounds does not interpret the
+ * round program: libqsv generates straight-line sm_100a CUDA for exactly this program (same tile geometry,
+ * TMA bulk load/store and round structure), compiles it once with NVRTC and caches the kernel by the
+ * program bytes.  These entry points expose the generator without a GPU:
+ *   qsv_jit_source   the generated CUDA source (also valid C++ with -DQSV_JIT_HOST: tests/ run it on the CPU)
+ *   qsv_jit_compile  compile (or fetch from the cache) and return the sm_100a cubin; safe to call from
+ *                    several host threads at once to prepare the kernels of a circuit in parallel
+ *   qsv_jit_wanted   1 if qsv_run_pass_rounds would take the specialised path for this pass
+ *   qsv_jit_stats    kernels compiled, cache hits and host seconds spent compiling since load
+ * buf may be NULL; *needed receives the full size.  tile_bits must be 12 with 4 register bits per round. */
+int  qsv_jit_source(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, char *buf,
+                    size_t buf_len, size_t *needed);
+int  qsv_jit_compile(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, char *cubin_buf,
+                     size_t buf_len, size_t *needed);
+int  qsv_jit_wanted(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes);
+void qsv_jit_stats(uint64_t *kernels_compiled, uint64_t *cache_hits, double *compile_seconds);
+
 /* Single-gate conveniences (host arguments only; each is one pass with a one-op program built by
  * the library).  `targets[0]` is the gate's port 0 = most-significant bit of the matrix index
  * (main/circuit.py:305-313).  Controls are physical positions that must be 1. */

@@ -1,0 +1,914 @@
+// Pass-specialised register kernel: the round program of one pass (qsv_rop_t list, include/qsv.h) is
+// turned into straight-line sm_100a CUDA for exactly that pass, compiled once with NVRTC, cached by the
+// program bytes and launched through the driver API.
+//
+// Why: k_pass_reg (qsv_tile_reg.cu) INTERPRETS the round program.  ncu showed it instruction-issue bound:
+// ~4400 instructions per thread and tile, of which only ~1100 are the FP64 arithmetic of the gates; the
+// rest is op decode (constant-bank loads, kind switch, predicates) and address bookkeeping that is the
+// same for every tile.  Here all of that is resolved when the kernel is generated:
+//   * op kinds, register bits, masks and matrix entries are literals; gates with entries 0, +-1, +-i
+//     lose their multiplications; negations are integer sign flips (ALU pipe, not FP64);
+//   * thread-level phases that depend only on the thread index are evaluated ONCE per CTA (before the
+//     persistent tile loop) instead of once per tile;
+//   * diagonal ops on register bits accumulate in a pending per-slot constant that is folded at
+//     generation time and applied once (together with the thread scalar) instead of once per op;
+//   * H-like real matrices (all entries +-h) are butterflies (1 add per component); their common factor
+//     h is deferred and folded into the next multiplication that touches every slot;
+//   * X / CNot / Toffoli stay address permutations of the shared-memory exchange (no data movement), with
+//     their conditions reduced to one LOP3+compare on literals.
+// Tile geometry, TMA bulk load/store and the round structure are those of k_pass_reg; the interpreter
+// remains the path for small states (where a ~1 s compile cannot pay off) and for QSV_JIT=0.
+//
+// The same generated source compiles as plain C++ (-DQSV_JIT_HOST) with the round functions driven by a
+// sequential loop over thread ids: that is how tests/ check the generator in a container without a GPU.
+#include "qsv_common.cuh"
+#include <dlfcn.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace qsv {
+namespace jit {
+
+// ------------------------------------------------------------------------------------------------
+// source generation
+// ------------------------------------------------------------------------------------------------
+
+struct Out {
+    std::string s;
+    void f(const char *fmt, ...) __attribute__((format(printf, 2, 3))) {
+        char buf[2048];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        s += buf;
+        s += '\n';
+    }
+};
+
+struct Cx {
+    double r, i;
+    bool is_one() const { return r == 1.0 && i == 0.0; }
+    bool operator==(const Cx &o) const { return r == o.r && i == o.i; }
+};
+static Cx cx_mul(Cx a, Cx b) { return {a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }
+
+static std::string dlit(double v) {
+    if (v == 0.0) return "0.0";
+    if (v == 1.0) return "1.0";
+    if (v == -1.0) return "(-1.0)";
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    char buf[48];
+    snprintf(buf, sizeof(buf), "QD(0x%016llxULL)", (unsigned long long)b);
+    return buf;
+}
+
+static std::string xr(int r) { return "x" + std::to_string(r) + "r"; }
+static std::string xi(int r) { return "x" + std::to_string(r) + "i"; }
+
+// x[r] *= c for a literal c
+static void emit_cmul_const(Out &o, int r, Cx c) {
+    const std::string R = xr(r), I = xi(r);
+    if (c.i == 0.0) {
+        if (c.r == 1.0) return;
+        if (c.r == -1.0) {
+            o.f("    %s = QNEG(%s); %s = QNEG(%s);", R.c_str(), R.c_str(), I.c_str(), I.c_str());
+            return;
+        }
+        o.f("    %s *= %s; %s *= %s;", R.c_str(), dlit(c.r).c_str(), I.c_str(), dlit(c.r).c_str());
+        return;
+    }
+    if (c.r == 0.0) {
+        if (c.i == 1.0) {
+            o.f("    { const double t = %s; %s = QNEG(%s); %s = t; }", R.c_str(), R.c_str(), I.c_str(), I.c_str());
+        } else if (c.i == -1.0) {
+            o.f("    { const double t = %s; %s = %s; %s = QNEG(t); }", R.c_str(), R.c_str(), I.c_str(), I.c_str());
+        } else {
+            o.f("    { const double t = %s; %s = %s * %s; %s = %s * t; }", R.c_str(), R.c_str(), dlit(-c.i).c_str(),
+                I.c_str(), I.c_str(), dlit(c.i).c_str());
+        }
+        return;
+    }
+    o.f("    { const double t = %s * %s - %s * %s; %s = %s * %s + %s * %s; %s = t; }", R.c_str(), dlit(c.r).c_str(),
+        I.c_str(), dlit(c.i).c_str(), I.c_str(), R.c_str(), dlit(c.i).c_str(), I.c_str(), dlit(c.r).c_str(), R.c_str());
+}
+
+// x[r] *= (mr, mi) for runtime variables
+static void emit_cmul_var(Out &o, int r, const char *mr, const char *mi) {
+    const std::string R = xr(r), I = xi(r);
+    o.f("    { const double t = %s * %s - %s * %s; %s = %s * %s + %s * %s; %s = t; }", R.c_str(), mr, I.c_str(), mi,
+        I.c_str(), R.c_str(), mi, I.c_str(), mr, R.c_str());
+}
+
+struct Term {
+    double c;
+    std::string v;
+};
+static std::string lin(const std::vector<Term> &t) {
+    std::string e;
+    for (const Term &x : t) {
+        if (x.c == 0.0) continue;
+        const bool neg = x.c < 0.0;
+        const double a = fabs(x.c);
+        std::string term = (a == 1.0) ? x.v : dlit(a) + " * " + x.v;
+        if (e.empty())
+            e = neg ? "-" + term : term;
+        else
+            e += (neg ? " - " : " + ") + term;
+    }
+    return e.empty() ? "0.0" : e;
+}
+
+static std::string cond_ext(uint64_t em, uint64_t ev) {
+    char b[96];
+    snprintf(b, sizeof(b), "((gbase & 0x%llxULL) == 0x%llxULL)", (unsigned long long)em, (unsigned long long)ev);
+    return b;
+}
+static std::string cond_thr(uint32_t tm, uint32_t tv) {
+    char b[96];
+    snprintf(b, sizeof(b), "((tb & 0x%xu) == 0x%xu)", tm, tv);
+    return b;
+}
+// condition of a register op: "" (always), or a C expression
+static std::string op_cond(const qsv_rop_t &op) {
+    std::string c;
+    if (op.ext_mask) c = cond_ext(op.ext_mask, op.ext_val);
+    if (op.tmask) c = c.empty() ? cond_thr(op.tmask, op.tval) : c + " && " + cond_thr(op.tmask, op.tval);
+    return c;
+}
+
+struct RoundInfo {
+    bool hoisted_S = false;      // qsv_S<k>(tid) exists
+    bool any_S = false;          // the round applies a runtime thread scalar
+    bool barrier = false;        // loads and stores of the round must be separated by a barrier
+};
+
+// Pending diagonal of a round: per-slot literal constants (register-bit phases without runtime
+// condition), multiplied out at generation time.
+struct Pending {
+    Cx c[16];
+    Pending() { reset(); }
+    void reset() { for (auto &v : c) v = {1.0, 0.0}; }
+    bool trivial() const {
+        for (auto &v : c) if (!v.is_one()) return false;
+        return true;
+    }
+    bool depends_on(int J) const {
+        for (int r = 0; r < 16; ++r) if (!(c[r] == c[r ^ (1 << J)])) return true;
+        return false;
+    }
+};
+
+static void flush_pending(Out &o, Pending &pd, double &scale, bool with_S, bool fold_scale) {
+    // with_S: the runtime thread scalar (Sr, Si) is applied to every slot together with the constants.
+    // fold_scale: the deferred real factor of the butterflies is folded in too (it then resets to 1).
+    double g = 1.0;
+    if (fold_scale && scale != 1.0) { g = scale; scale = 1.0; }
+    if (!with_S) {
+        for (int r = 0; r < 16; ++r) {
+            Cx c = {pd.c[r].r * g, pd.c[r].i * g};
+            emit_cmul_const(o, r, c);
+        }
+        pd.reset();
+        return;
+    }
+    // distinct constants -> one runtime multiplier each
+    std::vector<Cx> distinct;
+    int which[16];
+    for (int r = 0; r < 16; ++r) {
+        Cx c = {pd.c[r].r * g, pd.c[r].i * g};
+        int k = -1;
+        for (size_t j = 0; j < distinct.size(); ++j) if (distinct[j] == c) k = (int)j;
+        if (k < 0) { distinct.push_back(c); k = (int)distinct.size() - 1; }
+        which[r] = k;
+    }
+    for (size_t j = 0; j < distinct.size(); ++j) {
+        const Cx c = distinct[j];
+        if (c.is_one()) {
+            o.f("    const double m%zur = Sr, m%zui = Si;", j, j);
+        } else if (c.i == 0.0) {
+            o.f("    const double m%zur = Sr * %s, m%zui = Si * %s;", j, dlit(c.r).c_str(), j, dlit(c.r).c_str());
+        } else if (c.r == 0.0) {
+            o.f("    const double m%zur = Si * %s, m%zui = Sr * %s;", j, dlit(-c.i).c_str(), j, dlit(c.i).c_str());
+        } else {
+            o.f("    const double m%zur = Sr * %s - Si * %s, m%zui = Sr * %s + Si * %s;", j, dlit(c.r).c_str(),
+                dlit(c.i).c_str(), j, dlit(c.i).c_str(), dlit(c.r).c_str());
+        }
+    }
+    for (int r = 0; r < 16; ++r) {
+        char mr[16], mi[16];
+        snprintf(mr, sizeof(mr), "m%dr", which[r]);
+        snprintf(mi, sizeof(mi), "m%di", which[r]);
+        emit_cmul_var(o, r, mr, mi);
+    }
+    pd.reset();
+}
+
+static void emit_tb(Out &o, const qsv_round_t &R) {
+    o.f("    u32 tb = tid;");
+    for (int q = 0; q < 4; ++q)
+        o.f("    tb = ((tb >> %u) << %u) | (tb & 0x%xu);", R.rb[q], R.rb[q] + 1u, (1u << R.rb[q]) - 1u);
+}
+
+// address permutation list in application order [first, first+n) step dir; result: a0..a15 declared
+static void emit_addresses(Out &o, const qsv_round_t &R, const qsv_rop_t *ops, int first, int n, bool reverse,
+                           bool general, const char *pfx) {
+    auto opat = [&](int i) -> const qsv_rop_t & { return ops[reverse ? first + n - 1 - i : first + i]; };
+    if (!general) {
+        o.f("    u32 %sb = tb, %sd0 = 0x%xu, %sd1 = 0x%xu, %sd2 = 0x%xu, %sd3 = 0x%xu;", pfx, pfx, 1u << R.rb[0], pfx,
+            1u << R.rb[1], pfx, 1u << R.rb[2], pfx, 1u << R.rb[3]);
+        for (int i = 0; i < n; ++i) {
+            const qsv_rop_t &p = opat(i);
+            const uint32_t cm = p.tmask, cv = p.tval, xm = p.table_off, q = p.j, pbit = p.flags;
+            const uint32_t cmu = cm & ~pbit;
+            std::string e = p.ext_mask ? cond_ext(p.ext_mask, p.ext_val) + " && " : "";
+            if (cmu)
+                o.f("    { const u32 f = (%s((%sb & 0x%xu) == 0x%xu)) ? 0x%xu : 0u;", e.c_str(), pfx, cmu, cv & cmu, xm);
+            else if (p.ext_mask)
+                o.f("    { const u32 f = %s ? 0x%xu : 0u;", cond_ext(p.ext_mask, p.ext_val).c_str(), xm);
+            else
+                o.f("    { const u32 f = 0x%xu;", xm);
+            if (q == 0xffu || pbit == 0u) {
+                o.f("      %sb ^= f; }", pfx);
+            } else {
+                o.f("      const u32 fd = (%sd%u & 0x%xu) ? f : 0u;", pfx, q, pbit);
+                o.f("      %sb ^= (((%sb ^ 0x%xu) & 0x%xu) == 0u) ? f : 0u;", pfx, pfx, cv, pbit);
+                o.f("      %sd%u ^= fd; }", pfx, q);
+            }
+        }
+        o.f("    const u32 %s0 = %sb;", pfx, pfx);
+        for (int r = 1; r < 16; ++r) {
+            const int low = __builtin_ctz(r);
+            o.f("    const u32 %s%d = %s%d ^ %sd%d;", pfx, r, pfx, r & (r - 1), pfx, low);
+        }
+    } else {
+        for (int r = 0; r < 16; ++r) {
+            uint32_t off = 0;
+            for (int q = 0; q < 4; ++q) if ((r >> q) & 1) off |= 1u << R.rb[q];
+            o.f("    u32 %s%d = tb | 0x%xu;", pfx, r, off);
+        }
+        for (int i = 0; i < n; ++i) {
+            const qsv_rop_t &p = opat(i);
+            std::string e = p.ext_mask ? cond_ext(p.ext_mask, p.ext_val) + " && " : "";
+            for (int r = 0; r < 16; ++r)
+                o.f("    %s%d ^= (%s((%s%d & 0x%xu) == 0x%xu)) ? 0x%xu : 0u;", pfx, r, e.c_str(), pfx, r, p.tmask, p.tval,
+                    p.table_off);
+        }
+    }
+}
+
+static bool butterfly(const double *m, double &h, int sg[4]) {
+    // real matrix with all four entries of the same magnitude h
+    if (m[1] != 0.0 || m[3] != 0.0 || m[5] != 0.0 || m[7] != 0.0) return false;
+    h = fabs(m[0]);
+    if (h == 0.0) return false;
+    for (int k = 0; k < 4; ++k) {
+        if (fabs(m[2 * k]) != h) return false;
+        sg[k] = m[2 * k] < 0.0 ? -1 : 1;
+    }
+    return true;
+}
+
+static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, RoundInfo &info, bool last_round,
+                     double &scale, bool defer_scale, std::string &err) {
+    const int n_pre = R.n_pre & 0x7fff, n_post = R.n_post & 0x7fff;
+    const bool gen_pre = (R.n_pre & 0x8000) != 0, gen_post = (R.n_post & 0x8000) != 0;
+    const int n_reg = (int)(R.n_ops & 0xffffu), n_pt = (int)((R.n_ops >> 16) & 0x3fffu);
+    const int f_pre = (int)R.first_op, f_pt = f_pre + n_pre, f_reg = f_pt + n_pt, f_post = f_reg + n_reg;
+    info.barrier = (n_pre + n_post) > 0;
+
+    // ---- thread scalar, hoistable part: qsv_S<k>(tid)
+    int n_hoist = 0, n_ext_pt = 0;
+    for (int i = 0; i < n_pt; ++i) (ops[f_pt + i].ext_mask ? n_ext_pt : n_hoist)++;
+    info.hoisted_S = n_hoist > 0;
+    info.any_S = n_pt > 0;
+    if (info.hoisted_S) {
+        o.f("QSV_FN double2 qsv_S%d(const u32 tid) {", k);
+        emit_tb(o, R);
+        o.f("    double Sr = 1.0, Si = 0.0;");
+        for (int i = 0; i < n_pt; ++i) {
+            const qsv_rop_t &p = ops[f_pt + i];
+            if (p.ext_mask) continue;
+            const std::string c = p.tmask ? cond_thr(p.tmask, p.tval) : "true";
+            o.f("    if (%s) { const double t = Sr * %s - Si * %s; Si = Sr * %s + Si * %s; Sr = t; }", c.c_str(),
+                dlit(p.m[0]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[0]).c_str());
+        }
+        o.f("    return make_double2(Sr, Si);");
+        o.f("}");
+    }
+
+    o.f("QSV_FN void qsv_round%d(const double2 *tin, double2 *tout, const u32 tid, const u64 gbase, const double S0r,"
+        " const double S0i, const double2 *tables) {", k);
+    emit_tb(o, R);
+    emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
+    o.f("    double x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i, x4r, x4i, x5r, x5i, x6r, x6i, x7r, x7i;");
+    o.f("    double x8r, x8i, x9r, x9i, x10r, x10i, x11r, x11i, x12r, x12i, x13r, x13i, x14r, x14i, x15r, x15i;");
+    for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[a%d]; x%dr = v.x; x%di = v.y; }", r, r, r);
+
+    if (info.any_S) {
+        o.f("    double Sr = S0r, Si = S0i;");
+        for (int i = 0; i < n_pt; ++i) {
+            const qsv_rop_t &p = ops[f_pt + i];
+            if (!p.ext_mask) continue;
+            std::string c = cond_ext(p.ext_mask, p.ext_val);
+            if (p.tmask) c += " && " + cond_thr(p.tmask, p.tval);
+            o.f("    if (%s) { const double t = Sr * %s - Si * %s; Si = Sr * %s + Si * %s; Sr = t; }", c.c_str(),
+                dlit(p.m[0]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[0]).c_str());
+        }
+    }
+
+    Pending pd;
+    for (int i = 0; i < n_reg; ++i) {
+        const qsv_rop_t &p = ops[f_reg + i];
+        const std::string cnd = op_cond(p);
+        const int kind = p.kind;
+        if (kind >= QSV_ROP_DENSE1 && kind < QSV_ROP_PHASE1) {
+            const int J = kind & 3;
+            if (pd.depends_on(J)) flush_pending(o, pd, scale, false, false);
+            double h;
+            int sg[4];
+            const bool bf = butterfly(p.m, h, sg);
+            const bool defer = bf && defer_scale && cnd.empty();
+            if (!cnd.empty()) o.f("    if (%s) {", cnd.c_str());
+            for (int r = 0; r < 16; ++r) {
+                if ((r >> J) & 1) continue;
+                const int r1 = r | (1 << J);
+                o.f("    { const double p0r = %s, p0i = %s, p1r = %s, p1i = %s;", xr(r).c_str(), xi(r).c_str(),
+                    xr(r1).c_str(), xi(r1).c_str());
+                if (bf) {
+                    const std::string hs = defer ? "" : dlit(h) + " * ";
+                    auto comb = [&](int s0, int s1, const char *a, const char *b) {
+                        std::string e = "(";
+                        e += (s0 < 0 ? "-" : "");
+                        e += a;
+                        e += (s1 < 0 ? " - " : " + ");
+                        e += b;
+                        return e + ")";
+                    };
+                    o.f("      %s = %s%s; %s = %s%s;", xr(r).c_str(), hs.c_str(), comb(sg[0], sg[1], "p0r", "p1r").c_str(),
+                        xi(r).c_str(), hs.c_str(), comb(sg[0], sg[1], "p0i", "p1i").c_str());
+                    o.f("      %s = %s%s; %s = %s%s; }", xr(r1).c_str(), hs.c_str(), comb(sg[2], sg[3], "p0r", "p1r").c_str(),
+                        xi(r1).c_str(), hs.c_str(), comb(sg[2], sg[3], "p0i", "p1i").c_str());
+                } else {
+                    const double *m = p.m;      // a = m[0..1], b = m[2..3], c = m[4..5], d = m[6..7]
+                    o.f("      %s = %s;", xr(r).c_str(),
+                        lin({{m[0], "p0r"}, {-m[1], "p0i"}, {m[2], "p1r"}, {-m[3], "p1i"}}).c_str());
+                    o.f("      %s = %s;", xi(r).c_str(),
+                        lin({{m[0], "p0i"}, {m[1], "p0r"}, {m[2], "p1i"}, {m[3], "p1r"}}).c_str());
+                    o.f("      %s = %s;", xr(r1).c_str(),
+                        lin({{m[4], "p0r"}, {-m[5], "p0i"}, {m[6], "p1r"}, {-m[7], "p1i"}}).c_str());
+                    o.f("      %s = %s; }", xi(r1).c_str(),
+                        lin({{m[4], "p0i"}, {m[5], "p0r"}, {m[6], "p1i"}, {m[7], "p1r"}}).c_str());
+                }
+            }
+            if (!cnd.empty()) o.f("    }");
+            if (defer) scale *= h;
+        } else if ((kind >= QSV_ROP_PHASE1 && kind < QSV_ROP_GEN_PHASE) || kind == QSV_ROP_GEN_PHASE) {
+            uint32_t rmask = p.rmask, rval = p.rval;
+            if (kind != QSV_ROP_GEN_PHASE) {
+                const int J = (kind - QSV_ROP_PHASE1) >> 1, V = (kind - QSV_ROP_PHASE1) & 1;
+                rmask = 1u << J;
+                rval = (uint32_t)V << J;
+            }
+            const Cx s = {p.m[0], p.m[1]};
+            if (cnd.empty()) {
+                for (int r = 0; r < 16; ++r) if (((uint32_t)r & rmask) == rval) pd.c[r] = cx_mul(pd.c[r], s);
+            } else {
+                o.f("    if (%s) {", cnd.c_str());
+                for (int r = 0; r < 16; ++r) if (((uint32_t)r & rmask) == rval) emit_cmul_const(o, r, s);
+                o.f("    }");
+            }
+        } else if (kind == QSV_ROP_DIAG) {
+            // table lookup: index bits from thread-held positions, external positions and register bits
+            if (!cnd.empty()) o.f("    if (%s) {", cnd.c_str());
+            o.f("    { u32 di = 0u;");
+            const int kk = (int)p.k;
+            for (int q = 0; q < kk; ++q) {
+                const uint32_t s = p.dsrc[q];
+                if (s == 0xffu) continue;
+                if (s & 0x80u)
+                    o.f("      di |= (u32)((gbase >> %u) & 1ULL) << %d;", s & 0x7fu, kk - 1 - q);
+                else
+                    o.f("      di |= ((tb >> %u) & 1u) << %d;", s, kk - 1 - q);
+            }
+            o.f("      const double2 *tab = tables + %u;", p.table_off / 16u);
+            for (int r = 0; r < 16; ++r) {
+                if (((uint32_t)r & p.rmask) != p.rval) continue;
+                uint32_t d = 0;
+                for (int q = 0; q < 4; ++q) if ((r >> q) & 1) d |= p.rc[q];
+                o.f("      { const double2 m = QSV_LDG(tab + (di | 0x%xu));", d);
+                o.f("        const double t = %s * m.x - %s * m.y; %s = %s * m.y + %s * m.x; %s = t; }", xr(r).c_str(),
+                    xi(r).c_str(), xi(r).c_str(), xr(r).c_str(), xi(r).c_str(), xr(r).c_str());
+            }
+            o.f("    }");
+            if (!cnd.empty()) o.f("    }");
+        } else {
+            err = "register op kind " + std::to_string(kind) + " is not supported by the generator";
+            return 1;
+        }
+    }
+    // end of round: constants, thread scalar and (in the last round) the deferred butterfly factor
+    {
+        const bool fold = last_round && scale != 1.0;
+        if (info.any_S)
+            flush_pending(o, pd, scale, true, fold);
+        else if (!pd.trivial() || fold)
+            flush_pending(o, pd, scale, false, fold);
+    }
+    if (info.barrier) o.f("    QSV_BARRIER();");
+    emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, gen_post, "b");
+    for (int r = 0; r < 16; ++r) o.f("    tout[b%d] = make_double2(x%dr, x%di);", r, r, r);
+    o.f("}");
+    return 0;
+}
+
+static const char *kPrelude = R"SRC(// generated by libqsv (csrc/qsv_jit.cu) for ONE pass program - do not edit
+typedef unsigned int u32;
+typedef unsigned long long u64;
+#ifdef QSV_JIT_HOST
+#include <string.h>
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
+static inline double QD(u64 h) { double d; memcpy(&d, &h, 8); return d; }
+#define QNEG(v) (-(v))
+#define QSV_FN static inline
+#define QSV_BARRIER()
+#define QSV_LDG(p) (*(p))
+#else
+#define QD(h) __longlong_as_double((long long)(h))
+#define QNEG(v) __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v))
+#define QSV_FN __device__ __forceinline__
+#define QSV_BARRIER() __syncthreads()
+#define QSV_LDG(p) __ldg(p)
+#endif
+)SRC";
+
+static const char *kDeviceHelpers = R"SRC(
+#ifndef QSV_JIT_HOST
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+                 "r"(bytes) : "memory");
+}
+#endif
+)SRC";
+
+int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, std::string &src, std::string &err) {
+    const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
+    const uint8_t *body = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);
+    std::vector<qsv_round_t> rounds(hdr->n_rounds);
+    std::vector<qsv_rop_t> ops(hdr->n_ops);
+    memcpy(rounds.data(), body, sizeof(qsv_round_t) * hdr->n_rounds);
+    memcpy(ops.data(), body + sizeof(qsv_round_t) * hdr->n_rounds, sizeof(qsv_rop_t) * hdr->n_ops);
+    (void)prog_bytes;
+    if (P.tile_bits != 12) { err = "generator needs 12 tile bits"; return 1; }
+    const int L = P.low_bits, n_hi = P.n_hi;
+    const bool defer_scale = getenv("QSV_JIT_NO_DEFER") == nullptr;
+
+    Out o;
+    o.s += kPrelude;
+    o.s += kDeviceHelpers;
+    std::vector<RoundInfo> info(hdr->n_rounds);
+    double scale = 1.0;
+    for (uint32_t k = 0; k < hdr->n_rounds; ++k)
+        if (gen_round(o, (int)k, rounds[k], ops.data(), info[k], k + 1 == hdr->n_rounds, scale, defer_scale, err))
+            return 1;
+
+    // is a tile ever skipped?  (every op has an external condition)
+    bool always_active = false;
+    for (const qsv_rop_t &p : ops) always_active = always_active || p.ext_mask == 0;
+    std::string active = "false";
+    if (!always_active) {
+        std::vector<std::string> seen;
+        for (const qsv_rop_t &p : ops) {
+            std::string c = cond_ext(p.ext_mask, p.ext_val);
+            bool dup = false;
+            for (auto &s : seen) dup = dup || s == c;
+            if (!dup) { seen.push_back(c); active += " || " + c; }
+        }
+    }
+
+    // ---- tile base: insert a zero bit at every hi position (ascending)
+    Out tb;
+    tb.f("        u64 base = t << %d;", L);
+    for (int j = 0; j < n_hi; ++j)
+        tb.f("        base = ((base >> %u) << %u) | (base & 0x%llxULL);", P.hi_pos[j], P.hi_pos[j] + 1u,
+             (unsigned long long)((1ull << P.hi_pos[j]) - 1ull));
+    tb.f("        const u64 gbase = base | rank_bits;");
+    if (!always_active) tb.f("        if (!(%s)) continue;", active.c_str());
+
+    auto rounds_body = [&](Out &w, const char *tin, const char *tout_a, const char *tout_b, bool host) {
+        // host: rounds ping-pong between two buffers and are driven for all thread ids sequentially
+        for (uint32_t k = 0; k < hdr->n_rounds; ++k) {
+            const char *src_buf = host ? ((k & 1) ? tout_b : tout_a) : tin;
+            const char *dst_buf = host ? ((k & 1) ? tout_a : tout_b) : tin;
+            if (host) {
+                w.f("        for (u32 tid = 0; tid < 256u; ++tid) {");
+                if (info[k].hoisted_S)
+                    w.f("            const double2 S = qsv_S%u(tid);", k);
+                else
+                    w.f("            const double2 S = make_double2(1.0, 0.0);");
+                w.f("            qsv_round%u(%s, %s, tid, gbase, S.x, S.y, tables);", k, src_buf, dst_buf);
+                w.f("        }");
+            } else {
+                if (k > 0) w.f("        __syncthreads();");
+                if (info[k].hoisted_S)
+                    w.f("        qsv_round%u(%s, %s, tid, gbase, S%u.x, S%u.y, tables);", k, src_buf, dst_buf, k, k);
+                else
+                    w.f("        qsv_round%u(%s, %s, tid, gbase, 1.0, 0.0, tables);", k, src_buf, dst_buf);
+            }
+        }
+    };
+
+    // ---- device kernel
+    o.f("#ifndef QSV_JIT_HOST");
+    o.f("extern \"C\" __global__ void __launch_bounds__(256, 2)");
+    o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables) {");
+    o.f("    extern __shared__ __align__(128) unsigned char smem_raw[];");
+    o.f("    double2 *tile = reinterpret_cast<double2 *>(smem_raw);");
+    o.f("    __shared__ __align__(8) u64 mbar;");
+    o.f("    const u32 tid = threadIdx.x;");
+    o.f("    if (tid == 0) { mbar_init(&mbar, 1); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }");
+    o.f("    __syncthreads();");
+    for (uint32_t k = 0; k < hdr->n_rounds; ++k)
+        if (info[k].hoisted_S) o.f("    const double2 S%u = qsv_S%u(tid);", k, k);
+    // run r of the tile: 2^L amplitudes at state[base + offset(r)], offset = bits of r scattered to hi_pos
+    const int n_runs = 1 << n_hi;
+    const int lowb = n_hi < 3 ? n_hi : 3;         // run-index bits supplied by the warp id
+    o.f("    const u32 warp = tid >> 5;");
+    {
+        std::string e = "0ULL";
+        for (int j = 0; j < lowb; ++j)
+            e += " | ((u64)((warp >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
+        o.f("    const u64 off_w = %s;", e.c_str());
+    }
+    o.f("    const bool issuer = (tid & 31u) == 0u && warp < %du;", n_runs < 8 ? n_runs : 8);
+    o.f("    u32 parity = 0;");
+    o.f("    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {");
+    o.s += tb.s;
+    o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
+    o.f("        if (issuer) {");
+    const int per_warp = n_runs < 8 ? 1 : n_runs / 8;
+    for (int i = 0; i < per_warp; ++i) {
+        uint64_t off = 0;
+        for (int j = 3; j < n_hi; ++j) if ((i >> (j - 3)) & 1) off |= 1ull << P.hi_pos[j];
+        o.f("            bulk_g2s(tile + ((warp + %du) << %d), state + base + off_w + 0x%llxULL, %uu, &mbar);", 8 * i, L,
+            (unsigned long long)off, 16u << L);
+    }
+    o.f("        }");
+    o.f("        mbar_wait(&mbar, parity);");
+    o.f("        parity ^= 1u;");
+    rounds_body(o, "tile", "", "", false);
+    o.f("        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
+    o.f("        __syncthreads();");
+    o.f("        if (issuer) {");
+    for (int i = 0; i < per_warp; ++i) {
+        uint64_t off = 0;
+        for (int j = 3; j < n_hi; ++j) if ((i >> (j - 3)) & 1) off |= 1ull << P.hi_pos[j];
+        o.f("            bulk_s2g(state + base + off_w + 0x%llxULL, tile + ((warp + %du) << %d), %uu);",
+            (unsigned long long)off, 8 * i, L, 16u << L);
+    }
+    o.f("        }");
+    o.f("        asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");");
+    o.f("        asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");");
+    o.f("    }");
+    o.f("}");
+    o.f("#else");
+    // ---- host emulation driver (tests only): same round functions, threads run sequentially
+    o.f("extern \"C\" void qsv_jit_host_run(double2 *state, const u64 rank_bits, const u64 n_tiles, const double2 *tables) {");
+    o.f("    static double2 A[4096], B[4096];");
+    o.f("    for (u64 t = 0; t < n_tiles; ++t) {");
+    o.s += tb.s;
+    o.f("        for (u32 r = 0; r < %du; ++r) {", n_runs);
+    {
+        std::string e = "0ULL";
+        for (int j = 0; j < n_hi; ++j)
+            e += " | ((u64)((r >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
+        o.f("            const u64 off = %s;", e.c_str());
+    }
+    o.f("            memcpy(A + ((u64)r << %d), state + base + off, %uu);", L, 16u << L);
+    o.f("        }");
+    rounds_body(o, "", "A", "B", true);
+    o.f("        const double2 *fin = %s;", (hdr->n_rounds & 1) ? "B" : "A");
+    o.f("        for (u32 r = 0; r < %du; ++r) {", n_runs);
+    {
+        std::string e = "0ULL";
+        for (int j = 0; j < n_hi; ++j)
+            e += " | ((u64)((r >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
+        o.f("            const u64 off = %s;", e.c_str());
+    }
+    o.f("            memcpy(state + base + off, fin + ((u64)r << %d), %uu);", L, 16u << L);
+    o.f("        }");
+    o.f("    }");
+    o.f("}");
+    o.f("#endif");
+    src.swap(o.s);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NVRTC (dlopen'ed: the library must load in containers without the toolkit on the loader path)
+// ------------------------------------------------------------------------------------------------
+
+struct Nvrtc {
+    void *h = nullptr;
+    int (*CreateProgram)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    int (*CompileProgram)(void *, int, const char *const *) = nullptr;
+    int (*GetCUBINSize)(void *, size_t *) = nullptr;
+    int (*GetCUBIN)(void *, char *) = nullptr;
+    int (*GetProgramLogSize)(void *, size_t *) = nullptr;
+    int (*GetProgramLog)(void *, char *) = nullptr;
+    int (*DestroyProgram)(void **) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+
+static Nvrtc *nvrtc(std::string &err) {
+    static Nvrtc lib;
+    static std::once_flag once;
+    static std::string load_err;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("QSV_NVRTC_LIB"), "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                               "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"};
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            lib.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (lib.h) break;
+        }
+        if (!lib.h) {
+            load_err = "cannot load libnvrtc (set QSV_NVRTC_LIB or QSV_JIT=0)";
+            return;
+        }
+#define QSV_SYM(field, name)                                                        \
+    *reinterpret_cast<void **>(&lib.field) = dlsym(lib.h, name);                    \
+    if (!lib.field) load_err = std::string("libnvrtc lacks ") + name;
+        QSV_SYM(CreateProgram, "nvrtcCreateProgram")
+        QSV_SYM(CompileProgram, "nvrtcCompileProgram")
+        QSV_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+        QSV_SYM(GetCUBIN, "nvrtcGetCUBIN")
+        QSV_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+        QSV_SYM(GetProgramLog, "nvrtcGetProgramLog")
+        QSV_SYM(DestroyProgram, "nvrtcDestroyProgram")
+        QSV_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef QSV_SYM
+    });
+    if (!load_err.empty()) { err = load_err; return nullptr; }
+    return &lib;
+}
+
+static int compile_cubin(const std::string &src, std::string &cubin, std::string &err) {
+    Nvrtc *rt = nvrtc(err);
+    if (!rt) return 1;
+    void *prog = nullptr;
+    int rc = rt->CreateProgram(&prog, src.c_str(), "qsv_jit_pass.cu", 0, nullptr, nullptr);
+    if (rc != 0) { err = std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc); return 1; }
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+    rc = rt->CompileProgram(prog, 3, opts);
+    if (rc != 0) {
+        size_t n = 0;
+        rt->GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) rt->GetProgramLog(prog, &log[0]);
+        err = std::string("nvrtcCompileProgram: ") + rt->GetErrorString(rc) + "\n" + log.substr(0, 1500);
+        rt->DestroyProgram(&prog);
+        return 1;
+    }
+    size_t n = 0;
+    rt->GetCUBINSize(prog, &n);
+    cubin.assign(n, '\0');
+    rt->GetCUBIN(prog, &cubin[0]);
+    rt->DestroyProgram(&prog);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// driver API (dlopen'ed: libcuda.so.1 does not exist in the build container)
+// ------------------------------------------------------------------------------------------------
+
+struct Driver {
+    void *h = nullptr;
+    int (*ModuleLoadData)(void **, const void *) = nullptr;
+    int (*ModuleGetFunction)(void **, void *, const char *) = nullptr;
+    int (*FuncSetAttribute)(void *, int, int) = nullptr;
+    int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **,
+                        void **) = nullptr;
+    int (*GetErrorString)(int, const char **) = nullptr;
+};
+
+static Driver *driver(std::string &err) {
+    static Driver lib;
+    static std::once_flag once;
+    static std::string load_err;
+    std::call_once(once, [] {
+        lib.h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!lib.h) { load_err = "cannot load libcuda.so.1"; return; }
+#define QSV_SYM(field, name)                                                        \
+    *reinterpret_cast<void **>(&lib.field) = dlsym(lib.h, name);                    \
+    if (!lib.field) load_err = std::string("libcuda lacks ") + name;
+        QSV_SYM(ModuleLoadData, "cuModuleLoadData")
+        QSV_SYM(ModuleGetFunction, "cuModuleGetFunction")
+        QSV_SYM(FuncSetAttribute, "cuFuncSetAttribute")
+        QSV_SYM(LaunchKernel, "cuLaunchKernel")
+        QSV_SYM(GetErrorString, "cuGetErrorString")
+#undef QSV_SYM
+    });
+    if (!load_err.empty()) { err = load_err; return nullptr; }
+    return &lib;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cache: key = tile geometry + program bytes (n_local and rank_bits are kernel arguments)
+// ------------------------------------------------------------------------------------------------
+
+struct Entry {
+    std::mutex mu;
+    bool compiled = false, failed = false;
+    std::string cubin, err;
+    std::unordered_map<int, void *> fn;     // device ordinal -> CUfunction
+};
+
+static std::mutex g_mu;
+static std::unordered_map<std::string, Entry *> g_cache;
+static std::atomic<uint64_t> g_compiles{0}, g_hits{0}, g_compile_us{0};
+
+static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t bytes) {
+    std::string k;
+    k.append(reinterpret_cast<const char *>(&P.tile_bits), sizeof(P.tile_bits));
+    k.append(reinterpret_cast<const char *>(&P.low_bits), sizeof(P.low_bits));
+    k.append(reinterpret_cast<const char *>(P.hi_pos), sizeof(P.hi_pos));
+    k.append(getenv("QSV_JIT_NO_DEFER") ? "N" : "D");
+    k.append(static_cast<const char *>(prog), bytes);
+    return k;
+}
+
+static Entry *lookup(const qsv_pass_t &P, const void *prog, uint32_t bytes) {
+    const std::string k = cache_key(P, prog, bytes);
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_cache.find(k);
+    if (it != g_cache.end()) return it->second;
+    Entry *e = new Entry();
+    g_cache.emplace(k, e);
+    return e;
+}
+
+static int ensure_compiled(Entry *e, const qsv_pass_t &P, const void *prog, uint32_t bytes) {
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->compiled) { g_hits.fetch_add(1); return 0; }
+    if (e->failed) { set_error("qsv jit: %s", e->err.c_str()); return 1; }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string src;
+    if (generate(P, prog, bytes, src, e->err) || compile_cubin(src, e->cubin, e->err)) {
+        e->failed = true;
+        set_error("qsv jit: %s", e->err.c_str());
+        return 1;
+    }
+    e->compiled = true;
+    g_compiles.fetch_add(1);
+    g_compile_us.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(
+                               std::chrono::steady_clock::now() - t0).count());
+    return 0;
+}
+
+static int validate(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes) {
+    QSV_CHECK_ARG(P && prog_host, "qsv jit: NULL pointer");
+    QSV_CHECK_ARG(prog_bytes >= sizeof(qsv_rprog_hdr_t), "qsv jit: program too short");
+    const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
+    QSV_CHECK_ARG(hdr->n_rounds >= 1 && hdr->n_rounds <= QSV_RPROG_MAX_ROUNDS && hdr->n_ops <= QSV_RPROG_MAX_OPS,
+                  "qsv jit: %u rounds / %u ops exceed the limits", hdr->n_rounds, hdr->n_ops);
+    const size_t need = sizeof(qsv_rprog_hdr_t) + sizeof(qsv_round_t) * hdr->n_rounds + sizeof(qsv_rop_t) * hdr->n_ops;
+    QSV_CHECK_ARG(prog_bytes >= need, "qsv jit: prog_bytes=%u smaller than the %zu bytes the header implies", prog_bytes,
+                  need);
+    QSV_CHECK_ARG(P->tile_bits == 12 && P->n_hi >= 0 && P->n_hi <= 8 && P->low_bits == 12 - P->n_hi,
+                  "qsv jit: needs a 12-bit tile with at most 8 high positions");
+    QSV_CHECK_ARG(hdr->reserved == 0 || hdr->reserved == 4, "qsv jit: needs 4 register bits per round");
+    const qsv_round_t *rounds = reinterpret_cast<const qsv_round_t *>(static_cast<const uint8_t *>(prog_host) + 16);
+    for (uint32_t r = 0; r < hdr->n_rounds; ++r) {
+        const qsv_round_t &R = rounds[r];
+        QSV_CHECK_ARG(R.rb[0] < R.rb[1] && R.rb[1] < R.rb[2] && R.rb[2] < R.rb[3] && R.rb[3] < 12,
+                      "qsv jit: round %u register bits not ascending inside the tile", r);
+        QSV_CHECK_ARG((uint64_t)R.first_op + (R.n_pre & 0x7fffu) + (R.n_ops & 0xffffu) + ((R.n_ops >> 16) & 0x3fffu) +
+                              (R.n_post & 0x7fffu) <= hdr->n_ops, "qsv jit: round %u op range", r);
+    }
+    return 0;
+}
+
+// policy: QSV_JIT=0 never, =force always (tile_bits 12), default: states of >= 2^QSV_JIT_MIN_QUBITS amplitudes
+bool wanted(const qsv_pass_t *P, const void *prog_host) {
+    const char *m = getenv("QSV_JIT");
+    if (m && !strcmp(m, "0")) return false;
+    const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
+    if (P->tile_bits != 12 || !(hdr->reserved == 0 || hdr->reserved == 4)) return false;
+    if (m && !strcmp(m, "force")) return true;
+    const char *q = getenv("QSV_JIT_MIN_QUBITS");
+    const int minq = q ? atoi(q) : 28;
+    return P->n_local >= minq;
+}
+
+int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
+           cudaStream_t st, unsigned grid) {
+    if (validate(P, prog_host, prog_bytes)) return 1;
+    Entry *e = lookup(*P, prog_host, prog_bytes);
+    if (ensure_compiled(e, *P, prog_host, prog_bytes)) return 1;
+    int dev = 0;
+    QSV_CUDA(cudaGetDevice(&dev));
+    void *fn = nullptr;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->fn.find(dev);
+        if (it != e->fn.end()) fn = it->second;
+        if (!fn) {
+            std::string err;
+            Driver *d = driver(err);
+            QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
+            QSV_CUDA(cudaFree(0));        // the primary context is current before the first driver call
+            void *mod = nullptr;
+            int rc = d->ModuleLoadData(&mod, e->cubin.data());
+            const char *es = nullptr;
+            if (rc) { d->GetErrorString(rc, &es); set_error("qsv jit: cuModuleLoadData: %s", es ? es : "?"); return 2; }
+            rc = d->ModuleGetFunction(&fn, mod, "qsv_jit_pass");
+            if (rc) { d->GetErrorString(rc, &es); set_error("qsv jit: cuModuleGetFunction: %s", es ? es : "?"); return 2; }
+            rc = d->FuncSetAttribute(fn, /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/ 8, 16 << 12);
+            if (rc) { d->GetErrorString(rc, &es); set_error("qsv jit: cuFuncSetAttribute: %s", es ? es : "?"); return 2; }
+            e->fn[dev] = fn;
+        }
+    }
+    std::string err;
+    Driver *d = driver(err);
+    QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
+    unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
+    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev)};
+    const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u << 12, (void *)st, args, nullptr);
+    if (rc) {
+        const char *es = nullptr;
+        d->GetErrorString(rc, &es);
+        set_error("qsv jit: cuLaunchKernel: %s", es ? es : "?");
+        return 2;
+    }
+    count_launch();
+    return 0;
+}
+
+}  // namespace jit
+}  // namespace qsv
+
+using namespace qsv;
+
+static int copy_out(const std::string &s, char *buf, size_t buf_len, size_t *needed) {
+    if (needed) *needed = s.size();
+    if (buf && buf_len) {
+        const size_t n = s.size() < buf_len ? s.size() : buf_len;
+        memcpy(buf, s.data(), n);
+    }
+    return 0;
+}
+
+extern "C" int qsv_jit_source(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, char *buf,
+                              size_t buf_len, size_t *needed) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return 1;
+    std::string src, err;
+    if (jit::generate(*pass, prog_host, prog_bytes, src, err)) { set_error("qsv jit: %s", err.c_str()); return 1; }
+    return copy_out(src, buf, buf_len, needed);
+}
+
+extern "C" int qsv_jit_compile(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, char *cubin_buf,
+                               size_t buf_len, size_t *needed) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return 1;
+    jit::Entry *e = jit::lookup(*pass, prog_host, prog_bytes);
+    if (jit::ensure_compiled(e, *pass, prog_host, prog_bytes)) return 1;
+    return copy_out(e->cubin, cubin_buf, buf_len, needed);
+}
+
+extern "C" int qsv_jit_wanted(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes) {
+    if (!pass || !prog_host || prog_bytes < sizeof(qsv_rprog_hdr_t)) return 0;
+    return jit::wanted(pass, prog_host) ? 1 : 0;
+}
+
+extern "C" void qsv_jit_stats(uint64_t *kernels_compiled, uint64_t *cache_hits, double *compile_seconds) {
+    if (kernels_compiled) *kernels_compiled = jit::g_compiles.load();
+    if (cache_hits) *cache_hits = jit::g_hits.load();
+    if (compile_seconds) *compile_seconds = 1e-6 * (double)jit::g_compile_us.load();
+}

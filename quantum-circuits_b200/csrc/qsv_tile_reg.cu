@@ -10,6 +10,7 @@
 // time of the pass; here the cost is per round, not per op.
 #include "qsv_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace qsv {
 
@@ -328,8 +329,12 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
             }
             {
                 const qsv_rop_t *rg = ops + R.first_op + n_pre + n_pt;
+                // software pipelining of the op decode: the header of op i+1 is fetched while op i runs
+                uint4 hn = make_uint4(0u, 0u, 0u, 0u);
+                if (n_reg) hn = *reinterpret_cast<const uint4 *>(rg);
                 for (uint32_t i = 0; i < n_reg; ++i) {
-                    const uint4 h = *reinterpret_cast<const uint4 *>(rg + i);
+                    const uint4 h = hn;
+                    if (i + 1 < n_reg) hn = *reinterpret_cast<const uint4 *>(rg + i + 1);
                     if ((h.w & 1u) && (gbase & rg[i].ext_mask) != rg[i].ext_val) continue;     // uniform
                     if ((tb & h.y) == h.z) apply_rop<NS>(x, rg + i, h.x & 0xffu, sprog, tb, gbase);
                 }
@@ -368,6 +373,12 @@ k_pass_reg(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P,
 }  // namespace qsv
 
 using namespace qsv;
+
+namespace qsv { namespace jit {
+bool wanted(const qsv_pass_t *P, const void *prog_host);
+int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
+           cudaStream_t st, unsigned grid);
+} }
 
 static_assert(sizeof(qsv_rop_t) == 128, "qsv_rop_t must be 128 bytes");
 static_assert(sizeof(qsv_round_t) == 16 && sizeof(qsv_rprog_hdr_t) == 16, "round/program headers are 16 bytes");
@@ -434,6 +445,19 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
     // SMs; the per-CTA prologue (program copy, tables, mbarrier) is paid once per ~50+ tiles, not per tile
     const uint64_t resident = (uint64_t)sm_count() * 2ull * 4ull;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    // Large states run the pass-specialised kernel (qsv_jit.cu): same tile geometry and round structure,
+    // generated as straight-line code for this program and cached by its bytes.
+    if (RB == 4 && jit::wanted(P, prog_host)) {
+        const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid);
+        const char *mode = getenv("QSV_JIT");
+        if (rc == 0 || (mode && !strcmp(mode, "force"))) return rc;
+        static bool warned = false;
+        if (!warned) {
+            warned = true;
+            fprintf(stderr, "libqsv: specialised kernel unavailable (%s); using the interpreting kernel k_pass_reg\n",
+                    qsv_last_error());
+        }
+    }
     if (RB == 4) {
         QSV_CUDA(cudaFuncSetAttribute(k_pass_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
         k_pass_reg<4><<<grid, 256, smem, (cudaStream_t)stream>>>((double2 *)state_dev, *P, param,

@@ -37,6 +37,10 @@ SYMBOLS = {
     "qsv_init_basis": (C.c_int, [_P, _I, _U64, _U64, _P]),
     "qsv_run_pass": (C.c_int, [_P, C.POINTER(QsvPass), _P, _P, _I, _P]),
     "qsv_run_pass_rounds": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _P]),
+    "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "qsv_jit_compile": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "qsv_jit_wanted": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32]),
+    "qsv_jit_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_D)]),
     "qsv_apply_dense": (C.c_int, [_P, _I, _I, _IP, _I, _IP, C.POINTER(_D), _U64, _P]),
     "qsv_apply_diag": (C.c_int, [_P, _I, _I, _IP, C.POINTER(_D), _U64, _P]),
     "qsv_apply_phase": (C.c_int, [_P, _I, _I, _IP, _D, _D, _U64, _P]),

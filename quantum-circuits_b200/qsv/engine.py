@@ -77,9 +77,44 @@ class StateVector:
         run_program (so benchmarks can separate host scheduling from device time)."""
         passes = plan_passes(ops, self.n_local, self.tile_bits, self.low_bits)
         packed = pack_passes(passes)
+        self._prepare_kernels(packed)
         host = torch.from_numpy(packed.blob)
         dev = host.to(self.device, non_blocking=False)
         return (packed, dev)
+
+    def _cpass(self, ps):
+        cp = _cabi.QsvPass()
+        cp.n_local, cp.tile_bits, cp.low_bits = ps.n_local, ps.tile_bits, ps.low_bits
+        cp.n_hi = ps.tile_bits - ps.low_bits
+        for j, p in enumerate(ps.hi_pos):
+            cp.hi_pos[j] = p
+        cp.rank_bits = self.rank_bits
+        return cp
+
+    def _prepare_kernels(self, packed):
+        """Large states run pass-specialised kernels (csrc/qsv_jit.cu).  Generate + compile the ones this
+        program needs now, on all host cores (NVRTC, ~0.3 s per kernel, cached by program bytes inside
+        libqsv), so that the launches only look them up."""
+        todo = []
+        for ps, _, n_ops, extra in packed.passes:
+            if n_ops >= 0:
+                continue
+            prog = extra[0]
+            cp = self._cpass(ps)
+            cp.reserved = int(prog[12])
+            if self.lib.qsv_jit_wanted(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size)):
+                todo.append((cp, prog))
+        if not todo:
+            return
+
+        def compile_one(item):
+            cp, prog = item
+            return self.lib.qsv_jit_compile(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), None, 0, None)
+
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4, 32)) as ex:
+            list(ex.map(compile_one, todo))     # failures surface at launch time (with the fallback policy)
 
     def run_program(self, handle):
         packed, dev = handle
@@ -215,12 +250,7 @@ class StateVector:
     def _launch_pass(self, packed_meta, dev):
         ps, table_off, n_ops, maxk = packed_meta
         base = dev.data_ptr()
-        cp = _cabi.QsvPass()
-        cp.n_local, cp.tile_bits, cp.low_bits = ps.n_local, ps.tile_bits, ps.low_bits
-        cp.n_hi = ps.tile_bits - ps.low_bits
-        for j, p in enumerate(ps.hi_pos):
-            cp.hi_pos[j] = p
-        cp.rank_bits = self.rank_bits
+        cp = self._cpass(ps)
         if n_ops < 0:       # register-resident round program (host image, passed to the kernel by value)
             prog = maxk[0]
             cp.max_dense_k = 1

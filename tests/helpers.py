@@ -348,3 +348,58 @@ def emulate_sharded(ops, psi, n, g, tile_bits=None, low_bits=None):
             batch.append(op)
     flush()
     return shards.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# pass-specialised kernels (csrc/qsv_jit.cu): the generated source is also valid C++; with
+# -DQSV_JIT_HOST its round functions are driven sequentially over the thread ids, so the generator is
+# checked against emulate_round_program in a container without a GPU.
+# ------------------------------------------------------------------------------------------------
+
+def jit_cpass(ps, rank_bits=0):
+    from qsv import _cabi
+    cp = _cabi.QsvPass()
+    cp.n_local, cp.tile_bits, cp.low_bits = ps.n_local, ps.tile_bits, ps.low_bits
+    cp.n_hi = ps.tile_bits - ps.low_bits
+    for j, p in enumerate(ps.hi_pos):
+        cp.hi_pos[j] = p
+    cp.rank_bits = rank_bits
+    cp.reserved = 4
+    return cp
+
+
+def jit_source(ps, prog):
+    import ctypes as C
+    from qsv import _cabi
+    lib = _cabi.load()
+    cp = jit_cpass(ps)
+    need = C.c_size_t(0)
+    _cabi.check(lib.qsv_jit_source(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), None, 0, C.byref(need)),
+                "qsv_jit_source")
+    buf = C.create_string_buffer(need.value)
+    _cabi.check(lib.qsv_jit_source(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), buf, need.value,
+                                   C.byref(need)), "qsv_jit_source")
+    return buf.raw.decode()
+
+
+def jit_host_run(ps, prog, tables, psi, rank_bits, workdir):
+    """Compile the generated source of one pass as host C++ and run it on psi (numpy complex128)."""
+    import ctypes as C
+    import hashlib
+    import os
+    import subprocess
+    src = jit_source(ps, prog)
+    tag = hashlib.sha1(src.encode()).hexdigest()[:16]
+    cu, so = os.path.join(workdir, tag + ".cu"), os.path.join(workdir, tag + ".so")
+    if not os.path.exists(so):
+        with open(cu, "w") as f:
+            f.write(src)
+        r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DQSV_JIT_HOST", "-x", "c++", cu,
+                            "-o", so], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[:4000]
+    h = C.CDLL(so)
+    out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    tabs = np.frombuffer(bytes(tables) + b"\0" * 16, dtype=np.uint8).copy()
+    h.qsv_jit_host_run(C.c_void_p(out.ctypes.data), C.c_uint64(rank_bits), C.c_uint64(1 << (ps.n_local - ps.tile_bits)),
+                       C.c_void_p(tabs.ctypes.data))
+    return out

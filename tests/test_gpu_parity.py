@@ -357,3 +357,80 @@ def test_22q_layered_circuit_against_oracle(qsv_gpu):
     for M, wires, _ in so.random_layered_steps(n, 2, seed=5):
         ref = so.apply_gate(ref, n, wires, M)
     assert np.max(np.abs(sv.amplitudes() - ref)) <= TOL
+
+
+# ---- pass-specialised kernels (csrc/qsv_jit.cu): forced on at sizes the oracle can follow ---------
+
+def _jit_counts(lib):
+    n_c, n_h, secs = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+    lib.qsv_jit_stats(C.byref(n_c), C.byref(n_h), C.byref(secs))
+    return int(n_c.value), int(n_h.value)
+
+
+@pytest.mark.parametrize("workload", ["layered16", "qft15", "layered22"])
+def test_specialised_kernels_match_oracle_and_interpreter(qsv_gpu, monkeypatch, workload):
+    lib, engine, lowering, torch = qsv_gpu
+    from qsv import workloads
+    if workload == "qft15":
+        n = 15
+        c = workloads.qft_ladder_circuit(n)
+        in_v = [(i + 1) % 2 for i in range(n)]
+        steps = None
+    else:
+        n = int(workload[7:])
+        depth = 6 if n == 16 else 2
+        c = workloads.random_layered_circuit(n, depth, seed=21)
+        in_v = [0] * n
+        steps = so.random_layered_steps(n, depth, seed=21)
+    c.sort()
+    ops, src_pos = lowering.lower(c)
+    idx = lowering.basis_index(in_v)
+    out = {}
+    for mode in ("0", "force"):
+        monkeypatch.setenv("QSV_JIT", mode)
+        before = _jit_counts(lib)
+        sv = engine.StateVector(n)
+        sv.init_basis(idx)
+        sv.run_ops(ops)
+        out[mode] = sv.amplitudes()
+        after = _jit_counts(lib)
+        if mode == "force":
+            assert after[0] + after[1] > before[0] + before[1], "the specialised path did not run"
+        else:
+            assert after == before
+    assert np.max(np.abs(out["force"] - out["0"])) <= 1e-13
+    if steps is not None:
+        ref = so.initial_state(in_v)
+        for M, wires, _ in steps:
+            ref = so.apply_gate(ref, n, wires, M)
+        assert np.max(np.abs(out["force"] - ref)) <= TOL
+    else:
+        # QFT of a basis state: every outcome has probability 2^-n (the interpreter comparison above
+        # pins the phases)
+        w = np.abs(out["force"]) ** 2
+        assert np.max(np.abs(w - 2.0 ** -n)) <= TOL
+
+
+def test_specialised_kernels_external_conditions(qsv_gpu, monkeypatch):
+    """A shard of a larger register: controls and diagonal factors above n_local come from rank_bits."""
+    lib, engine, lowering, torch = qsv_gpu
+    from qsv.schedule import Op
+    from helpers import emulate_ops
+    n_local = 14
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    ph = complex(math.cos(0.3), math.sin(0.3))
+    ops = [Op("dense", (3,), (), matrix=H), Op("mcx", (2,), (15,)), Op("phase", (), (14, 3), scalar=ph),
+           Op("phase", (), (15, 12), scalar=-1.0 + 0j), Op("dense", (11,), (), matrix=H), Op("mcx", (7,), (11, 14)),
+           Op("phase", (), (14,), scalar=ph), Op("dense", (0,), (14,), matrix=H), Op("mcx", (13,), (1,)),
+           Op("diag", (2, 14, 9), (), matrix=np.exp(1j * np.arange(8)))]
+    monkeypatch.setenv("QSV_JIT", "force")
+    rng = np.random.default_rng(4)
+    psi = rng.standard_normal(1 << n_local) + 1j * rng.standard_normal(1 << n_local)
+    psi /= np.linalg.norm(psi)
+    for rank in range(4):
+        sv = engine.StateVector(n_local)
+        sv.rank = rank              # pretend to be shard `rank` of a 16-qubit register
+        sv.state.copy_(torch.from_numpy(psi).to(sv.device))
+        sv.run_ops(ops)
+        ref = emulate_ops(ops, psi, n_local, rank_bits=rank << n_local)
+        assert np.max(np.abs(sv.amplitudes() - ref)) <= 1e-13

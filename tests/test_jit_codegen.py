@@ -1,0 +1,160 @@
+"""The pass-specialised kernel generator (csrc/qsv_jit.cu) without a GPU: its output is compiled as host
+C++ (-DQSV_JIT_HOST) and must reproduce the numpy emulation of the interpreting kernel on the same packed
+round programs; NVRTC must accept the same source for sm_100a."""
+import ctypes as C
+import math
+import random
+
+import numpy as np
+import pytest
+
+from helpers import emulate_round_program, jit_cpass, jit_host_run, jit_source
+
+TOL = 1e-14      # same arithmetic up to FMA contraction and the deferred 2^-1/2 factors
+
+
+def _rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return psi / np.linalg.norm(psi)
+
+
+def _round_programs(ops, n_local):
+    from qsv import schedule
+    packed = schedule.pack_passes(schedule.plan_passes(ops, n_local, 12, 6))
+    blob = packed.blob.tobytes()
+    return [(ps, extra[0], blob[off:]) for ps, off, n_ops, extra in packed.passes if n_ops < 0]
+
+
+def _check(ops, n_local, tmp_path, rank_bits=0, seed=1):
+    progs = _round_programs(ops, n_local)
+    assert progs, "expected at least one register-resident pass"
+    psi = _rand_state(n_local, seed)
+    stats = {"general": 0, "rounds": 0}
+    for ps, prog, tables in progs:
+        ref = emulate_round_program(prog, tables, ps, psi, rank_bits)
+        got = jit_host_run(ps, prog, tables, psi, rank_bits, str(tmp_path))
+        assert np.max(np.abs(got - ref)) <= TOL
+        from qsv.schedule import ROUND_DTYPE
+        nr = int(np.frombuffer(bytes(prog), dtype="<u4", count=1)[0])
+        rounds = np.frombuffer(bytes(prog), dtype=ROUND_DTYPE, count=nr, offset=16)
+        stats["rounds"] += nr
+        stats["general"] += sum(1 for R in rounds if (int(R["n_pre"]) | int(R["n_post"])) & 0x8000)
+        psi = ref
+    return stats
+
+
+def test_layered_circuit_matches_interpreter_emulation(tmp_path):
+    from qsv import workloads, lowering
+    n = 14
+    c = workloads.random_layered_circuit(n, 6, seed=3)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    st = _check(ops, n, tmp_path)
+    assert st["rounds"] >= 4
+
+
+def test_qft_ladder_controlled_phases(tmp_path):
+    from qsv import workloads, lowering
+    n = 13
+    c = workloads.qft_ladder_circuit(n)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    _check(ops, n, tmp_path, seed=2)
+
+
+def test_toffoli_heavy_circuit_general_permutations(tmp_path):
+    """Toffoli / CNot chains whose conditions read several register-dependent bits leave the XOR-linear
+    address form: the generator must emit the per-slot general form for those lists."""
+    from qsv.schedule import Op
+    n = 13
+    rng = random.Random(7)
+    ops = []
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    Y = np.array([[0, -1j], [1j, 0]], dtype=np.complex128)
+    S = np.array([[0.5 + 0.5j, 0.5 - 0.5j], [0.5 - 0.5j, 0.5 + 0.5j]], dtype=np.complex128)
+    for _ in range(60):
+        r = rng.randrange(6)
+        a, b, c = rng.sample(range(n), 3)
+        if r == 0:
+            ops.append(Op("mcx", (a,), (b, c)))
+        elif r == 1:
+            ops.append(Op("mcx", (a,), (b,), cvals=(rng.randrange(2),)))
+        elif r == 2:
+            ops.append(Op("dense", (a,), (), matrix=rng.choice([H, Y, S])))
+        elif r == 3:
+            ops.append(Op("phase", (), (a, b), cvals=(1, rng.randrange(2)), scalar=complex(math.cos(1.1), math.sin(1.1))))
+        elif r == 4:
+            ops.append(Op("phase", (), (a,), scalar=-1.0 + 0j))
+        else:
+            ops.append(Op("dense", (a,), (b,), matrix=H))
+    st = _check(ops, n, tmp_path, seed=5)
+    assert st["general"] >= 1, "the circuit was meant to exercise the general permutation form"
+
+
+def test_external_conditions_read_rank_bits(tmp_path):
+    """Controls / diagonal factors on positions outside the shard (multi-GPU) come from rank_bits."""
+    from qsv.schedule import Op
+    n_local = 13
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    ph = complex(math.cos(0.3), math.sin(0.3))
+    ops = [Op("dense", (3,), (), matrix=H), Op("mcx", (2,), (14,)), Op("phase", (), (13, 3), scalar=ph),
+           Op("phase", (), (14, 12), scalar=-1.0 + 0j), Op("dense", (11,), (), matrix=H), Op("mcx", (7,), (11, 13)),
+           Op("phase", (), (13,), scalar=ph), Op("dense", (0,), (13,), matrix=H),
+           Op("diag", (2, 13, 9), (), matrix=np.exp(1j * np.arange(8)))]
+    for rank in range(4):
+        _check(ops, n_local, tmp_path, rank_bits=rank << n_local, seed=rank)
+
+
+def test_pass_whose_ops_are_all_conditional_skips_tiles(tmp_path):
+    from qsv.schedule import Op
+    n_local = 14
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    ops = [Op("dense", (1,), (13,), matrix=H), Op("mcx", (2,), (13,)), Op("phase", (), (13, 4), scalar=1j),
+           Op("dense", (5,), (13,), matrix=H)]
+    _check(ops, n_local, tmp_path)
+
+
+def test_nvrtc_accepts_generated_source_for_sm100a():
+    from qsv import _cabi, workloads, lowering
+    lib = _cabi.load()
+    n = 14
+    c = workloads.random_layered_circuit(n, 3, seed=9)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    ps, prog, _ = _round_programs(ops, n)[0]
+    src = jit_source(ps, prog)
+    assert "qsv_jit_pass" in src and "cp.async.bulk" in src
+    cp = jit_cpass(ps)
+    need = C.c_size_t(0)
+    rc = lib.qsv_jit_compile(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), None, 0, C.byref(need))
+    if rc != 0 and b"cannot load libnvrtc" in lib.qsv_last_error():
+        pytest.skip("NVRTC is not installed here")
+    assert rc == 0, lib.qsv_last_error()
+    cubin = C.create_string_buffer(need.value)
+    assert lib.qsv_jit_compile(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), cubin, need.value,
+                               C.byref(need)) == 0
+    assert cubin.raw[:4] == b"\x7fELF"
+    n_c, n_h, secs = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+    lib.qsv_jit_stats(C.byref(n_c), C.byref(n_h), C.byref(secs))
+    assert n_c.value >= 1 and n_h.value >= 1 and secs.value > 0
+
+
+def test_policy_small_states_stay_on_the_interpreter(monkeypatch):
+    from qsv import _cabi, workloads, lowering
+    lib = _cabi.load()
+    c = workloads.random_layered_circuit(14, 2, seed=9)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    ps, prog, _ = _round_programs(ops, 14)[0]
+    cp = jit_cpass(ps)
+    args = (C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size))
+    monkeypatch.delenv("QSV_JIT", raising=False)
+    assert lib.qsv_jit_wanted(*args) == 0
+    cp.n_local = 30
+    assert lib.qsv_jit_wanted(*args) == 1
+    monkeypatch.setenv("QSV_JIT", "0")
+    assert lib.qsv_jit_wanted(*args) == 0
+    cp.n_local = 14
+    monkeypatch.setenv("QSV_JIT", "force")
+    assert lib.qsv_jit_wanted(*args) == 1
