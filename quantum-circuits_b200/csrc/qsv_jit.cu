@@ -557,43 +557,39 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("    __syncthreads();");
     for (uint32_t k = 0; k < hdr->n_rounds; ++k)
         if (info[k].hoisted_S) o.f("    const double2 S%u = qsv_S%u(tid);", k, k);
-    // run r of the tile: 2^L amplitudes at state[base + offset(r)], offset = bits of r scattered to hi_pos
+    // run r of the tile: 2^L amplitudes at state[base + s_off[r]], s_off[r] = bits of r scattered to hi_pos.
+    // The offsets are read from a shared-memory table like in k_pass_reg.  (Literal 64-bit offsets in an
+    // unrolled issue sequence made ptxas 12.9 schedule a register copy AFTER its use across the ELECT
+    // waterfall loops of UBLKCP - the first tile of a CTA then copied from a garbage address whenever an
+    // offset needed a carry into the high word, i.e. tile bits at positions >= 28.)
     const int n_runs = 1 << n_hi;
-    const int lowb = n_hi < 3 ? n_hi : 3;         // run-index bits supplied by the warp id
-    o.f("    const u32 warp = tid >> 5;");
+    o.f("    __shared__ u64 s_off[%d];", n_runs);
+    o.f("    if (tid < %du) {", n_runs);
     {
         std::string e = "0ULL";
-        for (int j = 0; j < lowb; ++j)
-            e += " | ((u64)((warp >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
-        o.f("    const u64 off_w = %s;", e.c_str());
+        for (int j = 0; j < n_hi; ++j)
+            e += " | ((u64)((tid >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
+        o.f("        s_off[tid] = %s;", e.c_str());
     }
-    o.f("    const bool issuer = (tid & 31u) == 0u && warp < %du;", n_runs < 8 ? n_runs : 8);
+    o.f("    }");
+    o.f("    __syncthreads();");
+    o.f("    const u32 warp = tid >> 5;");
+    o.f("    const bool issuer = (tid & 31u) == 0u;");
     o.f("    u32 parity = 0;");
     o.f("    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {");
     o.s += tb.s;
     o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
-    o.f("        if (issuer) {");
-    const int per_warp = n_runs < 8 ? 1 : n_runs / 8;
-    for (int i = 0; i < per_warp; ++i) {
-        uint64_t off = 0;
-        for (int j = 3; j < n_hi; ++j) if ((i >> (j - 3)) & 1) off |= 1ull << P.hi_pos[j];
-        o.f("            bulk_g2s(tile + ((warp + %du) << %d), state + base + off_w + 0x%llxULL, %uu, &mbar);", 8 * i, L,
-            (unsigned long long)off, 16u << L);
-    }
-    o.f("        }");
+    o.f("        if (issuer)");
+    o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
+    o.f("                bulk_g2s(tile + ((u64)r << %d), state + base + s_off[r], %uu, &mbar);", L, 16u << L);
     o.f("        mbar_wait(&mbar, parity);");
     o.f("        parity ^= 1u;");
     rounds_body(o, "tile", "", "", false);
     o.f("        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
     o.f("        __syncthreads();");
-    o.f("        if (issuer) {");
-    for (int i = 0; i < per_warp; ++i) {
-        uint64_t off = 0;
-        for (int j = 3; j < n_hi; ++j) if ((i >> (j - 3)) & 1) off |= 1ull << P.hi_pos[j];
-        o.f("            bulk_s2g(state + base + off_w + 0x%llxULL, tile + ((warp + %du) << %d), %uu);",
-            (unsigned long long)off, 8 * i, L, 16u << L);
-    }
-    o.f("        }");
+    o.f("        if (issuer)");
+    o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
+    o.f("                bulk_s2g(state + base + s_off[r], tile + ((u64)r << %d), %uu);", L, 16u << L);
     o.f("        asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");");
     o.f("        asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");");
     o.f("    }");
@@ -625,6 +621,15 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("            memcpy(state + base + off, fin + ((u64)r << %d), %uu);", L, 16u << L);
     o.f("        }");
     o.f("    }");
+    o.f("}");
+    // one tile with a caller-chosen global base index (programs of states too large for a host array)
+    o.f("extern \"C\" void qsv_jit_host_tile(double2 *tile, const u64 gbase, const double2 *tables) {");
+    o.f("    static double2 A[4096], B[4096];");
+    o.f("    memcpy(A, tile, sizeof(A));");
+    o.f("    {");
+    rounds_body(o, "", "A", "B", true);
+    o.f("    }");
+    o.f("    memcpy(tile, %s, sizeof(A));", (hdr->n_rounds & 1) ? "B" : "A");
     o.f("}");
     o.f("#endif");
     src.swap(o.s);

@@ -143,8 +143,9 @@ def emulate_program(packed, psi, rank_bits=0):
     return psi
 
 
-def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
-    """numpy emulation of k_pass_reg (csrc/qsv_tile_reg.cu) on the host round program."""
+def emulate_round_program(prog, tables, ps, psi, rank_bits=0, single_tile_gbase=None):
+    """numpy emulation of k_pass_reg (csrc/qsv_tile_reg.cu) on the host round program.  With
+    single_tile_gbase, psi is ONE tile (2^T amplitudes) whose global base index is that value."""
     from qsv.schedule import ROP_DTYPE, ROUND_DTYPE
     prog = bytes(prog)
     n_rounds, total, n_ops, RB = (int(v) for v in np.frombuffer(prog, dtype="<u4", count=4))
@@ -200,14 +201,20 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
             a.append(a[r & (r - 1)] ^ d[low])
         return np.stack(a)
 
-    for t in range(1 << (ps.n_local - T)):
-        base = t << L
-        for p in hi:
-            base = _insert_zero(base, p)
-        gbase = base | rank_bits
+    def tiles():
+        if single_tile_gbase is not None:
+            yield None, single_tile_gbase
+            return
+        for t in range(1 << (ps.n_local - T)):
+            base = t << L
+            for p in hi:
+                base = _insert_zero(base, p)
+            yield base, base | rank_bits
+
+    for base, gbase in tiles():
         if not any((gbase & int(o["ext_mask"])) == int(o["ext_val"]) for o in rops):
             continue
-        tile = psi[base + gl_off].copy()
+        tile = psi.copy() if base is None else psi[base + gl_off].copy()
         for R in rounds:
             rb = [int(b) for b in R["rb"]][:RB]
             assert rb == sorted(rb) and len(set(rb)) == RB
@@ -274,6 +281,8 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0):
             assert np.unique(dst).size == dst.size, "store addresses must be a permutation of the tile"
             new_tile[dst] = x
             tile = new_tile
+        if base is None:
+            return tile
         psi[base + gl_off] = tile
     return psi
 
@@ -382,8 +391,9 @@ def jit_source(ps, prog):
     return buf.raw.decode()
 
 
-def jit_host_run(ps, prog, tables, psi, rank_bits, workdir):
-    """Compile the generated source of one pass as host C++ and run it on psi (numpy complex128)."""
+def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=None):
+    """Compile the generated source of one pass as host C++ and run it on psi (numpy complex128).  With
+    single_tile_gbase, psi is one tile and only the rounds run (state sizes no host array can hold)."""
     import ctypes as C
     import hashlib
     import os
@@ -400,6 +410,9 @@ def jit_host_run(ps, prog, tables, psi, rank_bits, workdir):
     h = C.CDLL(so)
     out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
     tabs = np.frombuffer(bytes(tables) + b"\0" * 16, dtype=np.uint8).copy()
+    if single_tile_gbase is not None:
+        h.qsv_jit_host_tile(C.c_void_p(out.ctypes.data), C.c_uint64(single_tile_gbase), C.c_void_p(tabs.ctypes.data))
+        return out
     h.qsv_jit_host_run(C.c_void_p(out.ctypes.data), C.c_uint64(rank_bits), C.c_uint64(1 << (ps.n_local - ps.tile_bits)),
                        C.c_void_p(tabs.ctypes.data))
     return out

@@ -434,3 +434,31 @@ def test_specialised_kernels_external_conditions(qsv_gpu, monkeypatch):
         sv.run_ops(ops)
         ref = emulate_ops(ops, psi, n_local, rank_bits=rank << n_local)
         assert np.max(np.abs(sv.amplitudes() - ref)) <= 1e-13
+
+
+def test_specialised_kernels_full_size_against_interpreter(qsv_gpu, monkeypatch):
+    """30 qubits (tile bits up to position 29, 2^18 tiles): the specialised kernels and the interpreting
+    kernel must produce the same 17 GB state (the oracle cannot follow at this size)."""
+    lib, engine, lowering, torch = qsv_gpu
+    from qsv import workloads
+    n = 30
+    c = workloads.random_layered_circuit(n, 3, seed=77)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    monkeypatch.setenv("QSV_JIT", "0")
+    sv = engine.StateVector(n)
+    sv.init_basis(5)
+    sv.run_ops(ops)
+    sv.synchronize()
+    ref = sv.state.clone()
+    monkeypatch.setenv("QSV_JIT", "force")
+    before = _jit_counts(lib)
+    sv.init_basis(5)
+    sv.run_ops(ops)
+    sv.synchronize()
+    after = _jit_counts(lib)
+    assert after[0] + after[1] > before[0] + before[1]
+    d = torch.view_as_real(sv.state) - torch.view_as_real(ref)
+    assert float(d.abs().max()) <= 1e-13
+    del d, ref
+    assert abs(float(sv.block_sums(None, 12).sum()) - 1.0) < 1e-10
