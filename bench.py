@@ -226,17 +226,15 @@ def main():
                    % (n - 1, args.iterations))
     circ.sort()
     n_gates = len(circ.gates)
-    if comm is None:
-        ops, src_pos = lowering.lower(circ)
-    else:
-        ops, src_pos = lowering.lower(circ, n_global=g)
+    # uncontrolled X gates are pushed back to the input by the lowering: they become `flip` of the start index
+    ops, src_pos, flip = lowering.lower(circ, n_global=g if comm is not None else 0, in_flip=True)
     t_host = time.perf_counter() - t_host0
 
     sv = engine.StateVector(n, comm=comm)
     t_prep0 = time.perf_counter()
     plan = sv.prepare(ops)          # pass planning, packing, H2D, and (large states) kernel specialisation
     t_prepare = time.perf_counter() - t_prep0
-    in_index = lowering.basis_index(in_bits)
+    in_index = lowering.basis_index(in_bits) ^ flip
 
     def step(u=0.37):
         sv.init_basis(in_index)
@@ -335,6 +333,7 @@ def main():
                 "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launch_groups"]),
                 "share_of_step": d["ms"] / ms_per_step if ms_per_step else None,
                 "gates_per_launch": d["ops"] / max(1, d["launch_groups"]),
+                "per_launch": [[round(t["ms"], 3), t["ops"]] for t in timed if t["kind"] == dom][:64],
                 "other_kernels": {k: {"ms_per_step": v["ms"], "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else 0.0}
                                   for k, v in by_kind.items() if k != dom}}
 

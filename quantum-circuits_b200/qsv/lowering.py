@@ -118,11 +118,15 @@ def lower_gate(gate, wires, layout, transposed=False):
     return classify_matrix(M, layout.positions(wires), name)
 
 
-def lower(circuit, transposed=False, presorted=True, n_global=0):
+def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False):
     """(ops, src_pos): ops in application order; src_pos[b] = physical position feeding bit b of the
     OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map.  With
     n_global > 0 the ops are placed on a register sharded by its top n_global positions
-    (qsv.schedule.place inserts the global<->local qubit swaps)."""
+    (qsv.schedule.place inserts the global<->local qubit swaps).
+
+    Uncontrolled X gates are pushed back to the circuit input (qsv.schedule.propagate_x).  With
+    in_flip=True the result is (ops, src_pos, flip) and the caller starts from |index ^ flip>; otherwise
+    the leftover flips are kept as explicit X ops at the head of the list (any input state)."""
     n = len(circuit)
     gates = circuit.gates if presorted else topological_gates(circuit)
     table, out_qubits = gate_targets(circuit, gates)
@@ -135,12 +139,21 @@ def lower(circuit, transposed=False, presorted=True, n_global=0):
         src_pos[n - 1 - i] = layout.pos[out_qubits[i]]
     if sorted(src_pos) != list(range(n)):
         raise RuntimeError("circuit outputs do not carry every qubit exactly once")
+    flip = 0
+    if os.environ.get("QSV_PROPAGATE_X", "1") != "0":
+        from .schedule import propagate_x
+        ops, flip = propagate_x(ops)
+        if not in_flip:
+            ops = [Op("mcx", (b,), (), name="X") for b in range(n) if (flip >> b) & 1] + ops
+            flip = 0
     if os.environ.get("QSV_FUSE_1Q", "1") != "0":
         from .schedule import fuse_1q
         ops = fuse_1q(ops)
     if n_global:
         from .schedule import place
         ops, src_pos = place(ops, n, n_global, src_pos)
+    if in_flip:
+        return ops, src_pos, flip
     return ops, src_pos
 
 
@@ -160,9 +173,9 @@ def last_run_stats():
 
 
 def evolve(circuit, in_v, transposed=False, presorted=True, comm=None):
-    ops, src_pos = lower(circuit, transposed, presorted)
+    ops, src_pos, flip = lower(circuit, transposed, presorted, in_flip=True)
     sv = _engine.StateVector(len(circuit), comm=comm)
-    sv.init_basis(basis_index(in_v))
+    sv.init_basis(basis_index(in_v) ^ flip)
     plan = sv.run_ops(ops)
     _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=0, passes=sv.passes_run)
     return sv, src_pos
@@ -226,7 +239,7 @@ def circuit_unitary_rows(circuit):
     """Rows of the whole-circuit unitary (get_subcircuit, main/circuit.py:122-157)."""
     circuit.sort()
     n = len(circuit)
-    ops, src_pos = lower(circuit, False, True)
+    ops, src_pos, flip = lower(circuit, False, True, in_flip=True)
     dim = 1 << n
     z = np.arange(dim, dtype=np.int64)
     y = np.zeros_like(z)
@@ -236,7 +249,7 @@ def circuit_unitary_rows(circuit):
     sv = _engine.StateVector(n)
     handle = None
     for c in range(dim):
-        sv.init_basis(c)
+        sv.init_basis(c ^ flip)
         sv.run_ops(ops)
         cols.append(sv.amplitudes()[y])
     U = np.stack(cols, axis=1)

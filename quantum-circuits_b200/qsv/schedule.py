@@ -324,6 +324,93 @@ def fuse_1q(ops):
 
 
 # ------------------------------------------------------------------------------------------------
+# Pauli-X propagation: X gates never touch the state
+# ------------------------------------------------------------------------------------------------
+
+def _flip_cvals(op, pend):
+    """cvals of op's controls with the ones under a pending X inverted (X_c G X_c for a control c)."""
+    ctrls = tuple(op.controls)
+    cv = tuple(op.cvals) if op.cvals is not None else (1,) * len(ctrls)
+    return tuple(int(v) ^ ((pend >> c) & 1) for c, v in zip(ctrls, cv))
+
+
+def propagate_x(ops):
+    """Remove every uncontrolled X from the op list by pushing it BACKWARDS to the input, where it is a
+    flip of the basis-state index (free).  Returns (ops', in_flip): running ops' on |index ^ in_flip> equals
+    running ops on |index>.
+
+    Walking the list from the end with a mask of pending X (X's that act right AFTER the current op):
+      X                      toggles the mask
+      control / phase / diagonal use of a pending qubit   X_c G X_c = G with that control value inverted
+                             (diagonal tables are re-indexed); the X moves on
+      target of a (multi-)controlled X                    commutes
+      uncontrolled dense gate on pending targets          X.M is a row permutation of M: absorbed, X gone
+      controlled dense gate                               M -> X M X, the X moves on
+      swap                   the two mask bits trade places
+      oracle / diffusion     like a controlled X / invariant (X|s> = |s>)
+      anything else (modexp, wide gates, re-layouts)      the pending X's it touches are emitted as real ops
+    Exact 0/1 matrices stay exact, so permutation circuits remain bit-exact."""
+    import copy
+    pend = 0
+    rev = []
+
+    def emit_x(bits):
+        nonlocal pend
+        for b in bits:
+            if (pend >> b) & 1:
+                rev.append(Op("mcx", (b,), (), name="X"))
+                pend ^= 1 << b
+
+    for op in reversed(list(ops)):
+        k = op.kind
+        if k == "mcx" and not op.controls:
+            pend ^= 1 << op.targets[0]
+            continue
+        touched = set(op.targets) | set(op.controls)
+        if not any((pend >> b) & 1 for b in touched) and k != "global_swap":
+            rev.append(op)
+            continue
+        o = copy.copy(op)
+        if k in ("mcx", "oracle"):
+            o.cvals = _flip_cvals(op, pend)
+        elif k == "phase":
+            o.cvals = _flip_cvals(op, pend)
+        elif k == "diag":
+            kk = len(op.targets)
+            mm = 0
+            for p_, t in enumerate(op.targets):
+                if (pend >> t) & 1:
+                    mm |= 1 << (kk - 1 - p_)
+            d = np.asarray(op.matrix, dtype=np.complex128)
+            o.matrix = d[np.arange(1 << kk) ^ mm].copy()
+        elif k == "dense":
+            kk = len(op.targets)
+            mm = 0
+            for p_, t in enumerate(op.targets):
+                if (pend >> t) & 1:
+                    mm |= 1 << (kk - 1 - p_)
+            M = np.asarray(op.matrix, dtype=np.complex128)
+            idx = np.arange(1 << kk) ^ mm
+            if op.controls:
+                o.cvals = _flip_cvals(op, pend)
+                o.matrix = M[idx][:, idx].copy()             # X M X: the X keeps moving
+            else:
+                o.matrix = M[idx].copy()                     # X M: absorbed
+                for t in op.targets:
+                    pend &= ~(1 << t)
+        elif k == "swap":
+            a, b = op.targets
+            ba, bb = (pend >> a) & 1, (pend >> b) & 1
+            pend = (pend & ~((1 << a) | (1 << b))) | (bb << a) | (ba << b)
+        elif k == "diffusion":
+            pass
+        else:
+            emit_x(sorted(touched) if k != "global_swap" else [b for b in range(pend.bit_length())])
+        rev.append(o)
+    return rev[::-1], pend
+
+
+# ------------------------------------------------------------------------------------------------
 # placement on a sharded register: virtual positions -> physical positions, global<->local swaps
 # ------------------------------------------------------------------------------------------------
 

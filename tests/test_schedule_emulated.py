@@ -22,12 +22,46 @@ def _final_output_order(psi, src_pos):
 
 def _run_emulated(c, in_v, transposed=False, tile_bits=None, low_bits=None):
     c.sort()
-    ops, src_pos = lower(c, transposed, True)
+    ops, src_pos, flip = lower(c, transposed, True, in_flip=True)      # the engine's path (lowering.evolve)
     n = len(c)
     psi = np.zeros(1 << n, dtype=np.complex128)
-    psi[basis_index(in_v)] = 1
+    psi[basis_index(in_v) ^ flip] = 1
     psi = emulate_ops(ops, psi, n, tile_bits, low_bits)
     return _final_output_order(psi, src_pos), ops
+
+
+def test_x_propagation_leaves_no_plain_x_and_keeps_results(golden):
+    """Uncontrolled X gates are pushed back to the input (a flip of the basis index); without in_flip the
+    leftover flips stay as explicit ops at the head of the list.  Both forms must equal the unpropagated
+    circuit on every basis input."""
+    import os
+    from qsv.schedule import propagate_x
+    meta, cases, arrays = golden
+    for name in ("paper5", "builtin_mix", "random_seed3", "random_seed7", "layered_n6_d2"):
+        c = build_circuit(cases[name], arrays)
+        c.sort()
+        n = len(c)
+        os.environ["QSV_PROPAGATE_X"] = "0"
+        try:
+            plain, src0 = lower(c, False, True)
+        finally:
+            del os.environ["QSV_PROPAGATE_X"]
+        ops, src_pos, flip = lower(c, False, True, in_flip=True)
+        compat, src1 = lower(c, False, True)
+        assert src0 == src_pos == src1
+        assert not any(op.kind == "mcx" and not op.controls for op in ops)
+        again, flip2 = propagate_x(ops)
+        assert flip2 == 0 and len(again) == len(ops)
+        for idx in range(1 << n):
+            e = np.zeros(1 << n, dtype=np.complex128)
+            e[idx] = 1
+            ref = emulate_ops(plain, e, n)
+            f = np.zeros(1 << n, dtype=np.complex128)
+            f[idx ^ flip] = 1
+            assert np.max(np.abs(emulate_ops(ops, f, n) - ref)) <= 1e-14
+            assert np.max(np.abs(emulate_ops(compat, e, n) - ref)) <= 1e-14
+            if n > 5 and idx > 8:
+                break
 
 
 @pytest.mark.parametrize("name", [
