@@ -89,8 +89,10 @@ typedef struct qsv_pass {
  * BY VALUE (constant bank), so op fields and matrix entries are read through the uniform datapath.
  * Diagonal tables (rare) stay in a device buffer; qsv_rop_t.table_off is a byte offset into it. */
 
-#define QSV_RPROG_MAX_ROUNDS 32
+#define QSV_RPROG_MAX_ROUNDS 32      /* interpreting kernel: the program travels as a kernel parameter */
 #define QSV_RPROG_MAX_OPS    120
+#define QSV_JIT_MAX_ROUNDS   256     /* pass-specialised kernel: the program becomes code, not data      */
+#define QSV_JIT_MAX_OPS      2048
 /* kind byte of qsv_rop_t.  0..17 are contiguous (one jump table in the kernel). */
 #define QSV_ROP_DENSE1       0   /* +J      complex 1-qubit matrix on register bit J                    */
 #define QSV_ROP_DENSE1_REAL  4   /* +J      real matrix                                                 */

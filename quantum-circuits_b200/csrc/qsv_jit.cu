@@ -146,8 +146,7 @@ static std::string op_cond(const qsv_rop_t &op) {
 }
 
 struct RoundInfo {
-    bool hoisted_S = false;      // qsv_S<k>(tid) exists
-    bool any_S = false;          // the round applies a runtime thread scalar
+    int n_hoisted = 0;           // doubles in qsv_H<k> (0: the struct carries a dummy)
     bool barrier = false;        // loads and stores of the round must be separated by a barrier
 };
 
@@ -167,49 +166,108 @@ struct Pending {
     }
 };
 
-static void flush_pending(Out &o, Pending &pd, double &scale, bool with_S, bool fold_scale) {
-    // with_S: the runtime thread scalar (Sr, Si) is applied to every slot together with the constants.
-    // fold_scale: the deferred real factor of the butterflies is folded in too (it then resets to 1).
-    double g = 1.0;
-    if (fold_scale && scale != 1.0) { g = scale; scale = 1.0; }
-    if (!with_S) {
-        for (int r = 0; r < 16; ++r) {
-            Cx c = {pd.c[r].r * g, pd.c[r].i * g};
-            emit_cmul_const(o, r, c);
-        }
-        pd.reset();
-        return;
+// A per-thread runtime scalar of a round: the product of phase factors whose conditions read thread-held
+// or external bits.  Index 0 is S (multiplies every slot); the others belong to one register bit J, value V
+// and "window" (the stretch of the op list between two dense gates on J, inside which diagonals commute).
+struct Factor {
+    std::string tcond;           // condition on the thread index ("" = none)
+    uint64_t ext_mask = 0, ext_val = 0;
+    Cx s;
+};
+struct Scalar {
+    int J = -1, V = 0, window = 0;
+    std::vector<Factor> f;
+    int hoist_slot = -1;         // index into qsv_H<k>.v of the part that depends on the thread index only
+    bool applied = false;
+    std::string re() const { return "q" + std::to_string(id) + "r"; }
+    std::string im() const { return "q" + std::to_string(id) + "i"; }
+    int id = 0;
+};
+
+static void emit_scalar_mul(Out &o, const char *ind, const std::string &re, const std::string &im, const std::string &cond,
+                            Cx c) {
+    // (re, im) *= c under cond
+    std::string body;
+    char buf[512];
+    if (c.i == 0.0) {
+        snprintf(buf, sizeof(buf), "{ %s *= %s; %s *= %s; }", re.c_str(), dlit(c.r).c_str(), im.c_str(), dlit(c.r).c_str());
+    } else if (c.r == 0.0) {
+        snprintf(buf, sizeof(buf), "{ const double t = %s; %s = %s * %s; %s = %s * t; }", re.c_str(), re.c_str(),
+                 dlit(-c.i).c_str(), im.c_str(), im.c_str(), dlit(c.i).c_str());
+    } else {
+        snprintf(buf, sizeof(buf), "{ const double t = %s * %s - %s * %s; %s = %s * %s + %s * %s; %s = t; }", re.c_str(),
+                 dlit(c.r).c_str(), im.c_str(), dlit(c.i).c_str(), im.c_str(), re.c_str(), dlit(c.i).c_str(), im.c_str(),
+                 dlit(c.r).c_str(), re.c_str());
     }
-    // distinct constants -> one runtime multiplier each
-    std::vector<Cx> distinct;
-    int which[16];
+    if (cond.empty())
+        o.f("%s%s", ind, buf);
+    else
+        o.f("%sif (%s) %s", ind, cond.c_str(), buf);
+}
+
+// Multiply slots by (literal constant) x (product of runtime scalars).  Products are built once per distinct
+// combination, sharing prefixes (S, S.P0, S.P0.P1, ...), then applied with one complex multiply per slot.
+struct SlotMul {
+    Cx c = {1.0, 0.0};
+    std::vector<int> sc;         // runtime scalar ids, ascending
+};
+static void apply_multipliers(Out &o, const SlotMul (&m)[16], const std::vector<Scalar> &scalars, int &tmp_id) {
+    std::vector<std::pair<std::string, std::string>> cache;     // key -> variable stem
+    auto find = [&](const std::string &k) -> std::string {
+        for (auto &e : cache) if (e.first == k) return e.second;
+        return "";
+    };
     for (int r = 0; r < 16; ++r) {
-        Cx c = {pd.c[r].r * g, pd.c[r].i * g};
-        int k = -1;
-        for (size_t j = 0; j < distinct.size(); ++j) if (distinct[j] == c) k = (int)j;
-        if (k < 0) { distinct.push_back(c); k = (int)distinct.size() - 1; }
-        which[r] = k;
-    }
-    for (size_t j = 0; j < distinct.size(); ++j) {
-        const Cx c = distinct[j];
-        if (c.is_one()) {
-            o.f("    const double m%zur = Sr, m%zui = Si;", j, j);
-        } else if (c.i == 0.0) {
-            o.f("    const double m%zur = Sr * %s, m%zui = Si * %s;", j, dlit(c.r).c_str(), j, dlit(c.r).c_str());
-        } else if (c.r == 0.0) {
-            o.f("    const double m%zur = Si * %s, m%zui = Sr * %s;", j, dlit(-c.i).c_str(), j, dlit(c.i).c_str());
-        } else {
-            o.f("    const double m%zur = Sr * %s - Si * %s, m%zui = Sr * %s + Si * %s;", j, dlit(c.r).c_str(),
-                dlit(c.i).c_str(), j, dlit(c.i).c_str(), dlit(c.r).c_str());
+        if (m[r].sc.empty()) {
+            emit_cmul_const(o, r, m[r].c);
+            continue;
         }
+        // runtime product, prefix by prefix
+        std::string key, stem;
+        for (size_t i = 0; i < m[r].sc.size(); ++i) {
+            const Scalar &sc = scalars[m[r].sc[i]];
+            key += "s" + std::to_string(sc.id) + ".";
+            if (i == 0) {
+                stem = "q" + std::to_string(sc.id);
+                continue;
+            }
+            std::string have = find(key);
+            if (have.empty()) {
+                have = "w" + std::to_string(tmp_id++);
+                o.f("    const double %sr = %sr * %s - %si * %s, %si = %sr * %s + %si * %s;", have.c_str(), stem.c_str(),
+                    sc.re().c_str(), stem.c_str(), sc.im().c_str(), have.c_str(), stem.c_str(), sc.im().c_str(),
+                    stem.c_str(), sc.re().c_str());
+                cache.push_back({key, have});
+            }
+            stem = have;
+        }
+        const Cx c = m[r].c;
+        if (!c.is_one()) {
+            char kb[64];
+            uint64_t br, bi;
+            memcpy(&br, &c.r, 8);
+            memcpy(&bi, &c.i, 8);
+            snprintf(kb, sizeof(kb), "c%llx,%llx", (unsigned long long)br, (unsigned long long)bi);
+            key += kb;
+            std::string have = find(key);
+            if (have.empty()) {
+                have = "w" + std::to_string(tmp_id++);
+                if (c.i == 0.0)
+                    o.f("    const double %sr = %sr * %s, %si = %si * %s;", have.c_str(), stem.c_str(), dlit(c.r).c_str(),
+                        have.c_str(), stem.c_str(), dlit(c.r).c_str());
+                else if (c.r == 0.0)
+                    o.f("    const double %sr = %si * %s, %si = %sr * %s;", have.c_str(), stem.c_str(), dlit(-c.i).c_str(),
+                        have.c_str(), stem.c_str(), dlit(c.i).c_str());
+                else
+                    o.f("    const double %sr = %sr * %s - %si * %s, %si = %sr * %s + %si * %s;", have.c_str(), stem.c_str(),
+                        dlit(c.r).c_str(), stem.c_str(), dlit(c.i).c_str(), have.c_str(), stem.c_str(), dlit(c.i).c_str(),
+                        stem.c_str(), dlit(c.r).c_str());
+                cache.push_back({key, have});
+            }
+            stem = have;
+        }
+        emit_cmul_var(o, r, (stem + "r").c_str(), (stem + "i").c_str());
     }
-    for (int r = 0; r < 16; ++r) {
-        char mr[16], mi[16];
-        snprintf(mr, sizeof(mr), "m%dr", which[r]);
-        snprintf(mi, sizeof(mi), "m%di", which[r]);
-        emit_cmul_var(o, r, mr, mi);
-    }
-    pd.reset();
 }
 
 static void emit_tb(Out &o, const qsv_round_t &R) {
@@ -277,6 +335,26 @@ static bool butterfly(const double *m, double &h, int sg[4]) {
     return true;
 }
 
+static bool is_phase_kind(int kind) { return kind >= QSV_ROP_PHASE1 && kind <= QSV_ROP_GEN_PHASE; }
+static void phase_rmask(const qsv_rop_t &p, uint32_t &rmask, uint32_t &rval) {
+    rmask = p.rmask;
+    rval = p.rval;
+    if (p.kind != QSV_ROP_GEN_PHASE) {
+        const int J = (p.kind - QSV_ROP_PHASE1) >> 1, V = (p.kind - QSV_ROP_PHASE1) & 1;
+        rmask = 1u << J;
+        rval = (uint32_t)V << J;
+    }
+}
+// a conditional phase on ONE register bit whose factor is not -1 joins a runtime scalar (a conditional -1
+// is 16 integer sign flips under a branch: cheaper than any multiplication)
+static bool joins_scalar(const qsv_rop_t &p) {
+    if (!is_phase_kind(p.kind) || (p.tmask == 0 && p.ext_mask == 0)) return false;
+    uint32_t rmask, rval;
+    phase_rmask(p, rmask, rval);
+    if (rmask == 0 || (rmask & (rmask - 1))) return false;
+    return !(p.m[0] == -1.0 && p.m[1] == 0.0);
+}
+
 static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, RoundInfo &info, bool last_round,
                      double &scale, bool defer_scale, std::string &err) {
     const int n_pre = R.n_pre & 0x7fff, n_post = R.n_post & 0x7fff;
@@ -285,54 +363,147 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     const int f_pre = (int)R.first_op, f_pt = f_pre + n_pre, f_reg = f_pt + n_pt, f_post = f_reg + n_reg;
     info.barrier = (n_pre + n_post) > 0;
 
-    // ---- thread scalar, hoistable part: qsv_S<k>(tid)
-    int n_hoist = 0, n_ext_pt = 0;
-    for (int i = 0; i < n_pt; ++i) (ops[f_pt + i].ext_mask ? n_ext_pt : n_hoist)++;
-    info.hoisted_S = n_hoist > 0;
-    info.any_S = n_pt > 0;
-    if (info.hoisted_S) {
-        o.f("QSV_FN double2 qsv_S%d(const u32 tid) {", k);
-        emit_tb(o, R);
-        o.f("    double Sr = 1.0, Si = 0.0;");
+    // ---- runtime scalars of the round
+    std::vector<Scalar> scalars;
+    std::vector<int> op_scalar(n_reg, -1);
+    if (n_pt > 0) {
+        Scalar S;
         for (int i = 0; i < n_pt; ++i) {
             const qsv_rop_t &p = ops[f_pt + i];
-            if (p.ext_mask) continue;
-            const std::string c = p.tmask ? cond_thr(p.tmask, p.tval) : "true";
-            o.f("    if (%s) { const double t = Sr * %s - Si * %s; Si = Sr * %s + Si * %s; Sr = t; }", c.c_str(),
-                dlit(p.m[0]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[0]).c_str());
+            Factor f;
+            f.tcond = p.tmask ? cond_thr(p.tmask, p.tval) : "";
+            f.ext_mask = p.ext_mask;
+            f.ext_val = p.ext_val;
+            f.s = {p.m[0], p.m[1]};
+            S.f.push_back(f);
         }
-        o.f("    return make_double2(Sr, Si);");
-        o.f("}");
+        scalars.push_back(S);
     }
+    const bool have_S = n_pt > 0;
+    {
+        int window[4] = {0, 0, 0, 0};
+        for (int i = 0; i < n_reg; ++i) {
+            const qsv_rop_t &p = ops[f_reg + i];
+            if (p.kind >= QSV_ROP_DENSE1 && p.kind < QSV_ROP_PHASE1) {
+                window[p.kind & 3]++;
+                continue;
+            }
+            if (!joins_scalar(p)) continue;
+            uint32_t rmask, rval;
+            phase_rmask(p, rmask, rval);
+            const int J = __builtin_ctz(rmask), V = rval ? 1 : 0;
+            int found = -1;
+            for (size_t j = 0; j < scalars.size(); ++j)
+                if (scalars[j].J == J && scalars[j].V == V && scalars[j].window == window[J]) found = (int)j;
+            if (found < 0) {
+                Scalar sc;
+                sc.J = J;
+                sc.V = V;
+                sc.window = window[J];
+                scalars.push_back(sc);
+                found = (int)scalars.size() - 1;
+            }
+            Factor f;
+            f.tcond = p.tmask ? cond_thr(p.tmask, p.tval) : "";
+            f.ext_mask = p.ext_mask;
+            f.ext_val = p.ext_val;
+            f.s = {p.m[0], p.m[1]};
+            scalars[found].f.push_back(f);
+            op_scalar[i] = found;
+        }
+    }
+    int n_hoist = 0;
+    for (size_t j = 0; j < scalars.size(); ++j) {
+        scalars[j].id = (int)j;
+        bool any = false;
+        for (const Factor &f : scalars[j].f) any = any || f.ext_mask == 0;
+        if (any) { scalars[j].hoist_slot = n_hoist; n_hoist += 2; }
+    }
+    info.n_hoisted = n_hoist;
 
-    o.f("QSV_FN void qsv_round%d(const double2 *tin, double2 *tout, const u32 tid, const u64 gbase, const double S0r,"
-        " const double S0i, const double2 *tables) {", k);
+    // ---- the part of the scalars that depends on the thread index only: once per CTA, not once per tile
+    o.f("struct qsv_H%d { double v[%d]; };", k, n_hoist ? n_hoist : 1);
+    o.f("QSV_FN qsv_H%d qsv_hoist%d(const u32 tid) {", k, k);
+    o.f("    qsv_H%d H;", k);
+    if (n_hoist) {
+        emit_tb(o, R);
+        for (const Scalar &sc : scalars) {
+            if (sc.hoist_slot < 0) continue;
+            o.f("    double %s = 1.0, %s = 0.0;", sc.re().c_str(), sc.im().c_str());
+            for (const Factor &f : sc.f)
+                if (f.ext_mask == 0) emit_scalar_mul(o, "    ", sc.re(), sc.im(), f.tcond, f.s);
+            o.f("    H.v[%d] = %s; H.v[%d] = %s;", sc.hoist_slot, sc.re().c_str(), sc.hoist_slot + 1, sc.im().c_str());
+        }
+    } else {
+        o.f("    H.v[0] = 0.0; (void)tid;");
+    }
+    o.f("    return H;");
+    o.f("}");
+
+    o.f("QSV_FN void qsv_round%d(const double2 *tin, double2 *tout, const u32 tid, const u64 gbase, const qsv_H%d &H,"
+        " const double2 *tables) {", k, k);
     emit_tb(o, R);
     emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
     o.f("    double x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i, x4r, x4i, x5r, x5i, x6r, x6i, x7r, x7i;");
     o.f("    double x8r, x8i, x9r, x9i, x10r, x10i, x11r, x11i, x12r, x12i, x13r, x13i, x14r, x14i, x15r, x15i;");
     for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[a%d]; x%dr = v.x; x%di = v.y; }", r, r, r);
+    o.f("    (void)H; (void)tables; (void)gbase;");
 
-    if (info.any_S) {
-        o.f("    double Sr = S0r, Si = S0i;");
-        for (int i = 0; i < n_pt; ++i) {
-            const qsv_rop_t &p = ops[f_pt + i];
-            if (!p.ext_mask) continue;
-            std::string c = cond_ext(p.ext_mask, p.ext_val);
-            if (p.tmask) c += " && " + cond_thr(p.tmask, p.tval);
-            o.f("    if (%s) { const double t = Sr * %s - Si * %s; Si = Sr * %s + Si * %s; Sr = t; }", c.c_str(),
-                dlit(p.m[0]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[1]).c_str(), dlit(p.m[0]).c_str());
+    // runtime scalars: hoisted part x the factors that read external bits (uniform per tile)
+    for (const Scalar &sc : scalars) {
+        if (sc.hoist_slot >= 0)
+            o.f("    double %s = H.v[%d], %s = H.v[%d];", sc.re().c_str(), sc.hoist_slot, sc.im().c_str(), sc.hoist_slot + 1);
+        else
+            o.f("    double %s = 1.0, %s = 0.0;", sc.re().c_str(), sc.im().c_str());
+        for (const Factor &f : sc.f) {
+            if (f.ext_mask == 0) continue;
+            std::string c = cond_ext(f.ext_mask, f.ext_val);
+            if (!f.tcond.empty()) c += " && " + f.tcond;
+            emit_scalar_mul(o, "    ", sc.re(), sc.im(), c, f.s);
         }
     }
 
     Pending pd;
+    int tmp_id = 0;
+    int window[4] = {0, 0, 0, 0};
+    // flush: constants (all of them) and the runtime scalars of register bit J's current window
+    // (J < 0: everything that is left, S included, and the deferred butterfly factor in the last round)
+    auto flush = [&](int J) {
+        SlotMul m[16];
+        bool any = false;
+        const bool final_flush = J < 0;
+        double g = 1.0;
+        if (final_flush && last_round && scale != 1.0) { g = scale; scale = 1.0; }
+        if (final_flush || pd.depends_on(J)) {
+            for (int r = 0; r < 16; ++r) {
+                m[r].c = {pd.c[r].r * g, pd.c[r].i * g};
+                any = any || !m[r].c.is_one();
+            }
+            pd.reset();
+        }
+        for (Scalar &sc : scalars) {
+            if (sc.applied) continue;
+            if (sc.J < 0) {
+                if (!final_flush) continue;
+                for (int r = 0; r < 16; ++r) m[r].sc.push_back(sc.id);
+            } else {
+                if (!final_flush && !(sc.J == J && sc.window == window[J])) continue;
+                for (int r = 0; r < 16; ++r) if (((r >> sc.J) & 1) == sc.V) m[r].sc.push_back(sc.id);
+            }
+            sc.applied = true;
+            any = true;
+        }
+        if (any) apply_multipliers(o, m, scalars, tmp_id);
+    };
+
     for (int i = 0; i < n_reg; ++i) {
         const qsv_rop_t &p = ops[f_reg + i];
         const std::string cnd = op_cond(p);
         const int kind = p.kind;
         if (kind >= QSV_ROP_DENSE1 && kind < QSV_ROP_PHASE1) {
             const int J = kind & 3;
-            if (pd.depends_on(J)) flush_pending(o, pd, scale, false, false);
+            flush(J);
+            window[J]++;
             double h;
             int sg[4];
             const bool bf = butterfly(p.m, h, sg);
@@ -371,13 +542,10 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             }
             if (!cnd.empty()) o.f("    }");
             if (defer) scale *= h;
-        } else if ((kind >= QSV_ROP_PHASE1 && kind < QSV_ROP_GEN_PHASE) || kind == QSV_ROP_GEN_PHASE) {
-            uint32_t rmask = p.rmask, rval = p.rval;
-            if (kind != QSV_ROP_GEN_PHASE) {
-                const int J = (kind - QSV_ROP_PHASE1) >> 1, V = (kind - QSV_ROP_PHASE1) & 1;
-                rmask = 1u << J;
-                rval = (uint32_t)V << J;
-            }
+        } else if (is_phase_kind(kind)) {
+            if (op_scalar[i] >= 0) continue;          // part of a runtime scalar, applied at its flush
+            uint32_t rmask, rval;
+            phase_rmask(p, rmask, rval);
             const Cx s = {p.m[0], p.m[1]};
             if (cnd.empty()) {
                 for (int r = 0; r < 16; ++r) if (((uint32_t)r & rmask) == rval) pd.c[r] = cx_mul(pd.c[r], s);
@@ -392,12 +560,12 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             o.f("    { u32 di = 0u;");
             const int kk = (int)p.k;
             for (int q = 0; q < kk; ++q) {
-                const uint32_t s = p.dsrc[q];
-                if (s == 0xffu) continue;
-                if (s & 0x80u)
-                    o.f("      di |= (u32)((gbase >> %u) & 1ULL) << %d;", s & 0x7fu, kk - 1 - q);
+                const uint32_t sb = p.dsrc[q];
+                if (sb == 0xffu) continue;
+                if (sb & 0x80u)
+                    o.f("      di |= (u32)((gbase >> %u) & 1ULL) << %d;", sb & 0x7fu, kk - 1 - q);
                 else
-                    o.f("      di |= ((tb >> %u) & 1u) << %d;", s, kk - 1 - q);
+                    o.f("      di |= ((tb >> %u) & 1u) << %d;", sb, kk - 1 - q);
             }
             o.f("      const double2 *tab = tables + %u;", p.table_off / 16u);
             for (int r = 0; r < 16; ++r) {
@@ -415,14 +583,8 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             return 1;
         }
     }
-    // end of round: constants, thread scalar and (in the last round) the deferred butterfly factor
-    {
-        const bool fold = last_round && scale != 1.0;
-        if (info.any_S)
-            flush_pending(o, pd, scale, true, fold);
-        else if (!pd.trivial() || fold)
-            flush_pending(o, pd, scale, false, fold);
-    }
+    flush(-1);
+    (void)have_S;
     if (info.barrier) o.f("    QSV_BARRIER();");
     emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, gen_post, "b");
     for (int r = 0; r < 16; ++r) o.f("    tout[b%d] = make_double2(x%dr, x%di);", r, r, r);
@@ -529,18 +691,12 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
             const char *dst_buf = host ? ((k & 1) ? tout_a : tout_b) : tin;
             if (host) {
                 w.f("        for (u32 tid = 0; tid < 256u; ++tid) {");
-                if (info[k].hoisted_S)
-                    w.f("            const double2 S = qsv_S%u(tid);", k);
-                else
-                    w.f("            const double2 S = make_double2(1.0, 0.0);");
-                w.f("            qsv_round%u(%s, %s, tid, gbase, S.x, S.y, tables);", k, src_buf, dst_buf);
+                w.f("            const qsv_H%u H = qsv_hoist%u(tid);", k, k);
+                w.f("            qsv_round%u(%s, %s, tid, gbase, H, tables);", k, src_buf, dst_buf);
                 w.f("        }");
             } else {
                 if (k > 0) w.f("        __syncthreads();");
-                if (info[k].hoisted_S)
-                    w.f("        qsv_round%u(%s, %s, tid, gbase, S%u.x, S%u.y, tables);", k, src_buf, dst_buf, k, k);
-                else
-                    w.f("        qsv_round%u(%s, %s, tid, gbase, 1.0, 0.0, tables);", k, src_buf, dst_buf);
+                w.f("        qsv_round%u(%s, %s, tid, gbase, H%u, tables);", k, src_buf, dst_buf, k);
             }
         }
     };
@@ -555,8 +711,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("    const u32 tid = threadIdx.x;");
     o.f("    if (tid == 0) { mbar_init(&mbar, 1); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }");
     o.f("    __syncthreads();");
-    for (uint32_t k = 0; k < hdr->n_rounds; ++k)
-        if (info[k].hoisted_S) o.f("    const double2 S%u = qsv_S%u(tid);", k, k);
+    for (uint32_t k = 0; k < hdr->n_rounds; ++k) o.f("    const qsv_H%u H%u = qsv_hoist%u(tid);", k, k, k);
     // run r of the tile: 2^L amplitudes at state[base + s_off[r]], s_off[r] = bits of r scattered to hi_pos.
     // The offsets are read from a shared-memory table like in k_pass_reg.  (Literal 64-bit offsets in an
     // unrolled issue sequence made ptxas 12.9 schedule a register copy AFTER its use across the ELECT
@@ -802,8 +957,9 @@ static int validate(const qsv_pass_t *P, const void *prog_host, uint32_t prog_by
     QSV_CHECK_ARG(P && prog_host, "qsv jit: NULL pointer");
     QSV_CHECK_ARG(prog_bytes >= sizeof(qsv_rprog_hdr_t), "qsv jit: program too short");
     const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
-    QSV_CHECK_ARG(hdr->n_rounds >= 1 && hdr->n_rounds <= QSV_RPROG_MAX_ROUNDS && hdr->n_ops <= QSV_RPROG_MAX_OPS,
-                  "qsv jit: %u rounds / %u ops exceed the limits", hdr->n_rounds, hdr->n_ops);
+    QSV_CHECK_ARG(hdr->n_rounds >= 1 && hdr->n_rounds <= QSV_JIT_MAX_ROUNDS && hdr->n_ops <= QSV_JIT_MAX_OPS,
+                  "qsv jit: %u rounds / %u ops exceed the limits (%d / %d)", hdr->n_rounds, hdr->n_ops,
+                  QSV_JIT_MAX_ROUNDS, QSV_JIT_MAX_OPS);
     const size_t need = sizeof(qsv_rprog_hdr_t) + sizeof(qsv_round_t) * hdr->n_rounds + sizeof(qsv_rop_t) * hdr->n_ops;
     QSV_CHECK_ARG(prog_bytes >= need, "qsv jit: prog_bytes=%u smaller than the %zu bytes the header implies", prog_bytes,
                   need);

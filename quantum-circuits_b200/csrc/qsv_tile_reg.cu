@@ -412,6 +412,23 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
         prev = P->hi_pos[j];
     }
     QSV_CHECK_ARG(prog_bytes >= sizeof(qsv_rprog_hdr_t), "qsv_run_pass_rounds: program too short");
+    // Large states run the pass-specialised kernel (qsv_jit.cu): same tile geometry and round structure,
+    // generated as straight-line code for this program and cached by its bytes.  It has its own (much
+    // larger) program capacity, so it is tried before the interpreter's kernel-parameter limits apply.
+    if (RB == 4 && jit::wanted(P, prog_host)) {
+        const uint64_t n_tiles_j = 1ull << (P->n_local - P->tile_bits);
+        const uint64_t resident_j = (uint64_t)sm_count() * 2ull * 4ull;
+        const unsigned grid_j = (unsigned)(n_tiles_j < resident_j ? n_tiles_j : resident_j);
+        const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid_j);
+        const char *mode = getenv("QSV_JIT");
+        if (rc == 0 || (mode && !strcmp(mode, "force"))) return rc;
+        static bool warned = false;
+        if (!warned) {
+            warned = true;
+            fprintf(stderr, "libqsv: specialised kernel unavailable (%s); using the interpreting kernel k_pass_reg\n",
+                    qsv_last_error());
+        }
+    }
     const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
     QSV_CHECK_ARG(hdr->n_rounds >= 1 && hdr->n_rounds <= QSV_RPROG_MAX_ROUNDS && hdr->n_ops <= QSV_RPROG_MAX_OPS,
                   "qsv_run_pass_rounds: %u rounds / %u ops exceed the limits (%d / %d)", hdr->n_rounds, hdr->n_ops,
@@ -445,19 +462,6 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
     // SMs; the per-CTA prologue (program copy, tables, mbarrier) is paid once per ~50+ tiles, not per tile
     const uint64_t resident = (uint64_t)sm_count() * 2ull * 4ull;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
-    // Large states run the pass-specialised kernel (qsv_jit.cu): same tile geometry and round structure,
-    // generated as straight-line code for this program and cached by its bytes.
-    if (RB == 4 && jit::wanted(P, prog_host)) {
-        const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid);
-        const char *mode = getenv("QSV_JIT");
-        if (rc == 0 || (mode && !strcmp(mode, "force"))) return rc;
-        static bool warned = false;
-        if (!warned) {
-            warned = true;
-            fprintf(stderr, "libqsv: specialised kernel unavailable (%s); using the interpreting kernel k_pass_reg\n",
-                    qsv_last_error());
-        }
-    }
     if (RB == 4) {
         QSV_CUDA(cudaFuncSetAttribute(k_pass_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12));
         k_pass_reg<4><<<grid, 256, smem, (cudaStream_t)stream>>>((double2 *)state_dev, *P, param,

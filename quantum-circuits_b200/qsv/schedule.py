@@ -675,14 +675,26 @@ def pack_passes(passes, register_kernel=None):
         register_kernel = use_register_kernel()
     round_progs = {}
     if register_kernel:
-        for i, ps in enumerate(passes):
+        passes = list(passes)
+        i = 0
+        while i < len(passes):
+            ps = passes[i]
             # one- and two-op passes stay on the shared-memory kernel: it is HBM-bound there (3 CTAs/SM,
             # 104-106 % of the measured copy peak) while the register kernel pays its round overhead
             rounds = plan_rounds(ps) if len(ps.ops) > int(os.environ.get("QSV_REG_MIN_OPS", "2")) else None
             if rounds is not None:
-                enc = encode_rounds(ps, rounds)
+                max_rounds, max_ops = program_capacity(ps)
+                enc = encode_rounds(ps, rounds, max_rounds, max_ops)
+                if enc is None and len(ps.ops) >= 8:
+                    # too long for the kernel that will run it: two passes over the same tile, in order
+                    # (one more sweep of the state, still far cheaper than one shared-memory round trip per op)
+                    h = len(ps.ops) // 2
+                    passes[i:i + 1] = [Pass(ps.n_local, ps.tile_bits, ps.low_bits, ps.hi_pos, ps.ops[:h]),
+                                       Pass(ps.n_local, ps.tile_bits, ps.low_bits, ps.hi_pos, ps.ops[h:])]
+                    continue
                 if enc is not None:
                     round_progs[i] = (enc[0], enc[1], len(rounds))
+            i += 1
     tables = 0
     for i, ps in enumerate(passes):
         if i not in round_progs:
@@ -732,7 +744,25 @@ ROP_DTYPE = np.dtype([
 assert ROP_DTYPE.itemsize == 128
 ROUND_DTYPE = np.dtype([("rb", "u1", (4,)), ("n_ops", "<u4"), ("first_op", "<u4"), ("n_pre", "<u2"), ("n_post", "<u2")])
 assert ROUND_DTYPE.itemsize == 16
-RPROG_MAX_ROUNDS, RPROG_MAX_OPS = 32, 120
+RPROG_MAX_ROUNDS, RPROG_MAX_OPS = 32, 120          # interpreting kernel (program = kernel parameter)
+JIT_MAX_ROUNDS, JIT_MAX_OPS = 256, 2048            # pass-specialised kernel (program = code)
+
+
+def program_capacity(ps):
+    """(max rounds, max ops) of the kernel qsv_run_pass_rounds will use for this pass: the library decides
+    (qsv_jit_wanted: state size, QSV_JIT), the limits mirror include/qsv.h."""
+    try:
+        import ctypes as C
+        lib = _cabi.load()
+        cp = _cabi.QsvPass()
+        cp.n_local, cp.tile_bits, cp.low_bits, cp.n_hi = ps.n_local, ps.tile_bits, ps.low_bits, ps.tile_bits - ps.low_bits
+        cp.reserved = reg_bits()
+        hdr = (C.c_uint32 * 4)(1, 16, 0, reg_bits())
+        if lib.qsv_jit_wanted(C.byref(cp), C.cast(hdr, C.c_void_p), 16):
+            return JIT_MAX_ROUNDS, JIT_MAX_OPS
+    except (RuntimeError, OSError, AttributeError):
+        pass
+    return RPROG_MAX_ROUNDS, RPROG_MAX_OPS
 ROP_DENSE1, ROP_DENSE1_REAL, ROP_PHASE1, ROP_GEN_PHASE, ROP_DIAG, ROP_PHASE_T, ROP_PERM = 0, 4, 8, 16, 17, 18, 19
 ROPF_REAL, ROPF_NEG = 1, 2
 
@@ -900,10 +930,10 @@ def linearize_perms(fields, rb):
     return out
 
 
-def encode_rounds(ps, rounds):
+def encode_rounds(ps, rounds, max_rounds=RPROG_MAX_ROUNDS, max_ops=RPROG_MAX_OPS):
     """Host image of a register-resident pass program -> (program bytes, diagonal-table bytes), or None
-    if it exceeds the kernel-parameter capacity (RPROG_MAX_ROUNDS / RPROG_MAX_OPS)."""
-    if len(rounds) > RPROG_MAX_ROUNDS:
+    if it exceeds the capacity of the kernel that will run it (program_capacity)."""
+    if len(rounds) > max_rounds:
         return None
     drop = os.environ.get("QSV_DEBUG_DROP", "")     # timing experiments only (results become wrong)
     if drop:
@@ -995,7 +1025,7 @@ def encode_rounds(ps, rounds):
         rnd[r]["n_ops"] = len(reg_ops) | (len(pt_ops) << 16)
         rops += pt_ops + reg_ops
         rops += [perm_rop(f, lin_post[i] if lin_post is not None else None) for i, f in enumerate(post)]
-    if len(rops) > RPROG_MAX_OPS:
+    if len(rops) > max_ops:
         return None
     hdr = np.array([len(rounds), 16 + 16 * len(rounds) + 128 * len(rops), len(rops), n_rb], dtype="<u4")
     blob = hdr.tobytes() + rnd.tobytes() + b"".join(h.tobytes() for h in rops)

@@ -158,3 +158,37 @@ def test_policy_small_states_stay_on_the_interpreter(monkeypatch):
     cp.n_local = 14
     monkeypatch.setenv("QSV_JIT", "force")
     assert lib.qsv_jit_wanted(*args) == 1
+
+
+def test_long_programs_capacity_and_splitting(tmp_path, monkeypatch):
+    """A pass with more ops than the interpreting kernel's parameter block holds (120) is one program for
+    the specialised kernel and is split into two sweeps for the interpreter; both give the same state."""
+    from qsv import workloads, lowering, schedule
+    from helpers import emulate_program
+    n = 15
+    c = workloads.qft_ladder_circuit(n)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    passes = schedule.plan_passes(ops, n, 12, 6)
+    psi = _rand_state(n, 11)
+    monkeypatch.setattr(schedule, "RPROG_MAX_OPS", 40)      # stand-in for 120 at a size the emulation follows
+
+    monkeypatch.setenv("QSV_JIT", "force")
+    packed = schedule.pack_passes(passes)
+    sizes = [int(np.frombuffer(bytes(m[3][0]), dtype="<u4", count=3)[2]) for m in packed.passes if m[2] < 0]
+    assert max(sizes) > schedule.RPROG_MAX_OPS, sizes
+    assert len(packed.passes) == len(passes)
+    ref = emulate_program(packed, psi)
+    blob = packed.blob.tobytes()
+    got = psi
+    for ps, off, n_ops, extra in packed.passes:
+        assert n_ops < 0
+        got = jit_host_run(ps, extra[0], blob[off:], got, 0, str(tmp_path))
+    assert np.max(np.abs(got - ref)) <= 1e-13
+
+    monkeypatch.setenv("QSV_JIT", "0")
+    split = schedule.pack_passes(passes)
+    assert len(split.passes) > len(passes)
+    for m in split.passes:
+        assert m[2] < 0 and int(np.frombuffer(bytes(m[3][0]), dtype="<u4", count=3)[2]) <= schedule.RPROG_MAX_OPS
+    assert np.max(np.abs(emulate_program(split, psi) - ref)) <= 1e-13
