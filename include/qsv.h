@@ -264,12 +264,15 @@ int qsv_unpack_slices(void *state_dev, const void *staging_dev, uint64_t n_chunk
 
 /* In-place global<->local qubit swap over NVLink PEER MEMORY (no staging, no NCCL on the data path).
  * `peer_state_ptrs[j]` is rank j's state pointer mapped into this process (CUDA VMM / symmetric memory);
- * entry [rank] is ignored.  The shard is P = 2^g blocks of S = 2^(n_local-g) amplitudes; block j of rank r
- * trades places with block r of rank j.  Every pair of ranks splits the work: in alternating granules one
- * of the two ranks reads both sides and writes both sides (one remote read + one remote write per
- * amplitude), so each amplitude crosses NVLink exactly once per direction and touches local HBM once.
+ * entry [rank] is ignored.  `positions[k]` (ascending local positions; NULL = the top g) trades places with
+ * global bit k.  Writing a local index as (field, rest) with field = the bits at `positions`, element
+ * (field = j, rest = e) of rank r trades places with element (field = r, rest = e) of rank j.  Every pair of
+ * ranks splits the work: in alternating granules one of the two ranks reads both sides and writes both sides
+ * (one remote read + one remote write per amplitude), so each amplitude crosses NVLink exactly once per
+ * direction and touches local HBM once.  Positions >= 9 keep every peer access a contiguous 8 KiB run.
  * The caller must barrier all ranks before and after the call. */
-int qsv_swap_peer(void *state_dev, const uint64_t *peer_state_ptrs, int n_local, int g, int rank, void *stream);
+int qsv_swap_peer(void *state_dev, const uint64_t *peer_state_ptrs, int n_local, int g, int rank,
+                  const int *positions, void *stream);
 
 #ifdef __cplusplus
 }

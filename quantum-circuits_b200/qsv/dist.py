@@ -73,13 +73,14 @@ class Comm:
                 self.peer_swap = False
         return torch.empty(n_amps, dtype=torch.complex128, device=device)
 
-    def _swap_peer(self, sv):
+    def _swap_peer(self, sv, positions=None):
         raw, hdl, ptrs = self._symm
         arr = (C.c_uint64 * self.world)(*ptrs)
+        pos = _cabi.int_array(positions) if positions is not None else None
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
         hdl.barrier()                                   # every rank's earlier kernels are done
-        _cabi.check(sv.lib.qsv_swap_peer(sv._ptr(sv.state), arr, sv.n_local, self.global_bits, self.rank,
+        _cabi.check(sv.lib.qsv_swap_peer(sv._ptr(sv.state), arr, sv.n_local, self.global_bits, self.rank, pos,
                                          sv._stream()), "qsv_swap_peer")
         hdl.barrier()                                   # nobody touches its shard before all swaps landed
         ev[1].record()
@@ -160,12 +161,17 @@ class Comm:
         self.swap_events = []
         return n, ms
 
-    def swap_global_local(self, sv, n_swap):
-        """Engine hook for a 'global_swap' op (CUDA pack/unpack kernels of libqsv)."""
+    def swap_global_local(self, sv, n_swap, positions=None):
+        """Engine hook for a 'global_swap' op: the peer-memory kernel (any local positions), or the chunked
+        NCCL all-to-all with the CUDA pack/unpack kernels of libqsv (top local positions only)."""
         if n_swap != self.global_bits:
             raise RuntimeError("qsv.dist: only full swaps of all %d global qubits are planned" % self.global_bits)
         if self.peer_swap and self._symm is not None and sv.state.data_ptr() == self._symm[2][self.rank]:
-            return self._swap_peer(sv)
+            return self._swap_peer(sv, positions)
+        top = list(range(sv.n_local - self.global_bits, sv.n_local))
+        if positions is not None and list(positions) != top:
+            raise RuntimeError("qsv.dist: the NCCL exchange swaps the top local positions only; lower the circuit "
+                               "with free_swap=False when peer memory is unavailable")
         lib = sv.lib
         P = 1 << self.global_bits
         S = 1 << (sv.n_local - self.global_bits)

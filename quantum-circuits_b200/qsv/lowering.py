@@ -118,7 +118,7 @@ def lower_gate(gate, wires, layout, transposed=False):
     return classify_matrix(M, layout.positions(wires), name)
 
 
-def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False):
+def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, free_swap=False):
     """(ops, src_pos): ops in application order; src_pos[b] = physical position feeding bit b of the
     OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map.  With
     n_global > 0 the ops are placed on a register sharded by its top n_global positions
@@ -126,7 +126,9 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False):
 
     Uncontrolled X gates are pushed back to the circuit input (qsv.schedule.propagate_x).  With
     in_flip=True the result is (ops, src_pos, flip) and the caller starts from |index ^ flip>; otherwise
-    the leftover flips are kept as explicit X ops at the head of the list (any input state)."""
+    the leftover flips are kept as explicit X ops at the head of the list (any input state).
+    free_swap: global<->local swaps may exchange any local positions (needs the peer-memory swap kernel,
+    Comm.peer_swap); otherwise the victims are first moved to the top local positions."""
     n = len(circuit)
     gates = circuit.gates if presorted else topological_gates(circuit)
     table, out_qubits = gate_targets(circuit, gates)
@@ -151,7 +153,7 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False):
         ops = fuse_1q(ops)
     if n_global:
         from .schedule import place
-        ops, src_pos = place(ops, n, n_global, src_pos)
+        ops, src_pos = place(ops, n, n_global, src_pos, free_swap=free_swap)
     if in_flip:
         return ops, src_pos, flip
     return ops, src_pos

@@ -414,7 +414,11 @@ def propagate_x(ops):
 # placement on a sharded register: virtual positions -> physical positions, global<->local swaps
 # ------------------------------------------------------------------------------------------------
 
-def place(ops, n, n_global, src_pos=None, lookahead=400):
+SWAP_MIN_POS = 9      # free-position swaps: lowest local position that may trade places with a global one
+                      # (2^9 amplitudes = the 8 KiB contiguous run k_swap_peer moves per peer access)
+
+
+def place(ops, n, n_global, src_pos=None, lookahead=400, free_swap=False):
     """Map ops written on VIRTUAL positions (single-device numbering, 0 = least significant) onto a
     register whose top `n_global` physical positions are the rank index.
 
@@ -422,7 +426,11 @@ def place(ops, n, n_global, src_pos=None, lookahead=400):
     qubits that are not needed for the longest time are moved to the top local positions (local 'swap'
     ops, fused into the surrounding passes) and one 'global_swap' op exchanges them with the global
     qubits (an all-to-all over NVLink).  Diagonal ops and controls on global qubits need no
-    communication.  Returns (physical ops, physical src_pos)."""
+    communication.  Returns (physical ops, physical src_pos).
+
+    free_swap=True (the peer-memory swap kernel, csrc/qsv_peer.cu): the victims are exchanged WHERE THEY ARE
+    ('global_swap' carries params["positions"], ascending local positions >= SWAP_MIN_POS; positions[k] trades
+    places with global bit k), so no re-layout CNots and none of the near-empty passes they cause."""
     phys = list(range(n))                       # virtual position -> physical position
     if n_global == 0:
         return list(ops), (list(src_pos) if src_pos is not None else None)
@@ -445,6 +453,18 @@ def place(ops, n, n_global, src_pos=None, lookahead=400):
             if len(local_virtual) < n_global:
                 raise RuntimeError("op %r needs more local qubits than one shard holds" % (op.name,))
             local_virtual.sort(key=lambda v: (-nxt.get(v, lookahead + 1), -phys[v]))
+            if free_swap:
+                high = [v for v in local_virtual if phys[v] >= min(SWAP_MIN_POS, n_local - n_global)]
+                victims = (high + [v for v in local_virtual if v not in high])[:n_global]
+                positions = sorted(phys[v] for v in victims)
+                out.append(Op("global_swap", (), (), params={"n_swap": n_global, "positions": positions},
+                              name="relayout"))
+                at = {phys[v]: v for v in range(n)}
+                for i, p_loc in enumerate(positions):
+                    a, b = at[p_loc], at[n_local + i]
+                    phys[a], phys[b] = n_local + i, p_loc
+                out.append(op.remapped(phys))
+                continue
             victims = local_virtual[:n_global]
             tops = list(range(n_local - n_global, n_local))
             # victims already sitting on a top position keep it; the others are swapped in
@@ -508,61 +528,183 @@ def _mask(bits):
     return m
 
 
-def plan_passes(ops, n_local, tile_bits=None, low_bits=None):
-    """Greedy partition of a list of TILED ops into passes (each one read+write of the state).
+PLAN_WINDOW = 600        # ops looked at when a pass chooses its tile
+PLAN_MAX_ROUNDS = 8      # improvement rounds of the tile search per pass
 
-    A pass's tile always holds positions 0..L-1 plus up to T-L higher positions.  Ops are taken in
-    program order; an op joins the current pass if all its non-diagonal targets fit in the tile and
-    it commutes past every op that had to be deferred (deferred ops block the bits they touch:
-    non-diagonal use blocks everything, diagonal/control use blocks only non-diagonal use).
-    """
+
+def _absorbed(masks, allowed, limit):
+    """How many of the first `limit` ops a pass could take if its tile held exactly the positions in
+    `allowed` (bit mask): program order, an op is taken if its non-diagonal targets are in the tile and it
+    commutes past everything that had to be left behind (same rule as the final selection)."""
+    blocked_nd = blocked_d = 0
+    count = 0
+    for nd_m, dg_m in masks[:limit]:
+        if not (nd_m & (blocked_nd | blocked_d)) and not (dg_m & blocked_nd) and not (nd_m & ~allowed):
+            count += 1
+        else:
+            blocked_nd |= nd_m
+            blocked_d |= dg_m
+    return count
+
+
+def _improve_tile(masks, hi, low_mask, n_free_slots, n_local, L):
+    """Local search over the tile's high positions: exchange one chosen position for a candidate as long as
+    the pass absorbs more ops.  The first-come choice fills the tile with whatever the next ops happen to
+    touch; a CNot whose target stays outside then freezes its control for the rest of the pass.  Picking
+    positions that interact with each other lets a pass run deeper (config 3 at 30 qubits: 19 -> 15 passes)."""
+    hi = set(hi)
+    cand = set()
+    for nd_m, _ in masks[:PLAN_WINDOW // 2]:
+        m = nd_m >> L
+        b = L
+        while m:
+            if m & 1:
+                cand.add(b)
+            m >>= 1
+            b += 1
+    cand = {b for b in cand if b < n_local}
+    # unused slots first: adding a position never hurts
+    best = _absorbed(masks, low_mask | _mask(hi), PLAN_WINDOW)
+    for _ in range(PLAN_MAX_ROUNDS):
+        improved = False
+        if len(hi) < n_free_slots:
+            for inn in sorted(cand - hi):
+                got = _absorbed(masks, low_mask | _mask(hi | {inn}), PLAN_WINDOW)
+                if got > best:
+                    best, hi, improved = got, hi | {inn}, True
+                    break
+            if improved:
+                continue
+        for out in sorted(hi):
+            for inn in sorted(cand - hi):
+                h2 = (hi - {out}) | {inn}
+                got = _absorbed(masks, low_mask | _mask(h2), PLAN_WINDOW)
+                if got > best:
+                    best, hi, improved = got, h2, True
+                    break
+            if improved:
+                break
+        if not improved:
+            break
+    return hi
+
+
+_NOT_TILED = 1 << 200     # sentinel bit: an op that can never join a pass
+
+
+def block_masks(op, n_local):
+    """(non-diagonal mask, diagonal mask) an op contributes to the planner's dependency tracking.  Tiled ops:
+    their target / control positions.  Whole-state ops and re-layouts never join a pass (sentinel bit) and
+    block every position they touch; a global<->local swap touches the local positions it exchanges and all
+    global positions, nothing else - ops on other positions commute with it and may be scheduled on either
+    side (their positions mean the same physical bits before and after)."""
+    if op.kind in TILED_KINDS:
+        nd = op.nondiag_bits()
+        if any(b >= n_local for b in nd):
+            raise RuntimeError("op %r targets a global qubit; it must be swapped local first" % (op.name,))
+        return _mask(nd), _mask(op.diag_bits())
+    if op.kind == "global_swap":
+        g = int(op.params["n_swap"])
+        pos = op.params.get("positions") or list(range(n_local - g, n_local))
+        return _NOT_TILED | _mask(pos) | _mask(range(n_local, n_local + g)), 0
+    if op.kind == "diffusion":
+        return _NOT_TILED | ((1 << 128) - 1), 0          # acts on (almost) everything: a full barrier
+    return _NOT_TILED | _mask(tuple(op.targets) + tuple(op.controls)), 0
+
+
+def _plan_one_pass(remaining, masks_of, n_local, T, L, search):
+    """One pass from the head of `remaining`: (Pass, rest)."""
+    low_mask = (1 << L) - 1
+    masks = [masks_of[id(op)] for op in remaining[:PLAN_WINDOW]]
+    # ---- first-come choice of the high positions
+    hi = []
+    free = T - L
+    blocked_nd = blocked_d = 0
+    for nd_m, dg_m in masks:
+        ok = not (nd_m & _NOT_TILED) and not (nd_m & (blocked_nd | blocked_d)) and not (dg_m & blocked_nd)
+        if ok:
+            new = [b for b in range(L, n_local) if (nd_m >> b) & 1 and b not in hi]
+            if len(new) <= free:
+                hi.extend(new)
+                free -= len(new)
+                continue
+        blocked_nd |= nd_m
+        blocked_d |= dg_m
+    if search:
+        hi = sorted(_improve_tile(masks, hi, low_mask, T - L, n_local, L))
+    free = T - L - len(hi)
+    # ---- selection with the tile fixed
+    allowed = low_mask | _mask(hi)
+    blocked_nd = blocked_d = 0
+    chosen, rest = [], []
+    for op in remaining:
+        nd_m, dg_m = masks_of[id(op)]
+        if not (nd_m & (blocked_nd | blocked_d)) and not (dg_m & blocked_nd) and not (nd_m & ~allowed):
+            chosen.append(op)
+            continue
+        blocked_nd |= nd_m
+        blocked_d |= dg_m
+        rest.append(op)
+    if not chosen:
+        raise RuntimeError("pass planner made no progress (op needs more than %d tile-local qubits)" % T)
+    # fill the unused tile slots with the lowest free positions, avoiding control/diagonal bits
+    # of the chosen ops so that those stay external (tiles they switch off are never loaded)
+    avoid = 0
+    for op in chosen:
+        avoid |= masks_of[id(op)][1]
+    hi = list(hi)
+    for rnd in (0, 1):
+        for b in range(L, n_local):
+            if free == 0:
+                break
+            if b in hi or (rnd == 0 and (avoid >> b) & 1):
+                continue
+            hi.append(b)
+            free -= 1
+    return Pass(n_local, T, L, tuple(sorted(hi)), chosen), rest
+
+
+def _geometry(n_local, tile_bits, low_bits):
     T = min(n_local, tile_bits if tile_bits is not None else default_tile_bits())
     T = min(T, _cabi.QSV_MAX_TILE_T)
     L = min(T, low_bits if low_bits is not None else default_low_bits())
     L = max(L, T - 8)
+    return T, L
+
+
+def plan_schedule(ops, n_local, tile_bits=None, low_bits=None):
+    """Whole op list (tiled ops, whole-state ops, global<->local swaps) -> [("pass", Pass) | ("op", op)] in
+    execution order.  A non-tiled op runs when it reaches the head of the list; until then it only blocks the
+    positions it touches, so passes keep absorbing later ops that commute with it - in particular the passes
+    before a qubit swap fill up with ops from behind the swap instead of ending in near-empty sweeps."""
+    T, L = _geometry(n_local, tile_bits, low_bits)
+    search = os.environ.get("QSV_PLAN_SEARCH", "1") != "0" and T - L > 0
     remaining = list(ops)
-    passes = []
+    masks_of = {id(op): block_masks(op, n_local) for op in remaining}
+    out = []
     while remaining:
-        hi = []
-        free = T - L
-        blocked_nd = 0
-        blocked_d = 0
-        chosen, rest = [], []
-        for op in remaining:
-            nd = list(op.nondiag_bits())
-            if any(b >= n_local for b in nd):
-                raise RuntimeError("op %r targets a global qubit; it must be swapped local first" % (op.name,))
-            dg = list(op.diag_bits())
-            nd_m, dg_m = _mask(nd), _mask(dg)
-            ok = not (nd_m & (blocked_nd | blocked_d)) and not (dg_m & blocked_nd)
-            if ok:
-                new = [b for b in set(nd) if b >= L and b not in hi]
-                if len(new) <= free:
-                    hi.extend(new)
-                    free -= len(new)
-                    chosen.append(op)
-                    continue
-            blocked_nd |= nd_m
-            blocked_d |= dg_m
-            rest.append(op)
-        if not chosen:
-            raise RuntimeError("pass planner made no progress (op needs more than %d tile-local qubits)" % T)
-        # fill the unused tile slots with the lowest free positions, avoiding control/diagonal bits
-        # of the chosen ops so that those stay external (tiles they switch off are never loaded)
-        avoid = 0
-        for op in chosen:
-            avoid |= _mask(op.diag_bits())
-        for rnd in (0, 1):
-            for b in range(L, n_local):
-                if free == 0:
-                    break
-                if b in hi or (rnd == 0 and (avoid >> b) & 1):
-                    continue
-                hi.append(b)
-                free -= 1
-        passes.append(Pass(n_local, T, L, tuple(sorted(hi)), chosen))
-        remaining = rest
-    return passes
+        if remaining[0].kind not in TILED_KINDS:
+            out.append(("op", remaining.pop(0)))
+            continue
+        ps, remaining = _plan_one_pass(remaining, masks_of, n_local, T, L, search)
+        out.append(("pass", ps))
+    return out
+
+
+def plan_passes(ops, n_local, tile_bits=None, low_bits=None):
+    """Partition of a list of TILED ops into passes (each one read+write of the state).
+
+    A pass's tile always holds positions 0..L-1 plus up to T-L higher positions.  Ops are taken in
+    program order; an op joins the current pass if all its non-diagonal targets fit in the tile and
+    it commutes past every op that had to be deferred (deferred ops block the bits they touch:
+    non-diagonal use blocks everything, diagonal/control use blocks only non-diagonal use).  The high
+    positions are first chosen first-come (greedy), then improved by a local search (_improve_tile;
+    QSV_PLAN_SEARCH=0 keeps the greedy choice).
+    """
+    for op in ops:
+        if op.kind not in TILED_KINDS:
+            raise RuntimeError("plan_passes takes tiled ops only (got %r); use plan_schedule" % op.kind)
+    return [item for kind, item in plan_schedule(ops, n_local, tile_bits, low_bits)]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -52,21 +52,29 @@ def main():
         ok = ok and bool(cond)
 
     # 1. layered circuits (H / X / phases / CNot / CZ on every wire -> global<->local swaps)
-    for n, depth, seed in ((10 + g, 4, 3), (14 + g, 6, 4)):
+    from qsv import schedule
+    for n, depth, seed, min_pos in ((10 + g, 4, 3, 9), (14 + g, 6, 4, 9), (14 + g, 6, 5, 2)):
         c = workloads.random_layered_circuit(n, depth, seed=seed)
         c.sort()
-        ops, src_pos = lowering.lower(c, n_global=g)
         sv = engine.StateVector(n, comm=comm)
-        sv.init_basis(5)
-        sv.run_ops(ops)
-        sv.synchronize()
-        full = gather_full(sv, comm)
         ref = np.zeros(1 << n, dtype=np.complex128)
         ref[5] = 1
         for M, wires, _ in so.random_layered_steps(n, depth, seed=seed):
             ref = so.apply_gate(ref, n, wires, M)
-        err = np.max(np.abs(to_output_order(full, src_pos) - ref))
-        check("layered n=%d depth=%d swaps=%d err=%.2e" % (n, depth, comm.swaps, err), err <= 1e-12)
+        # re-layout to the top positions (works with the NCCL exchange too), then - with peer memory - the
+        # free-position swaps the benchmarks use (victims exchanged where they are, X gates as an input flip)
+        for free in ([False, True] if comm.peer_swap else [False]):
+            schedule.SWAP_MIN_POS = min_pos
+            ops, src_pos, flip = lowering.lower(c, n_global=g, in_flip=True, free_swap=free)
+            schedule.SWAP_MIN_POS = 9
+            swaps0 = comm.swaps
+            sv.init_basis(5 ^ flip)
+            sv.run_ops(ops)
+            sv.synchronize()
+            full = gather_full(sv, comm)
+            err = np.max(np.abs(to_output_order(full, src_pos) - ref))
+            check("layered n=%d depth=%d free_swap=%s min_pos=%d swaps=%d err=%.2e"
+                  % (n, depth, free, min_pos, comm.swaps - swaps0, err), err <= 1e-12)
         # sampling: same distribution -> index must carry non-zero probability and be identical on all ranks
         z = sv.sample(0.4321, src_pos)
         zs = torch.tensor([z], device="cuda")

@@ -287,75 +287,76 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0, single_tile_gbase=
     return psi
 
 
-def emulate_ops(ops, psi, n_local, tile_bits=None, low_bits=None, rank_bits=0):
-    """Run a list of qsv.schedule.Op on a numpy state the way engine.run_ops would (tiled ops through
-    the packed-program emulator, whole-state ops through direct numpy restatements)."""
-    from qsv.schedule import TILED_KINDS, plan_passes, pack_passes
-    batch = []
+def _emulate_whole_state_op(op, psi):
+    idx = np.arange(psi.size)
+    k = len(op.targets)
+    c = np.zeros_like(idx)
+    for p, pos in enumerate(op.targets):
+        c |= ((idx >> pos) & 1) << (k - 1 - p)
+    tmask = sum(1 << p for p in op.targets)
 
-    def flush(psi):
-        if batch:
-            psi = emulate_program(pack_passes(plan_passes(batch, n_local, tile_bits, low_bits)), psi, rank_bits)
-            batch.clear()
-        return psi
-
-    for op in ops:
-        if op.kind in TILED_KINDS:
-            batch.append(op)
-            continue
-        psi = flush(psi)
-        idx = np.arange(psi.size)
-        k = len(op.targets)
-        c = np.zeros_like(idx)
+    def scatter(v):
+        o = np.zeros_like(idx)
         for p, pos in enumerate(op.targets):
-            c |= ((idx >> pos) & 1) << (k - 1 - p)
-        tmask = sum(1 << p for p in op.targets)
+            o |= ((v >> (k - 1 - p)) & 1) << pos
+        return o
+    if op.kind == "wide_perm":
+        out = np.empty_like(psi)
+        out[(idx & ~tmask) | scatter(op.perm[c].astype(np.int64))] = psi
+        return out
+    if op.kind == "wide_diag":
+        return psi * op.matrix[c]
+    if op.kind == "wide_dense":
+        out = np.zeros_like(psi)
+        for col in range(1 << k):
+            out += op.matrix[c, col] * psi[(idx & ~tmask) | scatter(np.full_like(idx, col))]
+        return out
+    raise AssertionError("emulation: unsupported op kind %s" % op.kind)
 
-        def scatter(v):
-            o = np.zeros_like(idx)
-            for p, pos in enumerate(op.targets):
-                o |= ((v >> (k - 1 - p)) & 1) << pos
-            return o
-        if op.kind == "wide_perm":
-            out = np.empty_like(psi)
-            out[(idx & ~tmask) | scatter(op.perm[c].astype(np.int64))] = psi
-            psi = out
-        elif op.kind == "wide_diag":
-            psi = psi * op.matrix[c]
-        elif op.kind == "wide_dense":
-            out = np.zeros_like(psi)
-            for col in range(1 << k):
-                out += op.matrix[c, col] * psi[(idx & ~tmask) | scatter(np.full_like(idx, col))]
-            psi = out
+
+def emulate_ops(ops, psi, n_local, tile_bits=None, low_bits=None, rank_bits=0):
+    """Run a list of qsv.schedule.Op on a numpy state the way engine.prepare/execute would: the schedule of
+    qsv.schedule.plan_schedule, passes through the packed-program emulator, whole-state ops through direct
+    numpy restatements."""
+    from qsv.schedule import plan_schedule, pack_passes
+    for kind, item in plan_schedule(ops, n_local, tile_bits, low_bits):
+        if kind == "pass":
+            psi = emulate_program(pack_passes([item]), psi, rank_bits)
         else:
-            raise AssertionError("emulate_ops: unsupported op kind %s" % op.kind)
-    return flush(psi)
+            psi = _emulate_whole_state_op(item, psi)
+    return psi
 
 
 def emulate_sharded(ops, psi, n, g, tile_bits=None, low_bits=None):
-    """Run PLACED ops (qsv.schedule.place) on P = 2^g virtual ranks held as rows of one numpy array:
-    tiled ops go through the packed-program emulator with each rank's rank_bits, 'global_swap' is the
-    all-to-all written as an axis swap.  Returns the full state in physical order."""
+    """Run PLACED ops (qsv.schedule.place) on P = 2^g virtual ranks held as rows of one numpy array, in the
+    order of qsv.schedule.plan_schedule (passes may absorb ops from behind a qubit swap): passes go through the
+    packed-program emulator with each rank's rank_bits, 'global_swap' is the exchange of the chosen local
+    positions with the global bits.  Returns the full state in physical order."""
+    from qsv.schedule import plan_schedule, pack_passes
     n_local = n - g
     P = 1 << g
     shards = psi.reshape(P, 1 << n_local).copy()
-    batch = []
-
-    def flush():
-        nonlocal shards
-        if batch:
+    for kind, item in plan_schedule(ops, n_local, tile_bits, low_bits):
+        if kind == "pass":
+            packed = pack_passes([item])
             for r in range(P):
-                shards[r] = emulate_ops(batch, shards[r], n_local, tile_bits, low_bits, rank_bits=r << n_local)
-            batch.clear()
-
-    for op in ops:
-        if op.kind == "global_swap":
-            flush()
-            t = shards.reshape(P, P, -1)            # [rank, top local field, rest]
-            shards = np.ascontiguousarray(t.transpose(1, 0, 2)).reshape(P, -1)
+                shards[r] = emulate_program(packed, shards[r], rank_bits=r << n_local)
+        elif item.kind == "global_swap":
+            pos = item.params.get("positions")
+            if pos is None:
+                t = shards.reshape(P, P, -1)            # [rank, top local field, rest]
+                shards = np.ascontiguousarray(t.transpose(1, 0, 2)).reshape(P, -1)
+            else:                                       # position pos[k] trades places with global bit k
+                full = shards.reshape(-1)
+                idx = np.arange(full.size)
+                src = idx.copy()
+                for k, p_loc in enumerate(pos):
+                    a, b = (idx >> p_loc) & 1, (idx >> (n_local + k)) & 1
+                    src = (src & ~((1 << p_loc) | (1 << (n_local + k)))) | (b << p_loc) | (a << (n_local + k))
+                shards = full[src].reshape(P, -1)
         else:
-            batch.append(op)
-    flush()
+            for r in range(P):
+                shards[r] = _emulate_whole_state_op(item, shards[r])
     return shards.reshape(-1)
 
 

@@ -26,15 +26,20 @@ def _permute_to_output(psi, src_pos):
     return psi[y]
 
 
+@pytest.mark.parametrize("free_swap", [False, True])
 @pytest.mark.parametrize("g", [1, 2, 3])
-def test_placed_circuit_on_virtual_ranks_matches_oracle(g):
+def test_placed_circuit_on_virtual_ranks_matches_oracle(g, free_swap, monkeypatch):
     n = 11
+    monkeypatch.setattr(schedule, "SWAP_MIN_POS", 3)     # small register: let the free swaps use low positions too
     steps = so.random_layered_steps(n, 5, seed=21 + g)
     c = circuit_from_steps(steps, n)
     c.sort()
-    ops, src_pos = lower(c, n_global=g)
+    ops, src_pos = lower(c, n_global=g, free_swap=free_swap)
     n_swaps = sum(op.kind == "global_swap" for op in ops)
     assert n_swaps >= 1, "a layered circuit on every wire must touch the global qubits"
+    if free_swap:
+        assert not any(op.name == "relayout" and op.kind == "mcx" for op in ops), "free swaps need no re-layout CNots"
+        assert any(op.params["positions"] != list(range(n - 2 * g, n - g)) for op in ops if op.kind == "global_swap")
     assert all(max(op.nondiag_bits(), default=0) < n - g for op in ops if op.kind != "global_swap")
     psi = np.zeros(1 << n, dtype=np.complex128)
     psi[0b101] = 1
@@ -110,17 +115,45 @@ def test_exchange_over_gloo(tmp_path, world):
         assert open(tmp_path / ("ok%d" % r)).read() == "1"
 
 
-@pytest.mark.parametrize("g,S", [(1, 1), (1, 2), (1, 8), (2, 4), (3, 16), (2, 8192), (1, 4096)])
-def test_peer_swap_kernel_index_logic(g, S):
-    """numpy restatement of k_swap_peer (csrc/qsv_peer.cu): every element of every block pair is swapped
-    exactly once, by exactly one of the two ranks, and the result equals the all-to-all transposition."""
+def _insert_zero(v, p):
+    return ((v >> p) << (p + 1)) | (v & ((1 << p) - 1))
+
+
+@pytest.mark.parametrize("g,S,low", [(1, 1, 0), (1, 2, 0), (1, 8, 0), (2, 4, 0), (3, 16, 0), (2, 8192, 0), (1, 4096, 0),
+                                     (1, 8, 1), (2, 16, 2), (3, 64, 3), (2, 8192, 5)])
+def test_peer_swap_kernel_index_logic(g, S, low):
+    """numpy restatement of k_swap_peer (csrc/qsv_peer.cu): every element of every pair is swapped exactly
+    once, by exactly one of the two ranks, and the result equals the exchange of the chosen local positions
+    with the global bits (low = 0: the top g positions, i.e. the all-to-all transposition of blocks;
+    low > 0: positions spread below the top, as the free-position placement produces them)."""
     P = 1 << g
+    n_local = g + (S.bit_length() - 1)
+    if low == 0:
+        q = list(range(n_local - g, n_local))
+    else:
+        q = sorted(np.random.default_rng(low).choice(np.arange(low, n_local), size=g, replace=False).tolist())
+
+    def field(j):
+        return sum(((j >> k) & 1) << q[k] for k in range(g))
+
+    def expand(e):
+        for k in range(g):
+            e = _insert_zero(e, q[k])
+        return e
     G = (S // 2 if S // 2 < 2048 else 2048) if S >= 2 else 1
     per_pair = S // 2 if S >= 2 else 1
     CH = min(per_pair, 512)
     rng = np.random.default_rng(S + g)
     shards = rng.normal(size=(P, P * S))
-    expect = np.ascontiguousarray(shards.reshape(P, P, S).transpose(1, 0, 2)).reshape(P, P * S)
+    full = shards.reshape(-1)
+    idx = np.arange(full.size)
+    src = idx.copy()
+    for k in range(g):
+        a, b = (idx >> q[k]) & 1, (idx >> (n_local + k)) & 1
+        src = (src & ~((1 << q[k]) | (1 << (n_local + k)))) | (b << q[k]) | (a << (n_local + k))
+    expect = full[src].reshape(P, P * S)
+    if low == 0:
+        assert np.array_equal(expect, np.ascontiguousarray(shards.reshape(P, P, S).transpose(1, 0, 2)).reshape(P, P * S))
     work = shards.copy()
     touched = np.zeros((P, P * S), dtype=int)
     for r in range(P):
@@ -134,12 +167,17 @@ def test_peer_swap_kernel_index_logic(g, S):
                 e = 0
                 if r > j:
                     continue
-            a, b = work[r, j * S + e], work[j, r * S + e]
-            work[r, j * S + e], work[j, r * S + e] = b, a
-            touched[r, j * S + e] += 1
-            touched[j, r * S + e] += 1
+            mine, theirs = expand(e) | field(j), expand(e) | field(r)
+            a, b = work[r, mine], work[j, theirs]
+            work[r, mine], work[j, theirs] = b, a
+            touched[r, mine] += 1
+            touched[j, theirs] += 1
     off_diag = np.ones((P, P * S), dtype=bool)
+    loc = np.arange(P * S)
     for r in range(P):
-        off_diag[r, r * S:(r + 1) * S] = False
+        own = np.ones(P * S, dtype=bool)
+        for k in range(g):
+            own &= ((loc >> q[k]) & 1) == ((r >> k) & 1)
+        off_diag[r, own] = False
     assert np.all(touched[off_diag] == 1) and np.all(touched[~off_diag] == 0)
     assert np.array_equal(work, expect)
