@@ -106,6 +106,9 @@ typedef struct qsv_pass {
                                     Linear lists: j = 0xff if the condition is slot-independent, else
                                     j = register index q, rval = position and flags = mask of the one
                                     condition bit that varies with r_q (flags = 0 when j = 0xff)        */
+#define QSV_ROP_MCX_REG     20   /* pass-specialised kernel only: (multi-)controlled X whose target is register bit j,
+                                    executed in the register phase: slots r (bit j clear) with (r & rmask) == rval trade
+                                    places with r | 1<<j where the thread / external condition holds */
 #define QSV_ROPF_REAL  1u   /* matrix entries are real                                               */
 #define QSV_ROPF_NEG   2u   /* PHASE: scalar is exactly -1                                            */
 

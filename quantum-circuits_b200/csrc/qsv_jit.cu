@@ -71,8 +71,12 @@ static std::string dlit(double v) {
     return buf;
 }
 
-static std::string xr(int r) { return "x" + std::to_string(r) + "r"; }
-static std::string xi(int r) { return "x" + std::to_string(r) + "i"; }
+// Slot r of the current round lives in the variables x<v>r / x<v>i with v = t_slot_var[r]: an unconditional
+// (or register-bit controlled) X / CNot on a register bit is a renaming of slots, not an instruction.
+static thread_local int t_slot_var[16];
+static void reset_slot_vars() { for (int r = 0; r < 16; ++r) t_slot_var[r] = r; }
+static std::string xr(int r) { return "x" + std::to_string(t_slot_var[r]) + "r"; }
+static std::string xi(int r) { return "x" + std::to_string(t_slot_var[r]) + "i"; }
 
 // x[r] *= c for a literal c
 static void emit_cmul_const(Out &o, int r, Cx c) {
@@ -388,6 +392,10 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
                 window[p.kind & 3]++;
                 continue;
             }
+            if (p.kind == QSV_ROP_MCX_REG) {
+                window[p.j & 3]++;
+                continue;
+            }
             if (!joins_scalar(p)) continue;
             uint32_t rmask, rval;
             phase_rmask(p, rmask, rval);
@@ -442,6 +450,7 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
 
     o.f("QSV_FN void qsv_round%d(const double2 *tin, double2 *tout, const u32 tid, const u64 gbase, const qsv_H%d &H,"
         " const double2 *tables) {", k, k);
+    reset_slot_vars();
     emit_tb(o, R);
     emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
     o.f("    double x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i, x4r, x4i, x5r, x5i, x6r, x6i, x7r, x7i;");
@@ -542,6 +551,29 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             }
             if (!cnd.empty()) o.f("    }");
             if (defer) scale *= h;
+        } else if (kind == QSV_ROP_MCX_REG) {
+            const int J = p.j & 3;
+            flush(J);                                  // diagonals that depend on bit J do not commute with it
+            window[J]++;
+            if (cnd.empty()) {
+                // slot renaming at generation time: zero instructions
+                for (int r = 0; r < 16; ++r) {
+                    if ((r >> J) & 1) continue;
+                    if (((uint32_t)r & p.rmask) != p.rval) continue;
+                    std::swap(t_slot_var[r], t_slot_var[r | (1 << J)]);
+                }
+            } else {
+                o.f("    if (%s) {", cnd.c_str());
+                for (int r = 0; r < 16; ++r) {
+                    if ((r >> J) & 1) continue;
+                    if (((uint32_t)r & p.rmask) != p.rval) continue;
+                    const int r1 = r | (1 << J);
+                    o.f("      { const double tr = %s, ti = %s; %s = %s; %s = %s; %s = tr; %s = ti; }", xr(r).c_str(),
+                        xi(r).c_str(), xr(r).c_str(), xr(r1).c_str(), xi(r).c_str(), xi(r1).c_str(), xr(r1).c_str(),
+                        xi(r1).c_str());
+                }
+                o.f("    }");
+            }
         } else if (is_phase_kind(kind)) {
             if (op_scalar[i] >= 0) continue;          // part of a runtime scalar, applied at its flush
             uint32_t rmask, rval;
@@ -587,7 +619,7 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     (void)have_S;
     if (info.barrier) o.f("    QSV_BARRIER();");
     emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, gen_post, "b");
-    for (int r = 0; r < 16; ++r) o.f("    tout[b%d] = make_double2(x%dr, x%di);", r, r, r);
+    for (int r = 0; r < 16; ++r) o.f("    tout[b%d] = make_double2(%s, %s);", r, xr(r).c_str(), xi(r).c_str());
     o.f("}");
     return 0;
 }

@@ -445,6 +445,9 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
     bool has_diag = false;
     for (uint32_t i = 0; i < hdr->n_ops; ++i) {
         has_diag = has_diag || param.ops[i].kind == QSV_ROP_DIAG;
+        QSV_CHECK_ARG(param.ops[i].kind != QSV_ROP_MCX_REG,
+                      "qsv_run_pass_rounds: the program holds in-register permutations (QSV_ROP_MCX_REG), which only "
+                      "the pass-specialised kernel implements, and that kernel is unavailable: %s", qsv_last_error());
         for (int q = 0; q < 4; ++q) (void)q;
     }
     for (uint32_t r = 0; r < hdr->n_rounds; ++r) {

@@ -226,7 +226,7 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0, single_tile_gbase=
             npost, gen_post = int(R["n_post"]) & 0x7FFF, bool(int(R["n_post"]) & 0x8000)
             n_pt, nreg0 = (int(R["n_ops"]) >> 16) & 0x3FFF, int(R["n_ops"]) & 0xFFFF
             assert all(int(o["kind"]) == 18 for o in rops[f0 + npre: f0 + npre + n_pt])
-            assert all(int(o["kind"]) < 18 for o in rops[f0 + npre + n_pt: f0 + npre + n_pt + nreg0])
+            assert all(int(o["kind"]) < 18 or int(o["kind"]) == 20 for o in rops[f0 + npre + n_pt: f0 + npre + n_pt + nreg0])
             nreg = n_pt + nreg0          # the phase_t list commutes with the ordered list: emulate in sequence
             x = tile[permute(tb, rb, rops[f0: f0 + npre][::-1], gbase, gen_pre)]           # [16, threads]
             for o in rops[f0 + npre: f0 + npre + nreg]:
@@ -258,6 +258,14 @@ def emulate_round_program(prog, tables, ps, psi, rank_bits=0, single_tile_gbase=
                     sc = complex(o["m"][0], o["m"][1])
                     for r in rsel:
                         x[r] = np.where(tp, x[r] * sc, x[r])
+                elif kind == 20:           # in-register (multi-)controlled X on register bit J
+                    assert J < RB and not (rm >> J) & 1
+                    for r in rsel:
+                        if (r >> J) & 1:
+                            continue
+                        x0, x1 = x[r].copy(), x[r | (1 << J)].copy()
+                        x[r] = np.where(tp, x1, x0)
+                        x[r | (1 << J)] = np.where(tp, x0, x1)
                 elif kind == 17:
                     k = int(o["k"])
                     tab = np.frombuffer(tables, dtype=np.complex128, count=1 << k, offset=int(o["table_off"]))

@@ -13,6 +13,13 @@ from helpers import emulate_round_program, jit_cpass, jit_host_run, jit_source
 TOL = 1e-14      # same arithmetic up to FMA contraction and the deferred 2^-1/2 factors
 
 
+@pytest.fixture(autouse=True)
+def _programs_for_the_specialised_kernel(monkeypatch):
+    """Pack the programs the way large states get them (in-register permutations, big programs): the planner
+    asks the library which kernel will run a pass, and QSV_JIT=force answers 'the specialised one'."""
+    monkeypatch.setenv("QSV_JIT", "force")
+
+
 def _rand_state(n, seed):
     rng = np.random.default_rng(seed)
     psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
@@ -52,6 +59,13 @@ def test_layered_circuit_matches_interpreter_emulation(tmp_path):
     ops, _ = lowering.lower(c)
     st = _check(ops, n, tmp_path)
     assert st["rounds"] >= 4
+    from qsv.schedule import ROP_DTYPE, ROP_MCX_REG
+    kinds = set()
+    for ps, prog, _ in _round_programs(ops, n):
+        hdr = np.frombuffer(bytes(prog), dtype="<u4", count=4)
+        rops = np.frombuffer(bytes(prog), dtype=ROP_DTYPE, count=int(hdr[2]), offset=16 + 16 * int(hdr[0]))
+        kinds |= set(int(k) for k in rops["kind"])
+    assert ROP_MCX_REG in kinds, "the layered circuit should produce in-register CNots"
 
 
 def test_qft_ladder_controlled_phases(tmp_path):
@@ -63,10 +77,13 @@ def test_qft_ladder_controlled_phases(tmp_path):
     _check(ops, n, tmp_path, seed=2)
 
 
-def test_toffoli_heavy_circuit_general_permutations(tmp_path):
-    """Toffoli / CNot chains whose conditions read several register-dependent bits leave the XOR-linear
-    address form: the generator must emit the per-slot general form for those lists."""
+@pytest.mark.parametrize("reg_mcx", ["1", "0"])
+def test_toffoli_heavy_circuit_general_permutations(tmp_path, monkeypatch, reg_mcx):
+    """Toffoli / CNot chains: as in-register permutations (slot renaming, predicated exchanges), and - with
+    those switched off - as address permutations whose conditions read several register-dependent bits, which
+    leave the XOR-linear form: the generator must emit the per-slot general form for those lists."""
     from qsv.schedule import Op
+    monkeypatch.setenv("QSV_REG_MCX", reg_mcx)
     n = 13
     rng = random.Random(7)
     ops = []
@@ -89,7 +106,8 @@ def test_toffoli_heavy_circuit_general_permutations(tmp_path):
         else:
             ops.append(Op("dense", (a,), (b,), matrix=H))
     st = _check(ops, n, tmp_path, seed=5)
-    assert st["general"] >= 1, "the circuit was meant to exercise the general permutation form"
+    if reg_mcx == "0":
+        assert st["general"] >= 1, "the circuit was meant to exercise the general permutation form"
 
 
 def test_external_conditions_read_rank_bits(tmp_path):
