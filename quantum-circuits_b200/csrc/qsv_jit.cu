@@ -359,8 +359,12 @@ static bool joins_scalar(const qsv_rop_t &p) {
     return !(p.m[0] == -1.0 && p.m[1] == 0.0);
 }
 
+// direct: 0 = the round stores to the shared-memory tile; 1 = LAST round of the direct-store kernel: once every
+// thread holds its registers the tile buffer is handed back (QSV_TILE_CONSUMED: barrier + TMA load of the CTA's
+// next tile) and the results go from registers straight to global memory.
 static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, RoundInfo &info, bool last_round,
-                     double &scale, bool defer_scale, std::string &err) {
+                     double &scale, bool defer_scale, std::string &err, int direct = 0, const char *suffix = "",
+                     bool emit_hoist = true) {
     const int n_pre = R.n_pre & 0x7fff, n_post = R.n_post & 0x7fff;
     const bool gen_pre = (R.n_pre & 0x8000) != 0, gen_post = (R.n_post & 0x8000) != 0;
     const int n_reg = (int)(R.n_ops & 0xffffu), n_pt = (int)((R.n_ops >> 16) & 0x3fffu);
@@ -430,6 +434,7 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     info.n_hoisted = n_hoist;
 
     // ---- the part of the scalars that depends on the thread index only: once per CTA, not once per tile
+    if (emit_hoist) {
     o.f("struct qsv_H%d { double v[%d]; };", k, n_hoist ? n_hoist : 1);
     o.f("QSV_FN qsv_H%d qsv_hoist%d(const u32 tid) {", k, k);
     o.f("    qsv_H%d H;", k);
@@ -447,9 +452,14 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     }
     o.f("    return H;");
     o.f("}");
+    }
 
-    o.f("QSV_FN void qsv_round%d(const double2 *tin, double2 *tout, const u32 tid, const u64 gbase, const qsv_H%d &H,"
-        " const double2 *tables) {", k, k);
+    if (direct)
+        o.f("QSV_FN void qsv_round%d%s(const double2 *tin, double2 *gout, const u64 tile_base, const u32 tid, const u64 gbase,"
+            " const qsv_H%d &H, const double2 *tables, const qsv_ctx &ctx) {", k, suffix, k);
+    else
+        o.f("QSV_FN void qsv_round%d%s(const double2 *tin, double2 *tout, const u32 tid, const u64 gbase, const qsv_H%d &H,"
+            " const double2 *tables) {", k, suffix, k);
     reset_slot_vars();
     emit_tb(o, R);
     emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
@@ -457,6 +467,7 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     o.f("    double x8r, x8i, x9r, x9i, x10r, x10i, x11r, x11i, x12r, x12i, x13r, x13i, x14r, x14i, x15r, x15i;");
     for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[a%d]; x%dr = v.x; x%di = v.y; }", r, r, r);
     o.f("    (void)H; (void)tables; (void)gbase;");
+    if (direct) o.f("    QSV_TILE_CONSUMED(ctx);");
 
     // runtime scalars: hoisted part x the factors that read external bits (uniform per tile)
     for (const Scalar &sc : scalars) {
@@ -617,6 +628,23 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     }
     flush(-1);
     (void)have_S;
+    if (direct) {
+        // registers -> global memory.  Tile-local address -> global index is a bit scatter (linear over XOR):
+        // index(r) = tile_base | S(base) ^ XOR_{q in r} S(d_q)
+        if (!gen_post) {
+            emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, false, "b");
+            o.f("    const u64 g0 = tile_base | qsv_scatter(bb);");
+            o.f("    const u64 gd0 = qsv_scatter(bd0), gd1 = qsv_scatter(bd1), gd2 = qsv_scatter(bd2), gd3 = qsv_scatter(bd3);");
+            for (int r = 1; r < 16; ++r)
+                o.f("    const u64 g%d = g%d ^ gd%d;", r, r & (r - 1), __builtin_ctz(r));
+        } else {
+            emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, true, "b");
+            for (int r = 0; r < 16; ++r) o.f("    const u64 g%d = tile_base | qsv_scatter(b%d);", r, r);
+        }
+        for (int r = 0; r < 16; ++r) o.f("    QSV_STG(gout + g%d, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
+        o.f("}");
+        return 0;
+    }
     if (info.barrier) o.f("    QSV_BARRIER();");
     emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, gen_post, "b");
     for (int r = 0; r < 16; ++r) o.f("    tout[b%d] = make_double2(%s, %s);", r, xr(r).c_str(), xi(r).c_str());
@@ -636,12 +664,17 @@ static inline double QD(u64 h) { double d; memcpy(&d, &h, 8); return d; }
 #define QSV_FN static inline
 #define QSV_BARRIER()
 #define QSV_LDG(p) (*(p))
+#define QSV_STG(p, re, im) (*(p) = make_double2(re, im))
+#define QSV_TILE_CONSUMED(c)
+struct qsv_ctx { int unused; };
 #else
 #define QD(h) __longlong_as_double((long long)(h))
 #define QNEG(v) __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v))
 #define QSV_FN __device__ __forceinline__
 #define QSV_BARRIER() __syncthreads()
 #define QSV_LDG(p) __ldg(p)
+#define QSV_STG(p, re, im) (*(p) = make_double2(re, im))
+#define QSV_TILE_CONSUMED(c) qsv_tile_consumed(c)
 #endif
 )SRC";
 
@@ -665,6 +698,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
                  "r"(bytes) : "memory");
@@ -683,15 +719,62 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     if (P.tile_bits != 12) { err = "generator needs 12 tile bits"; return 1; }
     const int L = P.low_bits, n_hi = P.n_hi;
     const bool defer_scale = getenv("QSV_JIT_NO_DEFER") == nullptr;
+    const char *pf = getenv("QSV_JIT_PREFETCH");
+    const bool prefetch_env = !(pf && !strcmp(pf, "0"));
+
+    const char *ds = getenv("QSV_JIT_DIRECT_STORE");
+    const bool direct = !(ds && !strcmp(ds, "0"));
+    const int n_runs = 1 << n_hi;
+    const uint32_t nr = hdr->n_rounds;
 
     Out o;
     o.s += kPrelude;
     o.s += kDeviceHelpers;
-    std::vector<RoundInfo> info(hdr->n_rounds);
+    // tile-local address -> offset inside the state (bit scatter of the high tile bits)
+    o.f("QSV_FN u64 qsv_scatter(const u32 a) {");
+    {
+        std::string e = "(u64)(a & 0x" + [&] { char b_[16]; snprintf(b_, sizeof(b_), "%x", (1u << L) - 1u); return std::string(b_); }() + "u)";
+        for (int j = 0; j < n_hi; ++j)
+            e += " | ((u64)((a >> " + std::to_string(L + j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
+        o.f("    return %s;", e.c_str());
+    }
+    o.f("}");
+    if (direct) {
+        // hand-back of the tile buffer inside the last round: every thread holds its amplitudes in registers,
+        // so the CTA's NEXT tile can stream into shared memory while this one is computed and stored
+        o.f("#ifndef QSV_JIT_HOST");
+        o.f("struct qsv_ctx { double2 *state; double2 *tile; u64 *mbar; const u64 *s_off; u64 next_base; u32 warp; u32 flags; };");
+        o.f("__device__ __forceinline__ void qsv_issue_load(const qsv_ctx &c) {");
+        o.f("    if (c.flags & 2u) mbar_expect_tx(c.mbar, %uu);", 16u << 12);
+        o.f("    u32 elected;");
+        o.f("    asm volatile(\"{\\n.reg .pred P;\\nelect.sync _|P, 0xffffffff;\\nselp.u32 %%0, 1, 0, P;\\n}\\n\" : \"=r\"(elected));");
+        o.f("    if (elected)");
+        o.f("        for (u32 r = c.warp; r < %du; r += 8u)", n_runs);
+        o.f("            bulk_g2s(c.tile + ((u64)r << %d), c.state + c.next_base + c.s_off[r], %uu, c.mbar);", L, 16u << L);
+        o.f("}");
+        o.f("__device__ __forceinline__ void qsv_tile_consumed(const qsv_ctx &c) {");
+        o.f("    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
+        o.f("    __syncthreads();");
+        o.f("    if (c.flags & 4u) qsv_issue_load(c);");
+        o.f("}");
+        o.f("#endif");
+    }
+    std::vector<RoundInfo> info(nr);
     double scale = 1.0;
-    for (uint32_t k = 0; k < hdr->n_rounds; ++k)
-        if (gen_round(o, (int)k, rounds[k], ops.data(), info[k], k + 1 == hdr->n_rounds, scale, defer_scale, err))
+    for (uint32_t k = 0; k < nr; ++k) {
+        const bool last = k + 1 == nr;
+        const double scale_before = scale;
+        if (gen_round(o, (int)k, rounds[k], ops.data(), info[k], last, scale, defer_scale, err, (last && direct) ? 1 : 0))
             return 1;
+        if (last && direct) {
+            // tile-local form of the last round for the single-tile host entry (tests)
+            o.f("#ifdef QSV_JIT_HOST");
+            double sc2 = scale_before;
+            RoundInfo dummy;
+            if (gen_round(o, (int)k, rounds[k], ops.data(), dummy, true, sc2, defer_scale, err, 0, "_local", false)) return 1;
+            o.f("#endif");
+        }
+    }
 
     // is a tile ever skipped?  (every op has an external condition)
     bool always_active = false;
@@ -702,34 +785,46 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         for (const qsv_rop_t &p : ops) {
             std::string c = cond_ext(p.ext_mask, p.ext_val);
             bool dup = false;
-            for (auto &s : seen) dup = dup || s == c;
+            for (auto &s_ : seen) dup = dup || s_ == c;
             if (!dup) { seen.push_back(c); active += " || " + c; }
         }
+    } else {
+        active = "true";
     }
+    o.f("QSV_FN bool qsv_active(const u64 gbase) { (void)gbase; return %s; }", active.c_str());
 
     // ---- tile base: insert a zero bit at every hi position (ascending)
-    Out tb;
-    tb.f("        u64 base = t << %d;", L);
+    o.f("QSV_FN u64 qsv_tile_base(const u64 t) {");
+    o.f("    u64 base = t << %d;", L);
     for (int j = 0; j < n_hi; ++j)
-        tb.f("        base = ((base >> %u) << %u) | (base & 0x%llxULL);", P.hi_pos[j], P.hi_pos[j] + 1u,
-             (unsigned long long)((1ull << P.hi_pos[j]) - 1ull));
-    tb.f("        const u64 gbase = base | rank_bits;");
-    if (!always_active) tb.f("        if (!(%s)) continue;", active.c_str());
+        o.f("    base = ((base >> %u) << %u) | (base & 0x%llxULL);", P.hi_pos[j], P.hi_pos[j] + 1u,
+            (unsigned long long)((1ull << P.hi_pos[j]) - 1ull));
+    o.f("    return base;");
+    o.f("}");
+    const bool prefetch = prefetch_env && always_active && !direct;      // skipped tiles must not be fetched
 
-    auto rounds_body = [&](Out &w, const char *tin, const char *tout_a, const char *tout_b, bool host) {
-        // host: rounds ping-pong between two buffers and are driven for all thread ids sequentially
-        for (uint32_t k = 0; k < hdr->n_rounds; ++k) {
-            const char *src_buf = host ? ((k & 1) ? tout_b : tout_a) : tin;
-            const char *dst_buf = host ? ((k & 1) ? tout_a : tout_b) : tin;
-            if (host) {
-                w.f("        for (u32 tid = 0; tid < 256u; ++tid) {");
-                w.f("            const qsv_H%u H = qsv_hoist%u(tid);", k, k);
-                w.f("            qsv_round%u(%s, %s, tid, gbase, H, tables);", k, src_buf, dst_buf);
-                w.f("        }");
-            } else {
+    // rounds of one tile.  mode 0: device, 1: host whole-state driver, 2: host single tile (tile-local stores)
+    auto rounds_body = [&](Out &w, int mode) {
+        for (uint32_t k = 0; k < nr; ++k) {
+            const bool last = k + 1 == nr;
+            if (mode == 0) {
                 if (k > 0) w.f("        __syncthreads();");
-                w.f("        qsv_round%u(%s, %s, tid, gbase, H%u, tables);", k, src_buf, dst_buf, k);
+                if (last && direct)
+                    w.f("        qsv_round%u(tile, state, base, tid, gbase, H%u, tables, ctx);", k, k);
+                else
+                    w.f("        qsv_round%u(tile, tile, tid, gbase, H%u, tables);", k, k);
+                continue;
             }
+            const char *src_buf = (k & 1) ? "B" : "A", *dst_buf = (k & 1) ? "A" : "B";
+            w.f("        for (u32 tid = 0; tid < 256u; ++tid) {");
+            w.f("            const qsv_H%u H = qsv_hoist%u(tid);", k, k);
+            if (last && direct && mode == 1)
+                w.f("            qsv_round%u(%s, state, base, tid, gbase, H, tables, ctx);", k, src_buf);
+            else if (last && direct)
+                w.f("            qsv_round%u_local(%s, %s, tid, gbase, H, tables);", k, src_buf, dst_buf);
+            else
+                w.f("            qsv_round%u(%s, %s, tid, gbase, H, tables);", k, src_buf, dst_buf);
+            w.f("        }");
         }
     };
 
@@ -743,70 +838,93 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("    const u32 tid = threadIdx.x;");
     o.f("    if (tid == 0) { mbar_init(&mbar, 1); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }");
     o.f("    __syncthreads();");
-    for (uint32_t k = 0; k < hdr->n_rounds; ++k) o.f("    const qsv_H%u H%u = qsv_hoist%u(tid);", k, k, k);
+    for (uint32_t k = 0; k < nr; ++k) o.f("    const qsv_H%u H%u = qsv_hoist%u(tid);", k, k, k);
     // run r of the tile: 2^L amplitudes at state[base + s_off[r]], s_off[r] = bits of r scattered to hi_pos.
     // The offsets are read from a shared-memory table like in k_pass_reg.  (Literal 64-bit offsets in an
     // unrolled issue sequence made ptxas 12.9 schedule a register copy AFTER its use across the ELECT
     // waterfall loops of UBLKCP - the first tile of a CTA then copied from a garbage address whenever an
     // offset needed a carry into the high word, i.e. tile bits at positions >= 28.)
-    const int n_runs = 1 << n_hi;
     o.f("    __shared__ u64 s_off[%d];", n_runs);
-    o.f("    if (tid < %du) {", n_runs);
-    {
-        std::string e = "0ULL";
-        for (int j = 0; j < n_hi; ++j)
-            e += " | ((u64)((tid >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
-        o.f("        s_off[tid] = %s;", e.c_str());
-    }
-    o.f("    }");
+    o.f("    if (tid < %du) s_off[tid] = qsv_scatter(tid << %d);", n_runs, L);
     o.f("    __syncthreads();");
     o.f("    const u32 warp = tid >> 5;");
-    o.f("    const bool issuer = (tid & 31u) == 0u;");
     o.f("    u32 parity = 0;");
-    o.f("    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {");
-    o.s += tb.s;
-    o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
-    o.f("        if (issuer)");
-    o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
-    o.f("                bulk_g2s(tile + ((u64)r << %d), state + base + s_off[r], %uu, &mbar);", L, 16u << L);
-    o.f("        mbar_wait(&mbar, parity);");
-    o.f("        parity ^= 1u;");
-    rounds_body(o, "tile", "", "", false);
-    o.f("        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
-    o.f("        __syncthreads();");
-    o.f("        if (issuer)");
-    o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
-    o.f("                bulk_s2g(state + base + s_off[r], tile + ((u64)r << %d), %uu);", L, 16u << L);
-    o.f("        asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");");
-    o.f("        asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");");
-    o.f("    }");
+    if (direct) {
+        // Persistent loop with the load of tile k+1 issued from inside tile k's last round.
+        o.f("    qsv_ctx ctx;");
+        o.f("    ctx.state = state; ctx.tile = tile; ctx.mbar = &mbar; ctx.s_off = s_off; ctx.warp = warp;");
+        o.f("    ctx.flags = (tid == 0 ? 2u : 0u) | 4u;");
+        o.f("    u64 t = blockIdx.x;");
+        o.f("    while (t < n_tiles && !qsv_active(qsv_tile_base(t) | rank_bits)) t += gridDim.x;");
+        o.f("    if (t >= n_tiles) return;");
+        o.f("    ctx.next_base = qsv_tile_base(t);");
+        o.f("    qsv_issue_load(ctx);");
+        o.f("    for (;;) {");
+        o.f("        const u64 base = qsv_tile_base(t);");
+        o.f("        const u64 gbase = base | rank_bits;");
+        o.f("        u64 tn = t + gridDim.x;");
+        o.f("        while (tn < n_tiles && !qsv_active(qsv_tile_base(tn) | rank_bits)) tn += gridDim.x;");
+        o.f("        ctx.next_base = tn < n_tiles ? qsv_tile_base(tn) : 0ULL;");
+        o.f("        ctx.flags = (ctx.flags & 3u) | (tn < n_tiles ? 4u : 0u);");
+        o.f("        mbar_wait(&mbar, parity);");
+        o.f("        parity ^= 1u;");
+        rounds_body(o, 0);
+        o.f("        if (tn >= n_tiles) break;");
+        o.f("        t = tn;");
+        o.f("    }");
+    } else {
+        // one elected lane per warp issues the bulk copies.  elect.sync (instead of lane == 0) tells ptxas that
+        // exactly one lane is active: addresses go through R2UR + uniform arithmetic straight into UBLKCP, without
+        // the ELECT/PLOP3/BRA.U.ANY waterfall loop it otherwise wraps around every copy (16 -> 8 instructions each)
+        o.f("    u32 elected;");
+        o.f("    asm volatile(\"{\\n.reg .pred P;\\nelect.sync _|P, 0xffffffff;\\nselp.u32 %%0, 1, 0, P;\\n}\\n\" : \"=r\"(elected));");
+        o.f("    const bool issuer = elected != 0u;");
+        o.f("    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {");
+        o.f("        const u64 base = qsv_tile_base(t);");
+        o.f("        const u64 gbase = base | rank_bits;");
+        o.f("        if (!qsv_active(gbase)) continue;");
+        o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
+        o.f("        if (issuer)");
+        o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
+        o.f("                bulk_g2s(tile + ((u64)r << %d), state + base + s_off[r], %uu, &mbar);", L, 16u << L);
+        if (prefetch) {
+            // the CTA's NEXT tile is pulled into L2 while this one is computed
+            o.f("        if (issuer && t + gridDim.x < n_tiles) {");
+            o.f("            const u64 nbase = qsv_tile_base(t + gridDim.x);");
+            o.f("            for (u32 r = warp; r < %du; r += 8u) bulk_prefetch_l2(state + nbase + s_off[r], %uu);", n_runs,
+                16u << L);
+            o.f("        }");
+        }
+        o.f("        mbar_wait(&mbar, parity);");
+        o.f("        parity ^= 1u;");
+        rounds_body(o, 0);
+        o.f("        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
+        o.f("        __syncthreads();");
+        o.f("        if (issuer)");
+        o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
+        o.f("                bulk_s2g(state + base + s_off[r], tile + ((u64)r << %d), %uu);", L, 16u << L);
+        o.f("        asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");");
+        o.f("        asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");");
+        o.f("    }");
+    }
     o.f("}");
     o.f("#else");
     // ---- host emulation driver (tests only): same round functions, threads run sequentially
     o.f("extern \"C\" void qsv_jit_host_run(double2 *state, const u64 rank_bits, const u64 n_tiles, const double2 *tables) {");
     o.f("    static double2 A[4096], B[4096];");
+    o.f("    qsv_ctx ctx; (void)ctx;");
     o.f("    for (u64 t = 0; t < n_tiles; ++t) {");
-    o.s += tb.s;
-    o.f("        for (u32 r = 0; r < %du; ++r) {", n_runs);
-    {
-        std::string e = "0ULL";
-        for (int j = 0; j < n_hi; ++j)
-            e += " | ((u64)((r >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
-        o.f("            const u64 off = %s;", e.c_str());
+    o.f("        const u64 base = qsv_tile_base(t);");
+    o.f("        const u64 gbase = base | rank_bits;");
+    o.f("        if (!qsv_active(gbase)) continue;");
+    o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
+    o.f("            memcpy(A + ((u64)r << %d), state + base + qsv_scatter(r << %d), %uu);", L, L, 16u << L);
+    rounds_body(o, 1);
+    if (!direct) {
+        o.f("        const double2 *fin = %s;", (nr & 1) ? "B" : "A");
+        o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
+        o.f("            memcpy(state + base + qsv_scatter(r << %d), fin + ((u64)r << %d), %uu);", L, L, 16u << L);
     }
-    o.f("            memcpy(A + ((u64)r << %d), state + base + off, %uu);", L, 16u << L);
-    o.f("        }");
-    rounds_body(o, "", "A", "B", true);
-    o.f("        const double2 *fin = %s;", (hdr->n_rounds & 1) ? "B" : "A");
-    o.f("        for (u32 r = 0; r < %du; ++r) {", n_runs);
-    {
-        std::string e = "0ULL";
-        for (int j = 0; j < n_hi; ++j)
-            e += " | ((u64)((r >> " + std::to_string(j) + ") & 1u) << " + std::to_string(P.hi_pos[j]) + ")";
-        o.f("            const u64 off = %s;", e.c_str());
-    }
-    o.f("            memcpy(state + base + off, fin + ((u64)r << %d), %uu);", L, 16u << L);
-    o.f("        }");
     o.f("    }");
     o.f("}");
     // one tile with a caller-chosen global base index (programs of states too large for a host array)
@@ -814,9 +932,9 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("    static double2 A[4096], B[4096];");
     o.f("    memcpy(A, tile, sizeof(A));");
     o.f("    {");
-    rounds_body(o, "", "A", "B", true);
+    rounds_body(o, 2);
     o.f("    }");
-    o.f("    memcpy(tile, %s, sizeof(A));", (hdr->n_rounds & 1) ? "B" : "A");
+    o.f("    memcpy(tile, %s, sizeof(A));", (nr & 1) ? "B" : "A");
     o.f("}");
     o.f("#endif");
     src.swap(o.s);
@@ -953,6 +1071,8 @@ static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t byt
     k.append(reinterpret_cast<const char *>(&P.low_bits), sizeof(P.low_bits));
     k.append(reinterpret_cast<const char *>(P.hi_pos), sizeof(P.hi_pos));
     k.append(getenv("QSV_JIT_NO_DEFER") ? "N" : "D");
+    { const char *ds = getenv("QSV_JIT_DIRECT_STORE"); k.append(ds && !strcmp(ds, "0") ? "s" : "S"); }
+    { const char *pf = getenv("QSV_JIT_PREFETCH"); k.append(pf && !strcmp(pf, "0") ? "p" : "P"); }
     k.append(static_cast<const char *>(prog), bytes);
     return k;
 }

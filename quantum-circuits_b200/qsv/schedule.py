@@ -824,7 +824,8 @@ def pack_passes(passes, register_kernel=None):
             # one- and two-op passes stay on the shared-memory kernel: it is HBM-bound there (3 CTAs/SM,
             # 104-106 % of the measured copy peak) while the register kernel pays its round overhead
             max_rounds, max_ops = program_capacity(ps)
-            specialised = max_ops > RPROG_MAX_OPS and os.environ.get("QSV_REG_MCX", "1") != "0"
+            mode = os.environ.get("QSV_REG_MCX", "1")
+            specialised = False if (max_ops <= RPROG_MAX_OPS or mode == "0") else ("all" if mode == "all" else True)
             rounds = plan_rounds(ps, reg_mcx=specialised) \
                 if len(ps.ops) > int(os.environ.get("QSV_REG_MIN_OPS", "2")) else None
             if rounds is not None:
@@ -944,9 +945,10 @@ def plan_rounds(ps, reg_mcx=False):
     """Split the ops of one pass into rounds of the register-resident kernel.
 
     reg_mcx (programs for the pass-specialised kernel only): an X / CNot / Toffoli whose target is a register
-    bit and that cannot ride on the loads may run IN the register phase (a renaming of the slot variables, or a
-    predicated exchange when a control is thread-held / external) instead of ending the round: far fewer
-    shared-memory round trips (config 3: 49 -> 36 rounds).
+    bit and that cannot ride on the loads may run IN the register phase instead of ending the round.  True:
+    only when every control is a register bit too - then it is a renaming of the slot variables at generation
+    time, zero instructions.  "all": also with thread-held / external controls (a predicated exchange of 16
+    doubles; measured: the saved rounds, 49 -> 36 on config 3, and the exchanges + register spills cancel).
 
     A round fixes 4 tile-local register bits.  Its ops are ordered [pre | reg | post]: `reg` ops (1-qubit
     dense with the target on a register bit, phases, diagonal tables) run on registers; X / CNot /
@@ -976,7 +978,8 @@ def plan_rounds(ps, reg_mcx=False):
                 if before_reg and before_post:      # commutes with everything queued: ride on the loads
                     pre.append(op)
                 elif reg_mcx and before_post and (l in rb or len(rb) < REG_BITS) \
-                        and l not in _dense_ctrl_bits(reg, ps):
+                        and l not in _dense_ctrl_bits(reg, ps) \
+                        and (reg_mcx == "all" or all(c < ps.n_local and ps.loc(c) in rb for c in op.controls)):
                     if l not in rb:
                         rb.append(l)
                     reg.append(op)

@@ -51,12 +51,13 @@ def _check(ops, n_local, tmp_path, rank_bits=0, seed=1):
     return stats
 
 
-def test_layered_circuit_matches_interpreter_emulation(tmp_path):
+def test_layered_circuit_matches_interpreter_emulation(tmp_path, monkeypatch):
     from qsv import workloads, lowering
     n = 14
     c = workloads.random_layered_circuit(n, 6, seed=3)
     c.sort()
     ops, _ = lowering.lower(c)
+    monkeypatch.setenv("QSV_REG_MCX", "all")
     st = _check(ops, n, tmp_path)
     assert st["rounds"] >= 4
     from qsv.schedule import ROP_DTYPE, ROP_MCX_REG
@@ -77,7 +78,7 @@ def test_qft_ladder_controlled_phases(tmp_path):
     _check(ops, n, tmp_path, seed=2)
 
 
-@pytest.mark.parametrize("reg_mcx", ["1", "0"])
+@pytest.mark.parametrize("reg_mcx", ["1", "all", "0"])
 def test_toffoli_heavy_circuit_general_permutations(tmp_path, monkeypatch, reg_mcx):
     """Toffoli / CNot chains: as in-register permutations (slot renaming, predicated exchanges), and - with
     those switched off - as address permutations whose conditions read several register-dependent bits, which
