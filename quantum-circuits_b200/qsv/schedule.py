@@ -555,6 +555,8 @@ def _improve_tile(masks, hi, low_mask, n_free_slots, n_local, L):
     hi = set(hi)
     cand = set()
     for nd_m, _ in masks[:PLAN_WINDOW // 2]:
+        if nd_m >> 200:
+            continue                    # never joins this pass (whole-state op, or target on a forbidden position)
         m = nd_m >> L
         b = L
         while m:
@@ -612,16 +614,24 @@ def block_masks(op, n_local):
     return _NOT_TILED | _mask(tuple(op.targets) + tuple(op.controls)), 0
 
 
-def _plan_one_pass(remaining, masks_of, n_local, T, L, search):
-    """One pass from the head of `remaining`: (Pass, rest)."""
+def _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=0):
+    """One pass from the head of `remaining`: (Pass, rest).  `forbidden`: positions the tile must not hold
+    (ops with a non-diagonal target there wait for a later pass); returns (None, remaining) if nothing fits."""
     low_mask = (1 << L) - 1
+    if forbidden:
+        keep = _NOT_TILED << 1          # a second sentinel: "touches a forbidden position non-diagonally"
+        masks_of = dict(masks_of)
+        for op in remaining:
+            nd_m, dg_m = masks_of[id(op)]
+            if nd_m & forbidden:
+                masks_of[id(op)] = (nd_m | keep, dg_m)
     masks = [masks_of[id(op)] for op in remaining[:PLAN_WINDOW]]
     # ---- first-come choice of the high positions
     hi = []
     free = T - L
     blocked_nd = blocked_d = 0
     for nd_m, dg_m in masks:
-        ok = not (nd_m & _NOT_TILED) and not (nd_m & (blocked_nd | blocked_d)) and not (dg_m & blocked_nd)
+        ok = not (nd_m >> 200) and not (nd_m & (blocked_nd | blocked_d)) and not (dg_m & blocked_nd)
         if ok:
             new = [b for b in range(L, n_local) if (nd_m >> b) & 1 and b not in hi]
             if len(new) <= free:
@@ -646,6 +656,8 @@ def _plan_one_pass(remaining, masks_of, n_local, T, L, search):
         blocked_d |= dg_m
         rest.append(op)
     if not chosen:
+        if forbidden:
+            return None, remaining
         raise RuntimeError("pass planner made no progress (op needs more than %d tile-local qubits)" % T)
     # fill the unused tile slots with the lowest free positions, avoiding control/diagonal bits
     # of the chosen ops so that those stay external (tiles they switch off are never loaded)
@@ -657,10 +669,12 @@ def _plan_one_pass(remaining, masks_of, n_local, T, L, search):
         for b in range(L, n_local):
             if free == 0:
                 break
-            if b in hi or (rnd == 0 and (avoid >> b) & 1):
+            if b in hi or (rnd == 0 and (avoid >> b) & 1) or (forbidden >> b) & 1:
                 continue
             hi.append(b)
             free -= 1
+    if free:
+        return None, remaining          # (only with forbidden positions on a tiny register)
     return Pass(n_local, T, L, tuple(sorted(hi)), chosen), rest
 
 
@@ -672,19 +686,34 @@ def _geometry(n_local, tile_bits, low_bits):
     return T, L
 
 
-def plan_schedule(ops, n_local, tile_bits=None, low_bits=None):
-    """Whole op list (tiled ops, whole-state ops, global<->local swaps) -> [("pass", Pass) | ("op", op)] in
-    execution order.  A non-tiled op runs when it reaches the head of the list; until then it only blocks the
-    positions it touches, so passes keep absorbing later ops that commute with it - in particular the passes
-    before a qubit swap fill up with ops from behind the swap instead of ending in near-empty sweeps."""
+def plan_schedule(ops, n_local, tile_bits=None, low_bits=None, fuse_swaps=False):
+    """Whole op list (tiled ops, whole-state ops, global<->local swaps) -> [("pass", Pass) | ("op", op) |
+    ("swap_pass", (swap op, Pass))] in execution order.  A non-tiled op runs when it reaches the head of the
+    list; until then it only blocks the positions it touches, so passes keep absorbing later ops that commute
+    with it - in particular the passes before a qubit swap fill up with ops from behind the swap instead of
+    ending in near-empty sweeps.
+
+    fuse_swaps (peer-memory engine): the pass that follows a free-position swap is planned with the swapped
+    positions kept OUT of its tile; swap and pass then run as ONE kernel that moves every tile across NVLink
+    and applies the pass on the way (csrc/qsv_jit.cu, fused variant) - the gate pass hides under the transfer."""
     T, L = _geometry(n_local, tile_bits, low_bits)
     search = os.environ.get("QSV_PLAN_SEARCH", "1") != "0" and T - L > 0
     remaining = list(ops)
     masks_of = {id(op): block_masks(op, n_local) for op in remaining}
     out = []
     while remaining:
-        if remaining[0].kind not in TILED_KINDS:
-            out.append(("op", remaining.pop(0)))
+        head = remaining[0]
+        if head.kind not in TILED_KINDS:
+            remaining.pop(0)
+            pos = head.params.get("positions") if head.kind == "global_swap" else None
+            if fuse_swaps and pos is not None and T == 12 and min(pos) >= L and remaining \
+                    and remaining[0].kind in TILED_KINDS:
+                ps, rest = _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=_mask(pos))
+                if ps is not None and plan_rounds(ps) is not None:
+                    out.append(("swap_pass", (head, ps)))
+                    remaining = rest
+                    continue
+            out.append(("op", head))
             continue
         ps, remaining = _plan_one_pass(remaining, masks_of, n_local, T, L, search)
         out.append(("pass", ps))
