@@ -29,6 +29,27 @@ def plan_exchange(n_local, g, staging_bytes=DEFAULT_STAGING_BYTES):
     return P, S, C_, S // C_
 
 
+_DEFAULT_COMM = None
+
+
+def default_comm():
+    """The communicator the public API (main.circuit.Circuit.run / run_method2) shards over: the default
+    process group when the program was launched with one process per GPU (torchrun, NCCL backend, 2^g ranks),
+    else None.  QSV_SHARD=0 keeps every rank on its own unsharded copy."""
+    global _DEFAULT_COMM
+    import os
+    if os.environ.get("QSV_SHARD", "1") == "0":
+        return None
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    world = dist.get_world_size()
+    if world < 2 or world & (world - 1) or dist.get_backend() != "nccl":
+        return None
+    if _DEFAULT_COMM is None or _DEFAULT_COMM.group is not dist.group.WORLD:
+        _DEFAULT_COMM = Comm(dist.group.WORLD)
+    return _DEFAULT_COMM
+
+
 class Comm:
     """Thin wrapper over a torch.distributed process group of size 2^g."""
 
@@ -88,7 +109,24 @@ class Comm:
         self.bytes_sent += 16 * (self.world - 1) * (1 << (sv.n_local - self.global_bits))
         self.swaps += 1
 
+    def release_state(self):
+        """Drop the symmetric-memory state (the StateVector that used it must be dropped as well)."""
+        self._symm = None
+        self.peer_swap = False
+
     # ------------------------------------------------------------------ collectives
+    def broadcast_float(self, value, src=0):
+        """The same float64 on every rank (rank `src`'s): one uniform draw per run, shared by all shards."""
+        t = torch.tensor([float(value)], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+        dist.broadcast(t, dist.get_global_rank(self.group, src), group=self.group)
+        return float(t.item())
+
+    def all_gather_local(self, t):
+        """Concatenation of every rank's 1-D tensor in rank order (physical index order of a sharded register)."""
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
     def all_reduce_sum(self, t):
         """In-place sum of a complex128 / float64 tensor over all ranks (NCCL has no complex type)."""
         v = torch.view_as_real(t) if t.is_complex() else t

@@ -152,8 +152,12 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
         from .schedule import fuse_1q
         ops = fuse_1q(ops)
     if n_global:
-        from .schedule import place
-        ops, src_pos = place(ops, n, n_global, src_pos, free_swap=free_swap)
+        from .schedule import place, place_joint, TILED_KINDS
+        if free_swap and os.environ.get("QSV_PLACE", "joint") != "list" and all(o.kind in TILED_KINDS for o in ops):
+            # placement and pass planning decided together: swaps happen when the passes run thin
+            ops, src_pos = place_joint(ops, n, n_global, src_pos)
+        else:
+            ops, src_pos = place(ops, n, n_global, src_pos, free_swap=free_swap)
     if in_flip:
         return ops, src_pos, flip
     return ops, src_pos
@@ -174,9 +178,51 @@ def last_run_stats():
     return dict(_last_stats)
 
 
-def evolve(circuit, in_v, transposed=False, presorted=True, comm=None):
-    ops, src_pos, flip = lower(circuit, transposed, presorted, in_flip=True)
-    sv = _engine.StateVector(len(circuit), comm=comm)
+SHARD_MIN_LOCAL_QUBITS = 20    # registers with fewer qubits per shard run unsharded (replicated) on every rank
+WEIGHTS_MAX_SHARDED_QUBITS = 28   # run_method2 on a sharded register gathers all 2^n weights on every rank up to here
+
+_sharded_pool = {}             # (n, id(comm)) -> StateVector on symmetric memory (rendezvous once, not per run)
+
+
+def _sharded_state(n, comm):
+    key = (n, id(comm))
+    sv = _sharded_pool.get(key)
+    if sv is None:
+        for k in list(_sharded_pool):          # one resident sharded register at a time
+            _sharded_pool.pop(k)
+            comm.release_state()
+        sv = _engine.StateVector(n, comm=comm)
+        _sharded_pool[key] = sv
+    return sv
+
+
+def release_sharded_states():
+    """Free the pooled sharded registers (their symmetric memory)."""
+    for k in list(_sharded_pool):
+        sv = _sharded_pool.pop(k)
+        if sv.comm is not None:
+            sv.comm.release_state()
+
+
+def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=True):
+    """Run the circuit on |in_v>: (StateVector, src_pos).  Under one-process-per-GPU launches (torchrun, NCCL)
+    the register is sharded over the ranks by its top qubits (qsv.dist.default_comm) unless it is small or
+    shard=False; every rank then holds one shard and must make the same calls."""
+    n = len(circuit)
+    if comm is None and shard:
+        from . import dist as _dist
+        comm = _dist.default_comm()
+        min_local = int(os.environ.get("QSV_SHARD_MIN_LOCAL", SHARD_MIN_LOCAL_QUBITS))
+        if comm is not None and n - comm.global_bits < min_local:
+            comm = None
+    if comm is None or comm.world < 2:
+        ops, src_pos, flip = lower(circuit, transposed, presorted, in_flip=True)
+        sv = _engine.StateVector(n, comm=comm)
+    else:
+        sv = _sharded_state(n, comm)
+        sv.d2h_bytes = 0
+        ops, src_pos, flip = lower(circuit, transposed, presorted, n_global=comm.global_bits, in_flip=True,
+                                   free_swap=bool(comm.peer_swap))
     sv.init_basis(basis_index(in_v) ^ flip)
     plan = sv.run_ops(ops)
     _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=0, passes=sv.passes_run)
@@ -206,9 +252,24 @@ class LazyWeights:
         return self._t
 
 
+def _gathered_weights(sv, src_pos):
+    """All 2^n weights of a sharded register in OUTPUT order, on every rank (main/circuit.py:329-337)."""
+    import torch
+    n = sv.n
+    if n > WEIGHTS_MAX_SHARDED_QUBITS:
+        raise RuntimeError("run_method2 on a sharded register of %d qubits would materialise 2^%d weights on every "
+                           "GPU; use run() (sampling) above %d qubits" % (n, n, WEIGHTS_MAX_SHARDED_QUBITS))
+    full = sv.comm.all_gather_local(sv.probs(None))          # physical index order: rank = top bits
+    z = torch.arange(1 << n, dtype=torch.int64, device=full.device)
+    y = torch.zeros_like(z)
+    for b in range(n):
+        y |= ((z >> b) & 1) << int(src_pos[b])
+    return full[y]
+
+
 def simulate_weights(circuit, in_v, transposed=False, presorted=True):
     sv, src_pos = evolve(circuit, in_v, transposed, presorted)
-    w = sv.probs(src_pos)
+    w = _gathered_weights(sv, src_pos) if (sv.comm is not None and sv.comm.world > 1) else sv.probs(src_pos)
     sv.synchronize()
     if len(circuit) <= LIST_WEIGHTS_MAX_QUBITS:
         _last_stats["d2h_bytes"] = 8 * w.numel()
@@ -219,6 +280,8 @@ def simulate_weights(circuit, in_v, transposed=False, presorted=True):
 def simulate_sample(circuit, in_v, rand_fn, transposed=False, presorted=True):
     sv, src_pos = evolve(circuit, in_v, transposed, presorted)
     u = rand_fn()                       # exactly one uniform draw per run, after the weights exist
+    if sv.comm is not None and sv.comm.world > 1:
+        u = sv.comm.broadcast_float(u)  # every rank drew once from its own generator; rank 0's value is used
     z = sv.sample(u, src_pos)
     sv.synchronize()
     _last_stats["d2h_bytes"] = sv.d2h_bytes
@@ -227,7 +290,7 @@ def simulate_sample(circuit, in_v, rand_fn, transposed=False, presorted=True):
 
 def simulate_amplitudes(circuit, in_v, transposed=False, presorted=True):
     """Final amplitudes in OUTPUT order as numpy complex128 (tests; the reference only exposes weights)."""
-    sv, src_pos = evolve(circuit, in_v, transposed, presorted)
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted, shard=False)
     amp = sv.amplitudes()
     n = len(circuit)
     z = np.arange(1 << n, dtype=np.int64)

@@ -614,9 +614,10 @@ def block_masks(op, n_local):
     return _NOT_TILED | _mask(tuple(op.targets) + tuple(op.controls)), 0
 
 
-def _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=0):
+def _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=0, allow_none=False):
     """One pass from the head of `remaining`: (Pass, rest).  `forbidden`: positions the tile must not hold
-    (ops with a non-diagonal target there wait for a later pass); returns (None, remaining) if nothing fits."""
+    (ops with a non-diagonal target there wait for a later pass); returns (None, remaining) if nothing fits
+    (only with `forbidden` or `allow_none`, otherwise that is an error)."""
     low_mask = (1 << L) - 1
     if forbidden:
         keep = _NOT_TILED << 1          # a second sentinel: "touches a forbidden position non-diagonally"
@@ -656,7 +657,7 @@ def _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=0):
         blocked_d |= dg_m
         rest.append(op)
     if not chosen:
-        if forbidden:
+        if forbidden or allow_none:
             return None, remaining
         raise RuntimeError("pass planner made no progress (op needs more than %d tile-local qubits)" % T)
     # fill the unused tile slots with the lowest free positions, avoiding control/diagonal bits
@@ -734,6 +735,174 @@ def plan_passes(ops, n_local, tile_bits=None, low_bits=None):
         if op.kind not in TILED_KINDS:
             raise RuntimeError("plan_passes takes tiled ops only (got %r); use plan_schedule" % op.kind)
     return [item for kind, item in plan_schedule(ops, n_local, tile_bits, low_bits)]
+
+
+# ------------------------------------------------------------------------------------------------
+# joint placement + pass planning on a sharded register
+# ------------------------------------------------------------------------------------------------
+
+_BLOCKED = _NOT_TILED << 2     # sentinel: non-diagonal target on a global position (waits for the next swap)
+
+# cost model of the schedule search, in units of one near-empty pass over the shard (measured at 2^33 amplitudes
+# per GPU, profiles/r01_bench_8gpu_36q_jit.json: a pass costs 43 ms + 0.55 ms per gate beyond 16, a swap of
+# 3 global qubits 180 ms = 7/8 of the shard over NVLink at 670 GB/s)
+PASS_GATE_COST = 0.55 / 43.0
+PASS_FREE_GATES = 16
+SWAP_COST_FULL = (180.0 / 43.0) / (7.0 / 8.0)      # cost of moving the WHOLE shard once
+
+
+def schedule_cost(order, n_global):
+    """Modelled device time of a placed op list (tiled ops grouped by `pass_id`, swaps in between)."""
+    cost = 0.0
+    for kind, n_ops in order:
+        if kind == "swap":
+            cost += SWAP_COST_FULL * (1.0 - 2.0 ** -n_global)
+        else:
+            cost += 1.0 + PASS_GATE_COST * max(0, n_ops - PASS_FREE_GATES)
+    return cost
+
+
+def _asap_levels(ops):
+    """Depth of every op in the commutation DAG (non-diagonal use of a position orders against every other use
+    of it; diagonal uses commute among themselves)."""
+    last_nd = {}        # position -> level of the last non-diagonal use
+    last_any = {}       # position -> highest level of any use
+    levels = []
+    for op in ops:
+        nd, dg = op.nondiag_bits(), op.diag_bits()
+        lv = 0
+        for b in nd:
+            lv = max(lv, last_any.get(b, -1) + 1)
+        for b in dg:
+            lv = max(lv, last_nd.get(b, -1) + 1)
+        for b in nd:
+            last_nd[b] = lv
+            last_any[b] = max(last_any.get(b, -1), lv)
+        for b in dg:
+            last_any[b] = max(last_any.get(b, -1), lv)
+        levels.append(lv)
+    return levels
+
+
+def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=float("inf")):
+    """One run of the joint planner with a fixed 'thin pass' threshold; returns (cost, ops, src_pos, order)."""
+    import copy
+    n_local = n - n_global
+    T, L = _geometry(n_local, None, None)
+    search = os.environ.get("QSV_PLAN_SEARCH", "1") != "0" and T - L > 0
+    gmask = _mask(range(n_local, n))
+    remaining = list(ops)
+    at = list(range(n))                 # physical position -> virtual position it currently holds
+    out, order = [], []
+    min_pos = min(max(SWAP_MIN_POS, L) if fuse_swaps else SWAP_MIN_POS, n_local - n_global)
+    forbidden = 0                       # positions of the swap just emitted (the pass fused into it avoids them)
+    just_swapped = False
+    cost_so_far = 0.0
+    while remaining:
+        if cost_so_far > cost_cap:
+            return float("inf"), None, None, order
+        masks_of = {}
+        blocked = False                 # an op at the FRONT of the commutation DAG waits for a global qubit
+        acc_nd = acc_d = 0
+        for op in remaining:
+            nd_m, dg_m = _mask(op.nondiag_bits()), _mask(op.diag_bits())
+            if nd_m & gmask:
+                if not (nd_m & (acc_nd | acc_d)) and not (dg_m & acc_nd):
+                    blocked = True
+                nd_m |= _BLOCKED
+            acc_nd |= nd_m & ~_BLOCKED
+            acc_d |= dg_m
+            masks_of[id(op)] = (nd_m, dg_m)
+        ps, rest = _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=forbidden, allow_none=True)
+        if forbidden and ps is None:
+            forbidden = 0
+            continue
+        n_ps = len(ps.ops) if ps is not None else 0
+        if blocked and not forbidden and not just_swapped and n_ps < thin:
+            # swap now: the passes that are left with this layout would be near-empty sweeps
+            lv = _asap_levels(remaining)
+            nxt = {}
+            for op, l in zip(remaining, lv):
+                for b in op.nondiag_bits():
+                    nxt.setdefault(b, l)
+            far = len(remaining) + 1
+            cand = [p for p in range(n_local)]
+            cand.sort(key=lambda p: (p < min_pos, -nxt.get(p, far), -p))
+            positions = sorted(cand[:n_global])
+            out.append(Op("global_swap", (), (), params={"n_swap": n_global, "positions": positions}, name="relayout"))
+            order.append(("swap", 0))
+            relabel = list(range(n))
+            for i, p_loc in enumerate(positions):
+                relabel[p_loc], relabel[n_local + i] = n_local + i, p_loc
+                at[p_loc], at[n_local + i] = at[n_local + i], at[p_loc]
+            remaining = [op.remapped(relabel) for op in remaining]
+            forbidden = _mask(positions) if fuse_swaps else 0
+            just_swapped = True
+            cost_so_far += SWAP_COST_FULL * (1.0 - 2.0 ** -n_global)
+            continue
+        if ps is None:
+            raise RuntimeError("sharded planner made no progress (op needs more than %d tile-local qubits)" % T)
+        out.extend(ps.ops)
+        order.append(("fused_pass" if forbidden else "pass", len(ps.ops)))
+        if not forbidden:
+            cost_so_far += 1.0 + PASS_GATE_COST * max(0, len(ps.ops) - PASS_FREE_GATES)
+        forbidden = 0
+        just_swapped = False
+        remaining = rest
+    phys_of = [0] * n
+    for p, v in enumerate(at):
+        phys_of[v] = p
+    new_src = [phys_of[v] for v in src_pos] if src_pos is not None else None
+    cost = schedule_cost([o for o in order if o[0] != "fused_pass"], n_global)
+    return cost, out, new_src, order
+
+
+def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
+    """Placement on a sharded register done TOGETHER with pass planning (tiled ops only, free-position swaps).
+
+    `place` walks the op list and swaps when the next op in list order needs a global qubit; everything that
+    precedes it in the list must then run before the swap, which ends every segment in near-empty passes.  Here
+    the planner builds pass after pass from the ops the current layout allows (ops with a non-diagonal target on
+    a global position wait, and block what depends on them) and swaps as soon as the best pass it can still form
+    is thinner than a threshold: the victims are the local positions whose next non-diagonal use lies deepest in
+    the commutation DAG.  Several thresholds are tried and the cheapest schedule under the measured cost model
+    (a swap = ~3.7 sweeps at 8 GPUs) is kept.  The result is an ordinary op list with `global_swap` ops, ordered
+    pass by pass, so plan_schedule reproduces the passes."""
+    key = (ops_digest(ops), n, n_global, tuple(src_pos) if src_pos is not None else None, fuse_swaps, SWAP_MIN_POS,
+           os.environ.get("QSV_PLACE_THIN"), os.environ.get("QSV_TILE_BITS"), os.environ.get("QSV_LOW_BITS"),
+           os.environ.get("QSV_PLAN_SEARCH"))
+    hit = _PLACE_CACHE.get(key)
+    if hit is not None:
+        return list(hit[0]), (list(hit[1]) if hit[1] is not None else None)
+    best = None
+    thins = [int(v) for v in os.environ.get("QSV_PLACE_THIN", "1,8,14,20").split(",")]
+    for thin in thins:
+        res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps,
+                                cost_cap=best[0] if best is not None else float("inf"))
+        if best is None or res[0] < best[0]:
+            best = res
+    if len(_PLACE_CACHE) >= 8:
+        _PLACE_CACHE.pop(next(iter(_PLACE_CACHE)))
+    _PLACE_CACHE[key] = (list(best[1]), list(best[2]) if best[2] is not None else None)
+    return best[1], best[2]
+
+
+_PLACE_CACHE = {}       # the search costs seconds on a 36-qubit circuit; Shor's sampling loop and benchmarks re-run one circuit
+
+
+def ops_digest(ops):
+    """Content hash of an op list (kinds, positions, control values, matrices, scalars, parameters)."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for op in ops:
+        h.update(repr((op.kind, tuple(op.targets), tuple(op.controls),
+                       None if op.cvals is None else tuple(int(v) for v in op.cvals),
+                       complex(op.scalar), sorted(op.params.items()) if op.params else None)).encode())
+        if op.matrix is not None:
+            h.update(np.ascontiguousarray(op.matrix, dtype=np.complex128).tobytes())
+        if op.perm is not None:
+            h.update(np.ascontiguousarray(op.perm).tobytes())
+    return h.digest()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -53,7 +53,7 @@ def main():
 
     # 1. layered circuits (H / X / phases / CNot / CZ on every wire -> global<->local swaps)
     from qsv import schedule
-    for n, depth, seed, min_pos in ((10 + g, 4, 3, 9), (14 + g, 6, 4, 9), (14 + g, 6, 5, 2)):
+    for n, depth, seed, min_pos in ((10 + g, 4, 3, 9), (14 + g, 6, 4, 9), (14 + g, 6, 5, 2), (15 + g, 16, 6, 6)):
         c = workloads.random_layered_circuit(n, depth, seed=seed)
         c.sort()
         sv = engine.StateVector(n, comm=comm)
@@ -113,6 +113,41 @@ def main():
     ref = so.evolve(steps, list(range(q)), in_v)
     err = np.max(np.abs(to_output_order(full, src_pos) - ref))
     check("shor N=21 a=17 err=%.2e" % err, err <= 1e-12)
+
+    # 4. the public API under a one-process-per-GPU launch: Circuit.run / run_method2 shard the register over
+    #    the ranks by themselves (qsv.dist.default_comm); weights in output order on every rank, one sample
+    #    shared by all ranks (rank 0's uniform draw)
+    import io
+    import contextlib
+    import random
+    os.environ["QSV_SHARD_MIN_LOCAL"] = "8"
+    n, depth, seed = 13 + g, 12, 9
+    c = workloads.random_layered_circuit(n, depth, seed=seed)
+    ref = so.initial_state([0] * n)
+    for M, wires, _ in so.random_layered_steps(n, depth, seed=seed):
+        ref = so.apply_gate(ref, n, wires, M)
+    wref = so.weights(ref)
+    with contextlib.redirect_stdout(io.StringIO()):
+        w = np.array(c.run_method2([0] * n))
+    st = lowering.last_run_stats()
+    err = float(np.max(np.abs(w - wref)))
+    from qsv.dist import default_comm
+    dc = default_comm()
+    check("API run_method2 sharded n=%d depth=%d (world=%d, peer_swap=%s, passes=%d) err=%.2e"
+          % (n, depth, dc.world if dc else 1, bool(dc and dc.peer_swap), st["passes"], err),
+          dc is not None and err <= 1e-12)
+    random.seed(100 + rank)                      # different generators per rank: rank 0's draw must win
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = c.run([0] * n, 2)
+    random.seed(100)
+    u0 = random.random()
+    zbits = torch.tensor(out, device="cuda")
+    allb = [torch.empty_like(zbits) for _ in range(comm.world)]
+    dist.all_gather(allb, zbits)
+    idx = lowering.basis_index(out)
+    check("API run sharded: same outcome on all ranks, non-zero weight (idx=%d, w=%.3e)" % (idx, wref[idx]),
+          all(bool((t == zbits).all()) for t in allb) and wref[idx] > 0)
+    lowering.release_sharded_states()
 
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -26,12 +26,18 @@ def _permute_to_output(psi, src_pos):
     return psi[y]
 
 
-@pytest.mark.parametrize("free_swap", [False, True])
+@pytest.mark.parametrize("free_swap", [False, True, "joint", "joint-deep"])
 @pytest.mark.parametrize("g", [1, 2, 3])
 def test_placed_circuit_on_virtual_ranks_matches_oracle(g, free_swap, monkeypatch):
+    """free_swap False: victims moved to the top positions first; True: list-order placement with swaps at any
+    position; "joint": placement decided together with pass planning (schedule.place_joint, the default)."""
     n = 11
     monkeypatch.setattr(schedule, "SWAP_MIN_POS", 3)     # small register: let the free swaps use low positions too
-    steps = so.random_layered_steps(n, 5, seed=21 + g)
+    monkeypatch.setenv("QSV_PLACE", "joint" if str(free_swap).startswith("joint") else "list")
+    monkeypatch.setenv("QSV_TILE_BITS", "6")
+    monkeypatch.setenv("QSV_LOW_BITS", "2")
+    depth = 14 if free_swap == "joint-deep" else 5
+    steps = so.random_layered_steps(n, depth, seed=21 + g)
     c = circuit_from_steps(steps, n)
     c.sort()
     ops, src_pos = lower(c, n_global=g, free_swap=free_swap)
@@ -39,7 +45,10 @@ def test_placed_circuit_on_virtual_ranks_matches_oracle(g, free_swap, monkeypatc
     assert n_swaps >= 1, "a layered circuit on every wire must touch the global qubits"
     if free_swap:
         assert not any(op.name == "relayout" and op.kind == "mcx" for op in ops), "free swaps need no re-layout CNots"
+    if free_swap is True:
         assert any(op.params["positions"] != list(range(n - 2 * g, n - g)) for op in ops if op.kind == "global_swap")
+    if free_swap == "joint-deep":
+        assert n_swaps >= 2
     assert all(max(op.nondiag_bits(), default=0) < n - g for op in ops if op.kind != "global_swap")
     psi = np.zeros(1 << n, dtype=np.complex128)
     psi[0b101] = 1
