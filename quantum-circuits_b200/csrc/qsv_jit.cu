@@ -274,10 +274,45 @@ static void apply_multipliers(Out &o, const SlotMul (&m)[16], const std::vector<
     }
 }
 
+// Shared-memory layout of the tile and the thread <-> tile-bit mapping (bank conflicts).
+// A 16-byte access is conflict-free when the 8 threads of a quarter-warp hit 8 different 16-byte bank groups, i.e.
+// differ in bits 0..2 of the slot index.  With the linear layout and thread bits in ascending order that fails as
+// soon as a round's register bits include tile bits 0..2 (the threads then differ only in higher bits: 2-, 4- or
+// 8-way conflicts on every exchange; ncu: 309 M conflict cycles in a 7.2 ms pass against 42 M in a 5.4 ms one).
+// Padded layout: run r (2^L amplitudes, one TMA bulk copy) starts at slot r * (2^L + 1), so tile bit L+j adds 2^j
+// to the bank group like tile bit j does.  Per round, thread-index bits 0..2 are given to one tile bit of each
+// class {0, L}, {1, L+1}, {2, L+2} that is not a register bit: all 8 combinations then fall into different groups.
+static thread_local int t_pad_L = -1;       // >= 0: padded layout with runs of 2^L amplitudes; -1: linear layout
+static void thread_bit_order(const qsv_round_t &R, int pos[8]) {
+    bool is_rb[12] = {false};
+    for (int q = 0; q < 4; ++q) is_rb[R.rb[q]] = true;
+    bool used[12] = {false};
+    int n = 0;
+    if (t_pad_L >= 0) {
+        for (int j = 0; j < 3; ++j) {
+            const int a = j, b = t_pad_L + j;
+            int pick = -1;
+            if (!is_rb[a]) pick = a;
+            else if (b < 12 && b > 2 && !is_rb[b]) pick = b;
+            if (pick >= 0 && !used[pick]) { pos[n++] = pick; used[pick] = true; }
+        }
+    }
+    for (int b = 0; b < 12 && n < 8; ++b)
+        if (!is_rb[b] && !used[b]) { pos[n++] = b; used[b] = true; }
+}
 static void emit_tb(Out &o, const qsv_round_t &R) {
-    o.f("    u32 tb = tid;");
-    for (int q = 0; q < 4; ++q)
-        o.f("    tb = ((tb >> %u) << %u) | (tb & 0x%xu);", R.rb[q], R.rb[q] + 1u, (1u << R.rb[q]) - 1u);
+    int pos[8];
+    thread_bit_order(R, pos);
+    std::string e;
+    for (int i = 0; i < 8;) {
+        int len = 1;
+        while (i + len < 8 && pos[i + len] == pos[i] + len) ++len;
+        char b[96];
+        snprintf(b, sizeof(b), "(((tid >> %d) & 0x%xu) << %d)", i, (1u << len) - 1u, pos[i]);
+        e += (e.empty() ? "" : " | ") + std::string(b);
+        i += len;
+    }
+    o.f("    const u32 tb = %s;", e.c_str());
 }
 
 // address permutation list in application order [first, first+n) step dir; result: a0..a15 declared
@@ -465,7 +500,7 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
     o.f("    double x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i, x4r, x4i, x5r, x5i, x6r, x6i, x7r, x7i;");
     o.f("    double x8r, x8i, x9r, x9i, x10r, x10i, x11r, x11i, x12r, x12i, x13r, x13i, x14r, x14i, x15r, x15i;");
-    for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[a%d]; x%dr = v.x; x%di = v.y; }", r, r, r);
+    for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[QP(a%d)]; x%dr = v.x; x%di = v.y; }", r, r, r);
     o.f("    (void)H; (void)tables; (void)gbase;");
     if (direct) o.f("    QSV_TILE_CONSUMED(ctx);");
 
@@ -647,7 +682,7 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     }
     if (info.barrier) o.f("    QSV_BARRIER();");
     emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, gen_post, "b");
-    for (int r = 0; r < 16; ++r) o.f("    tout[b%d] = make_double2(%s, %s);", r, xr(r).c_str(), xi(r).c_str());
+    for (int r = 0; r < 16; ++r) o.f("    tout[QP(b%d)] = make_double2(%s, %s);", r, xr(r).c_str(), xi(r).c_str());
     o.f("}");
     return 0;
 }
@@ -708,6 +743,13 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes) 
 #endif
 )SRC";
 
+static bool pad_enabled() {
+    const char *e = getenv("QSV_JIT_PAD");
+    return !(e && !strcmp(e, "0"));
+}
+// shared-memory slots (16 bytes each) of one tile: 2^12 amplitudes plus one pad slot per run
+static unsigned tile_slots(int n_hi) { return 4096u + (pad_enabled() ? (1u << n_hi) : 0u); }
+
 int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, std::string &src, std::string &err) {
     const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
     const uint8_t *body = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);
@@ -726,10 +768,18 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     const bool direct = !(ds && !strcmp(ds, "0"));
     const int n_runs = 1 << n_hi;
     const uint32_t nr = hdr->n_rounds;
+    const bool pad = pad_enabled();
+    t_pad_L = pad ? L : -1;
+    const unsigned run_stride = (1u << L) + (pad ? 1u : 0u);      // slots between the starts of two runs
 
     Out o;
     o.s += kPrelude;
     o.s += kDeviceHelpers;
+    if (pad)
+        o.f("#define QP(a) ((a) + ((a) >> %d))", L);
+    else
+        o.f("#define QP(a) (a)");
+    o.f("#define QSV_TILE_SLOTS %u", tile_slots(n_hi));
     // tile-local address -> offset inside the state (bit scatter of the high tile bits)
     o.f("QSV_FN u64 qsv_scatter(const u32 a) {");
     {
@@ -750,7 +800,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    asm volatile(\"{\\n.reg .pred P;\\nelect.sync _|P, 0xffffffff;\\nselp.u32 %%0, 1, 0, P;\\n}\\n\" : \"=r\"(elected));");
         o.f("    if (elected)");
         o.f("        for (u32 r = c.warp; r < %du; r += 8u)", n_runs);
-        o.f("            bulk_g2s(c.tile + ((u64)r << %d), c.state + c.next_base + c.s_off[r], %uu, c.mbar);", L, 16u << L);
+        o.f("            bulk_g2s(c.tile + (u64)r * %uu, c.state + c.next_base + c.s_off[r], %uu, c.mbar);", run_stride, 16u << L);
         o.f("}");
         o.f("__device__ __forceinline__ void qsv_tile_consumed(const qsv_ctx &c) {");
         o.f("    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
@@ -886,7 +936,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
         o.f("        if (issuer)");
         o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
-        o.f("                bulk_g2s(tile + ((u64)r << %d), state + base + s_off[r], %uu, &mbar);", L, 16u << L);
+        o.f("                bulk_g2s(tile + (u64)r * %uu, state + base + s_off[r], %uu, &mbar);", run_stride, 16u << L);
         if (prefetch) {
             // the CTA's NEXT tile is pulled into L2 while this one is computed
             o.f("        if (issuer && t + gridDim.x < n_tiles) {");
@@ -902,7 +952,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("        __syncthreads();");
         o.f("        if (issuer)");
         o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
-        o.f("                bulk_s2g(state + base + s_off[r], tile + ((u64)r << %d), %uu);", L, 16u << L);
+        o.f("                bulk_s2g(state + base + s_off[r], tile + (u64)r * %uu, %uu);", run_stride, 16u << L);
         o.f("        asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");");
         o.f("        asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");");
         o.f("    }");
@@ -911,30 +961,32 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("#else");
     // ---- host emulation driver (tests only): same round functions, threads run sequentially
     o.f("extern \"C\" void qsv_jit_host_run(double2 *state, const u64 rank_bits, const u64 n_tiles, const double2 *tables) {");
-    o.f("    static double2 A[4096], B[4096];");
+    o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
     o.f("    qsv_ctx ctx; (void)ctx;");
     o.f("    for (u64 t = 0; t < n_tiles; ++t) {");
     o.f("        const u64 base = qsv_tile_base(t);");
     o.f("        const u64 gbase = base | rank_bits;");
     o.f("        if (!qsv_active(gbase)) continue;");
     o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
-    o.f("            memcpy(A + ((u64)r << %d), state + base + qsv_scatter(r << %d), %uu);", L, L, 16u << L);
+    o.f("            memcpy(A + (u64)r * %uu, state + base + qsv_scatter(r << %d), %uu);", run_stride, L, 16u << L);
     rounds_body(o, 1);
     if (!direct) {
         o.f("        const double2 *fin = %s;", (nr & 1) ? "B" : "A");
         o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
-        o.f("            memcpy(state + base + qsv_scatter(r << %d), fin + ((u64)r << %d), %uu);", L, L, 16u << L);
+        o.f("            memcpy(state + base + qsv_scatter(r << %d), fin + (u64)r * %uu, %uu);", L, run_stride, 16u << L);
     }
     o.f("    }");
     o.f("}");
     // one tile with a caller-chosen global base index (programs of states too large for a host array)
     o.f("extern \"C\" void qsv_jit_host_tile(double2 *tile, const u64 gbase, const double2 *tables) {");
-    o.f("    static double2 A[4096], B[4096];");
-    o.f("    memcpy(A, tile, sizeof(A));");
+    o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
+    o.f("    for (u32 r = 0; r < %du; ++r) memcpy(A + (u64)r * %uu, tile + ((u64)r << %d), %uu);", n_runs, run_stride, L,
+        16u << L);
     o.f("    {");
     rounds_body(o, 2);
     o.f("    }");
-    o.f("    memcpy(tile, %s, sizeof(A));", (nr & 1) ? "B" : "A");
+    o.f("    for (u32 r = 0; r < %du; ++r) memcpy(tile + ((u64)r << %d), %s + (u64)r * %uu, %uu);", n_runs, L,
+        (nr & 1) ? "B" : "A", run_stride, 16u << L);
     o.f("}");
     o.f("#endif");
     src.swap(o.s);
@@ -1073,6 +1125,7 @@ static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t byt
     k.append(getenv("QSV_JIT_NO_DEFER") ? "N" : "D");
     { const char *ds = getenv("QSV_JIT_DIRECT_STORE"); k.append(ds && !strcmp(ds, "0") ? "s" : "S"); }
     { const char *pf = getenv("QSV_JIT_PREFETCH"); k.append(pf && !strcmp(pf, "0") ? "p" : "P"); }
+    k.append(pad_enabled() ? "B" : "b");
     k.append(static_cast<const char *>(prog), bytes);
     return k;
 }
@@ -1164,7 +1217,8 @@ int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t
             if (rc) { d->GetErrorString(rc, &es); set_error("qsv jit: cuModuleLoadData: %s", es ? es : "?"); return 2; }
             rc = d->ModuleGetFunction(&fn, mod, "qsv_jit_pass");
             if (rc) { d->GetErrorString(rc, &es); set_error("qsv jit: cuModuleGetFunction: %s", es ? es : "?"); return 2; }
-            rc = d->FuncSetAttribute(fn, /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/ 8, 16 << 12);
+            rc = d->FuncSetAttribute(fn, /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/ 8,
+                                     (int)(16u * tile_slots(P->n_hi)));
             if (rc) { d->GetErrorString(rc, &es); set_error("qsv jit: cuFuncSetAttribute: %s", es ? es : "?"); return 2; }
             e->fn[dev] = fn;
         }
@@ -1174,7 +1228,7 @@ int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t
     QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
     unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
     void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev)};
-    const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u << 12, (void *)st, args, nullptr);
+    const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u * tile_slots(P->n_hi), (void *)st, args, nullptr);
     if (rc) {
         const char *es = nullptr;
         d->GetErrorString(rc, &es);
