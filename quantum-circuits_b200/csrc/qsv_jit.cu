@@ -279,9 +279,10 @@ static void apply_multipliers(Out &o, const SlotMul (&m)[16], const std::vector<
 // differ in bits 0..2 of the slot index.  With the linear layout and thread bits in ascending order that fails as
 // soon as a round's register bits include tile bits 0..2 (the threads then differ only in higher bits: 2-, 4- or
 // 8-way conflicts on every exchange; ncu: 309 M conflict cycles in a 7.2 ms pass against 42 M in a 5.4 ms one).
-// Padded layout: run r (2^L amplitudes, one TMA bulk copy) starts at slot r * (2^L + 1), so tile bit L+j adds 2^j
-// to the bank group like tile bit j does.  Per round, thread-index bits 0..2 are given to one tile bit of each
-// class {0, L}, {1, L+1}, {2, L+2} that is not a register bit: all 8 combinations then fall into different groups.
+// Padded layout: slot(a) = a + (a >> L) + (a >> (L+3)), i.e. run r (2^L amplitudes, one TMA bulk copy) starts at
+// slot r * 2^L + r + (r >> 3), so tile bits L+j and L+3+j add 2^j to the bank group like tile bit j does.  Per round,
+// thread-index bits 0..2 are given to one tile bit of each class {j, L+j, L+3+j} that is not a register bit: all 8
+// combinations then fall into different groups (qsv.schedule.plan_rounds keeps one bit per class out of the registers).
 static thread_local int t_pad_L = -1;       // >= 0: padded layout with runs of 2^L amplitudes; -1: linear layout
 static void thread_bit_order(const qsv_round_t &R, int pos[8]) {
     bool is_rb[12] = {false};
@@ -290,11 +291,9 @@ static void thread_bit_order(const qsv_round_t &R, int pos[8]) {
     int n = 0;
     if (t_pad_L >= 0) {
         for (int j = 0; j < 3; ++j) {
-            const int a = j, b = t_pad_L + j;
-            int pick = -1;
-            if (!is_rb[a]) pick = a;
-            else if (b < 12 && b > 2 && !is_rb[b]) pick = b;
-            if (pick >= 0 && !used[pick]) { pos[n++] = pick; used[pick] = true; }
+            const int cand[3] = {j, t_pad_L + j, t_pad_L + 3 + j};
+            for (int c : cand)
+                if (c < 12 && !is_rb[c] && !used[c]) { pos[n++] = c; used[c] = true; break; }
         }
     }
     for (int b = 0; b < 12 && n < 8; ++b)
@@ -360,6 +359,15 @@ static void emit_addresses(Out &o, const qsv_round_t &R, const qsv_rop_t *ops, i
                     p.table_off);
         }
     }
+}
+
+// padded slot of a tile-local address known at generation time
+static uint32_t pad_slot(uint32_t a) { return t_pad_L >= 0 ? a + (a >> t_pad_L) + (a >> (t_pad_L + 3)) : a; }
+// tile-local offset of register slot r (the round's register bits set according to r)
+static uint32_t slot_offset(const qsv_round_t &R, int r) {
+    uint32_t off = 0;
+    for (int q = 0; q < 4; ++q) if ((r >> q) & 1) off |= 1u << R.rb[q];
+    return off;
 }
 
 static bool butterfly(const double *m, double &h, int sg[4]) {
@@ -497,10 +505,18 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             " const double2 *tables) {", k, suffix, k);
     reset_slot_vars();
     emit_tb(o, R);
-    emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
     o.f("    double x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i, x4r, x4i, x5r, x5i, x6r, x6i, x7r, x7i;");
     o.f("    double x8r, x8i, x9r, x9i, x10r, x10i, x11r, x11i, x12r, x12i, x13r, x13i, x14r, x14i, x15r, x15i;");
-    for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[QP(a%d)]; x%dr = v.x; x%di = v.y; }", r, r, r);
+    if (n_pre == 0) {
+        // no permutation rides on the loads: slot r sits at tb | offset(r); thread bits and register bits are
+        // disjoint, so the padded slot splits into QP(tb) + a literal (an immediate offset of the load)
+        o.f("    const u32 pa = QP(tb);");
+        for (int r = 0; r < 16; ++r)
+            o.f("    { const double2 v = tin[pa + %uu]; x%dr = v.x; x%di = v.y; }", pad_slot(slot_offset(R, r)), r, r);
+    } else {
+        emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
+        for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[QP(a%d)]; x%dr = v.x; x%di = v.y; }", r, r, r);
+    }
     o.f("    (void)H; (void)tables; (void)gbase;");
     if (direct) o.f("    QSV_TILE_CONSUMED(ctx);");
 
@@ -681,8 +697,14 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
         return 0;
     }
     if (info.barrier) o.f("    QSV_BARRIER();");
-    emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, gen_post, "b");
-    for (int r = 0; r < 16; ++r) o.f("    tout[QP(b%d)] = make_double2(%s, %s);", r, xr(r).c_str(), xi(r).c_str());
+    if (n_post == 0) {
+        o.f("    const u32 pb = QP(tb);");
+        for (int r = 0; r < 16; ++r)
+            o.f("    tout[pb + %uu] = make_double2(%s, %s);", pad_slot(slot_offset(R, r)), xr(r).c_str(), xi(r).c_str());
+    } else {
+        emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, gen_post, "b");
+        for (int r = 0; r < 16; ++r) o.f("    tout[QP(b%d)] = make_double2(%s, %s);", r, xr(r).c_str(), xi(r).c_str());
+    }
     o.f("}");
     return 0;
 }
@@ -748,7 +770,7 @@ static bool pad_enabled() {
     return !(e && !strcmp(e, "0"));
 }
 // shared-memory slots (16 bytes each) of one tile: 2^12 amplitudes plus one pad slot per run
-static unsigned tile_slots(int n_hi) { return 4096u + (pad_enabled() ? (1u << n_hi) : 0u); }
+static unsigned tile_slots(int n_hi) { return 4096u + (pad_enabled() ? (1u << n_hi) + ((1u << n_hi) >> 3) : 0u); }
 
 int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, std::string &src, std::string &err) {
     const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
@@ -768,18 +790,23 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     const bool direct = !(ds && !strcmp(ds, "0"));
     const int n_runs = 1 << n_hi;
     const uint32_t nr = hdr->n_rounds;
-    const bool pad = pad_enabled();
+    // padding only where it pays: a pass none of whose rounds holds tile bits 0..2 in registers is conflict-free
+    // with the linear layout, and the padded slot arithmetic (shift + add per permuted address) is pure overhead
+    bool low_rb = false;
+    for (const qsv_round_t &R : rounds)
+        for (int q = 0; q < 4; ++q) low_rb = low_rb || R.rb[q] < 3;
+    const char *pe = getenv("QSV_JIT_PAD");
+    const bool pad = pad_enabled() && (low_rb || (pe && !strcmp(pe, "all")));
     t_pad_L = pad ? L : -1;
-    const unsigned run_stride = (1u << L) + (pad ? 1u : 0u);      // slots between the starts of two runs
 
     Out o;
     o.s += kPrelude;
     o.s += kDeviceHelpers;
     if (pad)
-        o.f("#define QP(a) ((a) + ((a) >> %d))", L);
+        o.f("#define QP(a) ((a) + ((a) >> %d) + ((a) >> %d))", L, L + 3);
     else
         o.f("#define QP(a) (a)");
-    o.f("#define QSV_TILE_SLOTS %u", tile_slots(n_hi));
+    o.f("#define QSV_TILE_SLOTS %u", 4096u + (pad ? (unsigned)(n_runs + (n_runs >> 3)) : 0u));
     // tile-local address -> offset inside the state (bit scatter of the high tile bits)
     o.f("QSV_FN u64 qsv_scatter(const u32 a) {");
     {
@@ -800,7 +827,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    asm volatile(\"{\\n.reg .pred P;\\nelect.sync _|P, 0xffffffff;\\nselp.u32 %%0, 1, 0, P;\\n}\\n\" : \"=r\"(elected));");
         o.f("    if (elected)");
         o.f("        for (u32 r = c.warp; r < %du; r += 8u)", n_runs);
-        o.f("            bulk_g2s(c.tile + (u64)r * %uu, c.state + c.next_base + c.s_off[r], %uu, c.mbar);", run_stride, 16u << L);
+        o.f("            bulk_g2s(c.tile + (u64)QP(r << %d), c.state + c.next_base + c.s_off[r], %uu, c.mbar);", L, 16u << L);
         o.f("}");
         o.f("__device__ __forceinline__ void qsv_tile_consumed(const qsv_ctx &c) {");
         o.f("    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
@@ -936,7 +963,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
         o.f("        if (issuer)");
         o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
-        o.f("                bulk_g2s(tile + (u64)r * %uu, state + base + s_off[r], %uu, &mbar);", run_stride, 16u << L);
+        o.f("                bulk_g2s(tile + (u64)QP(r << %d), state + base + s_off[r], %uu, &mbar);", L, 16u << L);
         if (prefetch) {
             // the CTA's NEXT tile is pulled into L2 while this one is computed
             o.f("        if (issuer && t + gridDim.x < n_tiles) {");
@@ -952,7 +979,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("        __syncthreads();");
         o.f("        if (issuer)");
         o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
-        o.f("                bulk_s2g(state + base + s_off[r], tile + (u64)r * %uu, %uu);", run_stride, 16u << L);
+        o.f("                bulk_s2g(state + base + s_off[r], tile + (u64)QP(r << %d), %uu);", L, 16u << L);
         o.f("        asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");");
         o.f("        asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");");
         o.f("    }");
@@ -968,25 +995,25 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("        const u64 gbase = base | rank_bits;");
     o.f("        if (!qsv_active(gbase)) continue;");
     o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
-    o.f("            memcpy(A + (u64)r * %uu, state + base + qsv_scatter(r << %d), %uu);", run_stride, L, 16u << L);
+    o.f("            memcpy(A + (u64)QP(r << %d), state + base + qsv_scatter(r << %d), %uu);", L, L, 16u << L);
     rounds_body(o, 1);
     if (!direct) {
         o.f("        const double2 *fin = %s;", (nr & 1) ? "B" : "A");
         o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
-        o.f("            memcpy(state + base + qsv_scatter(r << %d), fin + (u64)r * %uu, %uu);", L, run_stride, 16u << L);
+        o.f("            memcpy(state + base + qsv_scatter(r << %d), fin + (u64)QP(r << %d), %uu);", L, L, 16u << L);
     }
     o.f("    }");
     o.f("}");
     // one tile with a caller-chosen global base index (programs of states too large for a host array)
     o.f("extern \"C\" void qsv_jit_host_tile(double2 *tile, const u64 gbase, const double2 *tables) {");
     o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
-    o.f("    for (u32 r = 0; r < %du; ++r) memcpy(A + (u64)r * %uu, tile + ((u64)r << %d), %uu);", n_runs, run_stride, L,
+    o.f("    for (u32 r = 0; r < %du; ++r) memcpy(A + (u64)QP(r << %d), tile + ((u64)r << %d), %uu);", n_runs, L, L,
         16u << L);
     o.f("    {");
     rounds_body(o, 2);
     o.f("    }");
-    o.f("    for (u32 r = 0; r < %du; ++r) memcpy(tile + ((u64)r << %d), %s + (u64)r * %uu, %uu);", n_runs, L,
-        (nr & 1) ? "B" : "A", run_stride, 16u << L);
+    o.f("    for (u32 r = 0; r < %du; ++r) memcpy(tile + ((u64)r << %d), %s + (u64)QP(r << %d), %uu);", n_runs, L,
+        (nr & 1) ? "B" : "A", L, 16u << L);
     o.f("}");
     o.f("#endif");
     src.swap(o.s);
@@ -1125,7 +1152,7 @@ static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t byt
     k.append(getenv("QSV_JIT_NO_DEFER") ? "N" : "D");
     { const char *ds = getenv("QSV_JIT_DIRECT_STORE"); k.append(ds && !strcmp(ds, "0") ? "s" : "S"); }
     { const char *pf = getenv("QSV_JIT_PREFETCH"); k.append(pf && !strcmp(pf, "0") ? "p" : "P"); }
-    k.append(pad_enabled() ? "B" : "b");
+    { const char *pe = getenv("QSV_JIT_PAD"); k.append(pe ? pe : "-"); k.append("|"); }
     k.append(static_cast<const char *>(prog), bytes);
     return k;
 }

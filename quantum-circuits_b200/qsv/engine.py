@@ -27,7 +27,7 @@ def _ops_fingerprint(ops, geometry):
     h.update(repr((geometry, os.environ.get("QSV_PLAN_SEARCH"), os.environ.get("QSV_REGISTER_KERNEL"),
                    os.environ.get("QSV_REG_BITS"), os.environ.get("QSV_REG_MIN_OPS"), os.environ.get("QSV_JIT"),
                    os.environ.get("QSV_JIT_MIN_QUBITS"), os.environ.get("QSV_TILE_BITS"),
-                   os.environ.get("QSV_LOW_BITS"), os.environ.get("QSV_DEBUG_DROP"))).encode())
+                   os.environ.get("QSV_LOW_BITS"), os.environ.get("QSV_DEBUG_DROP"), os.environ.get("QSV_FILL"))).encode())
     for op in ops:
         h.update(repr((op.kind, tuple(op.targets), tuple(op.controls),
                        None if op.cvals is None else tuple(int(v) for v in op.cvals),

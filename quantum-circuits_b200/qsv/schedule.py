@@ -1024,7 +1024,7 @@ def pack_passes(passes, register_kernel=None):
             max_rounds, max_ops = program_capacity(ps)
             mode = os.environ.get("QSV_REG_MCX", "1")
             specialised = False if (max_ops <= RPROG_MAX_OPS or mode == "0") else ("all" if mode == "all" else True)
-            rounds = plan_rounds(ps, reg_mcx=specialised) \
+            rounds = plan_rounds(ps, reg_mcx=specialised, padded_layout=max_ops > RPROG_MAX_OPS) \
                 if len(ps.ops) > int(os.environ.get("QSV_REG_MIN_OPS", "2")) else None
             if rounds is not None:
                 enc = encode_rounds(ps, rounds, max_rounds, max_ops)
@@ -1139,7 +1139,21 @@ class Round:
     post: list              # mcx ops applied as an address permutation when the round stores
 
 
-def plan_rounds(ps, reg_mcx=False):
+def bank_class(b, L):
+    """Which of the three bank-group bits tile bit b moves in the PADDED shared-memory layout of the specialised
+    kernel (slot(a) = a + (a >> L) + (a >> (L+3)), csrc/qsv_jit.cu): 0, 1, 2, or None for a bank-neutral bit."""
+    c = 0
+    if b < 3:
+        c += 1 << b
+    if b >= L:
+        c += 1 << (b - L)
+    if b >= L + 3:
+        c += 1 << (b - L - 3)
+    c &= 7
+    return {1: 0, 2: 1, 4: 2}.get(c)
+
+
+def plan_rounds(ps, reg_mcx=False, padded_layout=False):
     """Split the ops of one pass into rounds of the register-resident kernel.
 
     reg_mcx (programs for the pass-specialised kernel only): an X / CNot / Toffoli whose target is a register
@@ -1211,6 +1225,21 @@ def plan_rounds(ps, reg_mcx=False):
                 blocked_d |= dg_m
                 rest.append(op)
         avoid = _dense_ctrl_bits(reg, ps)
+        fill = os.environ.get("QSV_FILL", "neutral-mid")
+        if padded_layout and T == 12 and (fill == "neutral" or (fill == "neutral-mid" and rest)):
+            # specialised kernel: a quarter-warp is conflict-free when its three lowest thread bits move the three
+            # bank-group bits, i.e. one tile bit of every bank class must stay a thread bit.  Fill with bank-neutral
+            # bits first, then with bits of the class that keeps the most members.
+            while len(rb) < REG_BITS:
+                members = {c: [b for b in range(T) if b not in rb and bank_class(b, ps.low_bits) == c] for c in (0, 1, 2)}
+                cands = [l for l in range(T) if l not in rb and l not in avoid]
+                if not cands:
+                    break
+
+                def score(l):
+                    c = bank_class(l, ps.low_bits)
+                    return (c is None, 0 if c is None else len(members[c]), l)
+                rb.append(max(cands, key=score))
         for l in list(range(T - 1, -1, -1)):       # pad with the highest free tile bits (bank friendly)
             if len(rb) == REG_BITS:
                 break

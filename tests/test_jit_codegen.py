@@ -51,8 +51,13 @@ def _check(ops, n_local, tmp_path, rank_bits=0, seed=1):
     return stats
 
 
-def test_layered_circuit_matches_interpreter_emulation(tmp_path, monkeypatch):
+@pytest.mark.parametrize("pad", ["default", "0", "all"])
+def test_layered_circuit_matches_interpreter_emulation(tmp_path, monkeypatch, pad):
+    """pad: shared-memory layout of the tile - padded runs + per-round thread-bit mapping where a round keeps
+    tile bits 0..2 in registers (default), never ("0"), or in every pass ("all")."""
     from qsv import workloads, lowering
+    if pad != "default":
+        monkeypatch.setenv("QSV_JIT_PAD", pad)
     n = 14
     c = workloads.random_layered_circuit(n, 6, seed=3)
     c.sort()
