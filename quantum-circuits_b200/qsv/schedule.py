@@ -717,8 +717,35 @@ def plan_schedule(ops, n_local, tile_bits=None, low_bits=None, fuse_swaps=False)
             out.append(("op", head))
             continue
         ps, remaining = _plan_one_pass(remaining, masks_of, n_local, T, L, search)
+        ps, remaining = _trim_tail_rounds(ps, remaining, masks_of)
         out.append(("pass", ps))
     return out
+
+
+def _trim_tail_rounds(ps, rest, masks_of):
+    """Rounds cost shared-memory round trips (~0.5 ms per round beyond the second at 2^30 amplitudes); a trailing
+    round that holds only a couple of ops is handed back to the planner - its ops run first in the next pass,
+    whose tile the first-come choice builds around them.  QSV_TRIM_ROUNDS = largest tail round given back (0: off)."""
+    limit = int(os.environ.get("QSV_TRIM_ROUNDS", "1"))
+    if limit <= 0 or ps.tile_bits != 12 or not rest:
+        return ps, rest
+    rounds = plan_rounds(ps, reg_mcx=True, padded_layout=True)
+    if rounds is None or len(rounds) < 3:
+        return ps, rest
+    give_back = []
+    while len(rounds) >= 3:
+        last = rounds[-1]
+        tail = list(last.pre) + list(last.reg) + list(last.post)
+        if len(tail) > limit:
+            break
+        give_back = tail + give_back
+        rounds.pop()
+    if not give_back:
+        return ps, rest
+    ids = {id(op) for op in give_back}
+    kept = [op for op in ps.ops if id(op) not in ids]
+    back = [op for op in ps.ops if id(op) in ids]
+    return Pass(ps.n_local, ps.tile_bits, ps.low_bits, ps.hi_pos, kept), back + rest
 
 
 def plan_passes(ops, n_local, tile_bits=None, low_bits=None):
