@@ -231,7 +231,8 @@ def main():
     # uncontrolled X gates are pushed back to the input by the lowering: they become `flip` of the start index;
     # with the peer-memory swap kernel, global<->local swaps exchange the victims where they are (free_swap)
     ops, src_pos, flip = lowering.lower(circ, n_global=g if comm is not None else 0, in_flip=True,
-                                        free_swap=bool(comm is not None and comm.peer_swap))
+                                        free_swap=bool(comm is not None and comm.peer_swap),
+                                        fuse_swaps=sv.fuse_swaps())
     t_host = (t_host1 - t_host0) - 0.0 + (time.perf_counter() - t_host1)
     t_prep0 = time.perf_counter()
     plan = sv.prepare(ops)          # pass planning, packing, H2D, and (large states) kernel specialisation
@@ -281,6 +282,7 @@ def main():
         swap = {"swaps_per_step": n_sw / args.steps, "ms_per_step": sw_ms / args.steps,
                 "bytes_out_per_gpu_per_swap": out_bytes / max(1, n_sw), "achieved_GBps_out_per_gpu": gbs,
                 "nvlink_peak_GBps": nv_peak, "frac_of_nvlink": gbs / nv_peak,
+                "fused_with_pass_per_step": getattr(comm, "fused_swaps", 0) / max(1, args.steps + max(args.warmup, 3)),
                 "path": "k_swap_peer over NVLink peer memory" if comm.peer_swap else "NCCL all_to_all_single, chunked in place",
                 "note": "device time between the barriers around each swap (peer kernel) / incl. pack+unpack (NCCL)"}
     if world > 1:

@@ -277,6 +277,28 @@ int qsv_unpack_slices(void *state_dev, const void *staging_dev, uint64_t n_chunk
 int qsv_swap_peer(void *state_dev, const uint64_t *peer_state_ptrs, int n_local, int g, int rank,
                   const int *positions, void *stream);
 
+/* Global<->local qubit swap FUSED with the gate pass that follows it: one kernel over NVLink peer memory
+ * (SURVEY 8e's exchange step + one run of main/circuit.py:303-327's gate loop in a single sweep).  Contract of
+ * qsv_swap_peer followed by qsv_run_pass_rounds on the same state (pass_first = 0), or of qsv_run_pass_rounds followed
+ * by qsv_swap_peer (pass_first = 1: the ops see the rank and field bits the tile has BEFORE the swap, i.e. on the rank
+ * it is pulled from; pass->rank_bits is ignored), with these differences: the pass's tile must not
+ * hold any of `positions` (which must be >= pass->low_bits); every tile is TMA-loaded from the rank that holds it
+ * before the swap (pull), run through the rounds, and stored into the local shard after the rank pair has
+ * hand-shaken on that tile through `peer_flag_ptrs` (per rank an array of 16 * 1024 uint64 in peer-mapped memory,
+ * zero-initialised once; entry [rank] is the caller's own array).  `epoch` must be the same on all ranks and grow
+ * by at least 2^32 from one call to the next on the same flag arrays.  All ranks must have finished their earlier
+ * kernels on the state before the call (barrier); no barrier is needed after it.  Specialised kernel only
+ * (tile_bits 12); the grid is limited to the CTAs that are resident at once.
+ *   qsv_jit_source_swap / qsv_jit_compile_swap: generator access as for qsv_jit_source / qsv_jit_compile; the host
+ *   form of the source exports qsv_jit_host_run_swap(out_shard, shards_before_swap[], rank, rank_bits, n_tiles, tables). */
+int qsv_run_pass_rounds_swap(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                             const void *tables_dev, const uint64_t *peer_state_ptrs, const uint64_t *peer_flag_ptrs,
+                             int g, const int *positions, int pass_first, int rank, uint64_t epoch, void *stream);
+int qsv_jit_source_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
+                        const int *positions, int pass_first, char *buf, size_t buf_len, size_t *needed);
+int qsv_jit_compile_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
+                         const int *positions, int pass_first, char *cubin_buf, size_t buf_len, size_t *needed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -692,6 +693,7 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             emit_addresses(o, R, ops, f_post, n_post, /*reverse=*/false, true, "b");
             for (int r = 0; r < 16; ++r) o.f("    const u64 g%d = tile_base | qsv_scatter(b%d);", r, r);
         }
+        o.f("    QSV_WAIT_PEER(ctx);");
         for (int r = 0; r < 16; ++r) o.f("    QSV_STG(gout + g%d, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
         o.f("}");
         return 0;
@@ -723,6 +725,7 @@ static inline double QD(u64 h) { double d; memcpy(&d, &h, 8); return d; }
 #define QSV_LDG(p) (*(p))
 #define QSV_STG(p, re, im) (*(p) = make_double2(re, im))
 #define QSV_TILE_CONSUMED(c)
+#define QSV_WAIT_PEER(c)
 struct qsv_ctx { int unused; };
 #else
 #define QD(h) __longlong_as_double((long long)(h))
@@ -732,6 +735,11 @@ struct qsv_ctx { int unused; };
 #define QSV_LDG(p) __ldg(p)
 #define QSV_STG(p, re, im) (*(p) = make_double2(re, im))
 #define QSV_TILE_CONSUMED(c) qsv_tile_consumed(c)
+#ifdef QSV_FUSED_SWAP
+#define QSV_WAIT_PEER(c) qsv_wait_peer(c)
+#else
+#define QSV_WAIT_PEER(c)
+#endif
 #endif
 )SRC";
 
@@ -765,6 +773,11 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes) 
 #endif
 )SRC";
 
+// fused swap + pass: two tile buffers and one CTA per SM (QSV_FUSE_BUFFERS=2), or the single buffer and two CTAs per SM
+static bool fuse_two_buffers() {
+    const char *e = getenv("QSV_FUSE_BUFFERS");
+    return e && !strcmp(e, "2");
+}
 static bool pad_enabled() {
     const char *e = getenv("QSV_JIT_PAD");
     return !(e && !strcmp(e, "0"));
@@ -772,7 +785,15 @@ static bool pad_enabled() {
 // shared-memory slots (16 bytes each) of one tile: 2^12 amplitudes plus one pad slot per run
 static unsigned tile_slots(int n_hi) { return 4096u + (pad_enabled() ? (1u << n_hi) + ((1u << n_hi) >> 3) : 0u); }
 
-int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, std::string &src, std::string &err) {
+// Fused variant: the global<->local qubit swap that precedes the pass runs INSIDE the pass kernel.  `q[k]` (ascending
+// local positions outside the tile, >= low_bits) trades places with global bit k.
+// pre = 1: the pass is the one BEFORE the swap - its ops read the coordinates (rank, swapped field) the tile has on the
+// rank it is pulled from; pre = 0: the pass AFTER the swap (coordinates of the destination).
+struct SwapSpec { int g; int q[4]; int pre; int n_local; };
+constexpr unsigned kFlagCtas = 1024;      // flag slots per source rank in the peers' flag arrays
+
+int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, std::string &src, std::string &err,
+             const SwapSpec *sw = nullptr) {
     const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
     const uint8_t *body = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);
     std::vector<qsv_round_t> rounds(hdr->n_rounds);
@@ -787,7 +808,18 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     const bool prefetch_env = !(pf && !strcmp(pf, "0"));
 
     const char *ds = getenv("QSV_JIT_DIRECT_STORE");
-    const bool direct = !(ds && !strcmp(ds, "0"));
+    const bool direct = sw != nullptr || !(ds && !strcmp(ds, "0"));     // the fused variant stores from registers
+    if (sw) {
+        if (sw->g < 1 || sw->g > 4) { err = "fused swap: g out of range"; return 1; }
+        for (int k = 0; k < sw->g; ++k) {
+            if (sw->q[k] < L || sw->q[k] >= P.n_local || (k && sw->q[k] <= sw->q[k - 1])) {
+                err = "fused swap: positions must be ascending local positions >= low_bits";
+                return 1;
+            }
+            for (int j = 0; j < n_hi; ++j)
+                if (P.hi_pos[j] == sw->q[k]) { err = "fused swap: a swapped position is inside the tile"; return 1; }
+        }
+    }
     const int n_runs = 1 << n_hi;
     const uint32_t nr = hdr->n_rounds;
     // padding only where it pays: a pass none of whose rounds holds tile bits 0..2 in registers is conflict-free
@@ -800,6 +832,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     t_pad_L = pad ? L : -1;
 
     Out o;
+    if (sw) o.f("#define QSV_FUSED_SWAP 1");
     o.s += kPrelude;
     o.s += kDeviceHelpers;
     if (pad)
@@ -820,6 +853,10 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         // hand-back of the tile buffer inside the last round: every thread holds its amplitudes in registers,
         // so the CTA's NEXT tile can stream into shared memory while this one is computed and stored
         o.f("#ifndef QSV_JIT_HOST");
+        if (sw)
+            o.f("struct qsv_ctx { const double2 *next_src; double2 *tile; u64 *mbar; const u64 *s_off; const u64 *wait_flag;"
+                " u64 wait_val; u32 warp; u32 flags; };");
+        else
         o.f("struct qsv_ctx { double2 *state; double2 *tile; u64 *mbar; const u64 *s_off; u64 next_base; u32 warp; u32 flags; };");
         o.f("__device__ __forceinline__ void qsv_issue_load(const qsv_ctx &c) {");
         o.f("    if (c.flags & 2u) mbar_expect_tx(c.mbar, %uu);", 16u << 12);
@@ -827,8 +864,31 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    asm volatile(\"{\\n.reg .pred P;\\nelect.sync _|P, 0xffffffff;\\nselp.u32 %%0, 1, 0, P;\\n}\\n\" : \"=r\"(elected));");
         o.f("    if (elected)");
         o.f("        for (u32 r = c.warp; r < %du; r += 8u)", n_runs);
+        if (sw)
+            o.f("            bulk_g2s(c.tile + (u64)QP(r << %d), c.next_src + c.s_off[r], %uu, c.mbar);", L, 16u << L);
+        else
         o.f("            bulk_g2s(c.tile + (u64)QP(r << %d), c.state + c.next_base + c.s_off[r], %uu, c.mbar);", L, 16u << L);
         o.f("}");
+        if (sw) {
+            // per-tile handshake of a rank pair: "I have read your tile" (release store into the peer's flag array)
+            // / "has my tile been read?" (acquire loads of my own flag array) - before the tile is overwritten
+            o.f("__device__ __forceinline__ void qsv_signal_peer(u64 *flag, const u64 v) {");
+            // relaxed: what the flag orders is MY completed TMA read of the peer's tile (observed through the mbarrier)
+            // before the PEER's later stores - a release here would drain this CTA's own stores of the previous tile
+            o.f("    asm volatile(\"st.relaxed.sys.global.u64 [%%0], %%1;\" ::\"l\"(flag), \"l\"(v) : \"memory\");");
+            o.f("}");
+            o.f("__device__ __forceinline__ void qsv_wait_peer(const qsv_ctx &c) {");
+            o.f("    if (c.wait_flag) {");
+            o.f("        if (c.flags & 2u) {");
+            o.f("            u64 v;");
+            o.f("            do {");
+            o.f("                asm volatile(\"ld.relaxed.sys.global.u64 %%0, [%%1];\" : \"=l\"(v) : \"l\"(c.wait_flag) : \"memory\");");
+            o.f("            } while (v < c.wait_val);");
+            o.f("        }");
+            o.f("        __syncthreads();");
+            o.f("    }");
+            o.f("}");
+        }
         o.f("__device__ __forceinline__ void qsv_tile_consumed(const qsv_ctx &c) {");
         o.f("    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");");
         o.f("    __syncthreads();");
@@ -868,6 +928,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     } else {
         active = "true";
     }
+    if (sw) active = "true";       // every tile moves, whatever its ops' conditions say
     o.f("QSV_FN bool qsv_active(const u64 gbase) { (void)gbase; return %s; }", active.c_str());
 
     // ---- tile base: insert a zero bit at every hi position (ascending)
@@ -905,9 +966,39 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         }
     };
 
+    if (sw) {
+        // work item u -> (pair slot s = low g bits, rest): the tile whose swapped field equals j = rank ^ s.  The data
+        // it needs sits on rank j under field = rank; both ranks of a pair walk the same u sequence with the same CTA,
+        // so the per-tile handshake always finds its partner.  Consecutive u go to different peers: the traffic through
+        // the NVSwitch is a uniform all-to-all at every moment.
+        std::vector<int> ins;
+        for (int j = 0; j < n_hi; ++j) ins.push_back(P.hi_pos[j]);
+        for (int k = 0; k < sw->g; ++k) ins.push_back(sw->q[k]);
+        std::sort(ins.begin(), ins.end());
+        o.f("QSV_FN void qsv_fused_tile(const u64 u, const u32 rank, u64 &base, u64 &src_base, u32 &peer) {");
+        o.f("    peer = rank ^ (u32)(u & %uULL);", (1u << sw->g) - 1u);
+        o.f("    u64 rest = (u >> %d) << %d;", sw->g, L);
+        for (int pos : ins)
+            o.f("    rest = ((rest >> %d) << %d) | (rest & 0x%llxULL);", pos, pos + 1, (unsigned long long)((1ull << pos) - 1ull));
+        std::string fj = "0ULL", fr = "0ULL";
+        for (int k = 0; k < sw->g; ++k) {
+            fj += " | ((u64)((peer >> " + std::to_string(k) + ") & 1u) << " + std::to_string(sw->q[k]) + ")";
+            fr += " | ((u64)((rank >> " + std::to_string(k) + ") & 1u) << " + std::to_string(sw->q[k]) + ")";
+        }
+        o.f("    base = rest | %s;", fj.c_str());
+        o.f("    src_base = rest | %s;", fr.c_str());
+        o.f("}");
+    }
+
     // ---- device kernel
     o.f("#ifndef QSV_JIT_HOST");
-    o.f("extern \"C\" __global__ void __launch_bounds__(256, 2)");
+    if (sw) o.f("struct qsv_peers { double2 *state[16]; u64 *flags[16]; };");
+    const bool two_buf = sw && fuse_two_buffers();
+    o.f("extern \"C\" __global__ void __launch_bounds__(256, %d)", two_buf ? 1 : 2);
+    if (sw)
+        o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
+            " const __grid_constant__ qsv_peers peers, const u32 rank, const u64 epoch) {");
+    else
     o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables) {");
     o.f("    extern __shared__ __align__(128) unsigned char smem_raw[];");
     o.f("    double2 *tile = reinterpret_cast<double2 *>(smem_raw);");
@@ -926,7 +1017,79 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("    __syncthreads();");
     o.f("    const u32 warp = tid >> 5;");
     o.f("    u32 parity = 0;");
-    if (direct) {
+    if (sw) {
+        // Fused swap + pass (pull model): every tile is TMA-loaded from the rank that holds it BEFORE the swap, run
+        // through the rounds, and stored from registers to its place AFTER the swap in the local shard.  That place
+        // holds the tile the partner pulls: it is overwritten only once the partner has flagged "read" (it flags right
+        // after its TMA load of the tile completed).  All CTAs are co-resident (grid <= 2 per SM), so the partner CTA
+        // always makes progress; nobody touches a peer's memory except to read it and to set flags.
+        // Two tile buffers (one CTA per SM): the NVLink load of tile k+1 is in flight during ALL rounds of tile k.
+        // With the single buffer of the local kernel the link idles while a tile is being computed (measured at 2
+        // GPUs: 496 GB/s against the 677 GB/s of the plain swap kernel).
+        o.f("    __shared__ __align__(8) u64 mbar2;");
+        o.f("    if (tid == 0) { mbar_init(&mbar2, 1); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }");
+        o.f("    __syncthreads();");
+        o.f("    qsv_ctx ctx;");
+        o.f("    ctx.tile = tile; ctx.mbar = &mbar; ctx.s_off = s_off; ctx.warp = warp;");
+        o.f("    ctx.flags = (tid == 0 ? 2u : 0u)%s;", two_buf ? "" : " | 4u");
+        o.f("    u64 u = blockIdx.x;");
+        o.f("    if (u >= n_tiles) return;");
+        o.f("    u64 base, src_base; u32 peer;");
+        o.f("    qsv_fused_tile(u, rank, base, src_base, peer);");
+        o.f("    ctx.next_src = peers.state[peer] + src_base;");
+        o.f("    qsv_issue_load(ctx);");
+        o.f("    u64 it = 0;");
+        o.f("    u32 buf = 0, parity2 = 0;");
+        o.f("    for (;;) {");
+        if (sw->pre)
+            o.f("        const u64 gbase = src_base | ((u64)peer << %d);", sw->n_local);
+        else
+            o.f("        const u64 gbase = base | rank_bits;");
+        o.f("        const u32 cur_peer = peer;");
+        o.f("        const u64 cur_base = base;");
+        o.f("        const u64 un = u + gridDim.x;");
+        o.f("        double2 *tbuf = tile + (u64)buf * QSV_TILE_SLOTS;");
+        o.f("        if (un < n_tiles) {");
+        o.f("            qsv_fused_tile(un, rank, base, src_base, peer);");
+        o.f("            ctx.next_src = peers.state[peer] + src_base;");
+        if (two_buf) {
+            o.f("            // the other buffer was emptied into registers by the previous tile's last round (barrier inside)");
+            o.f("            ctx.tile = tile + (u64)(buf ^ 1u) * QSV_TILE_SLOTS;");
+            o.f("            ctx.mbar = buf ? &mbar : &mbar2;");
+            o.f("            qsv_issue_load(ctx);");
+        } else {
+            o.f("            ctx.flags |= 4u;        // issued from inside the last round, when the single buffer is free");
+        }
+        o.f("        } else {");
+        o.f("            ctx.flags &= 3u;");
+        o.f("        }");
+        o.f("        if (buf) { mbar_wait(&mbar2, parity2); parity2 ^= 1u; } else { mbar_wait(&mbar, parity); parity ^= 1u; }");
+        o.f("        ++it;");
+        o.f("        if (cur_peer != rank) {");
+        o.f("            if (tid == 0) qsv_signal_peer(peers.flags[cur_peer] + (u64)rank * %uu + blockIdx.x, epoch + it);", kFlagCtas);
+        o.f("            ctx.wait_flag = peers.flags[rank] + (u64)cur_peer * %uu + blockIdx.x;", kFlagCtas);
+        o.f("            ctx.wait_val = epoch + it;");
+        o.f("        } else {");
+        o.f("            ctx.wait_flag = nullptr; ctx.wait_val = 0;");
+        o.f("        }");
+        {
+            Out w;
+            rounds_body(w, 0);
+            // the rounds refer to the tile's base as `base`: give them the current tile's
+            std::string body = w.s;
+            size_t pos_ = 0;
+            while ((pos_ = body.find("state, base, tid", pos_)) != std::string::npos) body.replace(pos_, 16, "state, cur_base, tid");
+            pos_ = 0;
+            while ((pos_ = body.find("(tile, tile, ", pos_)) != std::string::npos) body.replace(pos_, 13, "(tbuf, tbuf, ");
+            pos_ = 0;
+            while ((pos_ = body.find("(tile, state, ", pos_)) != std::string::npos) body.replace(pos_, 14, "(tbuf, state, ");
+            o.s += body;
+        }
+        o.f("        if (un >= n_tiles) break;");
+        o.f("        u = un;");
+        if (two_buf) o.f("        buf ^= 1u;");
+        o.f("    }");
+    } else if (direct) {
         // Persistent loop with the load of tile k+1 issued from inside tile k's last round.
         o.f("    qsv_ctx ctx;");
         o.f("    ctx.state = state; ctx.tile = tile; ctx.mbar = &mbar; ctx.s_off = s_off; ctx.warp = warp;");
@@ -1004,6 +1167,26 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     }
     o.f("    }");
     o.f("}");
+    if (sw) {
+        // fused variant on the host: `state` is this rank's shard AFTER the swap (output), src_states[j] the shards
+        // BEFORE the swap (inputs, never written)
+        o.f("extern \"C\" void qsv_jit_host_run_swap(double2 *state, const double2 *const *src_states, const u32 rank,"
+            " const u64 rank_bits, const u64 n_tiles, const double2 *tables) {");
+        o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
+        o.f("    qsv_ctx ctx; (void)ctx;");
+        o.f("    for (u64 u = 0; u < n_tiles; ++u) {");
+        o.f("        u64 base, src_base; u32 peer;");
+        o.f("        qsv_fused_tile(u, rank, base, src_base, peer);");
+        if (sw->pre)
+            o.f("        const u64 gbase = src_base | ((u64)peer << %d); (void)rank_bits;", sw->n_local);
+        else
+            o.f("        const u64 gbase = base | rank_bits;");
+        o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
+        o.f("            memcpy(A + (u64)QP(r << %d), src_states[peer] + src_base + qsv_scatter(r << %d), %uu);", L, L, 16u << L);
+        rounds_body(o, 1);
+        o.f("    }");
+        o.f("}");
+    }
     // one tile with a caller-chosen global base index (programs of states too large for a host array)
     o.f("extern \"C\" void qsv_jit_host_tile(double2 *tile, const u64 gbase, const double2 *tables) {");
     o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
@@ -1106,6 +1289,7 @@ struct Driver {
     int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **,
                         void **) = nullptr;
     int (*GetErrorString)(int, const char **) = nullptr;
+    int (*OccupancyMaxActiveBlocks)(int *, void *, int, size_t) = nullptr;
 };
 
 static Driver *driver(std::string &err) {
@@ -1123,6 +1307,7 @@ static Driver *driver(std::string &err) {
         QSV_SYM(FuncSetAttribute, "cuFuncSetAttribute")
         QSV_SYM(LaunchKernel, "cuLaunchKernel")
         QSV_SYM(GetErrorString, "cuGetErrorString")
+        QSV_SYM(OccupancyMaxActiveBlocks, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
 #undef QSV_SYM
     });
     if (!load_err.empty()) { err = load_err; return nullptr; }
@@ -1144,8 +1329,12 @@ static std::mutex g_mu;
 static std::unordered_map<std::string, Entry *> g_cache;
 static std::atomic<uint64_t> g_compiles{0}, g_hits{0}, g_compile_us{0};
 
-static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t bytes) {
+static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr) {
     std::string k;
+    if (sw) {
+        k.append(fuse_two_buffers() ? "F2" : "F1");
+        k.append(reinterpret_cast<const char *>(sw), sizeof(*sw));
+    }
     k.append(reinterpret_cast<const char *>(&P.tile_bits), sizeof(P.tile_bits));
     k.append(reinterpret_cast<const char *>(&P.low_bits), sizeof(P.low_bits));
     k.append(reinterpret_cast<const char *>(P.hi_pos), sizeof(P.hi_pos));
@@ -1157,8 +1346,8 @@ static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t byt
     return k;
 }
 
-static Entry *lookup(const qsv_pass_t &P, const void *prog, uint32_t bytes) {
-    const std::string k = cache_key(P, prog, bytes);
+static Entry *lookup(const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr) {
+    const std::string k = cache_key(P, prog, bytes, sw);
     std::lock_guard<std::mutex> g(g_mu);
     auto it = g_cache.find(k);
     if (it != g_cache.end()) return it->second;
@@ -1167,13 +1356,13 @@ static Entry *lookup(const qsv_pass_t &P, const void *prog, uint32_t bytes) {
     return e;
 }
 
-static int ensure_compiled(Entry *e, const qsv_pass_t &P, const void *prog, uint32_t bytes) {
+static int ensure_compiled(Entry *e, const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr) {
     std::lock_guard<std::mutex> g(e->mu);
     if (e->compiled) { g_hits.fetch_add(1); return 0; }
     if (e->failed) { set_error("qsv jit: %s", e->err.c_str()); return 1; }
     const auto t0 = std::chrono::steady_clock::now();
     std::string src;
-    if (generate(P, prog, bytes, src, e->err) || compile_cubin(src, e->cubin, e->err)) {
+    if (generate(P, prog, bytes, src, e->err, sw) || compile_cubin(src, e->cubin, e->err)) {
         e->failed = true;
         set_error("qsv jit: %s", e->err.c_str());
         return 1;
@@ -1221,11 +1410,79 @@ bool wanted(const qsv_pass_t *P, const void *prog_host) {
     return P->n_local >= minq;
 }
 
+static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out);
+
 int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
            cudaStream_t st, unsigned grid) {
+    void *fn = nullptr;
+    if (int rc = get_function(P, prog_host, prog_bytes, nullptr, &fn)) return rc;
+    std::string err;
+    Driver *d = driver(err);
+    QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
+    unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
+    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev)};
+    const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u * tile_slots(P->n_hi), (void *)st, args, nullptr);
+    if (rc) {
+        const char *es = nullptr;
+        d->GetErrorString(rc, &es);
+        set_error("qsv jit: cuLaunchKernel: %s", es ? es : "?");
+        return 2;
+    }
+    count_launch();
+    return 0;
+}
+
+struct PeerTable { void *state[16]; void *flags[16]; };
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// fused swap + pass: all CTAs must be co-resident (they hand-shake with the partner rank's CTA of the same index)
+int launch_swap(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
+                const SwapSpec &sw, const PeerTable &peers, unsigned rank, unsigned long long epoch, cudaStream_t st) {
+    void *fn = nullptr;
+    if (int rc = get_function(P, prog_host, prog_bytes, &sw, &fn)) return rc;
+    std::string err;
+    Driver *d = driver(err);
+    QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
+    const unsigned smem = (fuse_two_buffers() ? 2u : 1u) * 16u * tile_slots(P->n_hi);
+    {
+        std::string e2;
+        Driver *d2 = driver(e2);
+        if (d2) d2->FuncSetAttribute(fn, /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/ 8, (int)smem);
+    }
+    int per_sm = 0;
+    int rc = d->OccupancyMaxActiveBlocks(&per_sm, fn, 256, smem);
+    QSV_CHECK_ARG(rc == 0 && per_sm >= 1, "qsv jit: occupancy query failed for the fused swap kernel (rc=%d, %d CTAs/SM)", rc, per_sm);
+    if (per_sm > 2) per_sm = 2;
+    unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
+    unsigned long long grid = (unsigned long long)sm_count() * (unsigned)per_sm;
+    if (grid > kFlagCtas) grid = kFlagCtas;
+    if (grid > n_tiles) grid = n_tiles;
+    PeerTable pt = peers;
+    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &pt, &rank, &epoch};
+    rc = d->LaunchKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, smem, (void *)st, args, nullptr);
+    if (rc) {
+        const char *es = nullptr;
+        d->GetErrorString(rc, &es);
+        set_error("qsv jit: cuLaunchKernel (fused swap): %s", es ? es : "?");
+        return 2;
+    }
+    count_launch();
+    return 0;
+}
+
+static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out) {
     if (validate(P, prog_host, prog_bytes)) return 1;
-    Entry *e = lookup(*P, prog_host, prog_bytes);
-    if (ensure_compiled(e, *P, prog_host, prog_bytes)) return 1;
+    Entry *e = lookup(*P, prog_host, prog_bytes, sw);
+    if (ensure_compiled(e, *P, prog_host, prog_bytes, sw)) return 1;
     int dev = 0;
     QSV_CUDA(cudaGetDevice(&dev));
     void *fn = nullptr;
@@ -1250,19 +1507,7 @@ int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t
             e->fn[dev] = fn;
         }
     }
-    std::string err;
-    Driver *d = driver(err);
-    QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
-    unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
-    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev)};
-    const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u * tile_slots(P->n_hi), (void *)st, args, nullptr);
-    if (rc) {
-        const char *es = nullptr;
-        d->GetErrorString(rc, &es);
-        set_error("qsv jit: cuLaunchKernel: %s", es ? es : "?");
-        return 2;
-    }
-    count_launch();
+    *fn_out = fn;
     return 0;
 }
 
@@ -1294,6 +1539,56 @@ extern "C" int qsv_jit_compile(const qsv_pass_t *pass, const void *prog_host, ui
     jit::Entry *e = jit::lookup(*pass, prog_host, prog_bytes);
     if (jit::ensure_compiled(e, *pass, prog_host, prog_bytes)) return 1;
     return copy_out(e->cubin, cubin_buf, buf_len, needed);
+}
+
+static int make_swap_spec(jit::SwapSpec &sw, int g, const int *positions, int pass_first, const qsv_pass_t *pass) {
+    QSV_CHECK_ARG(g >= 1 && g <= 4 && positions && pass, "qsv fused swap: g=%d out of range or NULL pointer", g);
+    memset(&sw, 0, sizeof(sw));
+    sw.g = g;
+    for (int k = 0; k < 4; ++k) sw.q[k] = k < g ? positions[k] : 0;
+    sw.pre = pass_first ? 1 : 0;
+    sw.n_local = sw.pre ? pass->n_local : 0;       // only the pass-first form bakes n_local into the code
+    return 0;
+}
+
+extern "C" int qsv_jit_source_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
+                                   const int *positions, int pass_first, char *buf, size_t buf_len, size_t *needed) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return 1;
+    jit::SwapSpec sw;
+    if (make_swap_spec(sw, g, positions, pass_first, pass)) return 1;
+    std::string src, err;
+    if (jit::generate(*pass, prog_host, prog_bytes, src, err, &sw)) { set_error("qsv jit: %s", err.c_str()); return 1; }
+    return copy_out(src, buf, buf_len, needed);
+}
+
+extern "C" int qsv_jit_compile_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
+                                    const int *positions, int pass_first, char *cubin_buf, size_t buf_len, size_t *needed) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return 1;
+    jit::SwapSpec sw;
+    if (make_swap_spec(sw, g, positions, pass_first, pass)) return 1;
+    jit::Entry *e = jit::lookup(*pass, prog_host, prog_bytes, &sw);
+    if (jit::ensure_compiled(e, *pass, prog_host, prog_bytes, &sw)) return 1;
+    return copy_out(e->cubin, cubin_buf, buf_len, needed);
+}
+
+extern "C" int qsv_run_pass_rounds_swap(void *state_dev, const qsv_pass_t *pass, const void *prog_host,
+                                        uint32_t prog_bytes, const void *tables_dev, const uint64_t *peer_state_ptrs,
+                                        const uint64_t *peer_flag_ptrs, int g, const int *positions, int pass_first,
+                                        int rank, uint64_t epoch, void *stream) {
+    QSV_CHECK_ARG(state_dev && pass && prog_host && peer_state_ptrs && peer_flag_ptrs, "qsv_run_pass_rounds_swap: NULL pointer");
+    jit::SwapSpec sw;
+    if (make_swap_spec(sw, g, positions, pass_first, pass)) return 1;
+    const int P = 1 << g;
+    QSV_CHECK_ARG(rank >= 0 && rank < P, "qsv_run_pass_rounds_swap: rank %d out of range", rank);
+    jit::PeerTable pt;
+    for (int j = 0; j < 16; ++j) { pt.state[j] = nullptr; pt.flags[j] = nullptr; }
+    for (int j = 0; j < P; ++j) {
+        pt.state[j] = j == rank ? state_dev : reinterpret_cast<void *>(peer_state_ptrs[j]);
+        pt.flags[j] = reinterpret_cast<void *>(peer_flag_ptrs[j]);
+        QSV_CHECK_ARG(pt.state[j] && pt.flags[j], "qsv_run_pass_rounds_swap: peer %d has no mapped pointer", j);
+    }
+    return jit::launch_swap(state_dev, pass, prog_host, prog_bytes, tables_dev, sw, pt, (unsigned)rank, epoch,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int qsv_jit_wanted(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes) {

@@ -40,6 +40,10 @@ SYMBOLS = {
     "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_compile": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_wanted": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32]),
+    "qsv_jit_source_swap": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _I, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "qsv_jit_compile_swap": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _I, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "qsv_run_pass_rounds_swap": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_uint64), _I, _IP, _I, _I, _U64, _P]),
     "qsv_jit_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_D)]),
     "qsv_apply_dense": (C.c_int, [_P, _I, _I, _IP, _I, _IP, C.POINTER(_D), _U64, _P]),
     "qsv_apply_diag": (C.c_int, [_P, _I, _I, _IP, C.POINTER(_D), _U64, _P]),

@@ -109,6 +109,42 @@ class Comm:
         self.bytes_sent += 16 * (self.world - 1) * (1 << (sv.n_local - self.global_bits))
         self.swaps += 1
 
+    def _flag_arrays(self, device):
+        """Peer-mapped flag arrays of the fused swap + pass kernel: per rank 16 x 1024 uint64, zeroed once."""
+        if getattr(self, "_flags", None) is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            raw = symm_mem.empty(16 * 1024, dtype=torch.int64, device=device)
+            raw.zero_()
+            hdl = symm_mem.rendezvous(raw, self.group)
+            torch.cuda.synchronize()
+            hdl.barrier()
+            self._flags = (raw, hdl, [int(p) for p in hdl.buffer_ptrs])
+            self._epoch = 0
+        return self._flags
+
+    def swap_pass(self, sv, positions, cpass, prog, tables_ptr, pass_first=0):
+        """Global<->local swap of `positions` + the gate pass that follows it as ONE kernel over peer memory
+        (qsv_run_pass_rounds_swap): tiles are pulled from the peers, transformed and stored locally; a per-tile flag
+        handshake keeps the exchange in place.  One barrier before (earlier kernels of all ranks are done), none after."""
+        raw, hdl, ptrs = self._symm
+        fraw, fhdl, fptrs = self._flag_arrays(sv.state.device)
+        self._epoch += 1
+        arr = (C.c_uint64 * self.world)(*ptrs)
+        farr = (C.c_uint64 * self.world)(*fptrs)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        hdl.barrier()
+        _cabi.check(sv.lib.qsv_run_pass_rounds_swap(sv._ptr(sv.state), C.byref(cpass), C.c_void_p(prog.ctypes.data),
+                                                    int(prog.size), tables_ptr, arr, farr, self.global_bits,
+                                                    _cabi.int_array(positions), int(pass_first), self.rank,
+                                                    self._epoch << 32,
+                                                    sv._stream()), "qsv_run_pass_rounds_swap")
+        ev[1].record()
+        self.swap_events.append(ev)
+        self.fused_swaps = getattr(self, "fused_swaps", 0) + 1
+        self.bytes_sent += 16 * (self.world - 1) * (1 << (sv.n_local - self.global_bits))
+        self.swaps += 1
+
     def release_state(self):
         """Drop the symmetric-memory state (the StateVector that used it must be dropped as well)."""
         self._symm = None

@@ -27,7 +27,8 @@ def _ops_fingerprint(ops, geometry):
     h.update(repr((geometry, os.environ.get("QSV_PLAN_SEARCH"), os.environ.get("QSV_REGISTER_KERNEL"),
                    os.environ.get("QSV_REG_BITS"), os.environ.get("QSV_REG_MIN_OPS"), os.environ.get("QSV_JIT"),
                    os.environ.get("QSV_JIT_MIN_QUBITS"), os.environ.get("QSV_TILE_BITS"),
-                   os.environ.get("QSV_LOW_BITS"), os.environ.get("QSV_DEBUG_DROP"), os.environ.get("QSV_FILL"))).encode())
+                   os.environ.get("QSV_LOW_BITS"), os.environ.get("QSV_DEBUG_DROP"), os.environ.get("QSV_FILL"), os.environ.get("QSV_FUSE_SWAP"),
+                   os.environ.get("QSV_TRIM_ROUNDS"))).encode())
     for op in ops:
         h.update(repr((op.kind, tuple(op.targets), tuple(op.controls),
                        None if op.cvals is None else tuple(int(v) for v in op.cvals),
@@ -117,7 +118,7 @@ class StateVector:
         cp.rank_bits = self.rank_bits
         return cp
 
-    def _prepare_kernels(self, packed):
+    def _prepare_kernels(self, packed, swap_positions=None, pass_first=0):
         """Large states run pass-specialised kernels (csrc/qsv_jit.cu).  Generate + compile the ones this
         program needs now, on all host cores (NVRTC, ~0.3 s per kernel, cached by program bytes inside
         libqsv), so that the launches only look them up."""
@@ -135,6 +136,10 @@ class StateVector:
 
         def compile_one(item):
             cp, prog = item
+            if swap_positions is not None:
+                return self.lib.qsv_jit_compile_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size),
+                                                     len(swap_positions), _cabi.int_array(swap_positions),
+                                                     int(pass_first), None, 0, None)
             return self.lib.qsv_jit_compile(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), None, 0, None)
 
         import os
@@ -248,13 +253,26 @@ class StateVector:
             from .schedule import plan_schedule
             host_plan = []
             batch = []
-            for kind, item in plan_schedule(ops, self.n_local, self.tile_bits, self.low_bits):
+            for kind, item in plan_schedule(ops, self.n_local, self.tile_bits, self.low_bits,
+                                            fuse_swaps=self.fuse_swaps()):
                 if kind == "pass":
                     batch.append(item)
                     continue
                 if batch:
                     host_plan.append(("program", pack_passes(batch)))
                     batch = []
+                if kind == "swap_pass":
+                    swap_op, ps, pass_first = item
+                    packed = pack_passes([ps])
+                    if len(packed.passes) == 1 and self._jit_runs(packed.passes[0]):
+                        host_plan.append(("swap_pass", (swap_op, packed, pass_first)))
+                    elif pass_first:            # not a single specialised kernel: the two steps on their own
+                        host_plan.append(("program", packed))
+                        host_plan.append(("op", swap_op))
+                    else:
+                        host_plan.append(("op", swap_op))
+                        host_plan.append(("program", packed))
+                    continue
                 host_plan.append(("op", item))
             if batch:
                 host_plan.append(("program", pack_passes(batch)))
@@ -270,6 +288,12 @@ class StateVector:
                 segments.append(("program", (item, dev)))
                 h2d += int(item.blob.size)
                 h2d += sum(int(m[3][0].size) for m in item.passes if m[2] < 0)     # by-value round programs
+            elif kind == "swap_pass":
+                swap_op, packed, pass_first = item
+                self._prepare_kernels(packed, swap_positions=swap_op.params["positions"], pass_first=pass_first)
+                dev = torch.from_numpy(packed.blob).to(self.device, non_blocking=False)
+                segments.append(("swap_pass", (swap_op, packed, dev, pass_first)))
+                h2d += int(packed.blob.size) + int(packed.passes[0][3][0].size)
             else:
                 segments.append(("op", item))
         return {"segments": segments, "h2d_bytes": h2d}
@@ -278,8 +302,44 @@ class StateVector:
         for kind, seg in plan["segments"]:
             if kind == "program":
                 self.run_program(seg)
+            elif kind == "swap_pass":
+                self._run_swap_pass(seg)
             else:
                 self._run_whole_state_op(seg)
+
+    def fuse_swaps(self):
+        """True when a global<->local swap and the pass after it may run as ONE kernel over peer memory
+        (csrc/qsv_jit.cu, fused variant): peer-mapped state, specialised kernels in use, QSV_FUSE_SWAP != 0."""
+        import os
+        if os.environ.get("QSV_FUSE_SWAP", "1") == "0":
+            return False
+        if self.comm is None or not getattr(self.comm, "peer_swap", False) or self.n_local < 12 + self.g:
+            return False
+        mode = os.environ.get("QSV_JIT")
+        if mode == "0":
+            return False
+        return mode == "force" or self.n_local >= int(os.environ.get("QSV_JIT_MIN_QUBITS", "28"))
+
+    def _jit_runs(self, meta):
+        ps, _, n_ops, extra = meta
+        if n_ops >= 0:
+            return False
+        prog = extra[0]
+        cp = self._cpass(ps)
+        cp.reserved = int(prog[12])
+        return bool(self.lib.qsv_jit_wanted(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size)))
+
+    def _run_swap_pass(self, seg):
+        swap_op, packed, dev, pass_first = seg
+        ps, table_off, n_ops, extra = packed.passes[0]
+        prog = extra[0]
+        cp = self._cpass(ps)
+        cp.max_dense_k = 1
+        cp.reserved = int(prog[12])
+        self.comm.swap_pass(self, swap_op.params["positions"], cp, prog, C.c_void_p(dev.data_ptr() + table_off),
+                            pass_first)
+        self.passes_run += 1
+        self._keep.append(dev)
 
     def run_ops(self, ops):
         """Apply ops (physical positions) in order; consecutive tiled ops share passes."""
@@ -347,7 +407,7 @@ class StateVector:
                         ms.append(e0.elapsed_time(e1))
                     out.append({"kind": "pass", "ms": sum(ms) / len(ms),
                                 "bytes": 32.0 * (1 << self.n_local) * next(fr), "ops": len(meta[0].ops)})
-            elif seg.kind != "global_swap":
+            elif kind == "op" and seg.kind != "global_swap":
                 ms = []
                 for _ in range(repeats):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

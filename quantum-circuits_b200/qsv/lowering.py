@@ -118,7 +118,7 @@ def lower_gate(gate, wires, layout, transposed=False):
     return classify_matrix(M, layout.positions(wires), name)
 
 
-def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, free_swap=False):
+def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, free_swap=False, fuse_swaps=False):
     """(ops, src_pos): ops in application order; src_pos[b] = physical position feeding bit b of the
     OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map.  With
     n_global > 0 the ops are placed on a register sharded by its top n_global positions
@@ -128,7 +128,9 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
     in_flip=True the result is (ops, src_pos, flip) and the caller starts from |index ^ flip>; otherwise
     the leftover flips are kept as explicit X ops at the head of the list (any input state).
     free_swap: global<->local swaps may exchange any local positions (needs the peer-memory swap kernel,
-    Comm.peer_swap); otherwise the victims are first moved to the top local positions."""
+    Comm.peer_swap); otherwise the victims are first moved to the top local positions.
+    fuse_swaps: the pass after every swap will run fused into it (StateVector.fuse_swaps()): the swapped positions
+    stay above the tile's low positions and the planner accounts for the pass that avoids them."""
     n = len(circuit)
     gates = circuit.gates if presorted else topological_gates(circuit)
     table, out_qubits = gate_targets(circuit, gates)
@@ -155,7 +157,7 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
         from .schedule import place, place_joint, TILED_KINDS
         if free_swap and os.environ.get("QSV_PLACE", "joint") != "list" and all(o.kind in TILED_KINDS for o in ops):
             # placement and pass planning decided together: swaps happen when the passes run thin
-            ops, src_pos = place_joint(ops, n, n_global, src_pos)
+            ops, src_pos = place_joint(ops, n, n_global, src_pos, fuse_swaps=fuse_swaps)
         else:
             ops, src_pos = place(ops, n, n_global, src_pos, free_swap=free_swap)
     if in_flip:
@@ -222,7 +224,7 @@ def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=Tru
         sv = _sharded_state(n, comm)
         sv.d2h_bytes = 0
         ops, src_pos, flip = lower(circuit, transposed, presorted, n_global=comm.global_bits, in_flip=True,
-                                   free_swap=bool(comm.peer_swap))
+                                   free_swap=bool(comm.peer_swap), fuse_swaps=sv.fuse_swaps())
     sv.init_basis(basis_index(in_v) ^ flip)
     plan = sv.run_ops(ops)
     _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=0, passes=sv.passes_run)

@@ -711,12 +711,21 @@ def plan_schedule(ops, n_local, tile_bits=None, low_bits=None, fuse_swaps=False)
                     and remaining[0].kind in TILED_KINDS:
                 ps, rest = _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=_mask(pos))
                 if ps is not None and plan_rounds(ps) is not None:
-                    out.append(("swap_pass", (head, ps)))
+                    out.append(("swap_pass", (head, ps, 0)))
                     remaining = rest
                     continue
             out.append(("op", head))
             continue
         ps, remaining = _plan_one_pass(remaining, masks_of, n_local, T, L, search)
+        nxt = remaining[0] if remaining else None
+        if fuse_swaps and nxt is not None and nxt.kind == "global_swap" and T == 12 \
+                and nxt.params.get("positions") is not None and min(nxt.params["positions"]) >= L \
+                and not set(nxt.params["positions"]) & set(ps.hi_pos) and plan_rounds(ps) is not None:
+            # the last pass before a swap whose tile avoids the swapped positions: it runs inside the swap kernel,
+            # on the tiles as they are pulled from the peers ("pass first": ops see the pre-swap coordinates)
+            remaining.pop(0)
+            out.append(("swap_pass", (nxt, ps, 1)))
+            continue
         ps, remaining = _trim_tail_rounds(ps, remaining, masks_of)
         out.append(("pass", ps))
     return out
@@ -824,6 +833,7 @@ def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floa
     min_pos = min(max(SWAP_MIN_POS, L) if fuse_swaps else SWAP_MIN_POS, n_local - n_global)
     forbidden = 0                       # positions of the swap just emitted (the pass fused into it avoids them)
     just_swapped = False
+    last_pass = None
     cost_so_far = 0.0
     while remaining:
         if cost_so_far > cost_cap:
@@ -854,8 +864,14 @@ def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floa
                     nxt.setdefault(b, l)
             far = len(remaining) + 1
             cand = [p for p in range(n_local)]
-            cand.sort(key=lambda p: (p < min_pos, -nxt.get(p, far), -p))
+            prev_tile = set(last_pass.hi_pos) if (fuse_swaps and last_pass is not None) else set()
+            cand.sort(key=lambda p: (p < min_pos, -nxt.get(p, far), p in prev_tile, -p))
             positions = sorted(cand[:n_global])
+            if fuse_swaps and last_pass is not None and order and order[-1][0] == "pass" \
+                    and not set(positions) & prev_tile and min(positions) >= L:
+                # the pass just emitted runs inside this swap ("pass first"): it costs nothing extra
+                cost_so_far -= 1.0 + PASS_GATE_COST * max(0, order[-1][1] - PASS_FREE_GATES)
+                order[-1] = ("fused_pass", order[-1][1])
             out.append(Op("global_swap", (), (), params={"n_swap": n_global, "positions": positions}, name="relayout"))
             order.append(("swap", 0))
             relabel = list(range(n))
@@ -863,13 +879,15 @@ def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floa
                 relabel[p_loc], relabel[n_local + i] = n_local + i, p_loc
                 at[p_loc], at[n_local + i] = at[n_local + i], at[p_loc]
             remaining = [op.remapped(relabel) for op in remaining]
-            forbidden = _mask(positions) if fuse_swaps else 0
+            forbidden = _mask(positions) if (fuse_swaps and not (order[-2:-1] and order[-2][0] == "fused_pass")) else 0
+            last_pass = None
             just_swapped = True
             cost_so_far += SWAP_COST_FULL * (1.0 - 2.0 ** -n_global)
             continue
         if ps is None:
             raise RuntimeError("sharded planner made no progress (op needs more than %d tile-local qubits)" % T)
         out.extend(ps.ops)
+        last_pass = ps
         order.append(("fused_pass" if forbidden else "pass", len(ps.ops)))
         if not forbidden:
             cost_so_far += 1.0 + PASS_GATE_COST * max(0, len(ps.ops) - PASS_FREE_GATES)

@@ -82,6 +82,31 @@ def main():
         dist.all_gather(allz, zs)
         check("sample n=%d z=%d" % (n, z), all(int(t) == z for t in allz) and abs(ref[z]) ** 2 > 0)
 
+    # 1b. swap + pass fused into one kernel over peer memory (specialised kernels forced at this small size)
+    if comm.peer_swap:
+        os.environ["QSV_JIT"] = "force"
+        for n, depth, seed in ((16 + g, 16, 12), (17 + g, 24, 13)):
+            c = workloads.random_layered_circuit(n, depth, seed=seed)
+            c.sort()
+            sv = engine.StateVector(n, comm=comm)
+            ref = np.zeros(1 << n, dtype=np.complex128)
+            ref[9] = 1
+            for M, wires, _ in so.random_layered_steps(n, depth, seed=seed):
+                ref = so.apply_gate(ref, n, wires, M)
+            ops, src_pos, flip = lowering.lower(c, n_global=g, in_flip=True, free_swap=True, fuse_swaps=sv.fuse_swaps())
+            fused0 = getattr(comm, "fused_swaps", 0)
+            for rep in range(2):                   # twice: the flag epochs must keep the handshake correct
+                sv.init_basis(9 ^ flip)
+                sv.run_ops(ops)
+                sv.synchronize()
+            full = gather_full(sv, comm)
+            err = np.max(np.abs(to_output_order(full, src_pos) - ref))
+            check("fused swap+pass n=%d depth=%d fused_kernels=%d err=%.2e"
+                  % (n, depth, getattr(comm, "fused_swaps", 0) - fused0, err),
+                  err <= 1e-12 and getattr(comm, "fused_swaps", 0) > fused0)
+            del sv
+        os.environ.pop("QSV_JIT")
+
     # 2. Grover with the dedicated oracle + diffusion kernels (all-reduce of the two means)
     ns, K, x = 9 + g, 5, 0b1011001 % (1 << (9 + g))
     c = workloads.grover_circuit(ns, x, K)

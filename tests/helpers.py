@@ -425,3 +425,43 @@ def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=No
     h.qsv_jit_host_run(C.c_void_p(out.ctypes.data), C.c_uint64(rank_bits), C.c_uint64(1 << (ps.n_local - ps.tile_bits)),
                        C.c_void_p(tabs.ctypes.data))
     return out
+
+
+def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pass_first=0):
+    """Fused swap + pass on the host: `shards` = the P = 2^g shards BEFORE the swap (numpy complex128 arrays).
+    Returns the list of shards after swap + pass, one call of the generated qsv_jit_host_run_swap per rank."""
+    import ctypes as C
+    import hashlib
+    import os
+    import subprocess
+    from qsv import _cabi
+    lib = _cabi.load()
+    g = len(positions)
+    cp = jit_cpass(ps)
+    pos = _cabi.int_array(positions)
+    need = C.c_size_t(0)
+    _cabi.check(lib.qsv_jit_source_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g, pos, pass_first,
+                                        None, 0, C.byref(need)), "qsv_jit_source_swap")
+    buf = C.create_string_buffer(need.value)
+    _cabi.check(lib.qsv_jit_source_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g, pos, pass_first,
+                                        buf, need.value, C.byref(need)), "qsv_jit_source_swap")
+    src = buf.raw.decode()
+    tag = "swap" + hashlib.sha1(src.encode()).hexdigest()[:16]
+    cu, so = os.path.join(workdir, tag + ".cu"), os.path.join(workdir, tag + ".so")
+    if not os.path.exists(so):
+        with open(cu, "w") as f:
+            f.write(src)
+        r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DQSV_JIT_HOST", "-x", "c++", cu,
+                            "-o", so], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[:4000]
+    h = C.CDLL(so)
+    tabs = np.frombuffer(bytes(tables) + b"\0" * 16, dtype=np.uint8).copy()
+    before = [np.ascontiguousarray(s_, dtype=np.complex128) for s_ in shards]
+    ptrs = (C.c_void_p * len(before))(*[b.ctypes.data for b in before])
+    out = []
+    for rank in range(1 << g):
+        dst = np.zeros(1 << n_local, dtype=np.complex128)
+        h.qsv_jit_host_run_swap(C.c_void_p(dst.ctypes.data), ptrs, C.c_uint32(rank), C.c_uint64(rank << n_local),
+                                C.c_uint64(1 << (n_local - ps.tile_bits)), C.c_void_p(tabs.ctypes.data))
+        out.append(dst)
+    return out

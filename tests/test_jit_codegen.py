@@ -216,3 +216,92 @@ def test_long_programs_capacity_and_splitting(tmp_path, monkeypatch):
     for m in split.passes:
         assert m[2] < 0 and int(np.frombuffer(bytes(m[3][0]), dtype="<u4", count=3)[2]) <= schedule.RPROG_MAX_OPS
     assert np.max(np.abs(emulate_program(split, psi) - ref)) <= 1e-13
+
+
+@pytest.mark.parametrize("g,positions", [(1, [13]), (2, [9, 14]), (3, [12, 13, 14])])
+def test_fused_swap_pass_matches_swap_then_pass(tmp_path, g, positions):
+    """The fused variant (qsv_run_pass_rounds_swap) on the host: every rank pulls its tiles from the shards before
+    the swap and applies the pass on the way.  Reference: the swap as an index exchange in numpy, then the unfused
+    generated pass on every shard.  Ops read the swapped and the global positions as controls / phases."""
+    from helpers import jit_host_run_swap
+    from qsv.schedule import Op, plan_schedule, pack_passes
+    n_local = 15
+    P = 1 << g
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    S = np.array([[0.5 + 0.5j, 0.5 - 0.5j], [0.5 - 0.5j, 0.5 + 0.5j]], dtype=np.complex128)
+    ph = complex(math.cos(0.7), math.sin(0.7))
+    free = [p for p in range(6, n_local) if p not in positions]
+    swap = Op("global_swap", (), (), params={"n_swap": g, "positions": positions})
+    ops = [swap,
+           Op("dense", (0,), (), matrix=H), Op("dense", (free[0],), (), matrix=S), Op("mcx", (free[1],), (positions[0],)),
+           Op("phase", (), (positions[-1], 3), scalar=ph), Op("phase", (), (n_local, free[2]), scalar=-1.0 + 0j),
+           Op("dense", (free[2],), (n_local + g - 1,), matrix=H), Op("mcx", (2,), (free[0], positions[0])),
+           Op("dense", (free[3],), (), matrix=H), Op("phase", (), (free[3],), scalar=ph), Op("dense", (1,), (), matrix=S),
+           Op("diag", (2, positions[0], n_local), (), matrix=np.exp(1j * np.arange(8))), Op("dense", (4,), (), matrix=H)]
+    sched = plan_schedule(ops, n_local, 12, 6, fuse_swaps=True)
+    assert sched[0][0] == "swap_pass" and sched[0][1][2] == 0, [k for k, _ in sched]
+    ps = sched[0][1][1]
+    assert not set(ps.hi_pos) & set(positions)
+    assert len(ps.ops) >= 8
+    packed = pack_passes([ps])
+    ps_, off, n_ops, extra = packed.passes[0]
+    assert n_ops < 0
+    prog, tables = extra[0], packed.blob.tobytes()[off:]
+    shards = [_rand_state(n_local, 40 + r) for r in range(P)]
+    got = jit_host_run_swap(ps_, prog, tables, shards, positions, n_local, str(tmp_path))
+    # reference: exchange (field = j, rest) of rank r with (field = r, rest) of rank j, then the plain pass
+    idx = np.arange(1 << n_local)
+    field = np.zeros_like(idx)
+    for k, q in enumerate(positions):
+        field |= ((idx >> q) & 1) << k
+    fmask = sum(1 << q for q in positions)
+    for r in range(P):
+        swapped = np.empty(1 << n_local, dtype=np.complex128)
+        for j in range(P):
+            sel = field == j
+            src_idx = (idx[sel] & ~fmask) | sum(((r >> k) & 1) << q for k, q in enumerate(positions))
+            swapped[sel] = shards[j][src_idx]
+        ref = jit_host_run(ps_, prog, tables, swapped, r << n_local, str(tmp_path))
+        assert np.max(np.abs(got[r] - ref)) == 0.0, "rank %d" % r
+
+
+@pytest.mark.parametrize("g,positions", [(1, [12]), (3, [10, 13, 14])])
+def test_fused_pass_then_swap_matches_pass_then_swap(tmp_path, g, positions):
+    """'Pass first' form: the last pass before a swap runs inside the swap kernel, on the tiles as they are pulled
+    from the peers; its ops see the coordinates (rank, swapped field) the tile had on the source rank."""
+    from helpers import jit_host_run_swap
+    from qsv.schedule import Op, plan_schedule, pack_passes
+    n_local = 15
+    P = 1 << g
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    S = np.array([[0.5 + 0.5j, 0.5 - 0.5j], [0.5 - 0.5j, 0.5 + 0.5j]], dtype=np.complex128)
+    ph = complex(math.cos(0.7), math.sin(0.7))
+    free = [p for p in range(6, n_local) if p not in positions]
+    swap = Op("global_swap", (), (), params={"n_swap": g, "positions": positions})
+    ops = [Op("dense", (0,), (), matrix=H), Op("dense", (free[0],), (), matrix=S), Op("mcx", (free[1],), (positions[0],)),
+           Op("phase", (), (positions[-1], 3), scalar=ph), Op("phase", (), (n_local, free[2]), scalar=-1.0 + 0j),
+           Op("dense", (free[2],), (n_local + g - 1,), matrix=H), Op("mcx", (2,), (free[0], positions[0])),
+           Op("dense", (free[3],), (), matrix=H), Op("phase", (), (free[3],), scalar=ph), Op("dense", (1,), (), matrix=S),
+           Op("diag", (2, positions[0], n_local), (), matrix=np.exp(1j * np.arange(8))), Op("dense", (4,), (), matrix=H),
+           swap]
+    sched = plan_schedule(ops, n_local, 12, 6, fuse_swaps=True)
+    assert [k for k, _ in sched] == ["swap_pass"] and sched[0][1][2] == 1, [k for k, _ in sched]
+    ps = sched[0][1][1]
+    packed = pack_passes([ps])
+    ps_, off, n_ops, extra = packed.passes[0]
+    prog, tables = extra[0], packed.blob.tobytes()[off:]
+    shards = [_rand_state(n_local, 60 + r) for r in range(P)]
+    got = jit_host_run_swap(ps_, prog, tables, shards, positions, n_local, str(tmp_path), pass_first=1)
+    after_pass = [jit_host_run(ps_, prog, tables, shards[r], r << n_local, str(tmp_path)) for r in range(P)]
+    idx = np.arange(1 << n_local)
+    field = np.zeros_like(idx)
+    for k, q in enumerate(positions):
+        field |= ((idx >> q) & 1) << k
+    fmask = sum(1 << q for q in positions)
+    for r in range(P):
+        ref = np.empty(1 << n_local, dtype=np.complex128)
+        for j in range(P):
+            sel = field == j
+            src_idx = (idx[sel] & ~fmask) | sum(((r >> k) & 1) << q for k, q in enumerate(positions))
+            ref[sel] = after_pass[j][src_idx]
+        assert np.max(np.abs(got[r] - ref)) == 0.0, "rank %d" % r
