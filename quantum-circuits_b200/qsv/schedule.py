@@ -820,7 +820,7 @@ def _asap_levels(ops):
     return levels
 
 
-def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=float("inf")):
+def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=float("inf"), tile_penalty=0):
     """One run of the joint planner with a fixed 'thin pass' threshold; returns (cost, ops, src_pos, order)."""
     import copy
     n_local = n - n_global
@@ -865,7 +865,10 @@ def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floa
             far = len(remaining) + 1
             cand = [p for p in range(n_local)]
             prev_tile = set(last_pass.hi_pos) if (fuse_swaps and last_pass is not None) else set()
-            cand.sort(key=lambda p: (p < min_pos, -nxt.get(p, far), p in prev_tile, -p))
+            # tile_penalty: DAG levels a position loses as a victim candidate when it sits in the tile of the pass
+            # just emitted (taking it would keep that pass from running inside the swap kernel)
+            cand.sort(key=lambda p: (p < min_pos, -(nxt.get(p, far) - (tile_penalty if p in prev_tile else 0)),
+                                     p in prev_tile, -p))
             positions = sorted(cand[:n_global])
             if fuse_swaps and last_pass is not None and order and order[-1][0] == "pass" \
                     and not set(positions) & prev_tile and min(positions) >= L:
@@ -922,10 +925,11 @@ def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
     best = None
     thins = [int(v) for v in os.environ.get("QSV_PLACE_THIN", "1,8,14,20").split(",")]
     for thin in thins:
-        res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps,
-                                cost_cap=best[0] if best is not None else float("inf"))
-        if best is None or res[0] < best[0]:
-            best = res
+        for pen in ((0, 2, 6) if fuse_swaps else (0,)):
+            res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps,
+                                    cost_cap=best[0] if best is not None else float("inf"), tile_penalty=pen)
+            if best is None or res[0] < best[0]:
+                best = res
     if len(_PLACE_CACHE) >= 8:
         _PLACE_CACHE.pop(next(iter(_PLACE_CACHE)))
     _PLACE_CACHE[key] = (list(best[1]), list(best[2]) if best[2] is not None else None)
