@@ -289,6 +289,7 @@ class Comm:
         totals = torch.empty(self.world, dtype=torch.float64, device=sums.device)
         dist.all_gather_into_tensor(totals, local_total, group=self.group)
         totals = totals.cpu().numpy()
+        sv.d2h_bytes += 8 * self.world + 8            # shard totals + the broadcast index
         cum = np.cumsum(totals)
         total = float(cum[-1])
         if not total > 0.0:
@@ -299,6 +300,7 @@ class Comm:
         if owner == self.rank:
             prefix_rank = float(cum[owner - 1]) if owner > 0 else 0.0
             lc = np.cumsum(sums.cpu().numpy()) + prefix_rank
+            sv.d2h_bytes += 8 * sums.numel()
             blk = min(int(np.searchsorted(lc, target, side="right")), len(lc) - 1)
             prefix = float(lc[blk - 1]) if blk > 0 else prefix_rank
             z, _ = sv._scan(None, blk << bb, (1 << sv.n_local) - 1, prefix, target)

@@ -118,7 +118,7 @@ class StateVector:
         cp.rank_bits = self.rank_bits
         return cp
 
-    def _prepare_kernels(self, packed, swap_positions=None, pass_first=0):
+    def _prepare_kernels(self, packed):
         """Large states run pass-specialised kernels (csrc/qsv_jit.cu).  Generate + compile the ones this
         program needs now, on all host cores (NVRTC, ~0.3 s per kernel, cached by program bytes inside
         libqsv), so that the launches only look them up."""
@@ -136,10 +136,6 @@ class StateVector:
 
         def compile_one(item):
             cp, prog = item
-            if swap_positions is not None:
-                return self.lib.qsv_jit_compile_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size),
-                                                     len(swap_positions), _cabi.int_array(swap_positions),
-                                                     int(pass_first), None, 0, None)
             return self.lib.qsv_jit_compile(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), None, 0, None)
 
         import os
@@ -290,10 +286,16 @@ class StateVector:
                 h2d += sum(int(m[3][0].size) for m in item.passes if m[2] < 0)     # by-value round programs
             elif kind == "swap_pass":
                 swap_op, packed, pass_first = item
-                self._prepare_kernels(packed, swap_positions=swap_op.params["positions"], pass_first=pass_first)
                 dev = torch.from_numpy(packed.blob).to(self.device, non_blocking=False)
-                segments.append(("swap_pass", (swap_op, packed, dev, pass_first)))
                 h2d += int(packed.blob.size) + int(packed.passes[0][3][0].size)
+                if self._compile_fused(packed, swap_op.params["positions"], pass_first):
+                    segments.append(("swap_pass", (swap_op, packed, dev, pass_first)))
+                else:
+                    # the fused kernel cannot be built (same answer on every rank: the program is rank independent):
+                    # run the two steps on their own rather than leave the peers waiting for a kernel that never starts
+                    self._prepare_kernels(packed)
+                    two = [("program", (packed, dev)), ("op", swap_op)]
+                    segments.extend(two if pass_first else two[::-1])
             else:
                 segments.append(("op", item))
         return {"segments": segments, "h2d_bytes": h2d}
@@ -319,6 +321,19 @@ class StateVector:
         if mode == "0":
             return False
         return mode == "force" or self.n_local >= int(os.environ.get("QSV_JIT_MIN_QUBITS", "28"))
+
+    def _compile_fused(self, packed, positions, pass_first):
+        ps, _, _, extra = packed.passes[0]
+        prog = extra[0]
+        cp = self._cpass(ps)
+        cp.reserved = int(prog[12])
+        rc = self.lib.qsv_jit_compile_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), len(positions),
+                                           _cabi.int_array(positions), int(pass_first), None, 0, None)
+        if rc != 0:
+            import warnings
+            warnings.warn("qsv: fused swap+pass kernel unavailable (%s); running swap and pass separately"
+                          % self.lib.qsv_last_error().decode("utf-8", "replace"))
+        return rc == 0
 
     def _jit_runs(self, meta):
         ps, _, n_ops, extra = meta
