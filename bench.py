@@ -290,6 +290,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
+    # the same K steps with the support hint switched off: every pass sweeps the whole state, as if the register
+    # did not start in a basis state (reported next to `value`, which is what the API path runs)
+    os.environ["QSV_SPARSE_START"] = "0"
+    step()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for _ in range(args.steps):
+        step()
+    ev3.record()
+    barrier()
+    ms_dense = ev2.elapsed_time(ev3)
+    os.environ.pop("QSV_SPARSE_START")
+    if world > 1:
+        t = torch.tensor([ms_dense], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dense = float(t.item())
+    ms_dense_per_step = ms_dense / args.steps
     circuit_gps = n_gates / (ms_per_step * 1e-3)
     # whole-job aggregate: every gate of the sharded circuit updates the shards of all N ranks, so the units all
     # ranks processed per step are gates x N (one unit = one gate applied to one 2^n_local-amplitude shard).  At
@@ -317,7 +335,7 @@ def main():
     # ---- roofline of the dominant kernel (k_pass): per-launch CUDA-event timing of every pass
     peak, peak_src = measured_peak_gbs()
     n_local = sv.n_local
-    timed = sv.time_plan(plan, repeats=2)
+    timed = sv.time_plan(plan, repeats=2, basis=in_index)      # every launch as a step runs it (support hints)
     by_kind = {}
     for t in timed:
         k = by_kind.setdefault(t["kind"], {"ms": 0.0, "bytes": 0.0, "launch_groups": 0, "ops": 0})
@@ -342,7 +360,10 @@ def main():
                 "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launch_groups"]),
                 "share_of_step": d["ms"] / ms_per_step if ms_per_step else None,
                 "gates_per_launch": d["ops"] / max(1, d["launch_groups"]),
-                "per_launch": [[round(t["ms"], 3), t["ops"]] for t in timed if t["kind"] == dom][:64],
+                "per_launch": [[round(t["ms"], 3), t["ops"]] + ([round(t["active"], 6)] if t["active"] < 1.0 else [])
+                               for t in timed if t["kind"] == dom][:64],
+                "per_launch_columns": "ms, gates, [fraction of the shard's tiles touched, if < 1: the register starts in "
+                                      "a basis state and early passes skip tiles that are still zero]",
                 "other_kernels": {k: {"ms_per_step": v["ms"], "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] else 0.0}
                                   for k, v in by_kind.items() if k != dom}}
 
@@ -425,6 +446,8 @@ def main():
                    "host_lowering_s": t_host, "jit": jit},
         "roofline": roofline, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
         "circuit_gates_per_sec": circuit_gps,
+        "dense_start": {"value": n_gates * world / (ms_dense_per_step * 1e-3), "ms_per_step": ms_dense_per_step,
+                        "note": "same steps with QSV_SPARSE_START=0: no support hint, every pass sweeps the whole state"},
         "amplitude_updates_per_sec": circuit_gps * float(1 << n),
     }
     if world > 1:

@@ -172,6 +172,14 @@ int qsv_run_pass(void *state_dev, const qsv_pass_t *pass, const void *prog_dev,
 int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
                         const void *tables_dev, void *stream);
 
+/* qsv_run_pass_rounds for a state whose SUPPORT is known: index bits under `fixed_mask` (local positions outside
+ * the tile and/or global positions, as in pass->rank_bits) equal `fixed_val` wherever the state is non-zero - true
+ * for a register that started in a basis state (main/circuit.py:290-301) on every position no gate has touched
+ * non-diagonally yet.  Tiles that disagree hold only zeros and, the pass being linear, stay zero: they are neither
+ * read nor written.  The result is identical to qsv_run_pass_rounds; kernels without the skip ignore the hint. */
+int qsv_run_pass_rounds_sparse(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                               const void *tables_dev, uint64_t fixed_mask, uint64_t fixed_val, void *stream);
+
 /* Pass-specialised form of qsv_run_pass_rounds.  For large states (n_local >= 28 by default; environment
  * QSV_JIT=0 never, QSV_JIT=force always, QSV_JIT_MIN_QUBITS=n) qsv_run_pass_rounds does not interpret the
  * round program: libqsv generates straight-line sm_100a CUDA for exactly this program (same tile geometry,

@@ -929,7 +929,12 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         active = "true";
     }
     if (sw) active = "true";       // every tile moves, whatever its ops' conditions say
-    o.f("QSV_FN bool qsv_active(const u64 gbase) { (void)gbase; return %s; }", active.c_str());
+    // sp_mask / sp_val: index bits known to be FIXED in the state's support (a register that started in a basis state
+    // and has not been touched non-diagonally on those positions): a tile that disagrees holds only zeros and, the
+    // pass being linear, stays zero - it is skipped like a tile whose ops are all switched off
+    o.f("QSV_FN bool qsv_active(const u64 gbase, const u64 sp_mask, const u64 sp_val) {");
+    o.f("    return ((gbase & sp_mask) == sp_val) && (%s);", active.c_str());
+    o.f("}");
 
     // ---- tile base: insert a zero bit at every hi position (ascending)
     o.f("QSV_FN u64 qsv_tile_base(const u64 t) {");
@@ -999,7 +1004,8 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
             " const __grid_constant__ qsv_peers peers, const u32 rank, const u64 epoch) {");
     else
-    o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables) {");
+    o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
+        " const u64 sp_mask, const u64 sp_val) {");
     o.f("    extern __shared__ __align__(128) unsigned char smem_raw[];");
     o.f("    double2 *tile = reinterpret_cast<double2 *>(smem_raw);");
     o.f("    __shared__ __align__(8) u64 mbar;");
@@ -1095,7 +1101,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    ctx.state = state; ctx.tile = tile; ctx.mbar = &mbar; ctx.s_off = s_off; ctx.warp = warp;");
         o.f("    ctx.flags = (tid == 0 ? 2u : 0u) | 4u;");
         o.f("    u64 t = blockIdx.x;");
-        o.f("    while (t < n_tiles && !qsv_active(qsv_tile_base(t) | rank_bits)) t += gridDim.x;");
+        o.f("    while (t < n_tiles && !qsv_active(qsv_tile_base(t) | rank_bits, sp_mask, sp_val)) t += gridDim.x;");
         o.f("    if (t >= n_tiles) return;");
         o.f("    ctx.next_base = qsv_tile_base(t);");
         o.f("    qsv_issue_load(ctx);");
@@ -1103,7 +1109,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("        const u64 base = qsv_tile_base(t);");
         o.f("        const u64 gbase = base | rank_bits;");
         o.f("        u64 tn = t + gridDim.x;");
-        o.f("        while (tn < n_tiles && !qsv_active(qsv_tile_base(tn) | rank_bits)) tn += gridDim.x;");
+        o.f("        while (tn < n_tiles && !qsv_active(qsv_tile_base(tn) | rank_bits, sp_mask, sp_val)) tn += gridDim.x;");
         o.f("        ctx.next_base = tn < n_tiles ? qsv_tile_base(tn) : 0ULL;");
         o.f("        ctx.flags = (ctx.flags & 3u) | (tn < n_tiles ? 4u : 0u);");
         o.f("        mbar_wait(&mbar, parity);");
@@ -1122,7 +1128,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {");
         o.f("        const u64 base = qsv_tile_base(t);");
         o.f("        const u64 gbase = base | rank_bits;");
-        o.f("        if (!qsv_active(gbase)) continue;");
+        o.f("        if (!qsv_active(gbase, sp_mask, sp_val)) continue;");
         o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
         o.f("        if (issuer)");
         o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
@@ -1150,13 +1156,14 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("}");
     o.f("#else");
     // ---- host emulation driver (tests only): same round functions, threads run sequentially
-    o.f("extern \"C\" void qsv_jit_host_run(double2 *state, const u64 rank_bits, const u64 n_tiles, const double2 *tables) {");
+    o.f("extern \"C\" void qsv_jit_host_run(double2 *state, const u64 rank_bits, const u64 n_tiles, const double2 *tables,"
+        " const u64 sp_mask, const u64 sp_val) {");
     o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
     o.f("    qsv_ctx ctx; (void)ctx;");
     o.f("    for (u64 t = 0; t < n_tiles; ++t) {");
     o.f("        const u64 base = qsv_tile_base(t);");
     o.f("        const u64 gbase = base | rank_bits;");
-    o.f("        if (!qsv_active(gbase)) continue;");
+    o.f("        if (!qsv_active(gbase, sp_mask, sp_val)) continue;");
     o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
     o.f("            memcpy(A + (u64)QP(r << %d), state + base + qsv_scatter(r << %d), %uu);", L, L, 16u << L);
     rounds_body(o, 1);
@@ -1413,14 +1420,14 @@ bool wanted(const qsv_pass_t *P, const void *prog_host) {
 static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out);
 
 int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
-           cudaStream_t st, unsigned grid) {
+           cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val) {
     void *fn = nullptr;
     if (int rc = get_function(P, prog_host, prog_bytes, nullptr, &fn)) return rc;
     std::string err;
     Driver *d = driver(err);
     QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
     unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
-    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev)};
+    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &sp_mask, &sp_val};
     const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u * tile_slots(P->n_hi), (void *)st, args, nullptr);
     if (rc) {
         const char *es = nullptr;

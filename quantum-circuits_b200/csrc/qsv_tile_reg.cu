@@ -377,7 +377,7 @@ using namespace qsv;
 namespace qsv { namespace jit {
 bool wanted(const qsv_pass_t *P, const void *prog_host);
 int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
-           cudaStream_t st, unsigned grid);
+           cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val);
 } }
 
 static_assert(sizeof(qsv_rop_t) == 128, "qsv_rop_t must be 128 bytes");
@@ -395,8 +395,23 @@ static int sm_count() {
     return n;
 }
 
+static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
+                           const void *tables_dev, void *stream, uint64_t sp_mask, uint64_t sp_val);
+
 extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
                                    const void *tables_dev, void *stream) {
+    return run_pass_rounds(state_dev, P, prog_host, prog_bytes, tables_dev, stream, 0, 0);
+}
+
+extern "C" int qsv_run_pass_rounds_sparse(void *state_dev, const qsv_pass_t *P, const void *prog_host,
+                                          uint32_t prog_bytes, const void *tables_dev, uint64_t fixed_mask,
+                                          uint64_t fixed_val, void *stream) {
+    QSV_CHECK_ARG((fixed_val & ~fixed_mask) == 0, "qsv_run_pass_rounds_sparse: fixed_val has bits outside fixed_mask");
+    return run_pass_rounds(state_dev, P, prog_host, prog_bytes, tables_dev, stream, fixed_mask, fixed_val);
+}
+
+static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
+                           const void *tables_dev, void *stream, uint64_t sp_mask, uint64_t sp_val) {
     QSV_CHECK_ARG(state_dev && P && prog_host, "qsv_run_pass_rounds: NULL pointer");
     QSV_CHECK_ARG(P->n_local >= 1 && P->n_local <= 40, "qsv_run_pass_rounds: n_local=%d out of range", P->n_local);
     const int RB = P->reserved ? P->reserved : 4;             // register bits per round (3 or 4)
@@ -419,7 +434,8 @@ extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const v
         const uint64_t n_tiles_j = 1ull << (P->n_local - P->tile_bits);
         const uint64_t resident_j = (uint64_t)sm_count() * 2ull * 4ull;
         const unsigned grid_j = (unsigned)(n_tiles_j < resident_j ? n_tiles_j : resident_j);
-        const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid_j);
+        const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid_j,
+                                   sp_mask, sp_val);
         const char *mode = getenv("QSV_JIT");
         if (rc == 0 || (mode && !strcmp(mode, "force"))) return rc;
         static bool warned = false;

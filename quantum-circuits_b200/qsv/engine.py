@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .schedule import Op, TILED_KINDS, plan_passes, pack_passes
+from .schedule import Op, TILED_KINDS, Support, plan_passes, pack_passes
 
 SCAN_BITS_EXACT = 20     # up to 2^20 outcomes: one fully sequential scan (bit-exact with random.choices)
 SAMPLE_BLOCK_BITS = 12   # larger states: block sums of 2^12 outcomes, then a sequential scan inside one block
@@ -71,6 +71,7 @@ class StateVector:
         self._scratch = None
         self._keep = []       # host/device buffers that must outlive the async launches
         self.passes_run = 0
+        self._basis = None
         self.d2h_bytes = 0
         self.tile_bits = None
         self.low_bits = None
@@ -95,6 +96,7 @@ class StateVector:
         """|index>: main/circuit.py:290-301."""
         _cabi.check(self.lib.qsv_init_basis(self._ptr(self.state), self.n_local, int(index), self.rank,
                                             self._stream()), "qsv_init_basis")
+        self._basis = int(index)         # the next execute() knows the support of the state (schedule.Support)
 
     # ------------------------------------------------------------------ gate application
     def upload_program(self, ops):
@@ -301,13 +303,46 @@ class StateVector:
         return {"segments": segments, "h2d_bytes": h2d}
 
     def execute(self, plan):
-        for kind, seg in plan["segments"]:
-            if kind == "program":
-                self.run_program(seg)
+        """Run a prepared plan on the current state.  Right after init_basis the support of the state is known and
+        the passes skip the tiles that are still zero (schedule.Support); any other state is treated as dense."""
+        for kind, seg, sp in self._walk(plan, self._basis):
+            if kind == "pass":
+                meta, dev = seg
+                self._launch_pass(meta, dev, sp)
+                self.passes_run += 1
+                self._keep.append(dev)
             elif kind == "swap_pass":
                 self._run_swap_pass(seg)
             else:
                 self._run_whole_state_op(seg)
+        self._basis = None
+
+    def _walk(self, plan, basis):
+        """Segments of a plan in execution order with the support hint of every pass:
+        ("pass", (meta, dev), (fixed_mask, fixed_val)) | ("swap_pass", seg, None) | ("op", op, None)."""
+        sup = Support(self.n, basis)
+        top = list(range(self.n_local - self.g, self.n_local))
+        for kind, seg in plan["segments"]:
+            if kind == "program":
+                packed, dev = seg
+                for meta in packed.passes:
+                    yield "pass", (meta, dev), sup.pass_mask(meta[0])
+                    sup.after_ops(meta[0].ops)
+            elif kind == "swap_pass":
+                swap_op, packed, dev, pass_first = seg
+                yield "swap_pass", seg, None
+                if pass_first:
+                    sup.after_ops(packed.passes[0][0].ops)
+                    sup.swap(swap_op.params["positions"], self.n_local)
+                else:
+                    sup.swap(swap_op.params["positions"], self.n_local)
+                    sup.after_ops(packed.passes[0][0].ops)
+            else:
+                yield "op", seg, None
+                if seg.kind == "global_swap":
+                    sup.swap(seg.params.get("positions") or top, self.n_local)
+                else:
+                    sup.dense()
 
     def fuse_swaps(self):
         """True when a global<->local swap and the pass after it may run as ONE kernel over peer memory
@@ -363,7 +398,7 @@ class StateVector:
         return plan
 
     # ------------------------------------------------------------------ instrumentation (bench.py)
-    def _launch_pass(self, packed_meta, dev):
+    def _launch_pass(self, packed_meta, dev, support=None):
         ps, table_off, n_ops, maxk = packed_meta
         base = dev.data_ptr()
         cp = self._cpass(ps)
@@ -371,6 +406,13 @@ class StateVector:
             prog = maxk[0]
             cp.max_dense_k = 1
             cp.reserved = int(prog[12])          # register bits per round (program header word 3)
+            if support is not None and support[0]:
+                _cabi.check(self.lib.qsv_run_pass_rounds_sparse(self._ptr(self.state), C.byref(cp),
+                                                                C.c_void_p(prog.ctypes.data), int(prog.size),
+                                                                C.c_void_p(base + table_off), int(support[0]),
+                                                                int(support[1]), self._stream()),
+                            "qsv_run_pass_rounds_sparse")
+                return
             _cabi.check(self.lib.qsv_run_pass_rounds(self._ptr(self.state), C.byref(cp),
                                                      C.c_void_p(prog.ctypes.data), int(prog.size),
                                                      C.c_void_p(base + table_off), self._stream()),
@@ -400,28 +442,34 @@ class StateVector:
                 out.append(sum(best) / len(best))
         return out
 
-    def time_plan(self, plan, repeats=1):
+    def time_plan(self, plan, repeats=1, basis=None):
         """CUDA-event duration of every launch group of the plan with its algorithmic bytes:
-        [{'kind': 'pass' | op kind, 'ms': .., 'bytes': ..}].  'global_swap' segments are skipped (they
-        are timed by the communicator)."""
+        [{'kind': 'pass' | op kind, 'ms': .., 'bytes': .., 'active': fraction of the shard's tiles the launch
+        touches}].  With `basis` (the index the register is initialised to in a step) every pass is launched with
+        the support hint it gets in execute(), so the list is what a step runs; without it every pass is a full
+        sweep.  'global_swap' and fused swap+pass segments are skipped (they are timed by the communicator)."""
         from .schedule import algorithmic_bytes
         stream = torch.cuda.current_stream(self.device)
         out = []
         fr = iter(self.pass_active_fractions(plan))
-        for kind, seg in plan["segments"]:
-            if kind == "program":
-                packed, dev = seg
-                for meta in packed.passes:
-                    ms = []
-                    for _ in range(repeats):
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record(stream)
-                        self._launch_pass(meta, dev)
-                        e1.record(stream)
-                        e1.synchronize()
-                        ms.append(e0.elapsed_time(e1))
-                    out.append({"kind": "pass", "ms": sum(ms) / len(ms),
-                                "bytes": 32.0 * (1 << self.n_local) * next(fr), "ops": len(meta[0].ops)})
+        local_mask = (1 << self.n_local) - 1
+        for kind, seg, sp in self._walk(plan, basis):
+            if kind == "pass":
+                meta, dev = seg
+                ms = []
+                for _ in range(repeats):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    self._launch_pass(meta, dev, sp)
+                    e1.record(stream)
+                    e1.synchronize()
+                    ms.append(e0.elapsed_time(e1))
+                active = next(fr)
+                if sp is not None and sp[0]:
+                    here = (self.rank_bits & sp[0] & ~local_mask) == (sp[1] & ~local_mask)
+                    active *= Support.fraction(sp[0] & local_mask) if here else 0.0
+                out.append({"kind": "pass", "ms": sum(ms) / len(ms), "bytes": 32.0 * (1 << self.n_local) * active,
+                            "ops": len(meta[0].ops), "active": active})
             elif kind == "op" and seg.kind != "global_swap":
                 ms = []
                 for _ in range(repeats):
@@ -432,7 +480,7 @@ class StateVector:
                     e1.synchronize()
                     ms.append(e0.elapsed_time(e1))
                 out.append({"kind": seg.kind, "ms": sum(ms) / len(ms), "bytes": float(algorithmic_bytes(seg, self.n_local)),
-                            "ops": 1})
+                            "ops": 1, "active": 1.0})
         return out
 
     def pass_active_fractions(self, plan):

@@ -955,6 +955,59 @@ def ops_digest(ops):
 
 
 # ------------------------------------------------------------------------------------------------
+# support tracking: a register that started in a basis state
+# ------------------------------------------------------------------------------------------------
+
+class Support:
+    """Which index bits are still FIXED in the support of the state while a plan runs on |basis>.
+
+    run_method2 always starts from a basis state (main/circuit.py:290-301).  A position no op has used
+    non-diagonally yet still carries its initial bit in every non-zero amplitude (diagonal factors and controls
+    never move amplitudes), so a tile whose outside-tile index bits disagree with those values holds only zeros
+    and stays zero under the (linear) pass: the kernels skip it (qsv_run_pass_rounds_sparse).  On config 3 at 30
+    qubits the first four sweeps touch 2^-18 .. 1/16 of the state and the next two half of it.
+
+    Positions are PHYSICAL (0 = LSB, global positions >= n_local included); `basis` is the global index the register
+    was initialised to (None: unknown state, nothing is fixed)."""
+
+    def __init__(self, n, basis):
+        self.n = n
+        self.all = (1 << n) - 1
+        self.known = basis is not None and os.environ.get("QSV_SPARSE_START", "1") != "0"
+        self.free = 0 if self.known else self.all         # positions that may be in superposition
+        self.vals = int(basis) & self.all if self.known else 0
+
+    def pass_mask(self, ps):
+        """(fixed_mask, fixed_val) for a pass with tile geometry ps (bits inside the tile are never part of it)."""
+        tile = _mask(list(range(ps.low_bits)) + list(ps.hi_pos))
+        fixed = self.all & ~self.free & ~tile
+        return fixed, self.vals & fixed
+
+    def after_ops(self, ops):
+        for op in ops:
+            if op.kind in TILED_KINDS:
+                self.free |= _mask(op.nondiag_bits())
+            else:
+                self.free = self.all
+
+    def swap(self, positions, n_local):
+        """global<->local swap: positions[k] trades places with global bit k."""
+        for k, q in enumerate(positions):
+            gq = n_local + k
+            fa, fb = (self.free >> q) & 1, (self.free >> gq) & 1
+            va, vb = (self.vals >> q) & 1, (self.vals >> gq) & 1
+            self.free = (self.free & ~((1 << q) | (1 << gq))) | (fb << q) | (fa << gq)
+            self.vals = (self.vals & ~((1 << q) | (1 << gq))) | (vb << q) | (va << gq)
+
+    def dense(self):
+        self.free = self.all
+
+    @staticmethod
+    def fraction(fixed_mask):
+        return 2.0 ** -bin(fixed_mask).count("1")
+
+
+# ------------------------------------------------------------------------------------------------
 # program packing (must mirror qsv_op_t in include/qsv.h)
 # ------------------------------------------------------------------------------------------------
 

@@ -462,3 +462,35 @@ def test_specialised_kernels_full_size_against_interpreter(qsv_gpu, monkeypatch)
     assert float(d.abs().max()) <= 1e-13
     del d, ref
     assert abs(float(sv.block_sums(None, 12).sum()) - 1.0) < 1e-10
+
+
+def test_support_hint_gives_the_same_state_as_full_sweeps(qsv_gpu, monkeypatch):
+    """A register that starts in a basis state skips the tiles that are still zero (schedule.Support ->
+    qsv_run_pass_rounds_sparse).  Bit-for-bit the same state as with the hint switched off, at a size where the
+    first passes touch a small fraction of the tiles; the hinted run must launch the same kernels."""
+    lib, engine, lowering, torch = qsv_gpu
+    from qsv import workloads
+    monkeypatch.setenv("QSV_JIT", "force")
+    n = 24
+    c = workloads.random_layered_circuit(n, 8, seed=31)
+    c.sort()
+    ops, _, flip = lowering.lower(c, in_flip=True)
+    idx = 0b1011 ^ flip
+    sv = engine.StateVector(n)
+    plan = sv.prepare(ops)
+    hints = [sp for kind, seg, sp in sv._walk(plan, idx) if kind == "pass"]
+    assert sum(1 for sp in hints if sp[0]) >= 2, "expected the first passes to carry a support hint"
+    monkeypatch.setenv("QSV_SPARSE_START", "0")
+    sv.init_basis(idx)
+    sv.execute(plan)
+    sv.synchronize()
+    ref = sv.state.clone()
+    monkeypatch.delenv("QSV_SPARSE_START")
+    sv.init_basis(idx)
+    sv.execute(plan)
+    sv.synchronize()
+    assert torch.equal(torch.view_as_real(sv.state), torch.view_as_real(ref))
+    assert abs(float(sv.block_sums(None, 12).sum()) - 1.0) < 1e-10
+    # a state of unknown support (no init_basis before execute) is swept completely
+    sv.execute(plan)
+    assert sv._basis is None

@@ -305,3 +305,30 @@ def test_fused_pass_then_swap_matches_pass_then_swap(tmp_path, g, positions):
             src_idx = (idx[sel] & ~fmask) | sum(((r >> k) & 1) << q for k, q in enumerate(positions))
             ref[sel] = after_pass[j][src_idx]
         assert np.max(np.abs(got[r] - ref)) == 0.0, "rank %d" % r
+
+
+def test_support_hint_skips_only_zero_tiles(tmp_path):
+    """qsv_run_pass_rounds_sparse on the host: with the state confined to index bits (fixed_mask, fixed_val) outside
+    the tile, the generated kernel gives the same result with and without the hint, and leaves tiles outside the
+    support untouched (they are poisoned with NaN here: a kernel that read them would spread the NaN)."""
+    from qsv import workloads, lowering, schedule
+    n = 15
+    c = workloads.random_layered_circuit(n, 3, seed=5)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    ps, prog, tables = _round_programs(ops, n)[0]
+    outside = [p for p in range(ps.low_bits, n) if p not in ps.hi_pos]
+    assert len(outside) == 3
+    fixed_mask = (1 << outside[0]) | (1 << outside[2])
+    fixed_val = 1 << outside[2]
+    idx = np.arange(1 << n)
+    inside = (idx & fixed_mask) == fixed_val
+    psi = _rand_state(n, 3)
+    psi[~inside] = 0
+    dense = jit_host_run(ps, prog, tables, psi, 0, str(tmp_path))
+    poisoned = psi.copy()
+    poisoned[~inside] = np.nan
+    hinted = jit_host_run(ps, prog, tables, poisoned, 0, str(tmp_path), fixed_mask=fixed_mask, fixed_val=fixed_val)
+    assert np.all(np.isnan(hinted[~inside])) and not np.any(np.isnan(hinted[inside]))
+    assert np.array_equal(hinted[inside], dense[inside])
+    assert np.all(dense[~inside] == 0)

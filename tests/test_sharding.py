@@ -190,3 +190,115 @@ def test_peer_swap_kernel_index_logic(g, S, low):
         off_diag[r, own] = False
     assert np.all(touched[off_diag] == 1) and np.all(touched[~off_diag] == 0)
     assert np.array_equal(work, expect)
+
+
+def test_support_tracking_with_fused_swap_pass_items(monkeypatch):
+    """Same invariant on a schedule that contains fused swap+pass items (12-bit tiles, one global qubit): the
+    tracker must follow the 'pass first' / 'pass after' order of the fused kernel."""
+    from helpers import emulate_program
+    from qsv.schedule import Support, plan_schedule, pack_passes
+    n, g = 15, 1
+    monkeypatch.setattr(schedule, "SWAP_MIN_POS", 6)
+    steps = so.random_layered_steps(n, 10, seed=5)
+    c = circuit_from_steps(steps, n)
+    c.sort()
+    ops, src_pos, flip = lower(c, n_global=g, in_flip=True, free_swap=True, fuse_swaps=True)
+    n_local, P = n - g, 1 << g
+    basis = 0b1101 ^ flip
+    full = np.zeros(1 << n, dtype=np.complex128)
+    full[basis] = 1
+    sup = Support(n, basis)
+    idx = np.arange(1 << n)
+
+    def run_pass(ps, full):
+        packed = pack_passes([ps])
+        shards = full.reshape(P, -1)
+        return np.concatenate([emulate_program(packed, shards[r], rank_bits=r << n_local) for r in range(P)])
+
+    def run_swap(pos, full):
+        src = idx.copy()
+        for k, p_loc in enumerate(pos):
+            a, b = (idx >> p_loc) & 1, (idx >> (n_local + k)) & 1
+            src = (src & ~((1 << p_loc) | (1 << (n_local + k)))) | (b << p_loc) | (a << (n_local + k))
+        return full[src]
+
+    kinds = []
+    for kind, item in plan_schedule(ops, n_local, fuse_swaps=True):
+        kinds.append(kind)
+        if kind == "pass":
+            fixed, val = sup.pass_mask(item)
+            assert np.all(full[(idx & fixed) != val] == 0)
+            full = run_pass(item, full)
+            sup.after_ops(item.ops)
+        elif kind == "swap_pass":
+            swap_op, ps, pass_first = item
+            pos = swap_op.params["positions"]
+            if pass_first:
+                full = run_swap(pos, run_pass(ps, full))
+                sup.after_ops(ps.ops)
+                sup.swap(pos, n_local)
+            else:
+                full = run_pass(ps, run_swap(pos, full))
+                sup.swap(pos, n_local)
+                sup.after_ops(ps.ops)
+        else:
+            assert item.kind == "global_swap"
+            full = run_swap(item.params["positions"], full)
+            sup.swap(item.params["positions"], n_local)
+    assert "swap_pass" in kinds, kinds
+    ref = np.zeros(1 << n, dtype=np.complex128)
+    ref[0b1101] = 1
+    for M, wires, _ in steps:
+        ref = so.apply_gate(ref, n, wires, M)
+    assert np.max(np.abs(_permute_to_output(full, src_pos) - ref)) <= TOL
+
+
+@pytest.mark.parametrize("g", [0, 2])
+def test_support_tracking_state_is_zero_outside_the_claimed_support(g, monkeypatch):
+    """schedule.Support: before every pass of a plan run on a basis state, every amplitude whose index disagrees
+    with (fixed_mask, fixed_val) on a position OUTSIDE the pass's tile must be exactly zero - that is what lets the
+    kernels skip those tiles (qsv_run_pass_rounds_sparse).  Checked on the numpy emulation of a (sharded) run."""
+    from helpers import emulate_program, _emulate_whole_state_op
+    from qsv.schedule import Support, plan_schedule, pack_passes
+    n = 12
+    monkeypatch.setattr(schedule, "SWAP_MIN_POS", 3)
+    monkeypatch.setenv("QSV_TILE_BITS", "6")
+    monkeypatch.setenv("QSV_LOW_BITS", "2")
+    steps = so.random_layered_steps(n, 6, seed=77)
+    c = circuit_from_steps(steps, n)
+    c.sort()
+    ops, src_pos, flip = lower(c, n_global=g, in_flip=True, free_swap=bool(g))
+    n_local, P = n - g, 1 << g
+    basis = 0b101101 ^ flip
+    full = np.zeros(1 << n, dtype=np.complex128)
+    full[basis] = 1
+    sup = Support(n, basis)
+    idx = np.arange(1 << n)
+    sparse_passes = 0
+    for kind, item in plan_schedule(ops, n_local, 6, 2):
+        if kind == "pass":
+            fixed, val = sup.pass_mask(item)
+            assert not fixed & schedule._mask(list(range(item.low_bits)) + list(item.hi_pos))
+            outside = (idx & fixed) != val
+            assert np.all(full[outside] == 0), "non-zero amplitude outside the claimed support"
+            sparse_passes += bool(fixed)
+            packed = pack_passes([item])
+            shards = full.reshape(P, -1)
+            full = np.concatenate([emulate_program(packed, shards[r], rank_bits=r << n_local) for r in range(P)])
+            sup.after_ops(item.ops)
+        elif item.kind == "global_swap":
+            pos = item.params["positions"]
+            src = idx.copy()
+            for k, p_loc in enumerate(pos):
+                a, b = (idx >> p_loc) & 1, (idx >> (n_local + k)) & 1
+                src = (src & ~((1 << p_loc) | (1 << (n_local + k)))) | (b << p_loc) | (a << (n_local + k))
+            full = full[src]
+            sup.swap(pos, n_local)
+        else:
+            raise AssertionError(item.kind)
+    assert sparse_passes >= 2
+    ref = np.zeros(1 << n, dtype=np.complex128)
+    ref[0b101101] = 1
+    for M, wires, _ in steps:
+        ref = so.apply_gate(ref, n, wires, M)
+    assert np.max(np.abs(_permute_to_output(full, src_pos) - ref)) <= TOL
