@@ -283,8 +283,11 @@ def main():
                 "bytes_out_per_gpu_per_swap": out_bytes / max(1, n_sw), "achieved_GBps_out_per_gpu": gbs,
                 "nvlink_peak_GBps": nv_peak, "frac_of_nvlink": gbs / nv_peak,
                 "fused_with_pass_per_step": getattr(comm, "fused_swaps", 0) / max(1, args.steps + max(args.warmup, 3)),
-                "path": "k_swap_peer over NVLink peer memory" if comm.peer_swap else "NCCL all_to_all_single, chunked in place",
-                "note": "device time between the barriers around each swap (peer kernel) / incl. pack+unpack (NCCL)"}
+                "path": ("k_swap_peer over NVLink peer memory; swaps that carry a gate pass run as the fused "
+                         "qsv_jit_pass swap+pass kernel (TMA pull from the peers + per-tile flag handshake)")
+                if comm.peer_swap else "NCCL all_to_all_single, chunked in place",
+                "note": "device time of the swap kernels on rank 0, from the barrier that starts them to their end "
+                        "(peer kernel, incl. the fused pass where one rides along) / incl. pack+unpack (NCCL)"}
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -99,12 +99,12 @@ class Comm:
         arr = (C.c_uint64 * self.world)(*ptrs)
         pos = _cabi.int_array(positions) if positions is not None else None
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
         hdl.barrier()                                   # every rank's earlier kernels are done
+        ev[0].record()                                  # (after the barrier: a rank that arrived early is not timed waiting)
         _cabi.check(sv.lib.qsv_swap_peer(sv._ptr(sv.state), arr, sv.n_local, self.global_bits, self.rank, pos,
                                          sv._stream()), "qsv_swap_peer")
-        hdl.barrier()                                   # nobody touches its shard before all swaps landed
         ev[1].record()
+        hdl.barrier()                                   # nobody touches its shard before all swaps landed
         self.swap_events.append(ev)
         self.bytes_sent += 16 * (self.world - 1) * (1 << (sv.n_local - self.global_bits))
         self.swaps += 1
@@ -132,8 +132,8 @@ class Comm:
         arr = (C.c_uint64 * self.world)(*ptrs)
         farr = (C.c_uint64 * self.world)(*fptrs)
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
         hdl.barrier()
+        ev[0].record()
         _cabi.check(sv.lib.qsv_run_pass_rounds_swap(sv._ptr(sv.state), C.byref(cpass), C.c_void_p(prog.ctypes.data),
                                                     int(prog.size), tables_ptr, arr, farr, self.global_bits,
                                                     _cabi.int_array(positions), int(pass_first), self.rank,
