@@ -10,7 +10,7 @@ import math
 import os
 import numpy as np
 
-from .schedule import Op, classify_matrix
+from .schedule import Op, classify_matrix, classify_rows
 from . import engine as _engine
 
 LIST_WEIGHTS_MAX_QUBITS = 22   # run_method2 returns a plain list up to here, a lazy sequence above
@@ -109,6 +109,9 @@ def lower_gate(gate, wires, layout, transposed=False):
         return ops
     if spec is not None and spec[0] == "qft" and spec[1] > QFT_DENSE_MAX:
         return _qft_ladder(wires, layout)          # symmetric matrix: transposition changes nothing
+    fast = classify_rows(m.rows, layout.positions(wires), name, transposed)
+    if fast is not None:
+        return fast
     M = np.array(m.rows, dtype=np.complex128)
     dim = 1 << len(wires)
     if M.shape != (dim, dim):

@@ -48,11 +48,8 @@ class Op:
 
     def remapped(self, phys):
         """Copy of the op with every position v replaced by phys[v]."""
-        import copy
-        o = copy.copy(self)
-        o.targets = tuple(phys[v] for v in self.targets)
-        o.controls = tuple(phys[v] for v in self.controls)
-        return o
+        return Op(self.kind, tuple(phys[v] for v in self.targets), tuple(phys[v] for v in self.controls),
+                  self.cvals, self.matrix, self.scalar, self.perm, self.params, self.name)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -154,6 +151,10 @@ def classify_matrix(M, pos, name=""):
         tmpl = _classify_matrix(M, tuple(range(k)), "")
         if len(_CLASSIFY_CACHE) < 4096:
             _CLASSIFY_CACHE[key] = tmpl
+    return _retarget(tmpl, pos, name)
+
+
+def _retarget(tmpl, pos, name):
     pos = tuple(int(p) for p in pos)
     out = []
     for op in tmpl:
@@ -161,6 +162,34 @@ def classify_matrix(M, pos, name=""):
         o.name = name
         out.append(o)
     return out
+
+
+_ROWS_CACHE = {}
+
+
+def classify_rows(rows, pos, name="", transposed=False):
+    """classify_matrix for a gate given as the reference's list-of-lists `Matrix.rows`, keyed by the entries
+    themselves (a tuple of tuples hashes in a few microseconds; 1, 1.0 and 1+0j are the same key and the same
+    numbers): the numpy conversion and the structural analysis run once per distinct small matrix.  Returns None
+    when the rows cannot be used as a key (the caller falls back to classify_matrix)."""
+    k = len(pos)
+    if k > 4:
+        return None
+    try:
+        key = (k, transposed, tuple(map(tuple, rows)))
+        tmpl = _ROWS_CACHE.get(key)
+    except TypeError:
+        return None
+    if tmpl is None:
+        M = np.array(rows, dtype=np.complex128)
+        if M.shape != (1 << k, 1 << k):
+            return None
+        if transposed:
+            M = M.T
+        tmpl = _classify_matrix(np.ascontiguousarray(M), tuple(range(k)), "")
+        if len(_ROWS_CACHE) < 4096:
+            _ROWS_CACHE[key] = tmpl
+    return _retarget(tmpl, pos, name)
 
 
 def _classify_matrix(M, pos, name=""):
