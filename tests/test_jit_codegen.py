@@ -332,3 +332,40 @@ def test_support_hint_skips_only_zero_tiles(tmp_path):
     assert np.all(np.isnan(hinted[~inside])) and not np.any(np.isnan(hinted[inside]))
     assert np.array_equal(hinted[inside], dense[inside])
     assert np.all(dense[~inside] == 0)
+
+
+def test_every_kernel_of_the_8_gpu_bench_plan_compiles_for_sm100a():
+    """The schedule bench.py runs at --gpus 8 (33 qubits, joint placement, fused swaps): every pass program - the
+    plain ones and the fused swap+pass forms - must be accepted by NVRTC for sm_100a.  No GPU needed."""
+    from qsv import _cabi, workloads, lowering, schedule
+    lib = _cabi.load()
+    n, g = 33, 3
+    c = workloads.random_layered_circuit(n, 20, seed=20261019)
+    c.sort()
+    ops, _, _ = lowering.lower(c, n_global=g, in_flip=True, free_swap=True, fuse_swaps=True)
+    sched = schedule.plan_schedule(ops, n - g, fuse_swaps=True)
+    assert any(k == "swap_pass" for k, _ in sched) and sum(k == "pass" for k, _ in sched) <= 18
+    compiled = fused = 0
+    for kind, it in sched:
+        if kind == "op":
+            continue
+        ps = it if kind == "pass" else it[1]
+        packed = schedule.pack_passes([ps])
+        for meta in packed.passes:
+            if meta[2] >= 0:
+                continue
+            prog, cp, need = meta[3][0], jit_cpass(meta[0]), C.c_size_t(0)
+            if kind == "swap_pass" and len(packed.passes) == 1:
+                rc = lib.qsv_jit_compile_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g,
+                                              _cabi.int_array(it[0].params["positions"]), int(it[2]), None, 0,
+                                              C.byref(need))
+                fused += 1
+            else:
+                rc = lib.qsv_jit_compile(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), None, 0,
+                                         C.byref(need))
+            if rc != 0 and b"cannot load libnvrtc" in lib.qsv_last_error():
+                pytest.skip("NVRTC is not installed here")
+            assert rc == 0, lib.qsv_last_error()
+            assert need.value > 10000
+            compiled += 1
+    assert compiled >= 12 and fused >= 1
