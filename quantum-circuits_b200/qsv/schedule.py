@@ -951,14 +951,31 @@ def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
     hit = _PLACE_CACHE.get(key)
     if hit is not None:
         return list(hit[0]), (list(hit[1]) if hit[1] is not None else None)
-    best = None
     thins = [int(v) for v in os.environ.get("QSV_PLACE_THIN", "1,8,14,20").split(",")]
+    cands, floor = [], float("inf")
     for thin in thins:
         for pen in ((0, 2, 6) if fuse_swaps else (0,)):
-            res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps,
-                                    cost_cap=best[0] if best is not None else float("inf"), tile_penalty=pen)
-            if best is None or res[0] < best[0]:
-                best = res
+            res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floor + 0.5,
+                                    tile_penalty=pen)
+            if res[1] is not None:
+                cands.append(res)
+                floor = min(floor, res[0])
+    # The estimate above is the planner's own pass sequence; plan_schedule re-derives the passes from the op list
+    # and may cut them differently.  Re-plan the few cheapest distinct candidates and keep the one whose REAL
+    # schedule is cheapest (fused passes ride on their swap for free).
+    cands.sort(key=lambda r: r[0])
+    best, best_cost, seen = None, float("inf"), set()
+    for res in cands:
+        sig = tuple(tuple(o.params["positions"]) for o in res[1] if o.kind == "global_swap"), tuple(id(o) for o in res[1][:8])
+        if sig in seen:
+            continue
+        seen.add(sig)
+        if len(seen) > int(os.environ.get("QSV_PLACE_REPLAN", "2")):
+            break
+        real = schedule_cost([("swap", 0) if kind != "pass" else ("pass", len(item.ops))
+                              for kind, item in plan_schedule(res[1], n - n_global, fuse_swaps=fuse_swaps)], n_global)
+        if real < best_cost:
+            best, best_cost = res, real
     if len(_PLACE_CACHE) >= 8:
         _PLACE_CACHE.pop(next(iter(_PLACE_CACHE)))
     _PLACE_CACHE[key] = (list(best[1]), list(best[2]) if best[2] is not None else None)
