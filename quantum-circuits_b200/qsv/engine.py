@@ -29,6 +29,10 @@ def _ops_fingerprint(ops, geometry):
                    os.environ.get("QSV_JIT_MIN_QUBITS"), os.environ.get("QSV_TILE_BITS"),
                    os.environ.get("QSV_LOW_BITS"), os.environ.get("QSV_DEBUG_DROP"), os.environ.get("QSV_FILL"), os.environ.get("QSV_FUSE_SWAP"),
                    os.environ.get("QSV_TRIM_ROUNDS"))).encode())
+    cached = getattr(ops, "digest", None)       # lowering.OpList: the digest the list was cached under
+    if cached is not None:
+        h.update(cached)
+        return h.digest()
     for op in ops:
         h.update(repr((op.kind, tuple(op.targets), tuple(op.controls),
                        None if op.cvals is None else tuple(int(v) for v in op.cvals),

@@ -121,6 +121,38 @@ def lower_gate(gate, wires, layout, transposed=False):
     return classify_matrix(M, layout.positions(wires), name)
 
 
+class OpList(list):
+    """Op list that remembers the content digest it was cached under (StateVector.prepare keys its plan cache by
+    it instead of hashing ~1000 ops again on every run of the same circuit)."""
+    digest = None
+
+
+_LOWER_CACHE = {}       # circuit signature -> (ops, src_pos, flip); Shor's sampling loop and benchmarks re-run one circuit
+
+
+def _circuit_signature(gates, table, out_qubits, extra):
+    """Hashable description of everything `lower` reads: per gate the wires it acts on and the ENTRIES of its matrix
+    (a tuple of tuples - callers may have written into Matrix.rows, so identity of the objects proves nothing),
+    plus the output wiring and the switches.  None if a gate cannot be described that way (structured gates with
+    their own lowering hook, unhashable entries): such circuits are lowered afresh every time."""
+    sig = []
+    try:
+        for g, wires in zip(gates, table):
+            if getattr(g, "_qsv_lower", None) is not None:
+                return None
+            d = g.matrix.__dict__
+            rows = d.get("rows")
+            if rows is not None:
+                sig.append((tuple(wires), tuple(map(tuple, rows))))
+            else:
+                sig.append((tuple(wires), "spec", repr(d.get("_spec")), d.get("_dim")))
+        key = (extra, tuple(out_qubits), tuple(sig))
+        hash(key)
+        return key
+    except (TypeError, AttributeError):
+        return None
+
+
 def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, free_swap=False, fuse_swaps=False):
     """(ops, src_pos): ops in application order; src_pos[b] = physical position feeding bit b of the
     OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map.  With
@@ -137,6 +169,19 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
     n = len(circuit)
     gates = circuit.gates if presorted else topological_gates(circuit)
     table, out_qubits = gate_targets(circuit, gates)
+    from . import schedule as _sched
+    sig = None
+    if os.environ.get("QSV_LOWER_CACHE", "1") != "0":
+        sig = _circuit_signature(gates, table, out_qubits, (
+            n, bool(transposed), int(n_global), bool(in_flip), bool(free_swap), bool(fuse_swaps), _sched.SWAP_MIN_POS,
+            QFT_DENSE_MAX, tuple(os.environ.get(k) for k in ("QSV_PROPAGATE_X", "QSV_FUSE_1Q", "QSV_PLACE",
+                                                             "QSV_PLACE_THIN", "QSV_PLACE_REPLAN", "QSV_TILE_BITS",
+                                                             "QSV_LOW_BITS", "QSV_PLAN_SEARCH"))))
+        hit = _LOWER_CACHE.get(sig) if sig is not None else None
+        if hit is not None:
+            ops = OpList(hit[0])
+            ops.digest = hit[0].digest
+            return (ops, list(hit[1]), hit[2]) if in_flip else (ops, list(hit[1]))
     layout = Layout(n)
     ops = []
     for g, wires in zip(gates, table):
@@ -163,6 +208,14 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
             ops, src_pos = place_joint(ops, n, n_global, src_pos, fuse_swaps=fuse_swaps)
         else:
             ops, src_pos = place(ops, n, n_global, src_pos, free_swap=free_swap)
+    ops = OpList(ops)
+    if sig is not None:
+        ops.digest = _sched.ops_digest(ops)
+        if len(_LOWER_CACHE) >= 8:
+            _LOWER_CACHE.pop(next(iter(_LOWER_CACHE)))
+        stored = OpList(ops)
+        stored.digest = ops.digest
+        _LOWER_CACHE[sig] = (stored, list(src_pos), flip)
     if in_flip:
         return ops, src_pos, flip
     return ops, src_pos

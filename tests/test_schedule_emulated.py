@@ -256,3 +256,32 @@ def test_large_qft_gate_uses_ladder_and_relabel():
     got = _final_output_order(emulate_ops(ops, psi0, n), src_pos)
     ref = so.apply_gate(psi0, n, list(range(1, 10)), so.mat_QFT(9))
     assert np.max(np.abs(got - ref)) < 1e-12
+
+
+def test_lowering_cache_is_keyed_by_matrix_entries_not_object_identity():
+    """lower() caches its result per circuit CONTENT: wires, output wiring and the entries of every gate matrix.
+    Callers write into Matrix.rows (main/Grover.py:18, main/Shor.py:78-80), so a gate whose rows were changed in
+    place must be lowered afresh; an untouched circuit must come back as a new list with the same ops."""
+    from main.circuit import Circuit, H, CNot
+    from qsv import lowering
+    from qsv.schedule import ops_digest
+    c = Circuit(3)
+    h, cn = c.add(H()), c.add(CNot())
+    c.add_wire(c, 0, h, 0)
+    c.add_wire(h, 0, cn, 0)
+    c.add_wire(c, 1, cn, 1)
+    c.add_wire(cn, 0, c, 0)
+    c.add_wire(cn, 1, c, 1)
+    c.add_wire(c, 2, c, 2)
+    c.sort()
+    ops1, src1 = lowering.lower(c)
+    ops2, src2 = lowering.lower(c)
+    assert ops1 is not ops2 and ops_digest(ops1) == ops_digest(ops2) and src1 == src2
+    assert getattr(ops2, "digest", None) == ops_digest(ops2)
+    ops2.append("scribble")                       # the caller's list is its own
+    assert len(lowering.lower(c)[0]) == len(ops1)
+    rows = h.matrix.rows                          # turn the H into a Z in place
+    rows[0][0], rows[0][1], rows[1][0], rows[1][1] = 1, 0, 0, -1
+    ops3, _ = lowering.lower(c)
+    assert ops_digest(ops3) != ops_digest(ops1)
+    assert not any(op.kind == "dense" for op in ops3)
