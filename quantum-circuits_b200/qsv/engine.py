@@ -16,6 +16,7 @@ SAMPLE_BLOCK_BITS = 12   # larger states: block sums of 2^12 outcomes, then a se
 
 
 _PLAN_CACHE = {}      # op-list fingerprint -> [("program", PackedProgram) | ("op", Op)] (host objects only)
+_KERNELS_READY = set()   # fingerprints whose specialised kernels are already in libqsv's cache (skip the compile pool)
 
 
 def _ops_fingerprint(ops, geometry):
@@ -283,9 +284,11 @@ class StateVector:
             _PLAN_CACHE[key] = host_plan
         segments = []
         h2d = 0
+        compiled = key in _KERNELS_READY        # this process has already generated + compiled this plan's kernels
         for kind, item in host_plan:
             if kind == "program":
-                self._prepare_kernels(item)
+                if not compiled:
+                    self._prepare_kernels(item)
                 dev = torch.from_numpy(item.blob).to(self.device, non_blocking=False)
                 segments.append(("program", (item, dev)))
                 h2d += int(item.blob.size)
@@ -304,6 +307,9 @@ class StateVector:
                     segments.extend(two if pass_first else two[::-1])
             else:
                 segments.append(("op", item))
+        if len(_KERNELS_READY) >= 64:
+            _KERNELS_READY.clear()
+        _KERNELS_READY.add(key)
         return {"segments": segments, "h2d_bytes": h2d}
 
     def execute(self, plan):
