@@ -197,6 +197,11 @@ int  qsv_jit_compile(const qsv_pass_t *pass, const void *prog_host, uint32_t pro
                      size_t buf_len, size_t *needed);
 int  qsv_jit_wanted(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes);
 void qsv_jit_stats(uint64_t *kernels_compiled, uint64_t *cache_hits, double *compile_seconds);
+/* Modelled shared-memory bank-group collisions of one pass program (sampled quarter-warps x slots x rounds; 0 = none):
+ * with the default thread-index mapping, and with the per-round mapping the opt-in search (QSV_JIT_BANKSEARCH=1) picks.
+ * A planning aid that needs no GPU (tools/plan_report.py --banks). */
+int  qsv_jit_bank_score(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                        uint64_t *default_score, uint64_t *searched_score);
 
 /* Single-gate conveniences (host arguments only; each is one pass with a one-op program built by
  * the library).  `targets[0]` is the gate's port 0 = most-significant bit of the matrix index

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -300,9 +301,135 @@ static void thread_bit_order(const qsv_round_t &R, int pos[8]) {
     for (int b = 0; b < 12 && n < 8; ++b)
         if (!is_rb[b] && !used[b]) { pos[n++] = b; used[b] = true; }
 }
+// ---- optional search (QSV_JIT_BANKSEARCH=1, off by default): score the ACTUAL slot addresses -----------------------
+// The class argument above is static: it ignores X / CNot / Toffoli that ride on a round's loads or stores and XOR
+// thread-dependent bits into the slot index (ncu after the padded layout: 140 M load conflicts per pass are left in
+// such rounds).  With the search on, every triple of non-register tile bits is tried as the low thread-index bits: the
+// generator evaluates the 16 slot addresses of 8 lanes for a few quarter-warps exactly as the emitted code will
+// (eval_addresses mirrors emit_addresses) and keeps the triple with the fewest bank-group collisions.
+static thread_local const int *t_tb_override = nullptr;     // mapping chosen for the round being generated
+
+static bool bank_search_enabled() {
+    const char *e = getenv("QSV_JIT_BANKSEARCH");
+    return e && !strcmp(e, "1");
+}
+
+static uint32_t pad_slot(uint32_t a);
+static uint32_t slot_offset(const qsv_round_t &R, int r);
+
+static void eval_addresses(const qsv_round_t &R, const qsv_rop_t *ops, int first, int n, bool reverse, bool general,
+                           uint32_t tb, bool ext_true, uint32_t a[16]) {
+    auto opat = [&](int i) -> const qsv_rop_t & { return ops[reverse ? first + n - 1 - i : first + i]; };
+    if (!general) {
+        uint32_t b = tb, d[4] = {1u << R.rb[0], 1u << R.rb[1], 1u << R.rb[2], 1u << R.rb[3]};
+        for (int i = 0; i < n; ++i) {
+            const qsv_rop_t &p = opat(i);
+            const uint32_t cm = p.tmask, cv = p.tval, xm = p.table_off, q = p.j, pbit = p.flags;
+            const uint32_t cmu = cm & ~pbit;
+            const bool e = p.ext_mask ? ext_true : true;
+            const uint32_t f = (e && (!cmu || (b & cmu) == (cv & cmu))) ? xm : 0u;
+            if (q == 0xffu || pbit == 0u) {
+                b ^= f;
+            } else {
+                const uint32_t fd = (d[q] & pbit) ? f : 0u;
+                b ^= (((b ^ cv) & pbit) == 0u) ? f : 0u;
+                d[q] ^= fd;
+            }
+        }
+        a[0] = b;
+        for (int r = 1; r < 16; ++r) a[r] = a[r & (r - 1)] ^ d[__builtin_ctz(r)];
+    } else {
+        for (int r = 0; r < 16; ++r) a[r] = tb | slot_offset(R, r);
+        for (int i = 0; i < n; ++i) {
+            const qsv_rop_t &p = opat(i);
+            const bool e = p.ext_mask ? ext_true : true;
+            for (int r = 0; r < 16; ++r)
+                if (e && (a[r] & p.tmask) == p.tval) a[r] ^= p.table_off;
+        }
+    }
+}
+
+static uint32_t deposit_tid(uint32_t tid, const int pos[8]) {
+    uint32_t tb = 0;
+    for (int i = 0; i < 8; ++i) tb |= ((tid >> i) & 1u) << pos[i];
+    return tb;
+}
+
+// bank-group collisions of one mapping: sum over sampled quarter-warps, slots and both values of the external
+// conditions of (largest number of lanes in one 16-byte bank group) - 1, for the round's loads and (unless the round
+// stores straight to global memory) its stores
+static long conflict_score(const qsv_round_t &R, const qsv_rop_t *ops, const int pos[8], bool score_stores) {
+    const int n_pre = R.n_pre & 0x7fff, n_post = R.n_post & 0x7fff;
+    const bool gen_pre = (R.n_pre & 0x8000) != 0, gen_post = (R.n_post & 0x8000) != 0;
+    const int n_reg = (int)(R.n_ops & 0xffffu), n_pt = (int)((R.n_ops >> 16) & 0x3fffu);
+    const int f_pre = (int)R.first_op, f_post = f_pre + n_pre + n_pt + n_reg;
+    static const int kQw[] = {0, 3, 6, 9, 13, 18, 22, 27, 31};
+    long score = 0;
+    for (int side = 0; side < (score_stores ? 2 : 1); ++side)
+        for (int ext = 0; ext < 2; ++ext)
+            for (int qw : kQw) {
+                uint32_t a[8][16];
+                for (int lane = 0; lane < 8; ++lane) {
+                    const uint32_t tb = deposit_tid((uint32_t)(qw * 8 + lane), pos);
+                    if (side == 0) eval_addresses(R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, tb, ext != 0, a[lane]);
+                    else eval_addresses(R, ops, f_post, n_post, /*reverse=*/false, gen_post, tb, ext != 0, a[lane]);
+                }
+                for (int r = 0; r < 16; ++r) {
+                    int cnt[8] = {0}, worst = 0;
+                    for (int lane = 0; lane < 8; ++lane) {
+                        const int g = (int)(pad_slot(a[lane][r]) & 7u);
+                        if (++cnt[g] > worst) worst = cnt[g];
+                    }
+                    score += worst - 1;
+                }
+            }
+    return score;
+}
+
+static void search_thread_bits(const qsv_round_t &R, const qsv_rop_t *ops, bool score_stores, int best[8]) {
+    thread_bit_order(R, best);
+    long best_score = conflict_score(R, ops, best, score_stores);
+    if (best_score == 0) return;
+    int free_bits[8], n = 0;
+    bool is_rb[12] = {false};
+    for (int q = 0; q < 4; ++q) is_rb[R.rb[q]] = true;
+    for (int b = 0; b < 12; ++b) if (!is_rb[b]) free_bits[n++] = b;
+    for (int i = 0; i < 8; ++i)
+        for (int j = i + 1; j < 8; ++j)
+            for (int k = j + 1; k < 8; ++k) {
+                int cand[8], m = 0;
+                cand[m++] = free_bits[i]; cand[m++] = free_bits[j]; cand[m++] = free_bits[k];
+                for (int t = 0; t < 8; ++t) if (t != i && t != j && t != k) cand[m++] = free_bits[t];
+                const long sc = conflict_score(R, ops, cand, score_stores);
+                if (sc < best_score) { best_score = sc; memcpy(best, cand, sizeof(cand)); }
+            }
+}
+
+// best layout (padded or linear) of a pass under the search, with the mapping of every round; returns "use padding"
+static bool search_layout(const std::vector<qsv_round_t> &rounds, const qsv_rop_t *ops, int L, bool direct, bool may_pad,
+                          std::vector<std::array<int, 8>> &maps, long *score_out = nullptr) {
+    long best = -1;
+    bool best_pad = false;
+    for (int padded = 0; padded < (may_pad ? 2 : 1); ++padded) {
+        t_pad_L = padded ? L : -1;
+        std::vector<std::array<int, 8>> m(rounds.size());
+        long total = 0;
+        for (size_t k = 0; k < rounds.size(); ++k) {
+            const bool stores = !(k + 1 == rounds.size() && direct);
+            search_thread_bits(rounds[k], ops, stores, m[k].data());
+            total += conflict_score(rounds[k], ops, m[k].data(), stores);
+        }
+        if (best < 0 || total < best) { best = total; best_pad = padded != 0; maps.swap(m); }
+    }
+    t_pad_L = -1;
+    if (score_out) *score_out = best;
+    return best_pad;
+}
+
 static void emit_tb(Out &o, const qsv_round_t &R) {
     int pos[8];
-    thread_bit_order(R, pos);
+    if (t_tb_override) memcpy(pos, t_tb_override, sizeof(pos));
+    else thread_bit_order(R, pos);
     std::string e;
     for (int i = 0; i < 8;) {
         int len = 1;
@@ -828,7 +955,14 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     for (const qsv_round_t &R : rounds)
         for (int q = 0; q < 4; ++q) low_rb = low_rb || R.rb[q] < 3;
     const char *pe = getenv("QSV_JIT_PAD");
-    const bool pad = pad_enabled() && (low_rb || (pe && !strcmp(pe, "all")));
+    const bool bank_search = bank_search_enabled();
+    bool pad = pad_enabled() && (low_rb || (pe && !strcmp(pe, "all")));
+    std::vector<std::array<int, 8>> tb_maps;
+    if (bank_search) {
+        // both layouts are scored with their best per-round mappings: padding turns XORs of run bits (tile bits >= L)
+        // into bank changes, which helps rounds with low register bits and can hurt permuted rounds without them
+        pad = search_layout(rounds, ops.data(), L, direct, pad_enabled(), tb_maps);
+    }
     t_pad_L = pad ? L : -1;
 
     Out o;
@@ -901,6 +1035,8 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     for (uint32_t k = 0; k < nr; ++k) {
         const bool last = k + 1 == nr;
         const double scale_before = scale;
+        // one mapping per round, shared by the hoisted scalars and both forms of the last round
+        t_tb_override = bank_search ? tb_maps[k].data() : nullptr;
         if (gen_round(o, (int)k, rounds[k], ops.data(), info[k], last, scale, defer_scale, err, (last && direct) ? 1 : 0))
             return 1;
         if (last && direct) {
@@ -912,6 +1048,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
             o.f("#endif");
         }
     }
+    t_tb_override = nullptr;
 
     // is a tile ever skipped?  (every op has an external condition)
     bool always_active = false;
@@ -1349,6 +1486,7 @@ static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t byt
     { const char *ds = getenv("QSV_JIT_DIRECT_STORE"); k.append(ds && !strcmp(ds, "0") ? "s" : "S"); }
     { const char *pf = getenv("QSV_JIT_PREFETCH"); k.append(pf && !strcmp(pf, "0") ? "p" : "P"); }
     { const char *pe = getenv("QSV_JIT_PAD"); k.append(pe ? pe : "-"); k.append("|"); }
+    k.append(bank_search_enabled() ? "S" : "s");
     k.append(static_cast<const char *>(prog), bytes);
     return k;
 }
@@ -1596,6 +1734,39 @@ extern "C" int qsv_run_pass_rounds_swap(void *state_dev, const qsv_pass_t *pass,
     }
     return jit::launch_swap(state_dev, pass, prog_host, prog_bytes, tables_dev, sw, pt, (unsigned)rank, epoch,
                             (cudaStream_t)stream);
+}
+
+extern "C" int qsv_jit_bank_score(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                                  uint64_t *default_score, uint64_t *searched_score) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return 1;
+    const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
+    const uint8_t *body = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);
+    std::vector<qsv_round_t> rounds(hdr->n_rounds);
+    std::vector<qsv_rop_t> ops(hdr->n_ops);
+    memcpy(rounds.data(), body, sizeof(qsv_round_t) * hdr->n_rounds);
+    memcpy(ops.data(), body + sizeof(qsv_round_t) * hdr->n_rounds, sizeof(qsv_rop_t) * hdr->n_ops);
+    bool low_rb = false;
+    for (const qsv_round_t &R : rounds)
+        for (int q = 0; q < 4; ++q) low_rb = low_rb || R.rb[q] < 3;
+    const bool direct = [] { const char *ds = getenv("QSV_JIT_DIRECT_STORE"); return !(ds && !strcmp(ds, "0")); }();
+    uint64_t d = 0, sch = 0;
+    for (uint32_t k = 0; k < hdr->n_rounds; ++k) {
+        const bool stores = !(k + 1 == hdr->n_rounds && direct);
+        int pos[8];
+        jit::t_pad_L = (jit::pad_enabled() && low_rb) ? pass->low_bits : -1;       // what the default kernel does
+        jit::thread_bit_order(rounds[k], pos);
+        d += (uint64_t)jit::conflict_score(rounds[k], ops.data(), pos, stores);
+    }
+    {
+        std::vector<std::array<int, 8>> maps;
+        long total = 0;
+        jit::search_layout(rounds, ops.data(), pass->low_bits, direct, jit::pad_enabled(), maps, &total);
+        sch = (uint64_t)total;
+    }
+    jit::t_pad_L = -1;
+    if (default_score) *default_score = d;
+    if (searched_score) *searched_score = sch;
+    return 0;
 }
 
 extern "C" int qsv_jit_wanted(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes) {

@@ -41,6 +41,7 @@ SYMBOLS = {
     "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_compile": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_wanted": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32]),
+    "qsv_jit_bank_score": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "qsv_jit_source_swap": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _I, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_compile_swap": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _I, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_run_pass_rounds_swap": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, C.POINTER(C.c_uint64),

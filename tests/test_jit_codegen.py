@@ -83,6 +83,44 @@ def test_qft_ladder_controlled_phases(tmp_path):
     _check(ops, n, tmp_path, seed=2)
 
 
+@pytest.mark.parametrize("workload", ["layered", "toffoli"])
+def test_bank_search_mapping_keeps_results_identical(tmp_path, monkeypatch, workload):
+    """QSV_JIT_BANKSEARCH=1 (opt-in): the low thread-index bits of every round are chosen by scoring the actual slot
+    addresses, permutations included.  Any choice is a relabelling of the threads: the state must come out exactly
+    as with the default mapping, and the generated source must differ (the search did pick other bits)."""
+    from qsv import workloads, lowering
+    from qsv.schedule import Op
+    if workload == "layered":
+        n = 14
+        c = workloads.random_layered_circuit(n, 6, seed=3)
+        c.sort()
+        ops, _ = lowering.lower(c)
+    else:
+        monkeypatch.setenv("QSV_REG_MCX", "0")
+        n = 13
+        rng = random.Random(7)
+        H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+        ops = []
+        for _ in range(50):
+            a, b, c_ = rng.sample(range(n), 3)
+            ops.append(rng.choice([Op("mcx", (a,), (b, c_)), Op("mcx", (a,), (b,)), Op("dense", (a,), (), matrix=H),
+                                   Op("phase", (), (a, b), scalar=1j)]))
+    progs = _round_programs(ops, n)
+    psi = _rand_state(n, 9)
+    differs = False
+    for ps, prog, tables in progs:
+        monkeypatch.delenv("QSV_JIT_BANKSEARCH", raising=False)
+        src0 = jit_source(ps, prog)
+        ref = jit_host_run(ps, prog, tables, psi, 0, str(tmp_path))
+        monkeypatch.setenv("QSV_JIT_BANKSEARCH", "1")
+        src1 = jit_source(ps, prog)
+        got = jit_host_run(ps, prog, tables, psi, 0, str(tmp_path))
+        differs = differs or src0 != src1
+        assert np.array_equal(got, ref)
+        psi = ref
+    assert differs or workload == "layered", "the search never changed a mapping"
+
+
 @pytest.mark.parametrize("reg_mcx", ["1", "all", "0"])
 def test_toffoli_heavy_circuit_general_permutations(tmp_path, monkeypatch, reg_mcx):
     """Toffoli / CNot chains: as in-register permutations (slot renaming, predicated exchanges), and - with
@@ -369,3 +407,27 @@ def test_every_kernel_of_the_8_gpu_bench_plan_compiles_for_sm100a():
             assert need.value > 10000
             compiled += 1
     assert compiled >= 12 and fused >= 1
+
+
+def test_bank_score_search_is_never_worse_than_the_default_mapping():
+    """qsv_jit_bank_score: modelled bank-group collisions of a pass with the default mapping and with the mapping /
+    layout the opt-in search picks.  The search starts from the default, so it can only improve on it; on the 30-qubit
+    bench plan it clears the passes that ncu showed load conflicts in."""
+    from qsv import _cabi, workloads, lowering, schedule
+    lib = _cabi.load()
+    n = 30
+    c = workloads.random_layered_circuit(n, 20, seed=20261019)
+    c.sort()
+    ops, _, _ = lowering.lower(c, in_flip=True)
+    tot_d = tot_s = 0
+    for kind, ps in schedule.plan_schedule(ops, n):
+        packed = schedule.pack_passes([ps])
+        m = packed.passes[0]
+        prog, cp = m[3][0], jit_cpass(m[0])
+        d, s_ = C.c_uint64(0), C.c_uint64(0)
+        assert lib.qsv_jit_bank_score(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), C.byref(d),
+                                      C.byref(s_)) == 0, lib.qsv_last_error()
+        assert s_.value <= d.value
+        tot_d += d.value
+        tot_s += s_.value
+    assert tot_s < tot_d
