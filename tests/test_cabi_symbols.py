@@ -97,3 +97,20 @@ def test_round_programs_pass_host_validation():
         assert rc != 0 and ("cuda" in msg.lower() or "kernel launch failed" in msg), msg
         seen += 1
     assert seen >= 1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on the host cores only (the oracle port): one JSON line with the contract's
+    keys, usable on a box without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-qubits", "12"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "gates/sec" and line["unit"] == "gates/sec"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "gates/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
