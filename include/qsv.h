@@ -289,6 +289,16 @@ int qsv_unpack_slices(void *state_dev, const void *staging_dev, uint64_t n_chunk
  * The caller must barrier all ranks before and after the call. */
 int qsv_swap_peer(void *state_dev, const uint64_t *peer_state_ptrs, int n_local, int g, int rank,
                   const int *positions, void *stream);
+/* General form.  `n_ranks` = 2^g ranks share the register; `n_swap` <= g qubits are exchanged: positions[k]
+ * (ascending local positions) trades places with global bit gbits[k] (ascending, NULL = 0..n_swap-1).  With
+ * n_swap < g this is a PARTIAL swap (pairwise exchange with rank ^ 2^j for one qubit): the peers of a
+ * rank are the 2^n_swap - 1 ranks that differ from it in those bits only and (1 - 2^-n_swap) of the shard moves.
+ * `sp_mask` / `sp_val`: index bits (local positions and, from bit n_local up, the rank) that are FIXED in the
+ * support of the state BEFORE the swap - a register that started in a basis state (main/circuit.py:290-301) is
+ * zero wherever such a bit disagrees.  Pairs of which neither element can be non-zero are not moved (0 / 0: dense). */
+int qsv_swap_peer_ex(void *state_dev, const uint64_t *peer_state_ptrs, int n_local, int n_ranks, int rank,
+                     int n_swap, const int *positions, const int *gbits, uint64_t sp_mask, uint64_t sp_val,
+                     void *stream);
 
 /* Global<->local qubit swap FUSED with the gate pass that follows it: one kernel over NVLink peer memory
  * (SURVEY 8e's exchange step + one run of main/circuit.py:303-327's gate loop in a single sweep).  Contract of
@@ -311,6 +321,24 @@ int qsv_jit_source_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t 
                         const int *positions, int pass_first, char *buf, size_t buf_len, size_t *needed);
 int qsv_jit_compile_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
                          const int *positions, int pass_first, char *cubin_buf, size_t buf_len, size_t *needed);
+/* General forms: partial swaps (`n_swap` of the log2(n_ranks) global qubits, positions[k] <-> global bit gbits[k],
+ * NULL = 0..n_swap-1) and the support hint of qsv_swap_peer_ex (`sp_mask` / `sp_val` over the index bits before
+ * the swap, the pass's tile bits excluded): tile pairs that hold only zeros on both ranks are neither moved nor
+ * computed.  The kernel is launched COOPERATIVELY (all CTAs co-resident or the launch fails) and its flag spin is
+ * bounded: after QSV_FUSE_WATCHDOG_MS (default 30000) without an answer from the partner the kernel traps and the
+ * launch reports an error instead of hanging the node.  The host form's qsv_jit_host_run_swap takes
+ * (..., tables, sp_mask, sp_val). */
+int qsv_run_pass_rounds_swap_ex(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                                const void *tables_dev, const uint64_t *peer_state_ptrs,
+                                const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
+                                const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
+                                uint64_t sp_val, void *stream);
+int qsv_jit_source_swap_ex(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_swap,
+                           const int *positions, const int *gbits, int pass_first, char *buf, size_t buf_len,
+                           size_t *needed);
+int qsv_jit_compile_swap_ex(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_swap,
+                            const int *positions, const int *gbits, int pass_first, char *cubin_buf, size_t buf_len,
+                            size_t *needed);
 
 #ifdef __cplusplus
 }

@@ -905,6 +905,11 @@ static bool fuse_two_buffers() {
     const char *e = getenv("QSV_FUSE_BUFFERS");
     return e && !strcmp(e, "2");
 }
+static unsigned long long watchdog_ns() {
+    const char *e = getenv("QSV_FUSE_WATCHDOG_MS");
+    const long long ms = e ? atoll(e) : 30000;
+    return (unsigned long long)(ms > 0 ? ms : 30000) * 1000000ull;
+}
 static bool pad_enabled() {
     const char *e = getenv("QSV_JIT_PAD");
     return !(e && !strcmp(e, "0"));
@@ -916,7 +921,8 @@ static unsigned tile_slots(int n_hi) { return 4096u + (pad_enabled() ? (1u << n_
 // local positions outside the tile, >= low_bits) trades places with global bit k.
 // pre = 1: the pass is the one BEFORE the swap - its ops read the coordinates (rank, swapped field) the tile has on the
 // rank it is pulled from; pre = 0: the pass AFTER the swap (coordinates of the destination).
-struct SwapSpec { int g; int q[4]; int pre; int n_local; };
+// `q[k]` trades places with global bit `gb[k]`; g may be smaller than the number of global qubits (partial swap).
+struct SwapSpec { int g; int q[4]; int gb[4]; int pre; int n_local; };
 constexpr unsigned kFlagCtas = 1024;      // flag slots per source rank in the peers' flag arrays
 
 int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, std::string &src, std::string &err,
@@ -966,7 +972,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     t_pad_L = pad ? L : -1;
 
     Out o;
-    if (sw) o.f("#define QSV_FUSED_SWAP 1");
+    if (sw) { o.f("#define QSV_FUSED_SWAP 1"); o.f("#define QSV_NLOCAL %d", P.n_local); }
     o.s += kPrelude;
     o.s += kDeviceHelpers;
     if (pad)
@@ -1013,11 +1019,19 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
             o.f("}");
             o.f("__device__ __forceinline__ void qsv_wait_peer(const qsv_ctx &c) {");
             o.f("    if (c.wait_flag) {");
+            // bounded spin: a partner that never shows up (failed launch, dead rank) must not hang the node - after
+            // QSV_FUSE_WATCHDOG_MS (default 30 s) of polling the CTA traps and the launch fails on the host
             o.f("        if (c.flags & 2u) {");
-            o.f("            u64 v;");
-            o.f("            do {");
+            o.f("            u64 v, t0 = 0; u32 polls = 0;");
+            o.f("            for (;;) {");
             o.f("                asm volatile(\"ld.relaxed.sys.global.u64 %%0, [%%1];\" : \"=l\"(v) : \"l\"(c.wait_flag) : \"memory\");");
-            o.f("            } while (v < c.wait_val);");
+            o.f("                if (v >= c.wait_val) break;");
+            o.f("                if ((++polls & 0x3ffu) == 0u) {");
+            o.f("                    u64 now; asm volatile(\"mov.u64 %%0, %%globaltimer;\" : \"=l\"(now));");
+            o.f("                    if (t0 == 0) t0 = now;");
+            o.f("                    else if (now - t0 > %lluULL) { asm volatile(\"trap;\"); }", watchdog_ns());
+            o.f("                }");
+            o.f("            }");
             o.f("        }");
             o.f("        __syncthreads();");
             o.f("    }");
@@ -1118,17 +1132,31 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         for (int k = 0; k < sw->g; ++k) ins.push_back(sw->q[k]);
         std::sort(ins.begin(), ins.end());
         o.f("QSV_FN void qsv_fused_tile(const u64 u, const u32 rank, u64 &base, u64 &src_base, u32 &peer) {");
-        o.f("    peer = rank ^ (u32)(u & %uULL);", (1u << sw->g) - 1u);
+        {
+            std::string dep = "0u";
+            for (int k = 0; k < sw->g; ++k)
+                dep += " | ((u32)((u >> " + std::to_string(k) + ") & 1ULL) << " + std::to_string(sw->gb[k]) + ")";
+            o.f("    peer = rank ^ (%s);", dep.c_str());
+        }
         o.f("    u64 rest = (u >> %d) << %d;", sw->g, L);
         for (int pos : ins)
             o.f("    rest = ((rest >> %d) << %d) | (rest & 0x%llxULL);", pos, pos + 1, (unsigned long long)((1ull << pos) - 1ull));
         std::string fj = "0ULL", fr = "0ULL";
         for (int k = 0; k < sw->g; ++k) {
-            fj += " | ((u64)((peer >> " + std::to_string(k) + ") & 1u) << " + std::to_string(sw->q[k]) + ")";
-            fr += " | ((u64)((rank >> " + std::to_string(k) + ") & 1u) << " + std::to_string(sw->q[k]) + ")";
+            fj += " | ((u64)((peer >> " + std::to_string(sw->gb[k]) + ") & 1u) << " + std::to_string(sw->q[k]) + ")";
+            fr += " | ((u64)((rank >> " + std::to_string(sw->gb[k]) + ") & 1u) << " + std::to_string(sw->q[k]) + ")";
         }
         o.f("    base = rest | %s;", fj.c_str());
         o.f("    src_base = rest | %s;", fr.c_str());
+        o.f("}");
+        // a tile pair of which neither side intersects the support of the state (sp_mask / sp_val over the index bits
+        // BEFORE the swap, tile bits excluded) holds only zeros on both ranks: it is neither moved nor computed.  The
+        // test is symmetric in the two ranks of a pair, so both skip the same work items and their per-tile
+        // handshake counters stay in step.
+        o.f("QSV_FN bool qsv_pair_active(const u64 base, const u64 src_base, const u32 peer, const u32 rank, const u64 sp_mask,"
+            " const u64 sp_val) {");
+        o.f("    return (((base | ((u64)rank << QSV_NLOCAL)) & sp_mask) == sp_val) ||"
+            " (((src_base | ((u64)peer << QSV_NLOCAL)) & sp_mask) == sp_val);");
         o.f("}");
     }
 
@@ -1139,7 +1167,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("extern \"C\" __global__ void __launch_bounds__(256, %d)", two_buf ? 1 : 2);
     if (sw)
         o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
-            " const __grid_constant__ qsv_peers peers, const u32 rank, const u64 epoch) {");
+            " const __grid_constant__ qsv_peers peers, const u32 rank, const u64 epoch, const u64 sp_mask, const u64 sp_val) {");
     else
     o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
         " const u64 sp_mask, const u64 sp_val) {");
@@ -1176,9 +1204,12 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    ctx.tile = tile; ctx.mbar = &mbar; ctx.s_off = s_off; ctx.warp = warp;");
         o.f("    ctx.flags = (tid == 0 ? 2u : 0u)%s;", two_buf ? "" : " | 4u");
         o.f("    u64 u = blockIdx.x;");
-        o.f("    if (u >= n_tiles) return;");
-        o.f("    u64 base, src_base; u32 peer;");
-        o.f("    qsv_fused_tile(u, rank, base, src_base, peer);");
+        o.f("    u64 base = 0, src_base = 0; u32 peer = 0;");
+        o.f("    for (;; u += gridDim.x) {");
+        o.f("        if (u >= n_tiles) return;");
+        o.f("        qsv_fused_tile(u, rank, base, src_base, peer);");
+        o.f("        if (qsv_pair_active(base, src_base, peer, rank, sp_mask, sp_val)) break;");
+        o.f("    }");
         o.f("    ctx.next_src = peers.state[peer] + src_base;");
         o.f("    qsv_issue_load(ctx);");
         o.f("    u64 it = 0;");
@@ -1190,10 +1221,13 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
             o.f("        const u64 gbase = base | rank_bits;");
         o.f("        const u32 cur_peer = peer;");
         o.f("        const u64 cur_base = base;");
-        o.f("        const u64 un = u + gridDim.x;");
+        o.f("        u64 un = u + gridDim.x;");
+        o.f("        for (; un < n_tiles; un += gridDim.x) {");
+        o.f("            qsv_fused_tile(un, rank, base, src_base, peer);");
+        o.f("            if (qsv_pair_active(base, src_base, peer, rank, sp_mask, sp_val)) break;");
+        o.f("        }");
         o.f("        double2 *tbuf = tile + (u64)buf * QSV_TILE_SLOTS;");
         o.f("        if (un < n_tiles) {");
-        o.f("            qsv_fused_tile(un, rank, base, src_base, peer);");
         o.f("            ctx.next_src = peers.state[peer] + src_base;");
         if (two_buf) {
             o.f("            // the other buffer was emptied into registers by the previous tile's last round (barrier inside)");
@@ -1315,12 +1349,13 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         // fused variant on the host: `state` is this rank's shard AFTER the swap (output), src_states[j] the shards
         // BEFORE the swap (inputs, never written)
         o.f("extern \"C\" void qsv_jit_host_run_swap(double2 *state, const double2 *const *src_states, const u32 rank,"
-            " const u64 rank_bits, const u64 n_tiles, const double2 *tables) {");
+            " const u64 rank_bits, const u64 n_tiles, const double2 *tables, const u64 sp_mask, const u64 sp_val) {");
         o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
         o.f("    qsv_ctx ctx; (void)ctx;");
         o.f("    for (u64 u = 0; u < n_tiles; ++u) {");
         o.f("        u64 base, src_base; u32 peer;");
         o.f("        qsv_fused_tile(u, rank, base, src_base, peer);");
+        o.f("        if (!qsv_pair_active(base, src_base, peer, rank, sp_mask, sp_val)) continue;");
         if (sw->pre)
             o.f("        const u64 gbase = src_base | ((u64)peer << %d); (void)rank_bits;", sw->n_local);
         else
@@ -1434,6 +1469,8 @@ struct Driver {
                         void **) = nullptr;
     int (*GetErrorString)(int, const char **) = nullptr;
     int (*OccupancyMaxActiveBlocks)(int *, void *, int, size_t) = nullptr;
+    int (*LaunchCooperativeKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *,
+                                   void **) = nullptr;
 };
 
 static Driver *driver(std::string &err) {
@@ -1452,6 +1489,7 @@ static Driver *driver(std::string &err) {
         QSV_SYM(LaunchKernel, "cuLaunchKernel")
         QSV_SYM(GetErrorString, "cuGetErrorString")
         QSV_SYM(OccupancyMaxActiveBlocks, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+        QSV_SYM(LaunchCooperativeKernel, "cuLaunchCooperativeKernel")
 #undef QSV_SYM
     });
     if (!load_err.empty()) { err = load_err; return nullptr; }
@@ -1580,18 +1618,25 @@ int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t
 struct PeerTable { void *state[16]; void *flags[16]; };
 
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
+    static std::mutex mu;
+    static std::unordered_map<int, int> per_device;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = per_device.find(dev);
+    if (it != per_device.end()) return it->second;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    per_device[dev] = n;
     return n;
 }
 
 // fused swap + pass: all CTAs must be co-resident (they hand-shake with the partner rank's CTA of the same index)
+// -> a COOPERATIVE launch: the driver starts the grid only when every CTA fits on the device at once (and refuses a
+// grid that never could), whatever else is resident; the flag spin inside is bounded by a watchdog.
 int launch_swap(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
-                const SwapSpec &sw, const PeerTable &peers, unsigned rank, unsigned long long epoch, cudaStream_t st) {
+                const SwapSpec &sw, const PeerTable &peers, unsigned rank, unsigned long long epoch,
+                unsigned long long sp_mask, unsigned long long sp_val, cudaStream_t st) {
     void *fn = nullptr;
     if (int rc = get_function(P, prog_host, prog_bytes, &sw, &fn)) return rc;
     std::string err;
@@ -1612,12 +1657,17 @@ int launch_swap(void *state_dev, const qsv_pass_t *P, const void *prog_host, uin
     if (grid > kFlagCtas) grid = kFlagCtas;
     if (grid > n_tiles) grid = n_tiles;
     PeerTable pt = peers;
-    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &pt, &rank, &epoch};
-    rc = d->LaunchKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, smem, (void *)st, args, nullptr);
+    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &pt, &rank, &epoch, &sp_mask,
+                    &sp_val};
+    const char *coop = getenv("QSV_FUSE_COOPERATIVE");
+    if (coop && !strcmp(coop, "0"))
+        rc = d->LaunchKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, smem, (void *)st, args, nullptr);
+    else
+        rc = d->LaunchCooperativeKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, smem, (void *)st, args);
     if (rc) {
         const char *es = nullptr;
         d->GetErrorString(rc, &es);
-        set_error("qsv jit: cuLaunchKernel (fused swap): %s", es ? es : "?");
+        set_error("qsv jit: cuLaunchCooperativeKernel (fused swap, grid %llu): %s", grid, es ? es : "?");
         return 2;
     }
     count_launch();
@@ -1686,54 +1736,83 @@ extern "C" int qsv_jit_compile(const qsv_pass_t *pass, const void *prog_host, ui
     return copy_out(e->cubin, cubin_buf, buf_len, needed);
 }
 
-static int make_swap_spec(jit::SwapSpec &sw, int g, const int *positions, int pass_first, const qsv_pass_t *pass) {
-    QSV_CHECK_ARG(g >= 1 && g <= 4 && positions && pass, "qsv fused swap: g=%d out of range or NULL pointer", g);
+static int make_swap_spec(jit::SwapSpec &sw, int j, const int *positions, const int *gbits, int pass_first,
+                          const qsv_pass_t *pass) {
+    QSV_CHECK_ARG(j >= 1 && j <= 4 && positions && pass, "qsv fused swap: n_swap=%d out of range or NULL pointer", j);
     memset(&sw, 0, sizeof(sw));
-    sw.g = g;
-    for (int k = 0; k < 4; ++k) sw.q[k] = k < g ? positions[k] : 0;
+    sw.g = j;
+    for (int k = 0; k < j; ++k) {
+        sw.q[k] = positions[k];
+        sw.gb[k] = gbits ? gbits[k] : k;
+        QSV_CHECK_ARG(sw.gb[k] >= 0 && sw.gb[k] < 4 && (k == 0 || sw.gb[k] > sw.gb[k - 1]),
+                      "qsv fused swap: global bits must be ascending in [0, 4)");
+    }
     sw.pre = pass_first ? 1 : 0;
-    sw.n_local = sw.pre ? pass->n_local : 0;       // only the pass-first form bakes n_local into the code
+    sw.n_local = pass->n_local;       // baked into the code (rank bits of the support test, pass-first coordinates)
     return 0;
 }
 
-extern "C" int qsv_jit_source_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
-                                   const int *positions, int pass_first, char *buf, size_t buf_len, size_t *needed) {
+extern "C" int qsv_jit_source_swap_ex(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_swap,
+                                      const int *positions, const int *gbits, int pass_first, char *buf, size_t buf_len,
+                                      size_t *needed) {
     if (jit::validate(pass, prog_host, prog_bytes)) return 1;
     jit::SwapSpec sw;
-    if (make_swap_spec(sw, g, positions, pass_first, pass)) return 1;
+    if (make_swap_spec(sw, n_swap, positions, gbits, pass_first, pass)) return 1;
     std::string src, err;
     if (jit::generate(*pass, prog_host, prog_bytes, src, err, &sw)) { set_error("qsv jit: %s", err.c_str()); return 1; }
     return copy_out(src, buf, buf_len, needed);
 }
 
-extern "C" int qsv_jit_compile_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
-                                    const int *positions, int pass_first, char *cubin_buf, size_t buf_len, size_t *needed) {
+extern "C" int qsv_jit_source_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
+                                   const int *positions, int pass_first, char *buf, size_t buf_len, size_t *needed) {
+    return qsv_jit_source_swap_ex(pass, prog_host, prog_bytes, g, positions, nullptr, pass_first, buf, buf_len, needed);
+}
+
+extern "C" int qsv_jit_compile_swap_ex(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_swap,
+                                       const int *positions, const int *gbits, int pass_first, char *cubin_buf,
+                                       size_t buf_len, size_t *needed) {
     if (jit::validate(pass, prog_host, prog_bytes)) return 1;
     jit::SwapSpec sw;
-    if (make_swap_spec(sw, g, positions, pass_first, pass)) return 1;
+    if (make_swap_spec(sw, n_swap, positions, gbits, pass_first, pass)) return 1;
     jit::Entry *e = jit::lookup(*pass, prog_host, prog_bytes, &sw);
     if (jit::ensure_compiled(e, *pass, prog_host, prog_bytes, &sw)) return 1;
     return copy_out(e->cubin, cubin_buf, buf_len, needed);
+}
+
+extern "C" int qsv_jit_compile_swap(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int g,
+                                    const int *positions, int pass_first, char *cubin_buf, size_t buf_len, size_t *needed) {
+    return qsv_jit_compile_swap_ex(pass, prog_host, prog_bytes, g, positions, nullptr, pass_first, cubin_buf, buf_len, needed);
+}
+
+extern "C" int qsv_run_pass_rounds_swap_ex(void *state_dev, const qsv_pass_t *pass, const void *prog_host,
+                                           uint32_t prog_bytes, const void *tables_dev, const uint64_t *peer_state_ptrs,
+                                           const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
+                                           const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
+                                           uint64_t sp_val, void *stream) {
+    QSV_CHECK_ARG(state_dev && pass && prog_host && peer_state_ptrs && peer_flag_ptrs, "qsv_run_pass_rounds_swap: NULL pointer");
+    jit::SwapSpec sw;
+    if (make_swap_spec(sw, n_swap, positions, gbits, pass_first, pass)) return 1;
+    QSV_CHECK_ARG(n_ranks >= 2 && n_ranks <= 16 && !(n_ranks & (n_ranks - 1)), "qsv_run_pass_rounds_swap: %d ranks", n_ranks);
+    QSV_CHECK_ARG(rank >= 0 && rank < n_ranks, "qsv_run_pass_rounds_swap: rank %d out of range", rank);
+    for (int k = 0; k < n_swap; ++k)
+        QSV_CHECK_ARG((1 << sw.gb[k]) < n_ranks, "qsv_run_pass_rounds_swap: global bit %d beyond %d ranks", sw.gb[k], n_ranks);
+    jit::PeerTable pt;
+    for (int j = 0; j < 16; ++j) { pt.state[j] = nullptr; pt.flags[j] = nullptr; }
+    for (int j = 0; j < n_ranks; ++j) {
+        pt.state[j] = j == rank ? state_dev : reinterpret_cast<void *>(peer_state_ptrs[j]);
+        pt.flags[j] = reinterpret_cast<void *>(peer_flag_ptrs[j]);
+        QSV_CHECK_ARG(pt.state[j] && pt.flags[j], "qsv_run_pass_rounds_swap: peer %d has no mapped pointer", j);
+    }
+    return jit::launch_swap(state_dev, pass, prog_host, prog_bytes, tables_dev, sw, pt, (unsigned)rank, epoch, sp_mask,
+                            sp_val, (cudaStream_t)stream);
 }
 
 extern "C" int qsv_run_pass_rounds_swap(void *state_dev, const qsv_pass_t *pass, const void *prog_host,
                                         uint32_t prog_bytes, const void *tables_dev, const uint64_t *peer_state_ptrs,
                                         const uint64_t *peer_flag_ptrs, int g, const int *positions, int pass_first,
                                         int rank, uint64_t epoch, void *stream) {
-    QSV_CHECK_ARG(state_dev && pass && prog_host && peer_state_ptrs && peer_flag_ptrs, "qsv_run_pass_rounds_swap: NULL pointer");
-    jit::SwapSpec sw;
-    if (make_swap_spec(sw, g, positions, pass_first, pass)) return 1;
-    const int P = 1 << g;
-    QSV_CHECK_ARG(rank >= 0 && rank < P, "qsv_run_pass_rounds_swap: rank %d out of range", rank);
-    jit::PeerTable pt;
-    for (int j = 0; j < 16; ++j) { pt.state[j] = nullptr; pt.flags[j] = nullptr; }
-    for (int j = 0; j < P; ++j) {
-        pt.state[j] = j == rank ? state_dev : reinterpret_cast<void *>(peer_state_ptrs[j]);
-        pt.flags[j] = reinterpret_cast<void *>(peer_flag_ptrs[j]);
-        QSV_CHECK_ARG(pt.state[j] && pt.flags[j], "qsv_run_pass_rounds_swap: peer %d has no mapped pointer", j);
-    }
-    return jit::launch_swap(state_dev, pass, prog_host, prog_bytes, tables_dev, sw, pt, (unsigned)rank, epoch,
-                            (cudaStream_t)stream);
+    return qsv_run_pass_rounds_swap_ex(state_dev, pass, prog_host, prog_bytes, tables_dev, peer_state_ptrs, peer_flag_ptrs,
+                                       1 << g, g, positions, nullptr, pass_first, rank, epoch, 0, 0, stream);
 }
 
 extern "C" int qsv_jit_bank_score(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,

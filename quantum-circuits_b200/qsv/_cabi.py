@@ -46,6 +46,12 @@ SYMBOLS = {
     "qsv_jit_compile_swap": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _I, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_run_pass_rounds_swap": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, C.POINTER(C.c_uint64),
                                           C.POINTER(C.c_uint64), _I, _IP, _I, _I, _U64, _P]),
+    "qsv_jit_source_swap_ex": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _IP, _I, _P, C.c_size_t,
+                                        C.POINTER(C.c_size_t)]),
+    "qsv_jit_compile_swap_ex": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _IP, _I, _P, C.c_size_t,
+                                         C.POINTER(C.c_size_t)]),
+    "qsv_run_pass_rounds_swap_ex": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, C.POINTER(C.c_uint64),
+                                             C.POINTER(C.c_uint64), _I, _I, _IP, _IP, _I, _I, _U64, _U64, _U64, _P]),
     "qsv_jit_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_D)]),
     "qsv_apply_dense": (C.c_int, [_P, _I, _I, _IP, _I, _IP, C.POINTER(_D), _U64, _P]),
     "qsv_apply_diag": (C.c_int, [_P, _I, _I, _IP, C.POINTER(_D), _U64, _P]),
@@ -63,6 +69,7 @@ SYMBOLS = {
     "qsv_block_sums": (C.c_int, [_P, _I, _IP, _I, _P, _P]),
     "qsv_sample_scan": (C.c_int, [_P, _I, _IP, _U64, _U64, _D, _D, _P, _P]),
     "qsv_swap_peer": (C.c_int, [_P, C.POINTER(C.c_uint64), _I, _I, _I, _IP, _P]),
+    "qsv_swap_peer_ex": (C.c_int, [_P, C.POINTER(C.c_uint64), _I, _I, _I, _I, _IP, _IP, _U64, _U64, _P]),
     "qsv_pack_slices": (C.c_int, [_P, _P, _U64, _U64, _U64, _U64, _P]),
     "qsv_unpack_slices": (C.c_int, [_P, _P, _U64, _U64, _U64, _U64, _P]),
 }

@@ -94,19 +94,30 @@ class Comm:
                 self.peer_swap = False
         return torch.empty(n_amps, dtype=torch.complex128, device=device)
 
-    def _swap_peer(self, sv, positions=None):
+    def _moved_bytes(self, sv, n_swap, support):
+        """Bytes this rank sends in a swap of n_swap qubits: (1 - 2^-n_swap) of the shard, times the fraction of the
+        exchanged pairs that are not known to be zero on both sides (support hint; an upper estimate)."""
+        full = 16 * ((1 << n_swap) - 1) * (1 << (sv.n_local - n_swap))
+        if support is None or not support[0]:
+            return full
+        local_fixed = bin(support[0] & ((1 << sv.n_local) - 1)).count("1")
+        return int(full * min(1.0, 2.0 * 2.0 ** -local_fixed))
+
+    def _swap_peer(self, sv, n_swap, positions=None, gbits=None, support=None):
         raw, hdl, ptrs = self._symm
         arr = (C.c_uint64 * self.world)(*ptrs)
         pos = _cabi.int_array(positions) if positions is not None else None
+        gb = _cabi.int_array(gbits) if gbits is not None else None
+        sp_mask, sp_val = support if support is not None else (0, 0)
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         hdl.barrier()                                   # every rank's earlier kernels are done
         ev[0].record()                                  # (after the barrier: a rank that arrived early is not timed waiting)
-        _cabi.check(sv.lib.qsv_swap_peer(sv._ptr(sv.state), arr, sv.n_local, self.global_bits, self.rank, pos,
-                                         sv._stream()), "qsv_swap_peer")
+        _cabi.check(sv.lib.qsv_swap_peer_ex(sv._ptr(sv.state), arr, sv.n_local, self.world, self.rank, int(n_swap), pos,
+                                            gb, int(sp_mask), int(sp_val), sv._stream()), "qsv_swap_peer_ex")
         ev[1].record()
         hdl.barrier()                                   # nobody touches its shard before all swaps landed
         self.swap_events.append(ev)
-        self.bytes_sent += 16 * (self.world - 1) * (1 << (sv.n_local - self.global_bits))
+        self.bytes_sent += self._moved_bytes(sv, n_swap, support)
         self.swaps += 1
 
     def _flag_arrays(self, device):
@@ -122,28 +133,38 @@ class Comm:
             self._epoch = 0
         return self._flags
 
-    def swap_pass(self, sv, positions, cpass, prog, tables_ptr, pass_first=0):
+    def swap_pass(self, sv, positions, cpass, prog, tables_ptr, pass_first=0, gbits=None, support=None):
         """Global<->local swap of `positions` + the gate pass that follows it as ONE kernel over peer memory
         (qsv_run_pass_rounds_swap): tiles are pulled from the peers, transformed and stored locally; a per-tile flag
         handshake keeps the exchange in place.  One barrier before (earlier kernels of all ranks are done), none after."""
+        self._check_owner(sv)
         raw, hdl, ptrs = self._symm
         fraw, fhdl, fptrs = self._flag_arrays(sv.state.device)
+        gb = list(gbits) if gbits is not None else list(range(len(positions)))
+        sp_mask, sp_val = support if support is not None else (0, 0)
         self._epoch += 1
         arr = (C.c_uint64 * self.world)(*ptrs)
         farr = (C.c_uint64 * self.world)(*fptrs)
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         hdl.barrier()
         ev[0].record()
-        _cabi.check(sv.lib.qsv_run_pass_rounds_swap(sv._ptr(sv.state), C.byref(cpass), C.c_void_p(prog.ctypes.data),
-                                                    int(prog.size), tables_ptr, arr, farr, self.global_bits,
-                                                    _cabi.int_array(positions), int(pass_first), self.rank,
-                                                    self._epoch << 32,
-                                                    sv._stream()), "qsv_run_pass_rounds_swap")
+        _cabi.check(sv.lib.qsv_run_pass_rounds_swap_ex(sv._ptr(sv.state), C.byref(cpass), C.c_void_p(prog.ctypes.data),
+                                                       int(prog.size), tables_ptr, arr, farr, self.world,
+                                                       len(positions), _cabi.int_array(positions), _cabi.int_array(gb),
+                                                       int(pass_first), self.rank, self._epoch << 32, int(sp_mask),
+                                                       int(sp_val), sv._stream()), "qsv_run_pass_rounds_swap_ex")
         ev[1].record()
         self.swap_events.append(ev)
         self.fused_swaps = getattr(self, "fused_swaps", 0) + 1
-        self.bytes_sent += 16 * (self.world - 1) * (1 << (sv.n_local - self.global_bits))
+        self.bytes_sent += self._moved_bytes(sv, len(positions), support)
         self.swaps += 1
+
+    def _check_owner(self, sv):
+        """The peer pointers on this communicator belong to ONE register (the last one alloc_state made): a kernel
+        over peer memory launched for any other StateVector would read another register's shards."""
+        if self._symm is None or sv.state.data_ptr() != self._symm[2][self.rank]:
+            raise RuntimeError("qsv.dist: this StateVector does not own the communicator's symmetric-memory state "
+                               "(a newer sharded register was allocated on the same Comm, or release_state() ran)")
 
     def release_state(self):
         """Drop the symmetric-memory state (the StateVector that used it must be dropped as well)."""
@@ -235,13 +256,15 @@ class Comm:
         self.swap_events = []
         return n, ms
 
-    def swap_global_local(self, sv, n_swap, positions=None):
-        """Engine hook for a 'global_swap' op: the peer-memory kernel (any local positions), or the chunked
-        NCCL all-to-all with the CUDA pack/unpack kernels of libqsv (top local positions only)."""
-        if n_swap != self.global_bits:
-            raise RuntimeError("qsv.dist: only full swaps of all %d global qubits are planned" % self.global_bits)
+    def swap_global_local(self, sv, n_swap, positions=None, gbits=None, support=None):
+        """Engine hook for a 'global_swap' op: the peer-memory kernel (any local positions, any subset of the global
+        bits, support hint), or the chunked NCCL all-to-all with the CUDA pack/unpack kernels of libqsv (all global
+        qubits against the top local positions only)."""
         if self.peer_swap and self._symm is not None and sv.state.data_ptr() == self._symm[2][self.rank]:
-            return self._swap_peer(sv, positions)
+            return self._swap_peer(sv, n_swap, positions, gbits, support)
+        if n_swap != self.global_bits or (gbits is not None and list(gbits) != list(range(n_swap))):
+            raise RuntimeError("qsv.dist: the NCCL exchange swaps all %d global qubits at once; partial swaps need the "
+                               "peer-memory kernel" % self.global_bits)
         top = list(range(sv.n_local - self.global_bits, sv.n_local))
         if positions is not None and list(positions) != top:
             raise RuntimeError("qsv.dist: the NCCL exchange swaps the top local positions only; lower the circuit "

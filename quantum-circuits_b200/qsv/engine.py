@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .schedule import Op, TILED_KINDS, Support, plan_passes, pack_passes
+from .schedule import Op, TILED_KINDS, Support, plan_passes, pack_passes, swap_fields
 
 SCAN_BITS_EXACT = 20     # up to 2^20 outcomes: one fully sequential scan (bit-exact with random.choices)
 SAMPLE_BLOCK_BITS = 12   # larger states: block sums of 2^12 outcomes, then a sequential scan inside one block
@@ -152,6 +152,7 @@ class StateVector:
 
     def run_program(self, handle):
         packed, dev = handle
+        self._basis = None          # the state is about to change outside execute(): the support hint is void
         for meta in packed.passes:
             self._launch_pass(meta, dev)
             self.passes_run += 1
@@ -160,17 +161,27 @@ class StateVector:
     def _adopt(self, out):
         """Make `out` the state after an out-of-place op.  A symmetric-memory state keeps its buffer
         (peers hold its address): the result is copied back instead of swapping references."""
-        if self.comm is not None and getattr(self.comm, "peer_swap", False):
+        self._basis = None
+        if self._owns_symm():
             self.state.copy_(out)
         else:
             self.state, self._scratch = out, self.state
+
+    def _owns_symm(self):
+        """True when this register's buffer is the communicator's peer-mapped symmetric memory (a Comm serves one
+        sharded register at a time; an older StateVector on the same Comm must not use its peer pointers)."""
+        symm = getattr(self.comm, "_symm", None) if self.comm is not None else None
+        return bool(symm is not None and getattr(self.comm, "peer_swap", False)
+                    and self.state.data_ptr() == symm[2][self.rank])
 
     def _scratch_state(self):
         if self._scratch is None:
             self._scratch = torch.empty_like(self.state)
         return self._scratch
 
-    def _run_whole_state_op(self, op):
+    def _run_whole_state_op(self, op, support=None):
+        if support is None:
+            self._basis = None      # called outside execute(): nothing is known about the support any more
         st = self._stream()
         if op.kind == "wide_dense":
             M = torch.from_numpy(np.ascontiguousarray(op.matrix, dtype=np.complex128)).to(self.device)
@@ -207,7 +218,8 @@ class StateVector:
         elif op.kind == "global_swap":
             if self.comm is None:
                 raise RuntimeError("qsv: global_swap op without a communicator")
-            self.comm.swap_global_local(self, op.params["n_swap"], op.params.get("positions"))
+            pos, gb = swap_fields(op, self.n_local)
+            self.comm.swap_global_local(self, len(pos), op.params.get("positions") and pos, gb, support=support)
         else:
             raise RuntimeError("qsv: unknown op kind %r" % op.kind)
 
@@ -250,7 +262,7 @@ class StateVector:
         swaps, qsv.schedule.plan_schedule) whose programs are packed and copied to HBM, interleaved with the
         whole-state ops.  The returned plan can be executed any number of times.  Planning + packing is
         cached by the content of the op list (Shor's sampling loop and benchmarks re-run one circuit)."""
-        key = _ops_fingerprint(ops, (self.n_local, self.tile_bits, self.low_bits))
+        key = _ops_fingerprint(ops, (self.n_local, self.tile_bits, self.low_bits, self.fuse_swaps(), self.g))
         host_plan = _PLAN_CACHE.get(key)
         if host_plan is None:
             from .schedule import plan_schedule
@@ -297,7 +309,7 @@ class StateVector:
                 swap_op, packed, pass_first = item
                 dev = torch.from_numpy(packed.blob).to(self.device, non_blocking=False)
                 h2d += int(packed.blob.size) + int(packed.passes[0][3][0].size)
-                if self._compile_fused(packed, swap_op.params["positions"], pass_first):
+                if self._compile_fused(packed, swap_fields(swap_op, self.n_local), pass_first):
                     segments.append(("swap_pass", (swap_op, packed, dev, pass_first)))
                 else:
                     # the fused kernel cannot be built (same answer on every rank: the program is rank independent):
@@ -315,23 +327,24 @@ class StateVector:
     def execute(self, plan):
         """Run a prepared plan on the current state.  Right after init_basis the support of the state is known and
         the passes skip the tiles that are still zero (schedule.Support); any other state is treated as dense."""
-        for kind, seg, sp in self._walk(plan, self._basis):
+        basis, self._basis = self._basis, None
+        for kind, seg, sp in self._walk(plan, basis):
             if kind == "pass":
                 meta, dev = seg
                 self._launch_pass(meta, dev, sp)
                 self.passes_run += 1
                 self._keep.append(dev)
             elif kind == "swap_pass":
-                self._run_swap_pass(seg)
+                self._run_swap_pass(seg, sp)
             else:
-                self._run_whole_state_op(seg)
+                self._run_whole_state_op(seg, sp if sp is not None else (0, 0))
         self._basis = None
 
     def _walk(self, plan, basis):
-        """Segments of a plan in execution order with the support hint of every pass:
-        ("pass", (meta, dev), (fixed_mask, fixed_val)) | ("swap_pass", seg, None) | ("op", op, None)."""
+        """Segments of a plan in execution order with the support hint of every launch:
+        ("pass", (meta, dev), (fixed_mask, fixed_val)) | ("swap_pass", seg, (mask, val) before the swap, the pass's
+        tile bits excluded) | ("op", op, (mask, val) before a global_swap, else None)."""
         sup = Support(self.n, basis)
-        top = list(range(self.n_local - self.g, self.n_local))
         for kind, seg in plan["segments"]:
             if kind == "program":
                 packed, dev = seg
@@ -340,19 +353,19 @@ class StateVector:
                     sup.after_ops(meta[0].ops)
             elif kind == "swap_pass":
                 swap_op, packed, dev, pass_first = seg
-                yield "swap_pass", seg, None
+                yield "swap_pass", seg, sup.pass_mask(packed.passes[0][0])
                 if pass_first:
                     sup.after_ops(packed.passes[0][0].ops)
-                    sup.swap(swap_op.params["positions"], self.n_local)
+                    sup.swap_op(swap_op, self.n_local)
                 else:
-                    sup.swap(swap_op.params["positions"], self.n_local)
+                    sup.swap_op(swap_op, self.n_local)
                     sup.after_ops(packed.passes[0][0].ops)
+            elif seg.kind == "global_swap":
+                yield "op", seg, sup.fixed()
+                sup.swap_op(seg, self.n_local)
             else:
                 yield "op", seg, None
-                if seg.kind == "global_swap":
-                    sup.swap(seg.params.get("positions") or top, self.n_local)
-                else:
-                    sup.dense()
+                sup.dense()
 
     def fuse_swaps(self):
         """True when a global<->local swap and the pass after it may run as ONE kernel over peer memory
@@ -360,7 +373,7 @@ class StateVector:
         import os
         if os.environ.get("QSV_FUSE_SWAP", "1") == "0":
             return False
-        if self.comm is None or not getattr(self.comm, "peer_swap", False) or self.n_local < 12 + self.g:
+        if not self._owns_symm() or self.n_local < 12 + self.g:
             return False
         mode = os.environ.get("QSV_JIT")
         if mode == "0":
@@ -372,8 +385,9 @@ class StateVector:
         prog = extra[0]
         cp = self._cpass(ps)
         cp.reserved = int(prog[12])
-        rc = self.lib.qsv_jit_compile_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), len(positions),
-                                           _cabi.int_array(positions), int(pass_first), None, 0, None)
+        pos, gb = positions
+        rc = self.lib.qsv_jit_compile_swap_ex(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), len(pos),
+                                              _cabi.int_array(pos), _cabi.int_array(gb), int(pass_first), None, 0, None)
         if rc != 0:
             import warnings
             warnings.warn("qsv: fused swap+pass kernel unavailable (%s); running swap and pass separately"
@@ -389,15 +403,16 @@ class StateVector:
         cp.reserved = int(prog[12])
         return bool(self.lib.qsv_jit_wanted(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size)))
 
-    def _run_swap_pass(self, seg):
+    def _run_swap_pass(self, seg, support=None):
         swap_op, packed, dev, pass_first = seg
         ps, table_off, n_ops, extra = packed.passes[0]
         prog = extra[0]
         cp = self._cpass(ps)
         cp.max_dense_k = 1
         cp.reserved = int(prog[12])
-        self.comm.swap_pass(self, swap_op.params["positions"], cp, prog, C.c_void_p(dev.data_ptr() + table_off),
-                            pass_first)
+        pos, gb = swap_fields(swap_op, self.n_local)
+        self.comm.swap_pass(self, pos, cp, prog, C.c_void_p(dev.data_ptr() + table_off), pass_first, gbits=gb,
+                            support=support)
         self.passes_run += 1
         self._keep.append(dev)
 
@@ -435,6 +450,7 @@ class StateVector:
     def time_passes(self, plan, repeats=1):
         """CUDA-event duration (ms) of every k_pass launch of the plan, on the launching stream."""
         stream = torch.cuda.current_stream(self.device)
+        self._basis = None
         out = []
         for kind, seg in plan["segments"]:
             if kind != "program":
@@ -460,6 +476,7 @@ class StateVector:
         sweep.  'global_swap' and fused swap+pass segments are skipped (they are timed by the communicator)."""
         from .schedule import algorithmic_bytes
         stream = torch.cuda.current_stream(self.device)
+        self._basis = None
         out = []
         fr = iter(self.pass_active_fractions(plan))
         local_mask = (1 << self.n_local) - 1
@@ -485,7 +502,7 @@ class StateVector:
                 for _ in range(repeats):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(stream)
-                    self._run_whole_state_op(seg)
+                    self._run_whole_state_op(seg, (0, 0))
                     e1.record(stream)
                     e1.synchronize()
                     ms.append(e0.elapsed_time(e1))

@@ -623,6 +623,19 @@ def _improve_tile(masks, hi, low_mask, n_free_slots, n_local, L):
 _NOT_TILED = 1 << 200     # sentinel bit: an op that can never join a pass
 
 
+def swap_fields(op, n_local):
+    """(local positions, global bits) of a 'global_swap' op: positions[k] trades places with global position
+    n_local + gbits[k].  Defaults: the top n_swap local positions / global bits 0..n_swap-1.  A swap of fewer
+    qubits than the register has global ones is a PARTIAL swap (pairwise exchange with rank ^ 2^j for one
+    qubit, half a shard each way; (1 - 2^-j) of the shard for j qubits)."""
+    j = int(op.params["n_swap"])
+    pos = op.params.get("positions") or list(range(n_local - j, n_local))
+    gb = op.params.get("gbits") or list(range(j))
+    if len(pos) != j or len(gb) != j:
+        raise RuntimeError("global_swap: n_swap, positions and gbits disagree")
+    return list(pos), list(gb)
+
+
 def block_masks(op, n_local):
     """(non-diagonal mask, diagonal mask) an op contributes to the planner's dependency tracking.  Tiled ops:
     their target / control positions.  Whole-state ops and re-layouts never join a pass (sentinel bit) and
@@ -635,9 +648,8 @@ def block_masks(op, n_local):
             raise RuntimeError("op %r targets a global qubit; it must be swapped local first" % (op.name,))
         return _mask(nd), _mask(op.diag_bits())
     if op.kind == "global_swap":
-        g = int(op.params["n_swap"])
-        pos = op.params.get("positions") or list(range(n_local - g, n_local))
-        return _NOT_TILED | _mask(pos) | _mask(range(n_local, n_local + g)), 0
+        pos, gb = swap_fields(op, n_local)
+        return _NOT_TILED | _mask(pos) | _mask(n_local + b for b in gb), 0
     if op.kind == "diffusion":
         return _NOT_TILED | ((1 << 128) - 1), 0          # acts on (almost) everything: a full barrier
     return _NOT_TILED | _mask(tuple(op.targets) + tuple(op.controls)), 0
@@ -808,22 +820,75 @@ def plan_passes(ops, n_local, tile_bits=None, low_bits=None):
 
 _BLOCKED = _NOT_TILED << 2     # sentinel: non-diagonal target on a global position (waits for the next swap)
 
-# cost model of the schedule search, in units of one near-empty pass over the shard (measured at 2^33 amplitudes
+# cost model of the schedule search, in units of one near-empty FULL sweep of the shard (measured at 2^33 amplitudes
 # per GPU, profiles/r01_bench_8gpu_36q_jit.json: a pass costs 43 ms + 0.55 ms per gate beyond 16, a swap of
 # 3 global qubits 180 ms = 7/8 of the shard over NVLink at 670 GB/s)
 PASS_GATE_COST = 0.55 / 43.0
 PASS_FREE_GATES = 16
 SWAP_COST_FULL = (180.0 / 43.0) / (7.0 / 8.0)      # cost of moving the WHOLE shard once
+PASS_OVERHEAD = 0.02        # launch + the scan over skipped tiles (0.1 ms of a 5.5 ms sweep at 2^30 amplitudes)
+SWAP_OVERHEAD = 0.03        # two device barriers + the scan over skipped chunks
+
+
+def _popcount(x):
+    return bin(x).count("1")
+
+
+def pass_cost(n_ops, frac=1.0):
+    """A pass that touches `frac` of the shard's tiles (the rest is known to be zero: schedule.Support)."""
+    return PASS_OVERHEAD + (1.0 + PASS_GATE_COST * max(0, n_ops - PASS_FREE_GATES)) * frac
+
+
+def swap_cost(j, frac=1.0):
+    """Swap of j global qubits; `frac` = fraction of the exchanged pairs that hold anything but zeros."""
+    return SWAP_OVERHEAD + SWAP_COST_FULL * (1.0 - 2.0 ** -j) * frac
 
 
 def schedule_cost(order, n_global):
-    """Modelled device time of a placed op list (tiled ops grouped by `pass_id`, swaps in between)."""
+    """Modelled device time of a placed op list on a DENSE state (tiled ops grouped by pass, swaps in between)."""
     cost = 0.0
     for kind, n_ops in order:
         if kind == "swap":
-            cost += SWAP_COST_FULL * (1.0 - 2.0 ** -n_global)
+            cost += swap_cost(n_ops if n_ops else n_global)
         else:
-            cost += 1.0 + PASS_GATE_COST * max(0, n_ops - PASS_FREE_GATES)
+            cost += pass_cost(n_ops)
+    return cost
+
+
+def plan_cost(items, n, n_global, sparse=True):
+    """Modelled device time of a schedule as plan_schedule returns it, following the support of a register that
+    starts in a basis state (sparse=True; schedule.Support): a pass costs the fraction of the shard's tiles the
+    busiest rank touches, a swap the fraction of exchanged pairs that are not known to be zero, a pass fused into a
+    swap rides along for free.  While global positions are still untouched the whole support sits on few ranks -
+    the local fraction is what the busiest rank sweeps either way."""
+    n_local = n - n_global
+    local = (1 << n_local) - 1
+    sup = Support(n, 0 if sparse else None)
+    if not sparse:
+        sup.dense()
+    cost = 0.0
+    for kind, it in items:
+        if kind == "pass":
+            fixed, _ = sup.pass_mask(it)
+            cost += pass_cost(len(it.ops), Support.fraction(fixed & local))
+            sup.after_ops(it.ops)
+        elif kind == "swap_pass":
+            sw, ps, first = it[0], it[1], it[2]
+            if first:
+                sup.after_ops(ps.ops)
+            j = int(sw.params["n_swap"])
+            frac = min(1.0, 2.0 * Support.fraction(sup.fixed()[0] & local))
+            cost += swap_cost(j, frac)
+            sup.swap_op(sw, n_local)
+            if not first:
+                sup.after_ops(ps.ops)
+        elif it.kind == "global_swap":
+            j = int(it.params["n_swap"])
+            cost += swap_cost(j, min(1.0, 2.0 * Support.fraction(sup.fixed()[0] & local)))
+            sup.swap_op(it, n_local)
+        else:
+            cost += 1.5
+            sup.dense()
     return cost
 
 
@@ -849,13 +914,21 @@ def _asap_levels(ops):
     return levels
 
 
-def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=float("inf"), tile_penalty=0):
-    """One run of the joint planner with a fixed 'thin pass' threshold; returns (cost, ops, src_pos, order)."""
-    import copy
+def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=float("inf"), tile_penalty=0, early=False,
+                      sparse=False):
+    """One run of the joint planner with a fixed 'thin pass' threshold; returns (cost, ops, src_pos, order).
+
+    sparse: the register starts in a basis state and the kernels skip what is still zero (schedule.Support) - costs
+    follow the support.  early (with sparse): as long as global positions are UNTOUCHED the whole support sits on
+    2^-(untouched globals) of the ranks and the others idle; as soon as enough touched local positions exist, the
+    untouched globals are exchanged with touched locals (a swap of a still-sparse state moves next to nothing), so
+    that every rank carries an equal share of the partial sweeps that follow."""
     n_local = n - n_global
     T, L = _geometry(n_local, None, None)
     search = os.environ.get("QSV_PLAN_SEARCH", "1") != "0" and T - L > 0
     gmask = _mask(range(n_local, n))
+    local = (1 << n_local) - 1
+    low_mask = (1 << L) - 1
     remaining = list(ops)
     at = list(range(n))                 # physical position -> virtual position it currently holds
     out, order = [], []
@@ -863,7 +936,38 @@ def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floa
     forbidden = 0                       # positions of the swap just emitted (the pass fused into it avoids them)
     just_swapped = False
     last_pass = None
+    last_pass_cost = 0.0
     cost_so_far = 0.0
+    free = 0 if sparse else (1 << n) - 1     # positions touched non-diagonally so far (Support.free)
+    partial = os.environ.get("QSV_PARTIAL_SWAP", "1") != "0"
+
+    def next_use():
+        lv = _asap_levels(remaining)
+        nxt = {}
+        for op, l in zip(remaining, lv):
+            for b in op.nondiag_bits():
+                nxt.setdefault(b, l)
+        return nxt
+
+    def emit_swap(positions, gbits):
+        nonlocal remaining, free, cost_so_far
+        j = len(positions)
+        frac = min(1.0, 2.0 * 2.0 ** -_popcount(local & ~free))
+        params = {"n_swap": j, "positions": list(positions)}
+        if list(gbits) != list(range(j)) or j != n_global:
+            params["gbits"] = list(gbits)
+        out.append(Op("global_swap", (), (), params=params, name="relayout"))
+        order.append(("swap", j))
+        relabel = list(range(n))
+        for p_loc, gb in zip(positions, gbits):
+            gq = n_local + gb
+            relabel[p_loc], relabel[gq] = gq, p_loc
+            at[p_loc], at[gq] = at[gq], at[p_loc]
+            fa, fb = (free >> p_loc) & 1, (free >> gq) & 1
+            free = (free & ~((1 << p_loc) | (1 << gq))) | (fb << p_loc) | (fa << gq)
+        remaining = [op.remapped(relabel) for op in remaining]
+        cost_so_far += swap_cost(j, frac)
+
     while remaining:
         if cost_so_far > cost_cap:
             return float("inf"), None, None, order
@@ -886,11 +990,7 @@ def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floa
         n_ps = len(ps.ops) if ps is not None else 0
         if blocked and not forbidden and not just_swapped and n_ps < thin:
             # swap now: the passes that are left with this layout would be near-empty sweeps
-            lv = _asap_levels(remaining)
-            nxt = {}
-            for op, l in zip(remaining, lv):
-                for b in op.nondiag_bits():
-                    nxt.setdefault(b, l)
+            nxt = next_use()
             far = len(remaining) + 1
             cand = [p for p in range(n_local)]
             prev_tile = set(last_pass.hi_pos) if (fuse_swaps and last_pass is not None) else set()
@@ -898,40 +998,56 @@ def _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floa
             # just emitted (taking it would keep that pass from running inside the swap kernel)
             cand.sort(key=lambda p: (p < min_pos, -(nxt.get(p, far) - (tile_penalty if p in prev_tile else 0)),
                                      p in prev_tile, -p))
-            positions = sorted(cand[:n_global])
+            # global positions no remaining op targets non-diagonally may stay global for good: a PARTIAL swap of
+            # the others moves (1 - 2^-j) of the shard instead of (1 - 2^-g)
+            needed = sorted(b - n_local for b in range(n_local, n) if b in nxt)
+            if not partial or not needed:
+                needed = list(range(n_global))
+            positions = sorted(cand[:len(needed)])
             if fuse_swaps and last_pass is not None and order and order[-1][0] == "pass" \
                     and not set(positions) & prev_tile and min(positions) >= L:
                 # the pass just emitted runs inside this swap ("pass first"): it costs nothing extra
-                cost_so_far -= 1.0 + PASS_GATE_COST * max(0, order[-1][1] - PASS_FREE_GATES)
+                cost_so_far -= last_pass_cost
                 order[-1] = ("fused_pass", order[-1][1])
-            out.append(Op("global_swap", (), (), params={"n_swap": n_global, "positions": positions}, name="relayout"))
-            order.append(("swap", 0))
-            relabel = list(range(n))
-            for i, p_loc in enumerate(positions):
-                relabel[p_loc], relabel[n_local + i] = n_local + i, p_loc
-                at[p_loc], at[n_local + i] = at[n_local + i], at[p_loc]
-            remaining = [op.remapped(relabel) for op in remaining]
+            emit_swap(positions, needed)
             forbidden = _mask(positions) if (fuse_swaps and not (order[-2:-1] and order[-2][0] == "fused_pass")) else 0
             last_pass = None
             just_swapped = True
-            cost_so_far += SWAP_COST_FULL * (1.0 - 2.0 ** -n_global)
             continue
         if ps is None:
             raise RuntimeError("sharded planner made no progress (op needs more than %d tile-local qubits)" % T)
         out.extend(ps.ops)
         last_pass = ps
         order.append(("fused_pass" if forbidden else "pass", len(ps.ops)))
+        frac = 2.0 ** -_popcount(local & ~free & ~(low_mask | _mask(ps.hi_pos)))
+        last_pass_cost = pass_cost(len(ps.ops), frac)
         if not forbidden:
-            cost_so_far += 1.0 + PASS_GATE_COST * max(0, len(ps.ops) - PASS_FREE_GATES)
+            cost_so_far += last_pass_cost
+        for op in ps.ops:
+            free |= _mask(op.nondiag_bits())
         forbidden = 0
         just_swapped = False
         remaining = rest
+        if early and sparse and remaining and (gmask & ~free):
+            # untouched global positions: trade them for touched local ones while the state is still sparse
+            gfix = [b - n_local for b in range(n_local, n) if not (free >> b) & 1]
+            touched = [p for p in range(min_pos, n_local) if (free >> p) & 1]
+            if len(touched) >= len(gfix) and (partial or len(gfix) == n_global):
+                nxt = next_use()
+                far = len(remaining) + 1
+                touched.sort(key=lambda p: (-nxt.get(p, far), -p))
+                emit_swap(sorted(touched[:len(gfix)]), gfix)
+                last_pass = None
+                just_swapped = True
     phys_of = [0] * n
     for p, v in enumerate(at):
         phys_of[v] = p
     new_src = [phys_of[v] for v in src_pos] if src_pos is not None else None
-    cost = schedule_cost([o for o in order if o[0] != "fused_pass"], n_global)
-    return cost, out, new_src, order
+    return cost_so_far, out, new_src, order
+
+
+def sparse_start_enabled():
+    return os.environ.get("QSV_SPARSE_START", "1") != "0"
 
 
 def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
@@ -942,44 +1058,66 @@ def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
     the planner builds pass after pass from the ops the current layout allows (ops with a non-diagonal target on
     a global position wait, and block what depends on them) and swaps as soon as the best pass it can still form
     is thinner than a threshold: the victims are the local positions whose next non-diagonal use lies deepest in
-    the commutation DAG.  Several thresholds are tried and the cheapest schedule under the measured cost model
-    (a swap = ~3.7 sweeps at 8 GPUs) is kept.  The result is an ordinary op list with `global_swap` ops, ordered
-    pass by pass, so plan_schedule reproduces the passes."""
+    the commutation DAG.  Several thresholds are tried, with and without the early exchange of untouched global
+    qubits (see _place_joint_once), and the cheapest schedule under the measured cost model (a swap = ~3.7 sweeps at
+    8 GPUs, everything scaled by the support of a register that starts in a basis state) is kept.  The result is an
+    ordinary op list with `global_swap` ops, ordered pass by pass, so plan_schedule reproduces the passes."""
+    sparse = sparse_start_enabled()
     key = (ops_digest(ops), n, n_global, tuple(src_pos) if src_pos is not None else None, fuse_swaps, SWAP_MIN_POS,
            os.environ.get("QSV_PLACE_THIN"), os.environ.get("QSV_TILE_BITS"), os.environ.get("QSV_LOW_BITS"),
-           os.environ.get("QSV_PLAN_SEARCH"))
+           os.environ.get("QSV_PLAN_SEARCH"), sparse, os.environ.get("QSV_EARLY_SWAP"),
+           os.environ.get("QSV_PARTIAL_SWAP"), os.environ.get("QSV_PLACE_REPLAN"))
     hit = _PLACE_CACHE.get(key)
+    if hit is None:
+        hit = _place_disk_cache(key)
+        if hit is not None:
+            _PLACE_CACHE[key] = hit
     if hit is not None:
         return list(hit[0]), (list(hit[1]) if hit[1] is not None else None)
     thins = [int(v) for v in os.environ.get("QSV_PLACE_THIN", "1,8,14,20").split(",")]
+    earlies = (False, True) if (sparse and os.environ.get("QSV_EARLY_SWAP", "1") != "0") else (False,)
     cands, floor = [], float("inf")
-    for thin in thins:
-        for pen in ((0, 2, 6) if fuse_swaps else (0,)):
-            res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floor + 0.5,
-                                    tile_penalty=pen)
-            if res[1] is not None:
-                cands.append(res)
-                floor = min(floor, res[0])
+    for early in earlies:
+        for thin in thins:
+            for pen in ((0, 2, 6) if fuse_swaps else (0,)):
+                res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floor + 0.5,
+                                        tile_penalty=pen, early=early, sparse=sparse)
+                if res[1] is not None:
+                    cands.append(res)
+                    floor = min(floor, res[0])
     # The estimate above is the planner's own pass sequence; plan_schedule re-derives the passes from the op list
     # and may cut them differently.  Re-plan the few cheapest distinct candidates and keep the one whose REAL
     # schedule is cheapest (fused passes ride on their swap for free).
     cands.sort(key=lambda r: r[0])
     best, best_cost, seen = None, float("inf"), set()
     for res in cands:
-        sig = tuple(tuple(o.params["positions"]) for o in res[1] if o.kind == "global_swap"), tuple(id(o) for o in res[1][:8])
+        sig = tuple((tuple(o.params["positions"]), tuple(o.params.get("gbits", ()))) for o in res[1]
+                    if o.kind == "global_swap"), tuple(id(o) for o in res[1][:8])
         if sig in seen:
             continue
         seen.add(sig)
         if len(seen) > int(os.environ.get("QSV_PLACE_REPLAN", "2")):
             break
-        real = schedule_cost([("swap", 0) if kind != "pass" else ("pass", len(item.ops))
-                              for kind, item in plan_schedule(res[1], n - n_global, fuse_swaps=fuse_swaps)], n_global)
+        real = plan_cost(plan_schedule(res[1], n - n_global, fuse_swaps=fuse_swaps), n, n_global, sparse)
         if real < best_cost:
             best, best_cost = res, real
     if len(_PLACE_CACHE) >= 8:
         _PLACE_CACHE.pop(next(iter(_PLACE_CACHE)))
     _PLACE_CACHE[key] = (list(best[1]), list(best[2]) if best[2] is not None else None)
+    _place_disk_cache(key, _PLACE_CACHE[key])
     return best[1], best[2]
+
+
+def _place_disk_cache(key, value=None):
+    """Joint placements survive the process (QSV_CACHE_DIR, default ~/.cache/qsv; QSV_DISK_CACHE=0 disables): the
+    search costs seconds on a 33..36-qubit circuit and a fresh process (Shor builds a new circuit per base, benchmarks
+    restart) would pay it again.  Keyed by the content digest of the op list and every planner switch."""
+    from . import cache as _cache
+    name = "place-" + _cache.digest(repr(key).encode())
+    if value is None:
+        return _cache.load_pickle(name)
+    _cache.store_pickle(name, value)
+    return None
 
 
 _PLACE_CACHE = {}       # the search costs seconds on a 36-qubit circuit; Shor's sampling loop and benchmarks re-run one circuit
@@ -1036,10 +1174,10 @@ class Support:
             else:
                 self.free = self.all
 
-    def swap(self, positions, n_local):
-        """global<->local swap: positions[k] trades places with global bit k."""
+    def swap(self, positions, n_local, gbits=None):
+        """global<->local swap: positions[k] trades places with global bit gbits[k] (default k)."""
         for k, q in enumerate(positions):
-            gq = n_local + k
+            gq = n_local + (gbits[k] if gbits is not None else k)
             fa, fb = (self.free >> q) & 1, (self.free >> gq) & 1
             va, vb = (self.vals >> q) & 1, (self.vals >> gq) & 1
             self.free = (self.free & ~((1 << q) | (1 << gq))) | (fb << q) | (fa << gq)
@@ -1047,6 +1185,15 @@ class Support:
 
     def dense(self):
         self.free = self.all
+
+    def fixed(self):
+        """(fixed_mask, fixed_val) over ALL n index bits (global positions included)."""
+        m = self.all & ~self.free
+        return m, self.vals & m
+
+    def swap_op(self, op, n_local):
+        pos, gb = swap_fields(op, n_local)
+        self.swap(pos, n_local, gb)
 
     @staticmethod
     def fraction(fixed_mask):

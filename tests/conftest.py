@@ -10,6 +10,11 @@ for p in (PKG, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# the suite must not read artefacts cached by earlier versions of the planner / generator
+import tempfile  # noqa: E402
+os.environ.setdefault("QSV_CACHE_DIR", tempfile.mkdtemp(prefix="qsv-cache-test-"))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 

@@ -335,6 +335,20 @@ def emulate_ops(ops, psi, n_local, tile_bits=None, low_bits=None, rank_bits=0):
     return psi
 
 
+def swap_positions(full, swap_op, n_local):
+    """Full state (physical order) after a 'global_swap' op: local position pos[k] trades places with global
+    position n_local + gbits[k]."""
+    from qsv.schedule import swap_fields
+    pos, gb = swap_fields(swap_op, n_local)
+    idx = np.arange(full.size)
+    src = idx.copy()
+    for p_loc, b_ in zip(pos, gb):
+        gq = n_local + b_
+        a, b = (idx >> p_loc) & 1, (idx >> gq) & 1
+        src = (src & ~((1 << p_loc) | (1 << gq))) | (b << p_loc) | (a << gq)
+    return full[src]
+
+
 def emulate_sharded(ops, psi, n, g, tile_bits=None, low_bits=None):
     """Run PLACED ops (qsv.schedule.place) on P = 2^g virtual ranks held as rows of one numpy array, in the
     order of qsv.schedule.plan_schedule (passes may absorb ops from behind a qubit swap): passes go through the
@@ -350,18 +364,11 @@ def emulate_sharded(ops, psi, n, g, tile_bits=None, low_bits=None):
             for r in range(P):
                 shards[r] = emulate_program(packed, shards[r], rank_bits=r << n_local)
         elif item.kind == "global_swap":
-            pos = item.params.get("positions")
-            if pos is None:
+            if item.params.get("positions") is None and item.params.get("gbits") is None:
                 t = shards.reshape(P, P, -1)            # [rank, top local field, rest]
                 shards = np.ascontiguousarray(t.transpose(1, 0, 2)).reshape(P, -1)
-            else:                                       # position pos[k] trades places with global bit k
-                full = shards.reshape(-1)
-                idx = np.arange(full.size)
-                src = idx.copy()
-                for k, p_loc in enumerate(pos):
-                    a, b = (idx >> p_loc) & 1, (idx >> (n_local + k)) & 1
-                    src = (src & ~((1 << p_loc) | (1 << (n_local + k)))) | (b << p_loc) | (a << (n_local + k))
-                shards = full[src].reshape(P, -1)
+            else:                                       # position pos[k] trades places with global bit gbits[k]
+                shards = swap_positions(shards.reshape(-1), item, n_local).reshape(P, -1)
         else:
             for r in range(P):
                 shards[r] = _emulate_whole_state_op(item, shards[r])
@@ -427,9 +434,12 @@ def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=No
     return out
 
 
-def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pass_first=0):
-    """Fused swap + pass on the host: `shards` = the P = 2^g shards BEFORE the swap (numpy complex128 arrays).
-    Returns the list of shards after swap + pass, one call of the generated qsv_jit_host_run_swap per rank."""
+def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pass_first=0, gbits=None, support=(0, 0),
+                      ):
+    """Fused swap + pass on the host: `shards` = the shards BEFORE the swap (numpy complex128 arrays, one per rank).
+    Returns the list of shards after swap + pass, one call of the generated qsv_jit_host_run_swap per rank.
+    gbits: positions[k] trades places with global bit gbits[k] (partial swaps); support = (fixed_mask, fixed_val) of the
+    state before the swap."""
     import ctypes as C
     import hashlib
     import os
@@ -439,12 +449,13 @@ def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pas
     g = len(positions)
     cp = jit_cpass(ps)
     pos = _cabi.int_array(positions)
+    gb = _cabi.int_array(gbits if gbits is not None else list(range(g)))
     need = C.c_size_t(0)
-    _cabi.check(lib.qsv_jit_source_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g, pos, pass_first,
-                                        None, 0, C.byref(need)), "qsv_jit_source_swap")
+    _cabi.check(lib.qsv_jit_source_swap_ex(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g, pos, gb,
+                                           pass_first, None, 0, C.byref(need)), "qsv_jit_source_swap_ex")
     buf = C.create_string_buffer(need.value)
-    _cabi.check(lib.qsv_jit_source_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g, pos, pass_first,
-                                        buf, need.value, C.byref(need)), "qsv_jit_source_swap")
+    _cabi.check(lib.qsv_jit_source_swap_ex(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g, pos, gb,
+                                           pass_first, buf, need.value, C.byref(need)), "qsv_jit_source_swap_ex")
     src = buf.raw.decode()
     tag = "swap" + hashlib.sha1(src.encode()).hexdigest()[:16]
     cu, so = os.path.join(workdir, tag + ".cu"), os.path.join(workdir, tag + ".so")
@@ -459,9 +470,11 @@ def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pas
     before = [np.ascontiguousarray(s_, dtype=np.complex128) for s_ in shards]
     ptrs = (C.c_void_p * len(before))(*[b.ctypes.data for b in before])
     out = []
-    for rank in range(1 << g):
-        dst = np.zeros(1 << n_local, dtype=np.complex128)
+    for rank in range(len(before)):
+        # tiles the kernel skips keep what the shard held before (zeros, by the support invariant)
+        dst = before[rank].copy() if support[0] else np.zeros(1 << n_local, dtype=np.complex128)
         h.qsv_jit_host_run_swap(C.c_void_p(dst.ctypes.data), ptrs, C.c_uint32(rank), C.c_uint64(rank << n_local),
-                                C.c_uint64(1 << (n_local - ps.tile_bits)), C.c_void_p(tabs.ctypes.data))
+                                C.c_uint64(1 << (n_local - ps.tile_bits)), C.c_void_p(tabs.ctypes.data),
+                                C.c_uint64(support[0]), C.c_uint64(support[1]))
         out.append(dst)
     return out

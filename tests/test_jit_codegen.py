@@ -382,7 +382,7 @@ def test_every_kernel_of_the_8_gpu_bench_plan_compiles_for_sm100a():
     c.sort()
     ops, _, _ = lowering.lower(c, n_global=g, in_flip=True, free_swap=True, fuse_swaps=True)
     sched = schedule.plan_schedule(ops, n - g, fuse_swaps=True)
-    assert any(k == "swap_pass" for k, _ in sched) and sum(k == "pass" for k, _ in sched) <= 18
+    assert any(k == "swap_pass" for k, _ in sched) and sum(k == "pass" for k, _ in sched) <= 20
     compiled = fused = 0
     for kind, it in sched:
         if kind == "op":
@@ -394,9 +394,10 @@ def test_every_kernel_of_the_8_gpu_bench_plan_compiles_for_sm100a():
                 continue
             prog, cp, need = meta[3][0], jit_cpass(meta[0]), C.c_size_t(0)
             if kind == "swap_pass" and len(packed.passes) == 1:
-                rc = lib.qsv_jit_compile_swap(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), g,
-                                              _cabi.int_array(it[0].params["positions"]), int(it[2]), None, 0,
-                                              C.byref(need))
+                pos, gb = schedule.swap_fields(it[0], n - g)
+                rc = lib.qsv_jit_compile_swap_ex(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), len(pos),
+                                                 _cabi.int_array(pos), _cabi.int_array(gb), int(it[2]), None, 0,
+                                                 C.byref(need))
                 fused += 1
             else:
                 rc = lib.qsv_jit_compile(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), None, 0,
@@ -431,3 +432,61 @@ def test_bank_score_search_is_never_worse_than_the_default_mapping():
         tot_d += d.value
         tot_s += s_.value
     assert tot_s < tot_d
+
+
+@pytest.mark.parametrize("world_bits,positions,gbits,pass_first,hint", [
+    (2, [13], [1], 0, False),            # partial swap: one of two global qubits, the HIGH one (peer = rank ^ 2)
+    (2, [12], [0], 1, False),            # partial swap, pass first
+    (3, [10, 14], [0, 2], 0, False),     # two of three global qubits, not adjacent
+    (2, [9, 14], [0, 1], 0, True),       # full swap of a still-sparse state: pairs of zeros are skipped
+    (2, [13], [1], 1, True),             # partial + hint + pass first
+])
+def test_fused_partial_swaps_and_support_hint(tmp_path, world_bits, positions, gbits, pass_first, hint):
+    """General form of the fused kernel (qsv_run_pass_rounds_swap_ex) on the host: positions[k] trades places with
+    global bit gbits[k], a subset of the register's global qubits; with the support hint, tile pairs that hold only
+    zeros on both ranks are skipped (the output keeps NaN poison there, the expected state is zero).  Reference: the
+    swap as an index exchange of the FULL state (helpers.swap_positions) and the plain generated pass."""
+    from helpers import jit_host_run_swap, swap_positions
+    from qsv.schedule import Op, plan_schedule, pack_passes
+    n_local = 15
+    n = n_local + world_bits
+    P = 1 << world_bits
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    S = np.array([[0.5 + 0.5j, 0.5 - 0.5j], [0.5 - 0.5j, 0.5 + 0.5j]], dtype=np.complex128)
+    ph = complex(math.cos(0.7), math.sin(0.7))
+    free = [p for p in range(6, n_local) if p not in positions]
+    swap = Op("global_swap", (), (), params={"n_swap": len(positions), "positions": positions, "gbits": gbits})
+    gates = [Op("dense", (0,), (), matrix=H), Op("dense", (free[0],), (), matrix=S), Op("mcx", (free[1],), (positions[0],)),
+             Op("phase", (), (positions[-1], 3), scalar=ph), Op("phase", (), (n_local, free[2]), scalar=-1.0 + 0j),
+             Op("dense", (free[2],), (n - 1,), matrix=H), Op("mcx", (2,), (free[0], positions[0])),
+             Op("dense", (free[3],), (), matrix=H), Op("phase", (), (free[3],), scalar=ph), Op("dense", (1,), (), matrix=S),
+             Op("diag", (2, positions[0], n_local + gbits[0]), (), matrix=np.exp(1j * np.arange(8))),
+             Op("dense", (4,), (), matrix=H)]
+    ops = gates + [swap] if pass_first else [swap] + gates
+    sched = plan_schedule(ops, n_local, 12, 6, fuse_swaps=True)
+    assert sched[0][0] == "swap_pass" and sched[0][1][2] == pass_first, [k for k, _ in sched]
+    ps = sched[0][1][1]
+    assert len(ps.ops) == len(gates)
+    packed = pack_passes([ps])
+    ps_, off, n_ops, extra = packed.passes[0]
+    prog, tables = extra[0], packed.blob.tobytes()[off:]
+    full = np.concatenate([_rand_state(n_local, 80 + r) for r in range(P)])
+    support = (0, 0)
+    if hint:
+        # a state confined to: one swapped position, one global bit, one local position outside the tile
+        outside = [p for p in range(6, n_local) if p not in ps.hi_pos and p not in positions]
+        fixed_mask = (1 << positions[0]) | (1 << (n_local + gbits[-1])) | (1 << outside[0])
+        fixed_val = (1 << (n_local + gbits[-1])) | (1 << outside[0])
+        idx = np.arange(1 << n)
+        full[(idx & fixed_mask) != fixed_val] = 0
+        support = (fixed_mask, fixed_val)
+    shards = [full[r << n_local: (r + 1) << n_local].copy() for r in range(P)]
+    got = jit_host_run_swap(ps_, prog, tables, shards, positions, n_local, str(tmp_path), pass_first=pass_first,
+                            gbits=gbits, support=support)
+
+    def run_pass(state):
+        return np.concatenate([jit_host_run(ps_, prog, tables, state[r << n_local: (r + 1) << n_local], r << n_local,
+                                            str(tmp_path)) for r in range(P)])
+    ref = swap_positions(run_pass(full), swap, n_local) if pass_first else run_pass(swap_positions(full, swap, n_local))
+    got = np.concatenate(got)
+    assert np.max(np.abs(got - ref)) == 0.0

@@ -128,68 +128,109 @@ def _insert_zero(v, p):
     return ((v >> p) << (p + 1)) | (v & ((1 << p) - 1))
 
 
-@pytest.mark.parametrize("g,S,low", [(1, 1, 0), (1, 2, 0), (1, 8, 0), (2, 4, 0), (3, 16, 0), (2, 8192, 0), (1, 4096, 0),
-                                     (1, 8, 1), (2, 16, 2), (3, 64, 3), (2, 8192, 5)])
-def test_peer_swap_kernel_index_logic(g, S, low):
-    """numpy restatement of k_swap_peer (csrc/qsv_peer.cu): every element of every pair is swapped exactly
-    once, by exactly one of the two ranks, and the result equals the exchange of the chosen local positions
-    with the global bits (low = 0: the top g positions, i.e. the all-to-all transposition of blocks;
-    low > 0: positions spread below the top, as the free-position placement produces them)."""
-    P = 1 << g
-    n_local = g + (S.bit_length() - 1)
+def _swap_expand(e, q):
+    for p in q:
+        e = _insert_zero(e, p)
+    return e
+
+
+@pytest.mark.parametrize("world_bits,gb,S,low,hint", [
+    (1, [0], 1, 0, False), (1, [0], 2, 0, False), (1, [0], 8, 0, False), (2, [0, 1], 4, 0, False),
+    (3, [0, 1, 2], 16, 0, False), (2, [0, 1], 8192, 0, False), (1, [0], 4096, 0, False),
+    (1, [0], 8, 1, False), (2, [0, 1], 16, 2, False), (3, [0, 1, 2], 64, 3, False), (2, [0, 1], 8192, 5, False),
+    # partial swaps: a subset of the global bits
+    (2, [1], 16, 0, False), (2, [0], 2048, 3, False), (3, [0, 2], 64, 2, False), (3, [1], 4096, 4, False),
+    # support hint: pairs that are zero on both sides are skipped, everything else still moves exactly once
+    (2, [0, 1], 4096, 0, True), (3, [0, 2], 2048, 3, True), (1, [0], 8192, 5, True),
+])
+def test_peer_swap_kernel_index_logic(world_bits, gb, S, low, hint):
+    """numpy restatement of k_swap_peer (csrc/qsv_peer.cu), chunk loop included: every element of every pair is
+    swapped exactly once, by exactly one of the two ranks, and the result equals the exchange of the chosen local
+    positions with the chosen global bits (low = 0: the top positions, i.e. the all-to-all transposition of blocks;
+    low > 0: positions spread below the top, as the free-position placement produces them).  With the support hint
+    only pairs of zeros are left alone."""
+    P = 1 << world_bits
+    j_sw = len(gb)
+    n_local = j_sw + (S.bit_length() - 1)
     if low == 0:
-        q = list(range(n_local - g, n_local))
+        q = list(range(n_local - j_sw, n_local))
     else:
-        q = sorted(np.random.default_rng(low).choice(np.arange(low, n_local), size=g, replace=False).tolist())
+        q = sorted(np.random.default_rng(low).choice(np.arange(low, n_local), size=j_sw, replace=False).tolist())
 
-    def field(j):
-        return sum(((j >> k) & 1) << q[k] for k in range(g))
+    def field(x):
+        return sum(((x >> gb[k]) & 1) << q[k] for k in range(j_sw))
 
-    def expand(e):
-        for k in range(g):
-            e = _insert_zero(e, q[k])
-        return e
     G = (S // 2 if S // 2 < 2048 else 2048) if S >= 2 else 1
     per_pair = S // 2 if S >= 2 else 1
     CH = min(per_pair, 512)
-    rng = np.random.default_rng(S + g)
-    shards = rng.normal(size=(P, P * S))
-    full = shards.reshape(-1)
-    idx = np.arange(full.size)
-    src = idx.copy()
-    for k in range(g):
-        a, b = (idx >> q[k]) & 1, (idx >> (n_local + k)) & 1
-        src = (src & ~((1 << q[k]) | (1 << (n_local + k)))) | (b << q[k]) | (a << (n_local + k))
-    expect = full[src].reshape(P, P * S)
-    if low == 0:
-        assert np.array_equal(expect, np.ascontiguousarray(shards.reshape(P, P, S).transpose(1, 0, 2)).reshape(P, P * S))
+    n_peers = (1 << j_sw) - 1
+    n_chunks = n_peers * (per_pair // CH)
+    rng = np.random.default_rng(S + world_bits)
+    N = 1 << n_local
+    shards = rng.normal(size=(P, N))
+    sp_mask = sp_val = 0
+    if hint:
+        cand = [p for p in range(n_local) if p not in q]
+        sp_mask = (1 << q[0]) | (1 << cand[-1]) | (1 << cand[0]) | (1 << (n_local + gb[-1]))
+        sp_val = (1 << cand[-1]) | (1 << (n_local + gb[-1]))
+        gidx = np.arange(P * N)
+        flat = shards.reshape(-1)
+        flat[(gidx & sp_mask) != sp_val] = 0.0
+    from helpers import swap_positions
+    from qsv.schedule import Op
+    swap_op = Op("global_swap", (), (), params={"n_swap": j_sw, "positions": q, "gbits": gb})
+    expect = swap_positions(shards.reshape(-1).copy(), swap_op, n_local).reshape(P, N)
+    if low == 0 and j_sw == world_bits and not hint:
+        assert np.array_equal(expect, np.ascontiguousarray(shards.reshape(P, P, S).transpose(1, 0, 2)).reshape(P, N))
     work = shards.copy()
-    touched = np.zeros((P, P * S), dtype=int)
+    touched = np.zeros((P, N), dtype=int)
+    var_mask = _swap_expand(CH - 1, q)
+    cm, cv = sp_mask & ~var_mask, sp_val & ~var_mask
+    skipped_chunks = 0
     for r in range(P):
-        for w in range((P - 1) * per_pair):
-            c = w // CH
-            j = r ^ (1 + c % (P - 1))
-            h = (c // (P - 1)) * CH + (w % CH)
+        fr = field(r)
+        for c in range(n_chunks):
+            s_ = 1 + c % n_peers
+            dj = sum(((s_ >> k) & 1) << gb[k] for k in range(j_sw))
+            j = r ^ dj
+            fj = field(j)
+            hb = (c // n_peers) * CH
             if S >= 2:
-                e = ((h // G) * 2 + (0 if r < j else 1)) * G + (h % G)
+                e0 = ((hb // G) * 2 + (0 if r < j else 1)) * G + (hb % G)
             else:
-                e = 0
+                e0 = 0
                 if r > j:
                     continue
-            mine, theirs = expand(e) | field(j), expand(e) | field(r)
-            a, b = work[r, mine], work[j, theirs]
-            work[r, mine], work[j, theirs] = b, a
-            touched[r, mine] += 1
-            touched[j, theirs] += 1
-    off_diag = np.ones((P, P * S), dtype=bool)
-    loc = np.arange(P * S)
-    for r in range(P):
-        own = np.ones(P * S, dtype=bool)
-        for k in range(g):
-            own &= ((loc >> q[k]) & 1) == ((r >> k) & 1)
-        off_diag[r, own] = False
-    assert np.all(touched[off_diag] == 1) and np.all(touched[~off_diag] == 0)
+            x0 = _swap_expand(e0, q)
+            mine_g, theirs_g = (r << n_local) | x0 | fj, (j << n_local) | x0 | fr
+            if (mine_g & cm) != cv and (theirs_g & cm) != cv:
+                skipped_chunks += 1
+                continue
+            for l in range(CH):
+                x = _swap_expand(e0 + l, q)
+                if sp_mask:
+                    mg, tg = (r << n_local) | x | fj, (j << n_local) | x | fr
+                    if (mg & sp_mask) != sp_val and (tg & sp_mask) != sp_val:
+                        continue
+                mine, theirs = x | fj, x | fr
+                a, b = work[r, mine], work[j, theirs]
+                work[r, mine], work[j, theirs] = b, a
+                touched[r, mine] += 1
+                touched[j, theirs] += 1
     assert np.array_equal(work, expect)
+    assert touched.max() <= 1
+    if not hint:
+        moves = np.ones((P, N), dtype=bool)
+        loc = np.arange(N)
+        for r in range(P):
+            own = np.ones(N, dtype=bool)
+            for k in range(j_sw):
+                own &= ((loc >> q[k]) & 1) == ((r >> gb[k]) & 1)
+            moves[r, own] = False
+        assert np.all(touched[moves] == 1) and np.all(touched[~moves] == 0)
+    else:
+        assert skipped_chunks > 0 or n_chunks < 4
+        assert touched.sum() < 0.6 * P * N
 
 
 @pytest.mark.parametrize("g,seed,must_fuse", [(1, 5, True), (2, 1, True), (2, 2, False), (3, 2, False)])
@@ -217,12 +258,9 @@ def test_support_tracking_with_fused_swap_pass_items(monkeypatch, g, seed, must_
         shards = full.reshape(P, -1)
         return np.concatenate([emulate_program(packed, shards[r], rank_bits=r << n_local) for r in range(P)])
 
-    def run_swap(pos, full):
-        src = idx.copy()
-        for k, p_loc in enumerate(pos):
-            a, b = (idx >> p_loc) & 1, (idx >> (n_local + k)) & 1
-            src = (src & ~((1 << p_loc) | (1 << (n_local + k)))) | (b << p_loc) | (a << (n_local + k))
-        return full[src]
+    def run_swap(swap_op, full):
+        from helpers import swap_positions
+        return swap_positions(full, swap_op, n_local)
 
     kinds = []
     for kind, item in plan_schedule(ops, n_local, fuse_swaps=True):
@@ -234,19 +272,22 @@ def test_support_tracking_with_fused_swap_pass_items(monkeypatch, g, seed, must_
             sup.after_ops(item.ops)
         elif kind == "swap_pass":
             swap_op, ps, pass_first = item
-            pos = swap_op.params["positions"]
+            fixed, val = sup.pass_mask(ps)                  # what the fused kernel is told: pairs outside are skipped
+            assert np.all(full[(idx & fixed) != val] == 0)
             if pass_first:
-                full = run_swap(pos, run_pass(ps, full))
+                full = run_swap(swap_op, run_pass(ps, full))
                 sup.after_ops(ps.ops)
-                sup.swap(pos, n_local)
+                sup.swap_op(swap_op, n_local)
             else:
-                full = run_pass(ps, run_swap(pos, full))
-                sup.swap(pos, n_local)
+                full = run_pass(ps, run_swap(swap_op, full))
+                sup.swap_op(swap_op, n_local)
                 sup.after_ops(ps.ops)
         else:
             assert item.kind == "global_swap"
-            full = run_swap(item.params["positions"], full)
-            sup.swap(item.params["positions"], n_local)
+            fixed, val = sup.fixed()                        # what k_swap_peer is told
+            assert np.all(full[(idx & fixed) != val] == 0)
+            full = run_swap(item, full)
+            sup.swap_op(item, n_local)
     assert "swap_pass" in kinds or not must_fuse, kinds
     assert "swap_pass" in kinds or "op" in kinds, kinds
     ref = np.zeros(1 << n, dtype=np.complex128)
@@ -290,13 +331,11 @@ def test_support_tracking_state_is_zero_outside_the_claimed_support(g, monkeypat
             full = np.concatenate([emulate_program(packed, shards[r], rank_bits=r << n_local) for r in range(P)])
             sup.after_ops(item.ops)
         elif item.kind == "global_swap":
-            pos = item.params["positions"]
-            src = idx.copy()
-            for k, p_loc in enumerate(pos):
-                a, b = (idx >> p_loc) & 1, (idx >> (n_local + k)) & 1
-                src = (src & ~((1 << p_loc) | (1 << (n_local + k)))) | (b << p_loc) | (a << (n_local + k))
-            full = full[src]
-            sup.swap(pos, n_local)
+            from helpers import swap_positions
+            fixed, val = sup.fixed()
+            assert np.all(full[(idx & fixed) != val] == 0)
+            full = swap_positions(full, item, n_local)
+            sup.swap_op(item, n_local)
         else:
             raise AssertionError(item.kind)
     assert sparse_passes >= 2

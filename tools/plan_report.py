@@ -48,24 +48,31 @@ for kind, it in schedule.plan_schedule(ops, n_local, fuse_swaps=bool(g)):
         total += 0.1 + sweep * frac
         dense += 0.1 + sweep
         rb = " ".join("".join("%x" % b for b in sorted(R.rb)) for R in rounds) if rounds else "shared-memory kernel"
-        print("  pass  %3d gates  %d rounds [%s]  tile hi %s  touches %.3g of the shard" % (len(it.ops), nr, rb, list(it.hi_pos), frac))
+        gfix = bin(fixed >> n_local).count("1")
+        print("  pass  %3d gates  %d rounds [%s]  tile hi %s  touches %.3g of the shard on %d of %d ranks"
+              % (len(it.ops), nr, rb, list(it.hi_pos), frac, a.gpus >> gfix, a.gpus))
         sup.after_ops(it.ops)
     elif kind == "swap_pass":
         sw, ps, first = it
+        j = int(sw.params["n_swap"])
+        swap_ms = 16.0 * (1 << n_local) * (1 - 2.0 ** -j) / 655e9 * 1e3
         total += swap_ms
         dense += swap_ms
         print("  SWAP %s fused with a pass of %d gates (%s)" % (sw.params["positions"], len(ps.ops), "pass first" if first else "pass after"))
         if first:
             sup.after_ops(ps.ops)
-            sup.swap(sw.params["positions"], n_local)
+            sup.swap_op(sw, n_local)
         else:
-            sup.swap(sw.params["positions"], n_local)
+            sup.swap_op(sw, n_local)
             sup.after_ops(ps.ops)
     else:
-        total += swap_ms
-        dense += swap_ms
-        pos = it.params.get("positions") or list(range(n_local - g, n_local))
-        print("  SWAP %s" % (pos,))
-        sup.swap(pos, n_local)
+        pos, gb = schedule.swap_fields(it, n_local)
+        j = len(pos)
+        frac = min(1.0, 2.0 * Support.fraction(sup.fixed()[0] & local))
+        one = 16.0 * (1 << n_local) * (1 - 2.0 ** -j) / 655e9 * 1e3
+        total += 0.1 + one * frac
+        dense += one
+        print("  SWAP %s <-> global bits %s  moves %.3g of its pairs" % (pos, gb, frac))
+        sup.swap_op(it, n_local)
 print("modelled step: %.1f ms (%.0f gates/s); with full sweeps %.1f ms (%.0f gates/s)"
       % (total, len(c.gates) / total * 1e3, dense, len(c.gates) / dense * 1e3))
