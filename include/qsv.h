@@ -197,6 +197,9 @@ int  qsv_jit_compile(const qsv_pass_t *pass, const void *prog_host, uint32_t pro
                      size_t buf_len, size_t *needed);
 int  qsv_jit_wanted(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes);
 void qsv_jit_stats(uint64_t *kernels_compiled, uint64_t *cache_hits, double *compile_seconds);
+/* Kernels served from the on-disk cubin cache instead of NVRTC since the library was loaded (QSV_CACHE_DIR, default
+ * ~/.cache/qsv; keyed by the generated source + compiler version; QSV_DISK_CACHE=0 disables). */
+uint64_t qsv_jit_disk_hits(void);
 /* Modelled shared-memory bank-group collisions of one pass program (sampled quarter-warps x slots x rounds; 0 = none):
  * with the default thread-index mapping, and with the per-round mapping the opt-in search (QSV_JIT_BANKSEARCH=1) picks.
  * A planning aid that needs no GPU (tools/plan_report.py --banks). */

@@ -23,6 +23,8 @@
 // sequential loop over thread ids: that is how tests/ check the generator in a container without a GPU.
 #include "qsv_common.cuh"
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1539,17 +1541,106 @@ static Entry *lookup(const qsv_pass_t &P, const void *prog, uint32_t bytes, cons
     return e;
 }
 
+// ---- on-disk cubin cache: a fresh process (Shor builds a new circuit per base; benchmarks and servers restart) finds
+// the kernels of circuits it has seen before instead of paying NVRTC again (~0.3-0.4 s of CPU per kernel).  Keyed by
+// the GENERATED SOURCE (so a change of the generator can never serve a stale kernel), the NVRTC options and the
+// compiler version.  QSV_CACHE_DIR (default ~/.cache/qsv), QSV_DISK_CACHE=0 disables.  Atomic writes (temp + rename).
+static bool disk_cache_dir(std::string &dir) {
+    const char *off = getenv("QSV_DISK_CACHE");
+    if (off && !strcmp(off, "0")) return false;
+    const char *d = getenv("QSV_CACHE_DIR");
+    if (d && *d) { dir = d; return true; }
+    const char *home = getenv("HOME");
+    if (!home || !*home) return false;
+    dir = std::string(home) + "/.cache/qsv";
+    return true;
+}
+
+static void hash128(const std::string &s_, uint64_t &h1, uint64_t &h2) {
+    h1 = 0xcbf29ce484222325ull; h2 = 0x9e3779b97f4a7c15ull;
+    for (unsigned char c : s_) {
+        h1 = (h1 ^ c) * 0x100000001b3ull;                         // FNV-1a
+        h2 = (h2 + c) * 0xff51afd7ed558ccdull; h2 ^= h2 >> 29;    // an independent multiply-xorshift chain
+    }
+    h2 ^= (uint64_t)s_.size() * 0xc4ceb9fe1a85ec53ull;
+}
+
+static std::string disk_cache_path(const std::string &src) {
+    std::string dir;
+    if (!disk_cache_dir(dir)) return std::string();
+    static std::string ver;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::string err;
+        int major = 0, minor = 0;
+        Nvrtc *rt = nvrtc(err);
+        if (rt) {
+            auto fn = reinterpret_cast<int (*)(int *, int *)>(dlsym(rt->h, "nvrtcVersion"));
+            if (fn) fn(&major, &minor);
+        }
+        ver = "nvrtc" + std::to_string(major) + "." + std::to_string(minor) + "|sm_100a|c++17|lineinfo|";
+    });
+    uint64_t h1, h2;
+    hash128(ver + src, h1, h2);
+    char name[80];
+    snprintf(name, sizeof(name), "/jit-%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
+    return dir + name;
+}
+
+static bool disk_cache_load(const std::string &path, std::string &cubin) {
+    if (path.empty()) return false;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::string data;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, n);
+    fclose(f);
+    if (data.size() < 64 || memcmp(data.data(), "\x7f" "ELF", 4) != 0) return false;     // truncated / foreign file
+    cubin.swap(data);
+    return true;
+}
+
+static void disk_cache_store(const std::string &path, const std::string &cubin) {
+    if (path.empty()) return;
+    const std::string dir = path.substr(0, path.rfind('/'));
+    for (size_t i = 1; i <= dir.size(); ++i)          // mkdir -p
+        if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+    char tmp[32];
+    snprintf(tmp, sizeof(tmp), ".tmp-%d-%p", (int)getpid(), (const void *)&cubin);
+    const std::string tpath = dir + "/" + tmp;
+    FILE *f = fopen(tpath.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    fclose(f);
+    if (!ok || rename(tpath.c_str(), path.c_str()) != 0) remove(tpath.c_str());
+}
+
+static std::atomic<uint64_t> g_disk_hits{0};
+
 static int ensure_compiled(Entry *e, const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr) {
     std::lock_guard<std::mutex> g(e->mu);
     if (e->compiled) { g_hits.fetch_add(1); return 0; }
     if (e->failed) { set_error("qsv jit: %s", e->err.c_str()); return 1; }
     const auto t0 = std::chrono::steady_clock::now();
     std::string src;
-    if (generate(P, prog, bytes, src, e->err, sw) || compile_cubin(src, e->cubin, e->err)) {
+    if (generate(P, prog, bytes, src, e->err, sw)) {
         e->failed = true;
         set_error("qsv jit: %s", e->err.c_str());
         return 1;
     }
+    const std::string cpath = disk_cache_path(src);
+    if (disk_cache_load(cpath, e->cubin)) {
+        e->compiled = true;
+        g_disk_hits.fetch_add(1);
+        return 0;
+    }
+    if (compile_cubin(src, e->cubin, e->err)) {
+        e->failed = true;
+        set_error("qsv jit: %s", e->err.c_str());
+        return 1;
+    }
+    disk_cache_store(cpath, e->cubin);
     e->compiled = true;
     g_compiles.fetch_add(1);
     g_compile_us.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(
@@ -1852,6 +1943,8 @@ extern "C" int qsv_jit_wanted(const qsv_pass_t *pass, const void *prog_host, uin
     if (!pass || !prog_host || prog_bytes < sizeof(qsv_rprog_hdr_t)) return 0;
     return jit::wanted(pass, prog_host) ? 1 : 0;
 }
+
+extern "C" uint64_t qsv_jit_disk_hits(void) { return jit::g_disk_hits.load(); }
 
 extern "C" void qsv_jit_stats(uint64_t *kernels_compiled, uint64_t *cache_hits, double *compile_seconds) {
     if (kernels_compiled) *kernels_compiled = jit::g_compiles.load();
