@@ -43,6 +43,13 @@ def parse():
                     help="layered = BASELINE config 3 (headline); qft = config 4 (H + controlled-phase ladder); "
                          "grover = config 5 (oracle + diffusion kernels)")
     ap.add_argument("--iterations", type=int, default=32, help="Grover iterations (config 5)")
+    ap.add_argument("--no-check", action="store_true", help="skip the in-run correctness check (norm, hint on/off, "
+                                                            "circuit^-1 o circuit round trip)")
+    ap.add_argument("--no-big", action="store_true",
+                    help="skip the 137 GB-per-GPU block (33 qubits on one GPU, 33+log2(N) on N: 36 on 8 = north star)")
+    ap.add_argument("--big-steps", type=int, default=3)
+    ap.add_argument("--cpu-threads", type=int, default=0,
+                    help="host threads of the CPU arm (default: min(host cores, 32), the same at every --gpus)")
     return ap.parse_args()
 
 
@@ -103,14 +110,17 @@ class ClockSampler:
 
 
 def traffic_from_profile(kind, n_local):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json: bytes per amplitude), scaled to this state size."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            per_amp = json.load(f)[kind]["dram_bytes_per_amplitude"]
-        return per_amp * (1 << n_local)
-    except (OSError, KeyError, ValueError):
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel for a DENSE sweep (every
+    tile touched), from the committed `ncu --set full` capture (profiles/*_traffic.json: bytes per amplitude),
+    scaled to this state size.  Returns (bytes per dense launch, bytes per amplitude, source)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                per_amp = json.load(f)[kind]["dram_bytes_per_amplitude"]
+            return per_amp * (1 << n_local), per_amp, "profiles/" + name
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None, None
 
 
 def measured_peak_gbs():
@@ -126,10 +136,26 @@ def measured_peak_gbs():
 # CPU baseline: the oracle port on the host cores (bounded sample of the same workload)
 # ------------------------------------------------------------------------------------------------
 
-def cpu_baseline(n_cpu, depth=1, budget_s=25.0):
+def cpu_threads(requested=0):
+    """Host threads of the CPU arm: the same number whatever --gpus is (torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which used to throttle the N>1 reference arm to one thread)."""
+    return int(requested) if requested else max(1, min(os.cpu_count() or 1, 32))
+
+
+def cpu_baseline(n_cpu, depth=1, budget_s=25.0, threads=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    want = cpu_threads(threads)
+    if "numpy" not in sys.modules:      # BLAS pools read these when the library loads
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = str(want)
     import numpy as np
     import statevec_oracle as so
+    limiter = None
+    try:
+        import threadpoolctl
+        limiter = threadpoolctl.threadpool_limits(limits=want)
+    except Exception:
+        pass
     steps = so.random_layered_steps(n_cpu, depth, seed=SEED)
     psi = so.initial_state([0] * n_cpu)
     done = 0
@@ -147,6 +173,8 @@ def cpu_baseline(n_cpu, depth=1, budget_s=25.0):
         threads = max([p["num_threads"] for p in threadpoolctl.threadpool_info()] or [1])
     except Exception:
         threads = 1
+    if limiter is not None:
+        limiter.restore_original_limits()
     return {"value": done / dt, "unit": METRIC, "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
             "sample": "oracle port (numpy restatement of Circuit.run_method2): config-3 generator, %d qubits, "
                       "first %d gates of layer 1 (the reference itself needs 86 s/gate at 10 qubits)" % (n_cpu, done)}
@@ -160,7 +188,7 @@ def run_reference_arm(args):
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(args.cpu_qubits, 1, budget_s=20.0)
+        base = cpu_baseline(args.cpu_qubits, 1, budget_s=20.0, threads=args.cpu_threads)
         if i >= args.warmup:
             vals.append(base["value"])
         if i == 0 and args.warmup > 0:
@@ -176,6 +204,162 @@ def run_reference_arm(args):
             "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
+
+
+# ------------------------------------------------------------------------------------------------
+# in-run correctness check of the layered workload (any N, any size: properties, not an oracle)
+# ------------------------------------------------------------------------------------------------
+
+def layered_check(sv, comm, n, depth, plan, in_index, src_pos, g, roundtrip=True):
+    """Three size-independent properties, evaluated on the state the timed steps produce:
+    (1) the all-reduced norm is 1; (2) the run with the support hint (tiles known to be zero are skipped) and the
+    run without it give bit-identical block sums of |psi|^2; (3) circuit followed by its inverse, lowered, placed
+    and planned like the timed circuit, returns to the input basis state (amplitude 1 at index 0 in output order,
+    and the sampler returns 0)."""
+    import torch
+    import torch.distributed as dist
+    from qsv import lowering, workloads
+    world = comm.world if comm is not None else 1
+    rank = comm.rank if comm is not None else 0
+
+    def allsum(x):
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t.item())
+
+    def allmin(x):
+        t = torch.tensor([int(x)], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
+    sv.init_basis(in_index)
+    sv.execute(plan)
+    sums_hint = sv.block_sums(None, 12).clone()
+    norm = allsum(sums_hint.sum().item())
+    old = os.environ.get("QSV_SPARSE_START")
+    os.environ["QSV_SPARSE_START"] = "0"
+    sv.init_basis(in_index)
+    sv.execute(plan)
+    sums_dense = sv.block_sums(None, 12)
+    if old is None:
+        os.environ.pop("QSV_SPARSE_START")
+    else:
+        os.environ["QSV_SPARSE_START"] = old
+    identical = bool(allmin(int(torch.equal(sums_hint, sums_dense))))
+    out = {"norm_error": abs(norm - 1.0), "hint_on_off_block_sums_bit_identical": identical, "tolerance": 1e-10}
+    ok = abs(norm - 1.0) <= 1e-10 and identical
+    if roundtrip:
+        rt = workloads.random_layered_roundtrip_circuit(n, depth, seed=SEED)
+        rt.sort()
+        ops, rt_src, flip = lowering.lower(rt, n_global=g if comm is not None else 0, in_flip=True,
+                                           free_swap=bool(comm is not None and comm.peer_swap),
+                                           fuse_swaps=sv.fuse_swaps())
+        rt_plan = sv.prepare(ops)
+        sv.init_basis(0 ^ flip)
+        sv.execute(rt_plan)
+        a0 = sv.state[0:1].clone() if rank == 0 else torch.zeros(1, dtype=torch.complex128, device="cuda")
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(a0))
+        a0 = complex(a0[0].item())
+        rt_norm = allsum(sv.block_sums(None, 12).sum().item())
+        z = sv.sample(0.37, rt_src)
+        out.update({"roundtrip_gates": len(rt.gates), "roundtrip_amp0_error": abs(a0 - 1.0),
+                    "roundtrip_norm_error": abs(rt_norm - 1.0), "roundtrip_sampled_index": int(z)})
+        ok = ok and abs(a0 - 1.0) <= 1e-10 and abs(rt_norm - 1.0) <= 1e-10 and int(z) == 0
+        del rt_plan
+    out["ok"] = bool(ok)
+    return out
+
+
+def run_big_shard(args, comm, g, world, rank, barrier):
+    """The 137 GB-per-GPU point: config-3 generator at 33 qubits on one GPU and 33 + log2(N) qubits on N GPUs
+    (36 qubits / 1.1 TB on 8 = BASELINE configs[4] sizing).  Timed like the headline (K steps between
+    barriers, CUDA events, max over ranks), with and without the support hint, plus the in-run check."""
+    import torch
+    import torch.distributed as dist
+    from qsv import engine, lowering, workloads
+    n = 33 + g
+    need = (16 << 33) + (2 << 30)
+    torch.cuda.empty_cache()
+    free = torch.cuda.mem_get_info()[0]
+    t = torch.tensor([free], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    free = int(t.item())
+    if free < need:
+        return {"qubits": n, "skipped": "needs %.1f GB free per GPU, %.1f GB available" % (need / 1e9, free / 1e9)}
+    circ = workloads.random_layered_circuit(n, args.depth, seed=SEED)
+    circ.sort()
+    n_gates = len(circ.gates)
+    t0 = time.perf_counter()
+    sv = engine.StateVector(n, comm=comm)
+    ops, src_pos, flip = lowering.lower(circ, n_global=g if comm is not None else 0, in_flip=True,
+                                        free_swap=bool(comm is not None and comm.peer_swap),
+                                        fuse_swaps=sv.fuse_swaps())
+    plan = sv.prepare(ops)
+    t_prep = time.perf_counter() - t0
+    in_index = 0 ^ flip
+
+    def step():
+        sv.init_basis(in_index)
+        sv.execute(plan)
+        return sv.sample(0.37, src_pos)
+
+    def timed(k):
+        for _ in range(2):
+            step()
+        if comm is not None:
+            comm.swap_stats()
+        b0 = comm.bytes_sent if comm is not None else 0
+        f0 = getattr(comm, "fused_swaps", 0) if comm is not None else 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0 = sv.passes_run
+        barrier()
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        sw = None
+        if comm is not None:
+            n_sw, sw_ms = comm.swap_stats()
+            out_b = comm.bytes_sent - b0
+            gbs = out_b / (sw_ms * 1e-3) / 1e9 if sw_ms > 0 else 0.0
+            sw = {"swaps_per_step": n_sw / k, "ms_per_step": sw_ms / k, "bytes_out_per_gpu_per_step": out_b / k,
+                  "achieved_GBps_out_per_gpu": gbs, "frac_of_nvlink": gbs / 770.0,
+                  "fused_with_pass_per_step": (getattr(comm, "fused_swaps", 0) - f0) / k}
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms / k, (sv.passes_run - p0) // k, sw
+
+    k = max(1, args.big_steps)
+    ms_hint, passes, sw_hint = timed(k)
+    os.environ["QSV_SPARSE_START"] = "0"
+    ms_dense, _, sw_dense = timed(k)
+    os.environ.pop("QSV_SPARSE_START")
+    check = None if args.no_check else layered_check(sv, comm, n, args.depth, plan, in_index, src_pos, g)
+    out = {"qubits": n, "gates": n_gates, "state_bytes_per_gpu": 16 << sv.n_local, "steps": k, "warmup": 2,
+           "ms_per_step": ms_hint, "circuit_gates_per_sec": n_gates / (ms_hint * 1e-3),
+           "value": n_gates * world / (ms_hint * 1e-3), "passes_per_step": passes,
+           "dense_start": {"ms_per_step": ms_dense, "circuit_gates_per_sec": n_gates / (ms_dense * 1e-3)},
+           "prepare_wall_s": t_prep, "check": check,
+           "workload": "config-3 generator, %d qubits, depth %d, %d gates, complex128, one sample per step; "
+                       "2^33 amplitudes (137.4 GB) per GPU" % (n, args.depth, n_gates)}
+    if sw_hint is not None:
+        out["swap"] = sw_hint
+        out["dense_start"]["swap"] = sw_dense
+    del plan
+    sv.state = None
+    del sv
+    if comm is not None:
+        comm.release_state()
+    torch.cuda.empty_cache()
+    return out
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
@@ -356,8 +540,16 @@ def main():
                    if jc.value else "qsv::k_pass_reg / k_pass (tiled TMA gate pass)")
     names = {"pass": pass_kernel,
              "diffusion": "qsv::k_diff_partial + k_diff_update (Grover diffusion)"}
+    tr_bytes, tr_per_amp, tr_src = traffic_from_profile(dom, n_local)
     roofline = {"bound": "hbm", "kernel": names.get(dom, dom), "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(dom, n_local),
+                "unit": "GB/s", "frac": achieved / peak, "traffic": tr_bytes,
+                "traffic_note": (None if tr_bytes is None else
+                                 "DRAM read+write bytes of ONE DENSE sweep (every tile touched) of this kernel, from the "
+                                 "ncu --set full capture in %s scaled to 2^%d amplitudes: %.3f B/amplitude = %.3f x the "
+                                 "algorithmic 32 B/amplitude (no re-reads); compare with algorithmic_bytes_per_dense_launch,"
+                                 " not with the per-launch average below, which includes launches that skip zero tiles"
+                                 % (tr_src, n_local, tr_per_amp, tr_per_amp / 32.0)),
+                "algorithmic_bytes_per_dense_launch": 32.0 * (1 << n_local),
                 "peak_source": peak_src, "launches_timed": d["launch_groups"],
                 "avg_launch_ms": d["ms"] / max(1, d["launch_groups"]),
                 "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launch_groups"]),
@@ -373,6 +565,9 @@ def main():
     gate_pass = None
     if not args.no_gate_pass and rank == 0 and world == 1:
         gate_pass = single_gate_sweep(sv, peak)
+
+    if args.workload == "layered" and not args.no_check:
+        check = layered_check(sv, comm, n, args.depth, plan, in_index, src_pos, g)
 
     # ---- end to end through the public API: Circuit.run(in_v, 2) with host inputs
     in_v = in_bits
@@ -431,6 +626,17 @@ def main():
                "api": "main.circuit.Circuit.run(in_v, 2) on every rank (register sharded by qsv.dist.default_comm)"}
         lowering.release_sharded_states()
 
+    # ---- the 137 GB-per-GPU point (33 qubits on one GPU / 33 + log2(N) on N; 36 qubits on 8 = the north star)
+    big = None
+    if args.workload == "layered" and not args.no_big and not args.qubits:
+        sv = plan = timed = None
+        if comm is not None:
+            comm.release_state()
+        lowering.release_sharded_states()
+        engine._PLAN_CACHE.clear()
+        torch.cuda.empty_cache()
+        big = run_big_shard(args, comm, g, world, rank, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -464,8 +670,13 @@ def main():
         line["swap"] = swap
     if check is not None:
         line["check"] = check
+    if big is not None:
+        key = ("north_star_36q" if big["qubits"] == 36 else
+               "one_gpu_33q" if world == 1 else "big_shard_%dq" % big["qubits"])
+        line[key] = big
+        line["big_shard_key"] = key
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(args.cpu_qubits)
+        line["cpu_baseline"] = cpu_baseline(args.cpu_qubits, threads=args.cpu_threads)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,10 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - Every function returns 0 on success, non-zero on error; qsv_last_error() then returns a
  *     thread-local message.  Nothing here ever falls back to the CPU.
+ *   - Threading: every entry point may be called from several host threads at once (each on its own
+ *     stream and state, or for compilation only); the library keeps no per-call state in shared statics
+ *     (the kernel cache is mutex-protected, launch scratch and the error string are thread-local).
+ *     Two calls that touch the SAME state buffer must be ordered by the caller (same stream or events).
  */
 #ifndef QSV_H
 #define QSV_H

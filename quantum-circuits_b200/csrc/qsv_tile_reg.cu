@@ -385,13 +385,13 @@ static_assert(sizeof(qsv_round_t) == 16 && sizeof(qsv_rprog_hdr_t) == 16, "round
 static_assert(sizeof(qsv_op_t) == 88 && sizeof(qsv_pass_t) == 48, "struct layout mirrored in qsv/schedule.py");
 
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
+    static int cached[64] = {0};           // per device ordinal (benign race: every writer stores the same value)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
     return n;
 }
 
@@ -452,7 +452,9 @@ static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *pro
     const size_t need = sizeof(qsv_rprog_hdr_t) + sizeof(qsv_round_t) * hdr->n_rounds + sizeof(qsv_rop_t) * hdr->n_ops;
     QSV_CHECK_ARG(prog_bytes >= need, "qsv_run_pass_rounds: prog_bytes=%u smaller than the %zu bytes the header implies",
                   prog_bytes, need);
-    static RProgParam param;       // repacked: fixed-capacity arrays inside the kernel parameter
+    // repacked: fixed-capacity arrays inside the kernel parameter.  Per thread (not a shared static): host threads may
+    // launch passes concurrently, each on its own stream; the launch copies the parameter before it returns.
+    static thread_local RProgParam param;
     memset(&param, 0, sizeof(param));
     param.hdr = *hdr;
     const uint8_t *src = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);

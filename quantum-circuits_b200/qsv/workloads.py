@@ -16,43 +16,65 @@ from . import gates as xg
 
 # ---- config 3: random H / X / T8 / phase layers + CNot / CZ matchings ----------------------------
 
-def random_layered_circuit(n, depth, seed=20261019):
-    """Per layer: one 1-qubit gate on every wire drawn from {H, X, phase(pi/4), phase(uniform)}, then a
-    random perfect matching of the wires with CNot or CZ on each pair: n + n//2 gates per layer."""
+def _layered_specs(n, depth, seed):
+    """Gate list of the config-3 generator: [(kind, wires, angle)], kind in H / X / T8 / P / CNot / CZ."""
     rng = random.Random(seed)
-    c = mc.Circuit(n)
-    last = [(c, i) for i in range(n)]
-
-    def put(gate, wires):
-        c.add(gate)
-        for p, w in enumerate(wires):
-            c.add_wire(last[w][0], last[w][1], gate, p)
-            last[w] = (gate, p)
-
-    k = 0
+    specs = []
     for _ in range(depth):
         for w in range(n):
             r = rng.randrange(4)
             if r == 0:
-                g = mc.H(1, "H_%d" % k)
+                specs.append(("H", (w,), None))
             elif r == 1:
-                g = mc.X(1, "X_%d" % k)
+                specs.append(("X", (w,), None))
             elif r == 2:
-                g = xg.Phase(math.pi / 4, "T8_%d" % k)
+                specs.append(("T8", (w,), math.pi / 4))
             else:
-                g = xg.Phase(rng.uniform(0, 2 * math.pi), "P_%d" % k)
-            put(g, [w])
-            k += 1
+                specs.append(("P", (w,), rng.uniform(0, 2 * math.pi)))
         order = list(range(n))
         rng.shuffle(order)
         for i in range(0, n - 1, 2):
-            a, b = order[i], order[i + 1]
-            g = mc.CNot("CNot_%d" % k) if rng.randrange(2) == 0 else xg.CZ("CZ_%d" % k)
-            put(g, [a, b])
-            k += 1
+            specs.append(("CNot" if rng.randrange(2) == 0 else "CZ", (order[i], order[i + 1]), None))
+    return specs
+
+
+def _circuit_from_specs(n, specs):
+    c = mc.Circuit(n)
+    last = [(c, i) for i in range(n)]
+    for k, (kind, wires, angle) in enumerate(specs):
+        name = "%s_%d" % (kind, k)
+        if kind == "H":
+            g = mc.H(1, name)
+        elif kind == "X":
+            g = mc.X(1, name)
+        elif kind in ("T8", "P"):
+            g = xg.Phase(angle, name)
+        elif kind == "CNot":
+            g = mc.CNot(name)
+        else:
+            g = xg.CZ(name)
+        c.add(g)
+        for p, w in enumerate(wires):
+            c.add_wire(last[w][0], last[w][1], g, p)
+            last[w] = (g, p)
     for w in range(n):
         c.add_wire(last[w][0], last[w][1], c, w)
     return c
+
+
+def random_layered_circuit(n, depth, seed=20261019):
+    """Per layer: one 1-qubit gate on every wire drawn from {H, X, phase(pi/4), phase(uniform)}, then a
+    random perfect matching of the wires with CNot or CZ on each pair: n + n//2 gates per layer."""
+    return _circuit_from_specs(n, _layered_specs(n, depth, seed))
+
+
+def random_layered_roundtrip_circuit(n, depth, seed=20261019):
+    """The config-3 circuit followed by its inverse (gates in reverse order, phases conjugated; H, X, CNot
+    and CZ are their own inverses): maps every basis state to itself.  A size-independent correctness
+    check for registers far beyond the oracle's reach (bench.py `check`, 30-36 qubits)."""
+    fwd = _layered_specs(n, depth, seed)
+    inv = [(kind, wires, None if angle is None else -angle) for kind, wires, angle in reversed(fwd)]
+    return _circuit_from_specs(n, fwd + inv)
 
 
 # ---- config 4: QFT as H + controlled-phase ladder ------------------------------------------------

@@ -107,6 +107,34 @@ def main():
             del sv
         os.environ.pop("QSV_JIT")
 
+    # 1c. QFT as H + controlled-phase ladder on a sharded register (config 4): every wire gets one H, so every global
+    #     qubit has to come down once; closed form of Matrix.QFT on a basis state (main/matrix.py:212-219, sign +i):
+    #     psi[k] = exp(2 pi i x k / 2^n) / sqrt(2^n) in output order (the bit reversal sits in the output wiring)
+    for n, jit in ((12 + g, None), (16 + g, "force")) if comm.peer_swap else ((12 + g, None),):
+        if jit:
+            os.environ["QSV_JIT"] = jit
+        c = workloads.qft_ladder_circuit(n)
+        c.sort()
+        in_v = [(i + 1) % 2 for i in range(n)]
+        x = lowering.basis_index(in_v)
+        k = np.arange(1 << n, dtype=np.float64)
+        ref = np.exp(2j * np.pi * ((x * k) % (1 << n)) / (1 << n)) / np.sqrt(float(1 << n))
+        sv = engine.StateVector(n, comm=comm)
+        for free in ([False, True] if comm.peer_swap else [False]):
+            ops, src_pos, flip = lowering.lower(c, n_global=g, in_flip=True, free_swap=free,
+                                                fuse_swaps=sv.fuse_swaps() if free else False)
+            swaps0, fused0 = comm.swaps, getattr(comm, "fused_swaps", 0)
+            sv.init_basis(x ^ flip)
+            sv.run_ops(ops)
+            sv.synchronize()
+            full = gather_full(sv, comm)
+            err = np.max(np.abs(to_output_order(full, src_pos) - ref))
+            check("qft ladder n=%d jit=%s free_swap=%s swaps=%d fused=%d err=%.2e"
+                  % (n, jit, free, comm.swaps - swaps0, getattr(comm, "fused_swaps", 0) - fused0, err), err <= 1e-12)
+        del sv
+        if jit:
+            os.environ.pop("QSV_JIT")
+
     # 2. Grover with the dedicated oracle + diffusion kernels (all-reduce of the two means)
     ns, K, x = 9 + g, 5, 0b1011001 % (1 << (9 + g))
     c = workloads.grover_circuit(ns, x, K)
