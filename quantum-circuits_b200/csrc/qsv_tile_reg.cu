@@ -432,7 +432,14 @@ static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *pro
     // larger) program capacity, so it is tried before the interpreter's kernel-parameter limits apply.
     if (RB == 4 && jit::wanted(P, prog_host)) {
         const uint64_t n_tiles_j = 1ull << (P->n_local - P->tile_bits);
-        const uint64_t resident_j = (uint64_t)sm_count() * 2ull * 4ull;
+        // persistent CTAs, 2 resident per SM; the grid holds QSV_JIT_WAVES (default 16; measured 4 -> 16: single-gate sweep 5.45 -> 5.2 ms) times as many, so that the
+        // hardware scheduler evens out SMs that run at different speeds (the tail of a static split is one CTA long)
+        static const unsigned waves = [] {
+            const char *e = getenv("QSV_JIT_WAVES");
+            const int v = e ? atoi(e) : 16;
+            return (unsigned)(v >= 1 && v <= 4096 ? v : 16);
+        }();
+        const uint64_t resident_j = (uint64_t)sm_count() * 2ull * waves;
         const unsigned grid_j = (unsigned)(n_tiles_j < resident_j ? n_tiles_j : resident_j);
         const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid_j,
                                    sp_mask, sp_val);
