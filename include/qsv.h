@@ -170,6 +170,14 @@ int qsv_init_basis(void *state_dev, int n_local, uint64_t index, uint64_t rank, 
 int qsv_run_pass(void *state_dev, const qsv_pass_t *pass, const void *prog_dev,
                  const uint32_t *op_offsets_dev, int n_ops, void *stream);
 
+/* qsv_run_pass restricted to the tiles whose global base index equals `fixed_val` on the bits of `fixed_mask`
+ * (local positions outside the tile and/or global positions as in pass->rank_bits; bits inside the tile are ignored).
+ * The caller pins what it knows: the support of a register that started in a basis state (main/circuit.py:290-301,
+ * see qsv_run_pass_rounds_sparse) and/or a control value shared by every op of the program.  The grid enumerates the
+ * remaining tiles only, so a CZ / Toffoli pass spends no CTA on the 3/4 of the tiles it would skip anyway. */
+int qsv_run_pass_sparse(void *state_dev, const qsv_pass_t *pass, const void *prog_dev, const uint32_t *op_offsets_dev,
+                        int n_ops, uint64_t fixed_mask, uint64_t fixed_val, void *stream);
+
 /* Same contract as qsv_run_pass for a register-resident program (see qsv_rop_t).  `prog_host` is HOST
  * memory (at most QSV_RPROG_MAX_ROUNDS rounds / QSV_RPROG_MAX_OPS ops); `tables_dev` is the device
  * buffer diagonal ops index with table_off (may be NULL if the program has none).  tile_bits >= 4. */

@@ -20,7 +20,7 @@ void set_error(const char *fmt, ...) {
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int launch_pass(void *state_dev, const qsv_pass_t *P, const void *prog_dev, const uint32_t *op_off_dev, int n_ops,
-                bool wide_k, cudaStream_t st);
+                bool wide_k, cudaStream_t st, uint64_t fixed_mask = 0, uint64_t fixed_val = 0);
 
 constexpr int kDefaultT = 12;
 constexpr int kDefaultL = 6;
@@ -113,7 +113,9 @@ static int run_single(void *state_dev, const Plan &pl, OpBuilder &ob, int dense_
     QSV_CUDA(cudaMemcpyAsync(dev, host.data(), total, cudaMemcpyHostToDevice, st));
     qsv_pass_t pass = pl.pass;
     pass.max_dense_k = dense_k;
-    int rc = launch_pass(state_dev, &pass, dev, reinterpret_cast<const uint32_t *>(dev), 1, dense_k > 3, st);
+    // the single op's external controls pin those index bits for every tile the launch has to visit
+    int rc = launch_pass(state_dev, &pass, dev, reinterpret_cast<const uint32_t *>(dev), 1, dense_k > 3, st,
+                         ob.hdr()->ext_ctrl_mask, ob.hdr()->ext_ctrl_val);
     cudaFreeAsync(dev, st);
     return rc;
 }
@@ -143,6 +145,17 @@ extern "C" int qsv_run_pass(void *state_dev, const qsv_pass_t *pass, const void 
                   "qsv_run_pass: max_dense_k=%d exceeds %d", pass->max_dense_k, QSV_MAX_TILE_K);
     return launch_pass(state_dev, pass, prog_dev, op_offsets_dev, n_ops, pass->max_dense_k > 3,
                        (cudaStream_t)stream);
+}
+
+extern "C" int qsv_run_pass_sparse(void *state_dev, const qsv_pass_t *pass, const void *prog_dev,
+                                   const uint32_t *op_offsets_dev, int n_ops, uint64_t fixed_mask, uint64_t fixed_val,
+                                   void *stream) {
+    QSV_CHECK_ARG(pass, "qsv_run_pass_sparse: pass is NULL");
+    QSV_CHECK_ARG(pass->max_dense_k >= 0 && pass->max_dense_k <= QSV_MAX_TILE_K,
+                  "qsv_run_pass_sparse: max_dense_k=%d exceeds %d", pass->max_dense_k, QSV_MAX_TILE_K);
+    QSV_CHECK_ARG((fixed_val & ~fixed_mask) == 0, "qsv_run_pass_sparse: fixed_val has bits outside fixed_mask");
+    return launch_pass(state_dev, pass, prog_dev, op_offsets_dev, n_ops, pass->max_dense_k > 3,
+                       (cudaStream_t)stream, fixed_mask, fixed_val);
 }
 
 extern "C" int qsv_apply_dense(void *state_dev, int n_local, int k, const int *targets, int n_ctrl,

@@ -9,6 +9,7 @@
 // back with bulk stores.  Controls and diagonal factors on bits OUTSIDE the tile are constants of
 // the tile; a tile for which every op is switched off by its external controls is never loaded.
 #include "qsv_common.cuh"
+#include <string.h>
 
 namespace qsv {
 
@@ -198,10 +199,16 @@ __device__ __forceinline__ void tile_diag(double2 *tile, const OpView &v, int T,
     }
 }
 
+struct TileFix {          // pinned bits of the tile index, ascending; bit k of `val` is the value of entry k
+    int32_t n;
+    uint8_t bit[40];
+    uint64_t val;
+};
+
 template <int KMAX>
 __global__ void __launch_bounds__(kThreads, (KMAX <= 3) ? 3 : 1)
 k_pass(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P, const uint8_t *__restrict__ prog,
-       const uint32_t *__restrict__ op_off, int n_ops, uint64_t n_tiles) {
+       const uint32_t *__restrict__ op_off, int n_ops, uint64_t n_tiles, const __grid_constant__ TileFix fix) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *tile = reinterpret_cast<double2 *>(smem_raw);
     __shared__ __align__(8) uint64_t mbar;
@@ -225,7 +232,12 @@ k_pass(double2 *__restrict__ state, const __grid_constant__ qsv_pass_t P, const 
     __syncthreads();
 
     uint32_t parity = 0;
-    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // `n_tiles` counts the CANDIDATE tiles: tile-index bits listed in `fix` are pinned (support of the state and/or a
+    // control shared by every op), the grid enumerates the others only - no CTA is spent on a tile known to be skipped
+    for (uint64_t c = blockIdx.x; c < n_tiles; c += gridDim.x) {
+        uint64_t t = c;
+        for (int k = 0; k < fix.n; ++k)
+            t = insert_zero(t, fix.bit[k]) | (((fix.val >> k) & 1ull) << fix.bit[k]);
         uint64_t base = t << L;
         for (int j = 0; j < n_hi; ++j) base = insert_zero(base, P.hi_pos[j]);
         const uint64_t gbase = base | P.rank_bits;
@@ -295,11 +307,29 @@ static int validate_pass(const qsv_pass_t *P) {
 }
 
 int launch_pass(void *state_dev, const qsv_pass_t *P, const void *prog_dev, const uint32_t *op_off_dev, int n_ops,
-                bool wide_k, cudaStream_t st) {
+                bool wide_k, cudaStream_t st, uint64_t fixed_mask, uint64_t fixed_val) {
     if (int rc = validate_pass(P)) return rc;
     QSV_CHECK_ARG(state_dev && prog_dev && op_off_dev, "qsv_run_pass: NULL device pointer");
     if (n_ops <= 0) return 0;
-    const uint64_t n_tiles = 1ull << (P->n_local - P->tile_bits);
+    // index bits the caller pins (support hint / controls common to all ops): global ones decide whether this shard
+    // has any work at all, local ones outside the tile shrink the grid; bits inside the tile cannot skip anything
+    TileFix fix;
+    memset(&fix, 0, sizeof(fix));
+    const uint64_t local_mask = (1ull << P->n_local) - 1ull;
+    if ((fixed_mask & ~local_mask) && ((P->rank_bits ^ fixed_val) & fixed_mask & ~local_mask)) return 0;
+    {
+        int idx_bit = 0, j = 0;
+        for (int p = P->low_bits; p < P->n_local; ++p) {
+            if (j < P->n_hi && P->hi_pos[j] == p) { ++j; continue; }
+            if ((fixed_mask >> p) & 1ull) {
+                fix.bit[fix.n] = (uint8_t)idx_bit;
+                fix.val |= ((fixed_val >> p) & 1ull) << fix.n;
+                ++fix.n;
+            }
+            ++idx_bit;
+        }
+    }
+    const uint64_t n_tiles = 1ull << (P->n_local - P->tile_bits - fix.n);
     const size_t smem = (size_t)16 << P->tile_bits;
     const unsigned grid = (unsigned)(n_tiles < (1ull << 30) ? n_tiles : (1ull << 30));
     static bool attr_done[2] = {false, false};
@@ -314,10 +344,10 @@ int launch_pass(void *state_dev, const qsv_pass_t *P, const void *prog_dev, cons
     }
     if (wide_k)
         k_pass<5><<<grid, kThreads, smem, st>>>((double2 *)state_dev, *P, (const uint8_t *)prog_dev, op_off_dev,
-                                                 n_ops, n_tiles);
+                                                 n_ops, n_tiles, fix);
     else
         k_pass<3><<<grid, kThreads, smem, st>>>((double2 *)state_dev, *P, (const uint8_t *)prog_dev, op_off_dev,
-                                                 n_ops, n_tiles);
+                                                 n_ops, n_tiles, fix);
     QSV_LAUNCH_CHECK();
     return 0;
 }

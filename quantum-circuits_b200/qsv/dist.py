@@ -94,14 +94,36 @@ class Comm:
                 self.peer_swap = False
         return torch.empty(n_amps, dtype=torch.complex128, device=device)
 
-    def _moved_bytes(self, sv, n_swap, support):
-        """Bytes this rank sends in a swap of n_swap qubits: (1 - 2^-n_swap) of the shard, times the fraction of the
-        exchanged pairs that are not known to be zero on both sides (support hint; an upper estimate)."""
-        full = 16 * ((1 << n_swap) - 1) * (1 << (sv.n_local - n_swap))
-        if support is None or not support[0]:
-            return full
-        local_fixed = bin(support[0] & ((1 << sv.n_local) - 1)).count("1")
-        return int(full * min(1.0, 2.0 * 2.0 ** -local_fixed))
+    def _moved_bytes(self, sv, positions, gbits, support):
+        """Bytes this rank sends in a swap of local `positions` against global bits `gbits`: 16 B for every element
+        that changes rank, (1 - 2^-j) of the shard, and - with a support hint - only for the pairs of which at least
+        one side can be non-zero (the kernels skip the others).  Exact: only the swapped bits and the pinned bits
+        decide, every other local bit is a factor of two."""
+        nl, j = sv.n_local, len(positions)
+        mask, val = support if support is not None else (0, 0)
+        local_mask = (1 << nl) - 1
+        swapped_g = sum(1 << (nl + b) for b in gbits)
+        if ((self.rank << nl) ^ val) & mask & ~local_mask & ~swapped_g:
+            return 0                    # a pinned global bit outside the swap: the whole shard is zero on both sides
+        pos_mask = sum(1 << p for p in positions)
+        free = nl - j - bin(mask & local_mask & ~pos_mask).count("1")
+        rg = [(self.rank >> b) & 1 for b in gbits]
+
+        def in_support(pbits, gvals):
+            for k in range(j):
+                gp = nl + gbits[k]
+                if (mask >> positions[k]) & 1 and pbits[k] != (val >> positions[k]) & 1:
+                    return False
+                if (mask >> gp) & 1 and gvals[k] != (val >> gp) & 1:
+                    return False
+            return True
+
+        count = 0
+        for a in range(1 << j):
+            ab = [(a >> k) & 1 for k in range(j)]
+            if ab != rg and (in_support(ab, rg) or in_support(rg, ab)):
+                count += 1
+        return (16 * count) << free
 
     def _swap_peer(self, sv, n_swap, positions=None, gbits=None, support=None):
         raw, hdl, ptrs = self._symm
@@ -117,7 +139,9 @@ class Comm:
         ev[1].record()
         hdl.barrier()                                   # nobody touches its shard before all swaps landed
         self.swap_events.append(ev)
-        self.bytes_sent += self._moved_bytes(sv, n_swap, support)
+        self.bytes_sent += self._moved_bytes(sv, list(positions) if positions is not None else
+                                             list(range(sv.n_local - n_swap, sv.n_local)),
+                                             list(gbits) if gbits is not None else list(range(n_swap)), support)
         self.swaps += 1
 
     def _flag_arrays(self, device):
@@ -156,7 +180,7 @@ class Comm:
         ev[1].record()
         self.swap_events.append(ev)
         self.fused_swaps = getattr(self, "fused_swaps", 0) + 1
-        self.bytes_sent += self._moved_bytes(sv, len(positions), support)
+        self.bytes_sent += self._moved_bytes(sv, list(positions), gb, support)
         self.swaps += 1
 
     def _check_owner(self, sv):

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .schedule import Op, TILED_KINDS, Support, plan_passes, pack_passes, swap_fields
+from .schedule import Op, TILED_KINDS, Support, plan_passes, pack_passes, swap_fields, common_external_controls
 
 SCAN_BITS_EXACT = 20     # up to 2^20 outcomes: one fully sequential scan (bit-exact with random.choices)
 SAMPLE_BLOCK_BITS = 12   # larger states: block sums of 2^12 outcomes, then a sequential scan inside one block
@@ -278,7 +278,8 @@ class StateVector:
                     batch = []
                 if kind == "swap_pass":
                     swap_op, ps, pass_first = item
-                    packed = pack_passes([ps])
+                    packed = pack_passes([ps], min_ops=0)   # a round program whatever its size: only those can ride
+
                     if len(packed.passes) == 1 and self._jit_runs(packed.passes[0]):
                         host_plan.append(("swap_pass", (swap_op, packed, pass_first)))
                     elif pass_first:            # not a single specialised kernel: the two steps on their own
@@ -444,8 +445,16 @@ class StateVector:
                         "qsv_run_pass_rounds")
             return
         cp.max_dense_k = maxk
-        _cabi.check(self.lib.qsv_run_pass(self._ptr(self.state), C.byref(cp), C.c_void_p(base),
-                                          C.c_void_p(base + table_off), n_ops, self._stream()), "qsv_run_pass")
+        # tiles that cannot hold work are not even enumerated: the support hint plus the external controls every op
+        # of the pass shares (a lone CZ / Toffoli / controlled phase touches 1/4 of the tiles)
+        mask, val = common_external_controls(ps)
+        if support is not None and support[0]:
+            if (support[1] ^ val) & support[0] & mask:
+                return                      # the shared control contradicts the support: nothing to do
+            mask, val = mask | support[0], val | support[1]
+        _cabi.check(self.lib.qsv_run_pass_sparse(self._ptr(self.state), C.byref(cp), C.c_void_p(base),
+                                                 C.c_void_p(base + table_off), n_ops, int(mask), int(val),
+                                                 self._stream()), "qsv_run_pass_sparse")
 
     def time_passes(self, plan, repeats=1):
         """CUDA-event duration (ms) of every k_pass launch of the plan, on the launching stream."""

@@ -1301,7 +1301,25 @@ def use_register_kernel():
     return os.environ.get("QSV_REGISTER_KERNEL", "1") != "0"
 
 
-def pack_passes(passes, register_kernel=None):
+def common_external_controls(ps):
+    """(mask, val) over physical index bits: the control values EVERY op of the pass requires on positions outside
+    its tile (local or global).  A tile whose base index disagrees is skipped by all ops, so launches enumerate the
+    others only (qsv_run_pass_sparse)."""
+    common = None
+    for op in ps.ops:
+        cv = op.cvals if op.cvals is not None else (1,) * len(op.controls)
+        ext = {(c, 1 if v else 0) for c, v in zip(op.controls, cv) if c >= ps.n_local or ps.loc(c) < 0}
+        common = ext if common is None else common & ext
+        if not common:
+            return 0, 0
+    mask = val = 0
+    for c, v in common or ():
+        mask |= 1 << c
+        val |= v << c
+    return mask, val
+
+
+def pack_passes(passes, register_kernel=None, min_ops=None):
     """Device image [offset tables | ops] for the passes that run on the shared-memory kernel (op
     offsets relative to the start of the buffer).  Passes the register-resident kernel can run carry a
     HOST round program instead (it is passed to the kernel by value) plus, if they use diagonal tables,
@@ -1320,7 +1338,7 @@ def pack_passes(passes, register_kernel=None):
             mode = os.environ.get("QSV_REG_MCX", "1")
             specialised = False if (max_ops <= RPROG_MAX_OPS or mode == "0") else ("all" if mode == "all" else True)
             rounds = plan_rounds(ps, reg_mcx=specialised, padded_layout=max_ops > RPROG_MAX_OPS) \
-                if len(ps.ops) > int(os.environ.get("QSV_REG_MIN_OPS", "2")) else None
+                if len(ps.ops) > (int(os.environ.get("QSV_REG_MIN_OPS", "2")) if min_ops is None else min_ops) else None
             if rounds is not None:
                 enc = encode_rounds(ps, rounds, max_rounds, max_ops)
                 if enc is None and len(ps.ops) >= 8:

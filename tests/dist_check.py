@@ -85,6 +85,7 @@ def main():
     # 1b. swap + pass fused into one kernel over peer memory (specialised kernels forced at this small size)
     if comm.peer_swap:
         os.environ["QSV_JIT"] = "force"
+        fused_total = 0
         for n, depth, seed in ((16 + g, 16, 12), (17 + g, 24, 13)):
             c = workloads.random_layered_circuit(n, depth, seed=seed)
             c.sort()
@@ -101,10 +102,13 @@ def main():
                 sv.synchronize()
             full = gather_full(sv, comm)
             err = np.max(np.abs(to_output_order(full, src_pos) - ref))
+            fused_total += getattr(comm, "fused_swaps", 0) - fused0
             check("fused swap+pass n=%d depth=%d fused_kernels=%d err=%.2e"
-                  % (n, depth, getattr(comm, "fused_swaps", 0) - fused0, err),
-                  err <= 1e-12 and getattr(comm, "fused_swaps", 0) > fused0)
+                  % (n, depth, getattr(comm, "fused_swaps", 0) - fused0, err), err <= 1e-12)
             del sv
+        # whether a given swap can carry a pass is the planner's call (victims outside the pass's tile); across the two
+        # circuits at least one fused kernel must have run, or this section tested nothing
+        check("fused swap+pass kernels executed: %d" % fused_total, fused_total > 0)
         os.environ.pop("QSV_JIT")
 
     # 1c. QFT as H + controlled-phase ladder on a sharded register (config 4): every wire gets one H, so every global
