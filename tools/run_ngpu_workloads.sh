@@ -23,4 +23,4 @@ PY
 qa=""; [ "$QQ" != "0" ] && qa="--qubits $QQ"
 ga=""; [ "$GQ" != "0" ] && ga="--qubits $GQ"
 run qft --workload qft $qa --no-cpu-baseline --no-gate-pass --no-big
-run grover --workload grover $ga --no-cpu-baseline --no-gate-pass --no-big
+run grover --workload grover $ga --steps 3 --no-cpu-baseline --no-gate-pass --no-big
