@@ -275,6 +275,43 @@ int qsv_probs(const void *state_dev, int n_local, const int *src_pos, void *out_
 /* sums_dev[j] = sum of |psi|^2 over output indices z in [j*2^block_bits, (j+1)*2^block_bits). */
 int qsv_block_sums(const void *state_dev, int n_local, const int *src_pos, int block_bits,
                    void *sums_dev, void *stream);
+/* ---- exact sampling on large and sharded registers (csrc/qsv_sample.cu) -----------------------------------------
+ * random.choices (main/circuit.py:360-364) picks index = bisect_right(accumulate(weights), u * total, 0, N - 1).  Above
+ * 2^20 outcomes, and on every sharded register, that rule is evaluated in OUTPUT order with exact 128-bit fixed-point
+ * sums (2^-96 units; integer addition is associative, so the outcome is the same for 1, 2, 4 or 8 shards) by a radix
+ * descent over the output index: per level qsv_sample_level accumulates 2^n_bits bucket sums over the elements still
+ * compatible with the bits chosen so far, the caller all-reduces the int64 bucket arrays over the ranks, and
+ * qsv_sample_select picks the bucket holding the target; qsv_sample_leaf + qsv_sample_select resolve the last <= 12
+ * bits.  Only the 64-byte state below returns to the host. */
+#define QSV_SAMPLE_MAX_LEVEL_BITS 12
+typedef struct {
+    uint64_t fixed_val;     /* physical index bits (global ones included) pinned by the levels so far          */
+    uint64_t z;             /* output index bits chosen so far: the outcome once every level has run            */
+    uint64_t target[2];     /* remaining target weight, fixed point 2^-96 (lo, hi)                               */
+    uint64_t total[2];      /* total weight of the state (set by the first select)                               */
+    uint64_t status;        /* 0 = ok, 1 = the total weight is zero (random.choices raises ValueError)           */
+    uint64_t levels_done;
+} qsv_sample_state_t;
+/* Zero the device-side state before a new draw. */
+int qsv_sample_begin(void *sel_dev, void *stream);
+/* Bucket sums of one level.  `fixed_mask`: physical positions (local and pre-shifted global) pinned by earlier levels;
+ * `bucket_pos[k]`: physical position feeding bucket bit k (k = 0 least significant; at most two of them among the ten
+ * lowest free local positions - split the level otherwise); `buckets_dev`: int64[4 << n_bits], zeroed here, four
+ * 32-bit limbs per bucket held in 64-bit words (sums of up to 2^32 ranks/CTAs cannot overflow). */
+int qsv_sample_level(const void *state_dev, int n_local, uint64_t rank_bits, uint64_t fixed_mask, int n_bits,
+                     const int *bucket_pos, const void *sel_dev, void *buckets_dev, void *stream);
+/* The last bits: every remaining element is stored at its own slot of `buckets_dev` (same layout). */
+int qsv_sample_leaf(const void *state_dev, int n_local, uint64_t rank_bits, uint64_t fixed_mask, int n_bits,
+                    const int *leaf_pos, const void *sel_dev, void *buckets_dev, void *stream);
+/* Pick the bucket that holds the target and update *sel_dev.  first != 0: also computes the total and the target
+ * floor(total * u) for u = u_mant * 2^-u_shift (u_mant < 2^53: math.frexp of the Python float, exact). */
+int qsv_sample_select(const void *buckets_dev, int n_bits, const int *bucket_pos, const int *out_bits, int first,
+                      uint64_t u_mant, int u_shift, void *sel_dev, void *stream);
+/* Registers of up to 2^20 outcomes on one GPU: the sequential float scan (bit-exact with CPython's accumulate +
+ * bisect) in ONE launch - total, then target = u * total, then the search.  result_dev: {uint64 index, double total}. */
+int qsv_sample_sequential(const void *state_dev, int n_local, const int *src_pos, double u, void *result_dev,
+                          void *stream);
+
 /* Sequential left-to-right accumulation from `prefix`, starting at output index z_start: writes the
  * first z with cum > target to result_dev[0] (uint64), clamped to z_last, and the running sum at
  * the point where the scan stopped to result_dev[1] (double) — with target = +inf that is the

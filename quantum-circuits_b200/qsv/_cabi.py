@@ -70,6 +70,11 @@ SYMBOLS = {
     "qsv_probs": (C.c_int, [_P, _I, _IP, _P, _P]),
     "qsv_block_sums": (C.c_int, [_P, _I, _IP, _I, _P, _P]),
     "qsv_sample_scan": (C.c_int, [_P, _I, _IP, _U64, _U64, _D, _D, _P, _P]),
+    "qsv_sample_begin": (C.c_int, [_P, _P]),
+    "qsv_sample_level": (C.c_int, [_P, _I, _U64, _U64, _I, _IP, _P, _P, _P]),
+    "qsv_sample_leaf": (C.c_int, [_P, _I, _U64, _U64, _I, _IP, _P, _P, _P]),
+    "qsv_sample_select": (C.c_int, [_P, _I, _IP, _IP, _I, _U64, _I, _P, _P]),
+    "qsv_sample_sequential": (C.c_int, [_P, _I, _IP, _D, _P, _P]),
     "qsv_swap_peer": (C.c_int, [_P, C.POINTER(C.c_uint64), _I, _I, _I, _IP, _P]),
     "qsv_swap_peer_ex": (C.c_int, [_P, C.POINTER(C.c_uint64), _I, _I, _I, _I, _IP, _IP, _U64, _U64, _P]),
     "qsv_pack_slices": (C.c_int, [_P, _P, _U64, _U64, _U64, _U64, _P]),

@@ -322,41 +322,13 @@ class Comm:
         self.exchange(sv.state, sv.n_local, pack, unpack)
 
     # ------------------------------------------------------------------ measurement
+    def all_reduce_int64(self, t):
+        """In-place integer sum over the ranks (bucket arrays of the exact sampler: order-independent)."""
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
     def sample(self, sv, u, src_pos=None):
-        """One outcome for the uniform draw u on a sharded register.  Shard totals are all-gathered
-        (P doubles), the owning rank runs the block search + sequential scan of the single-GPU path, and
-        the index is broadcast.  Accumulation runs in PHYSICAL index order; the outcome is mapped to the
-        output order through src_pos, so it is a sample of the same distribution (bit-exact agreement
-        with random.choices is only defined for the unsharded order)."""
-        from . import engine as E
-        import numpy as np
-        bb = min(E.SAMPLE_BLOCK_BITS, sv.n_local)
-        sums = sv.block_sums(None, bb)
-        local_total = sums.sum().reshape(1)
-        totals = torch.empty(self.world, dtype=torch.float64, device=sums.device)
-        dist.all_gather_into_tensor(totals, local_total, group=self.group)
-        totals = totals.cpu().numpy()
-        sv.d2h_bytes += 8 * self.world + 8            # shard totals + the broadcast index
-        cum = np.cumsum(totals)
-        total = float(cum[-1])
-        if not total > 0.0:
-            raise ValueError("Total of weights must be greater than zero")
-        target = u * total
-        owner = min(int(np.searchsorted(cum, target, side="right")), self.world - 1)
-        res = torch.zeros(1, dtype=torch.int64, device=sums.device)
-        if owner == self.rank:
-            prefix_rank = float(cum[owner - 1]) if owner > 0 else 0.0
-            lc = np.cumsum(sums.cpu().numpy()) + prefix_rank
-            sv.d2h_bytes += 8 * sums.numel()
-            blk = min(int(np.searchsorted(lc, target, side="right")), len(lc) - 1)
-            prefix = float(lc[blk - 1]) if blk > 0 else prefix_rank
-            z, _ = sv._scan(None, blk << bb, (1 << sv.n_local) - 1, prefix, target)
-            res[0] = (self.rank << sv.n_local) | z
-        dist.broadcast(res, dist.get_global_rank(self.group, owner), group=self.group)
-        y = int(res.item())
-        if src_pos is None:
-            return y
-        z = 0
-        for b, p in enumerate(src_pos):
-            z |= ((y >> p) & 1) << b
-        return z
+        """One outcome for the uniform draw u on a sharded register: StateVector.sample runs the exact radix descent
+        in OUTPUT order, all-reducing the bucket sums of every level over the ranks, so every rank ends with the
+        same index - the one an unsharded register returns for the same u (main/circuit.py:360-364)."""
+        return sv.sample(u, src_pos)

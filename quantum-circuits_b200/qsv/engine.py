@@ -77,6 +77,7 @@ class StateVector:
         self._keep = []       # host/device buffers that must outlive the async launches
         self.passes_run = 0
         self._basis = None
+        self._sampler = None
         self.d2h_bytes = 0
         self.tile_bits = None
         self.low_bits = None
@@ -554,27 +555,30 @@ class StateVector:
 
     def sample(self, u, src_pos=None):
         """Outcome index of random.choices(states, weights) for the uniform draw u
-        (main/circuit.py:360-364): bisect_right(accumulate(weights), u*total, 0, N-1)."""
-        if self.comm is not None and self.comm.world > 1:
-            return self.comm.sample(self, u, src_pos)
-        sp = _cabi.int_array(src_pos) if src_pos is not None else None
-        last = (1 << self.n_local) - 1
-        if self.n_local <= SCAN_BITS_EXACT:
-            _, total = self._scan(sp, 0, last, 0.0, float("inf"))
-            if not total > 0.0:
+        (main/circuit.py:360-364): bisect_right(accumulate(weights), u*total, 0, N-1) over the weights in OUTPUT order.
+
+        Up to 2^20 outcomes on one GPU: the sequential float scan, one launch, bit-exact with CPython.  Larger and
+        sharded registers: the same rule with exact fixed-point sums (qsv.sampling / csrc/qsv_sample.cu) - the
+        outcome is independent of the shard count and differs from the float rule only when u*total lies within one
+        rounding error of a cumulative sum.  One small D2H per draw (16 / 64 bytes)."""
+        sharded = self.comm is not None and self.comm.world > 1
+        if not sharded and self.n_local <= SCAN_BITS_EXACT:
+            sp = _cabi.int_array(src_pos) if src_pos is not None else None
+            res = torch.empty(2, dtype=torch.int64, device=self.device)
+            _cabi.check(self.lib.qsv_sample_sequential(self._ptr(self.state), self.n_local, sp, float(u), self._ptr(res),
+                                                       self._stream()), "qsv_sample_sequential")
+            host = res.cpu().numpy()
+            self.d2h_bytes += 16
+            if not float(host.view(np.float64)[1]) > 0.0:
                 raise ValueError("Total of weights must be greater than zero")
-            z, _ = self._scan(sp, 0, last, 0.0, u * total)
-            return z
-        sums = self.block_sums(src_pos, SAMPLE_BLOCK_BITS).cpu().numpy()
-        self.d2h_bytes += 8 * sums.size
-        cum = np.cumsum(sums)
-        total = float(cum[-1])
-        if not total > 0.0:
-            raise ValueError("Total of weights must be greater than zero")
-        target = u * total
-        blk = min(int(np.searchsorted(cum, target, side="right")), len(cum) - 1)
-        prefix = float(cum[blk - 1]) if blk > 0 else 0.0
-        z, _ = self._scan(sp, blk << SAMPLE_BLOCK_BITS, last, prefix, target)
+            return int(host[0])
+        if self._sampler is None:
+            from .sampling import ExactSampler
+            self._sampler = ExactSampler(self.lib, self.device)
+        z, nbytes = self._sampler.draw(self.state, self.n, self.n_local, self.rank, src_pos, u,
+                                       torch.cuda.current_stream(self.device).cuda_stream,
+                                       self.comm.all_reduce_int64 if sharded else None)
+        self.d2h_bytes += nbytes
         return z
 
     def block_sums(self, src_pos=None, block_bits=SAMPLE_BLOCK_BITS):

@@ -777,7 +777,8 @@ def _trim_tail_rounds(ps, rest, masks_of):
     round that holds only a couple of ops is handed back to the planner - its ops run first in the next pass,
     whose tile the first-come choice builds around them.  QSV_TRIM_ROUNDS = largest tail round given back (0: off)."""
     limit = int(os.environ.get("QSV_TRIM_ROUNDS", "1"))
-    if limit <= 0 or ps.tile_bits != 12 or not rest:
+    cap = int(os.environ.get("QSV_MAX_ROUNDS", "0"))        # > 0: rounds beyond the cap go back whatever they hold
+    if (limit <= 0 and cap <= 0) or ps.tile_bits != 12 or not rest:
         return ps, rest
     rounds = plan_rounds(ps, reg_mcx=True, padded_layout=True)
     if rounds is None or len(rounds) < 3:
@@ -786,7 +787,7 @@ def _trim_tail_rounds(ps, rest, masks_of):
     while len(rounds) >= 3:
         last = rounds[-1]
         tail = list(last.pre) + list(last.reg) + list(last.post)
-        if len(tail) > limit:
+        if len(tail) > limit and not (cap > 0 and len(rounds) > cap):
             break
         give_back = tail + give_back
         rounds.pop()

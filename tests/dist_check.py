@@ -75,12 +75,23 @@ def main():
             err = np.max(np.abs(to_output_order(full, src_pos) - ref))
             check("layered n=%d depth=%d free_swap=%s min_pos=%d swaps=%d err=%.2e"
                   % (n, depth, free, min_pos, comm.swaps - swaps0, err), err <= 1e-12)
-        # sampling: same distribution -> index must carry non-zero probability and be identical on all ranks
-        z = sv.sample(0.4321, src_pos)
-        zs = torch.tensor([z], device="cuda")
-        allz = [torch.empty_like(zs) for _ in range(comm.world)]
-        dist.all_gather(allz, zs)
-        check("sample n=%d z=%d" % (n, z), all(int(t) == z for t in allz) and abs(ref[z]) ** 2 > 0)
+        # sampling (main/circuit.py:360-364): the exact rule in OUTPUT order - identical on all ranks, equal to the
+        # brute-force bisect over the exact cumulative sums of the gathered device weights, i.e. to what ONE GPU
+        # returns for the same state and draw, and equal to the oracle's float rule away from ties
+        import helpers
+        wparts = [torch.empty(1 << sv.n_local, dtype=torch.float64, device="cuda") for _ in range(comm.world)]
+        dist.all_gather(wparts, sv.probs(None))
+        w_phys = torch.cat(wparts).cpu().numpy()
+        for u in (0.4321, 0.0, 0.87654321):
+            z = sv.sample(u, src_pos)
+            zs = torch.tensor([z], device="cuda")
+            allz = [torch.empty_like(zs) for _ in range(comm.world)]
+            dist.all_gather(allz, zs)
+            want = helpers.exact_draw_bruteforce(w_phys, n, src_pos, u) if rank == 0 else z
+            w_out = np.abs(ref) ** 2
+            check("sample n=%d u=%.4f z=%d (exact rule %d, float rule of the oracle %d)"
+                  % (n, u, z, want, so.sample_index_np(w_out, u)),
+                  all(int(t) == z for t in allz) and z == want and z == so.sample_index_np(w_out, u))
 
     # 1b. swap + pass fused into one kernel over peer memory (specialised kernels forced at this small size)
     if comm.peer_swap:
@@ -205,6 +216,14 @@ def main():
     check("API run sharded: same outcome on all ranks, non-zero weight (idx=%d, w=%.3e)" % (idx, wref[idx]),
           all(bool((t == zbits).all()) for t in allb) and wref[idx] > 0)
     lowering.release_sharded_states()
+    # the same call on ONE GPU (every rank on its own unsharded copy) under the same seed returns the same bits
+    os.environ["QSV_SHARD"] = "0"
+    random.seed(100)
+    with contextlib.redirect_stdout(io.StringIO()):
+        out1 = c.run([0] * n, 2)
+    os.environ.pop("QSV_SHARD")
+    check("API run: %d-GPU outcome == 1-GPU outcome under the same seed (%s)" % (comm.world, "".join(map(str, out1))),
+          out1 == out)
 
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

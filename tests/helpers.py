@@ -478,3 +478,82 @@ def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pas
                                 C.c_uint64(support[0]), C.c_uint64(support[1]))
         out.append(dst)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# exact sampler (qsv/sampling.py + csrc/qsv_sample.cu): integer restatement on the host
+# ------------------------------------------------------------------------------------------------
+
+def weight_fix(w):
+    """floor(w * 2^96) of a non-negative double, as the device computes it (weight_fix in csrc/qsv_sample.cu)."""
+    from fractions import Fraction
+    return int(Fraction(float(w)) * (1 << 96))
+
+
+def exact_draw_bruteforce(weights_phys, n, src_pos, u):
+    """bisect_right over the EXACT cumulative weights in output order: first z with cum(z) > floor(u * total)."""
+    from qsv.sampling import u_fixed
+    src = list(src_pos) if src_pos is not None else list(range(n))
+    q = [weight_fix(w) for w in weights_phys]
+    total = sum(q)
+    mant, shift = u_fixed(u)
+    target = (total * mant) >> shift
+    cum = 0
+    for z in range(1 << n):
+        y = 0
+        for b in range(n):
+            y |= ((z >> b) & 1) << src[b]
+        cum += q[y]
+        if cum > target:
+            return z
+    return (1 << n) - 1
+
+
+def exact_draw_emulated(weights_phys, n, g, src_pos, u):
+    """The radix descent of qsv.sampling.level_plan over 2^g virtual ranks, kernel by kernel (level / leaf bucket sums,
+    integer all-reduce, select) with Python integers."""
+    from qsv.sampling import level_plan, u_fixed
+    n_local = n - g
+    local = (1 << n_local) - 1
+    q = [weight_fix(w) for w in weights_phys]
+    mant, shift = u_fixed(u)
+    fixed_val = z = 0
+    target = None
+    for kind, out_bits, positions, fixed in level_plan(src_pos, n, n_local):
+        nb = len(out_bits)
+        buckets = [0] * (1 << nb)
+        if kind == "leaf":
+            assert sorted(p for p in positions if p < n_local) == [p for p in range(n_local) if not (fixed >> p) & 1]
+        else:
+            run = [p for p in range(n_local) if not (fixed >> p) & 1][:10]
+            assert sum(1 for p in positions if p in run) <= 2 and 1 <= nb <= 12
+        for rank in range(1 << g):
+            rank_bits = rank << n_local
+            if (fixed_val ^ rank_bits) & fixed & ~local:
+                continue
+            for y in range(1 << n_local):
+                if (y ^ fixed_val) & fixed & local:
+                    continue
+                full = y | rank_bits
+                idx = 0
+                for k, p in enumerate(positions):
+                    idx |= ((full >> p) & 1) << k
+                buckets[idx] += q[full]
+        if target is None:
+            total = sum(buckets)
+            if total == 0:
+                raise ValueError("Total of weights must be greater than zero")
+            target = (total * mant) >> shift
+        cum = 0
+        found = (1 << nb) - 1
+        for b_, v in enumerate(buckets):
+            if cum + v > target:
+                found = b_
+                break
+            cum += v
+        target -= cum
+        for k in range(nb):
+            bit = (found >> k) & 1
+            fixed_val |= bit << positions[k]
+            z |= bit << out_bits[k]
+    return z

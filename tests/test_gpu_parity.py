@@ -279,16 +279,87 @@ def test_measurement_kernels_and_sampling(qsv_gpu):
         assert sv.sample(u, src) == so.sample_index(w, u)
     assert sv.sample(0.0, src) == so.sample_index(w, 0.0)
     assert sv.sample(0.9999999999999999, src) == so.sample_index(w, 0.9999999999999999)
-    # blocked path (used above 2^20 outcomes) agrees with the exact path away from ties
+    # the exact fixed-point descent (used above 2^20 outcomes and on sharded registers) forced at this size: identical
+    # to the brute-force bisect over exact cumulative sums of the DEVICE's weights, and to the float rule away from ties
+    import helpers
+    w_phys = sv.probs(None).cpu().numpy()
     engine_mod = engine
     old = engine_mod.SCAN_BITS_EXACT
     engine_mod.SCAN_BITS_EXACT = 4
     try:
         for _ in range(40):
             u = rng.random()
-            assert sv.sample(u, src) == so.sample_index(w, u)
+            got = sv.sample(u, src)
+            assert got == helpers.exact_draw_bruteforce(w_phys, n, src, u)
+            assert got == so.sample_index(w, u)
+        for u in (0.0, 0.9999999999999999):
+            assert sv.sample(u, src) == helpers.exact_draw_bruteforce(w_phys, n, src, u)
     finally:
         engine_mod.SCAN_BITS_EXACT = old
+
+
+@pytest.mark.parametrize("n,kind", [(14, "identity"), (15, "reversed"), (16, "shuffled"), (16, "sparse")])
+def test_exact_sampler_descent_bit_exact(qsv_gpu, n, kind):
+    """Every level shape of the radix descent (high-position levels, levels with one or two bucket bits inside a run,
+    leaf) against the integer brute force: the outcome index is bit-exact by construction."""
+    lib, engine, lowering, torch = qsv_gpu
+    import helpers
+    sv = engine.StateVector(n)
+    psi = _rand_state(n, 31 + n)
+    if kind == "sparse":
+        keep = np.random.default_rng(9).random(1 << n) < 0.002
+        psi = np.where(keep, psi, 0)
+        psi /= np.linalg.norm(psi)
+    sv.state.copy_(torch.from_numpy(psi))
+    src = {"identity": list(range(n)), "reversed": list(range(n - 1, -1, -1))}.get(kind)
+    if src is None:
+        src = [int(v) for v in np.random.default_rng(n).permutation(n)]
+    w_phys = sv.probs(None).cpu().numpy()
+    old = engine.SCAN_BITS_EXACT
+    engine.SCAN_BITS_EXACT = 4
+    rng = random.Random(n)
+    try:
+        for u in [0.0, 1.0 - 2.0 ** -53] + [rng.random() for _ in range(12)]:
+            assert sv.sample(u, src) == helpers.exact_draw_bruteforce(w_phys, n, src, u)
+    finally:
+        engine.SCAN_BITS_EXACT = old
+    sv.state.zero_()
+    engine.SCAN_BITS_EXACT = 4
+    try:
+        with pytest.raises(ValueError):
+            sv.sample(0.5, src)
+    finally:
+        engine.SCAN_BITS_EXACT = old
+
+
+def test_exact_sampler_at_22_qubits_matches_vectorised_integer_rule(qsv_gpu):
+    """Above 2^20 outcomes the sampler is the default path: 22 qubits, shuffled output wiring, against exact integer
+    cumulative sums built with numpy object arrays."""
+    lib, engine, lowering, torch = qsv_gpu
+    from qsv.sampling import u_fixed
+    n = 22
+    sv = engine.StateVector(n)
+    sv.state.copy_(torch.from_numpy(_rand_state(n, 5)))
+    src = [int(v) for v in np.random.default_rng(22).permutation(n)]
+    w_out = sv.probs(src).cpu().numpy()
+    mant, ex = np.frexp(w_out)
+    m = (mant * float(1 << 53)).astype(np.uint64).astype(object)
+    sh = ex.astype(np.int64) - 53 + 96
+    q = np.array([int(a) << int(b) if b >= 0 else int(a) >> int(-b) for a, b in zip(m, sh)], dtype=object)
+    cum = np.cumsum(q)
+    total = int(cum[-1])
+    rng = random.Random(1)
+    for u in [0.0] + [rng.random() for _ in range(6)]:
+        mu, su = u_fixed(u)
+        target = (total * mu) >> su
+        lo, hi = 0, (1 << n) - 1
+        while lo < hi:                       # first index with cum > target
+            mid = (lo + hi) // 2
+            if cum[mid] > target:
+                hi = mid
+            else:
+                lo = mid + 1
+        assert sv.sample(u, src) == lo
 
 
 def test_grover_kernels_closed_form_25q(qsv_gpu):

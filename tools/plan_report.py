@@ -5,8 +5,8 @@ every pass touches when the register starts in a basis state (schedule.Support),
     python tools/plan_report.py --qubits 36 --gpus 8        # sharded: joint placement + fused swaps
     python tools/plan_report.py --qubits 33 --workload qft
 
-Model (measured at 2^30 amplitudes per GPU): a full sweep costs 5.45 ms + 0.45 ms per round beyond
-the second, scaled by the touched fraction and by the shard size; a swap moves (1 - 2^-g) of the shard at 655 GB/s
+Model (measured at 2^30 amplitudes per GPU, round 2: profiles/r02_bench_*): a full sweep costs max(5.2 ms, 1.75 ms per
+round) - HBM-bound up to three rounds, bound by the SM beyond -, scaled by the touched fraction and by the shard size; a swap moves (1 - 2^-g) of the shard at 655 GB/s
 and hides the pass fused into it."""
 import argparse
 import os
@@ -44,7 +44,7 @@ for kind, it in schedule.plan_schedule(ops, n_local, fuse_swaps=bool(g)):
         frac = Support.fraction(fixed & local)
         rounds = schedule.plan_rounds(it, reg_mcx=True, padded_layout=True)
         nr = len(rounds) if rounds else 0
-        sweep = (5.45 + 0.45 * max(0, nr - 2)) * scale
+        sweep = max(5.2, 1.75 * nr + (0.5 if nr == 3 else 0.0)) * scale
         total += 0.1 + sweep * frac
         dense += 0.1 + sweep
         rb = " ".join("".join("%x" % b for b in sorted(R.rb)) for R in rounds) if rounds else "shared-memory kernel"
