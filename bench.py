@@ -519,6 +519,34 @@ def main():
         err = max(abs(complex(val[0]) - expect), abs(complex(val[1]) + expect))
         check = {"marked_pair_amplitude_error": err, "expected": expect, "tolerance": 1e-12, "ok": bool(err < 1e-12)}
 
+    if args.workload == "qft" and not args.no_check:
+        # closed form of Matrix.QFT on a basis state (main/matrix.py:212-219, sign +i): every outcome has weight 2^-n
+        # and psi[k] = exp(2 pi i x k / 2^n) / sqrt(2^n) in output order; sampled at 16 output indices, plus the norm
+        import cmath
+        import random as _random
+        step()
+        x_in = lowering.basis_index(in_bits)
+        rng = _random.Random(7)
+        worst = 0.0
+        for _ in range(16):
+            k = rng.getrandbits(n)
+            y = 0
+            for b in range(n):
+                y |= ((k >> b) & 1) << src_pos[b]
+            val = torch.zeros(1, dtype=torch.complex128, device="cuda")
+            if (y >> sv.n_local) == (comm.rank if comm else 0):
+                loc = y & ((1 << sv.n_local) - 1)
+                val = sv.state[loc: loc + 1].clone()
+            if world > 1:
+                dist.all_reduce(torch.view_as_real(val))
+            expect = cmath.exp(2j * cmath.pi * ((x_in * k) % (1 << n)) / (1 << n)) * 2.0 ** (-n / 2)
+            worst = max(worst, abs(complex(val[0]) - expect) * 2.0 ** (n / 2))
+        nrm = torch.tensor([float(sv.block_sums(None, 12).sum())], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(nrm)
+        check = {"relative_amplitude_error_16_samples": worst, "norm_error": abs(float(nrm.item()) - 1.0),
+                 "tolerance": 1e-10, "ok": bool(worst < 1e-10 and abs(float(nrm.item()) - 1.0) < 1e-10)}
+
     # ---- roofline of the dominant kernel (k_pass): per-launch CUDA-event timing of every pass
     peak, peak_src = measured_peak_gbs()
     n_local = sv.n_local
