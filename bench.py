@@ -505,12 +505,13 @@ def main():
     if args.workload == "grover":
         # closed form: amplitude of the marked pair after K iterations = +-sin((2K+1) theta)/sqrt(2)
         import math
-        idx = (x_marked << 1)
-        owner = idx >> sv.n_local
         val = torch.zeros(2, dtype=torch.complex128, device="cuda")
-        if owner == (comm.rank if comm else 0):
-            loc = idx & ((1 << sv.n_local) - 1)
-            val = sv.state[loc: loc + 2].clone()
+        for i, idx in enumerate(((x_marked << 1), (x_marked << 1) | 1)):       # output order: ancilla = last wire = LSB
+            y = 0
+            for b in range(n):
+                y |= ((idx >> b) & 1) << src_pos[b]          # the layout the swaps left (output bit b <- position)
+            if (y >> sv.n_local) == (comm.rank if comm else 0):
+                val[i] = sv.state[y & ((1 << sv.n_local) - 1)]
         if world > 1:
             v = torch.view_as_real(val)
             dist.all_reduce(v)
