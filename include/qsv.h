@@ -162,6 +162,12 @@ void        qsv_reset_launch_count(void);
  * == rank) writes the 1. */
 int qsv_init_basis(void *state_dev, int n_local, uint64_t index, uint64_t rank, void *stream);
 
+/* All basis inputs of an n-qubit circuit in ONE register of 2n qubits (Circuit.get_subcircuit,
+ * main/circuit.py:122-157: the whole-circuit unitary column by column): amplitude 1 at index (c << n) | (c ^ flip)
+ * for every column c, 0 elsewhere.  The circuit's ops act on positions < n; afterwards state[(c << n) | y] is
+ * entry (y, c) of the unitary in physical order.  `flip` = the X gates the lowering pushed back to the input. */
+int qsv_init_columns(void *state_dev, int n, uint64_t flip, void *stream);
+
 /* ---- gate application: replaces P2*psi; M*psi; P1*psi, main/circuit.py:303-327 ----------- */
 
 /* Apply `n_ops` ops to every tile of one pass.  `op_offsets_dev[i]` is the byte offset of op i

@@ -8,6 +8,13 @@ namespace qsv {
 // |in_v>: replaces main/circuit.py:290-301 (tensor product of e0/e1 columns).
 __global__ void k_set_one(double2 *state, uint64_t idx) { state[idx] = make_double2(1.0, 0.0); }
 
+// All 2^n basis inputs of an n-qubit circuit at once (get_subcircuit, main/circuit.py:122-157): a register of 2n
+// qubits whose high half holds the column index c and whose low half starts in |c ^ flip>.
+__global__ void k_set_columns(double2 *state, int n, uint64_t flip) {
+    const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (c < (1ull << n)) state[(c << n) | (c ^ flip)] = make_double2(1.0, 0.0);
+}
+
 __device__ __forceinline__ uint64_t scatter_bits(uint32_t c, const PosList &t) {
     // bit (k-1-p) of c goes to physical position t.pos[p]  (t.pos[0] = gate MSB = port 0)
     uint64_t o = 0;
@@ -102,6 +109,18 @@ extern "C" int qsv_init_basis(void *state_dev, int n_local, uint64_t index, uint
         k_set_one<<<1, 1, 0, st>>>((double2 *)state_dev, index & ((1ull << n_local) - 1ull));
         QSV_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+extern "C" int qsv_init_columns(void *state_dev, int n, uint64_t flip, void *stream) {
+    QSV_CHECK_ARG(state_dev, "qsv_init_columns: NULL state");
+    QSV_CHECK_ARG(n >= 1 && n <= 15, "qsv_init_columns: n=%d out of range (the batch register has 2n qubits)", n);
+    QSV_CHECK_ARG(flip < (1ull << n), "qsv_init_columns: flip does not fit n bits");
+    cudaStream_t st = (cudaStream_t)stream;
+    QSV_CUDA(cudaMemsetAsync(state_dev, 0, (size_t)16 << (2 * n), st));
+    const uint64_t cols = 1ull << n;
+    k_set_columns<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>((double2 *)state_dev, n, flip);
+    QSV_LAUNCH_CHECK();
     return 0;
 }
 

@@ -35,6 +35,7 @@ SYMBOLS = {
     "qsv_launch_count": (C.c_uint64, []),
     "qsv_reset_launch_count": (None, []),
     "qsv_init_basis": (C.c_int, [_P, _I, _U64, _U64, _P]),
+    "qsv_init_columns": (C.c_int, [_P, _I, _U64, _P]),
     "qsv_run_pass": (C.c_int, [_P, C.POINTER(QsvPass), _P, _P, _I, _P]),
     "qsv_run_pass_sparse": (C.c_int, [_P, C.POINTER(QsvPass), _P, _P, _I, _U64, _U64, _P]),
     "qsv_run_pass_rounds": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _P]),

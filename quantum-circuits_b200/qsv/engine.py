@@ -104,6 +104,15 @@ class StateVector:
                                             self._stream()), "qsv_init_basis")
         self._basis = int(index)         # the next execute() knows the support of the state (schedule.Support)
 
+    def init_columns(self, n, flip=0):
+        """Every basis input of an n-qubit circuit at once: this register has 2n qubits, column c sits under the
+        high half = c with the low half in |c ^ flip> (Circuit.get_subcircuit, main/circuit.py:122-157)."""
+        if self.n != 2 * n or self.g:
+            raise RuntimeError("qsv: init_columns needs an unsharded register of 2n qubits")
+        _cabi.check(self.lib.qsv_init_columns(self._ptr(self.state), int(n), int(flip), self._stream()),
+                    "qsv_init_columns")
+        self._basis = None               # 2^n non-zero amplitudes: not a basis state, no support hint
+
     # ------------------------------------------------------------------ gate application
     def upload_program(self, ops):
         """Plan + pack a run of tiled ops and copy the image to the device.  Returns a handle for

@@ -358,8 +358,14 @@ def simulate_amplitudes(circuit, in_v, transposed=False, presorted=True):
     return amp[y]
 
 
-def circuit_unitary_rows(circuit):
-    """Rows of the whole-circuit unitary (get_subcircuit, main/circuit.py:122-157)."""
+BATCHED_UNITARY_MAX_QUBITS = 13      # 2n = 26 qubits = 1 GiB batch register
+
+
+def circuit_unitary(circuit):
+    """Whole-circuit unitary (get_subcircuit, main/circuit.py:122-157) as a numpy complex128 array, U[z, c] =
+    amplitude of output index z for basis input c.  All 2^n columns run as ONE batched register of 2n qubits (the
+    column index rides on the high half, which no op touches): one program, one pass schedule, one D2H - instead
+    of 2^n separate runs.  Above 13 qubits (a 4^n-entry matrix nobody can hold as Python lists) column by column."""
     circuit.sort()
     n = len(circuit)
     ops, src_pos, flip = lower(circuit, False, True, in_flip=True)
@@ -368,12 +374,24 @@ def circuit_unitary_rows(circuit):
     y = np.zeros_like(z)
     for b in range(n):
         y |= ((z >> b) & 1) << src_pos[b]
+    if n <= BATCHED_UNITARY_MAX_QUBITS and not any(op.kind == "diffusion" for op in ops):
+        import torch                    # (the fused diffusion kernel assumes its register IS the whole state)
+        sv = _engine.StateVector(2 * n)
+        sv.init_columns(n, flip)
+        plan = sv.run_ops(ops)
+        cols = sv.state.view(dim, dim)                                   # [column c, physical index]
+        U = cols[:, torch.from_numpy(y).to(cols.device)].transpose(0, 1).contiguous().cpu().numpy()
+        _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=16 * dim * dim, passes=sv.passes_run)
+        return U
     cols = []
     sv = _engine.StateVector(n)
-    handle = None
     for c in range(dim):
         sv.init_basis(c ^ flip)
         sv.run_ops(ops)
         cols.append(sv.amplitudes()[y])
-    U = np.stack(cols, axis=1)
-    return [[complex(v) for v in row] for row in U]
+    return np.stack(cols, axis=1)
+
+
+def circuit_unitary_rows(circuit):
+    """Rows of the whole-circuit unitary as lists of Python complex (the reference's Matrix layout)."""
+    return circuit_unitary(circuit).tolist()

@@ -184,3 +184,24 @@ def test_get_subcircuit_against_reference_matrices(golden):
             for col in range(1 << info["n"]):
                 assert np.max(np.abs(U[:, col] - so.evolve(steps, sq, so.index_bits(col, info["n"])))) <= TOL
     assert seen >= 5
+
+
+def test_get_subcircuit_batched_10_qubits():
+    """All 1024 columns of a 10-qubit layered circuit in ONE 20-qubit batch register (lowering.circuit_unitary):
+    sampled columns against the oracle, unitarity of the whole matrix, and a single D2H of the matrix."""
+    from qsv import lowering, workloads
+    n = 10
+    c = workloads.random_layered_circuit(n, 5, seed=21)
+    U = lowering.circuit_unitary(c)
+    st = lowering.last_run_stats()
+    assert U.shape == (1 << n, 1 << n) and st["d2h_bytes"] == 16 << (2 * n)
+    steps = so.random_layered_steps(n, 5, seed=21)
+    for col in (0, 1, 513, 1023, 700):
+        ref = np.zeros(1 << n, dtype=np.complex128)
+        ref[col] = 1
+        for M, wires, _ in steps:
+            ref = so.apply_gate(ref, n, wires, M)
+        assert np.max(np.abs(U[:, col] - ref)) <= TOL
+    assert np.max(np.abs(U.conj().T @ U - np.eye(1 << n))) <= 1e-12
+    g = c.get_subcircuit("layered")
+    assert len(g) == n and g.matrix.rows[3][5] == complex(U[3, 5])
