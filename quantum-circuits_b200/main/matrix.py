@@ -163,6 +163,13 @@ class Matrix(object):
         return out
 
     def isUnitary(self):
+        """(self * self^dagger).Round(12) == Id  (reference main/matrix.py:90-94; Round keeps real parts only).
+        The reference evaluates the O(n^3) product entry by entry in Python - 80 % of its run time at 8 qubits
+        (SURVEY 8a-4).  Numeric matrices take the same test through one BLAS product; the entries differ from the
+        reference's sums by rounding (1e-16), far inside the 12-decimal comparison."""
+        fast = _is_unitary_fast(self.rows)
+        if fast is not None:
+            return fast
         return (self * (self.getConjugate())).Round(12) == Matrix.Id(len(self))
 
     def bintensor(self, M):
@@ -265,6 +272,19 @@ class Matrix(object):
         m.rows[6] = [0, 0, 0, 0, 0, 0, 0, 1]
         m.rows[7] = [0, 0, 0, 0, 0, 0, 1, 0]
         return m
+
+
+def _is_unitary_fast(rows):
+    """numpy form of the unitarity test, or None when the rows are not a plain numeric square matrix."""
+    try:
+        import numpy as np
+        a = np.array(rows, dtype=np.complex128)
+    except (TypeError, ValueError):
+        return None
+    if a.ndim != 2 or a.shape[0] != a.shape[1] or a.shape[0] < 16:
+        return None                              # small matrices: the reference's own arithmetic is instant
+    p = a @ a.conj().T
+    return bool(np.array_equal(np.round(p.real, 12), np.eye(a.shape[0])))
 
 
 def _qft_rows(size):
