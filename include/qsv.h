@@ -224,6 +224,20 @@ uint64_t qsv_jit_disk_hits(void);
 int  qsv_jit_bank_score(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
                         uint64_t *default_score, uint64_t *searched_score);
 
+/* ---- host-side pass planning (no device work; qsv.schedule) ---------------------------------------------------
+ * The reference applies one gate per full-state product (main/circuit.py:315-327); here a PASS (one read+write of the
+ * state) applies every op whose non-diagonal targets lie inside its tile and that commutes past what stays behind.
+ * Op i of the pending list is described by nd[i] / dg[i] (bit masks of the positions it uses non-diagonally /
+ * diagonally or as a control) and never[i] != 0 when it cannot join a pass at all (whole-state ops, swaps).
+ * qsv_plan_absorbed: how many of the n_ops ops a pass whose tile holds exactly the positions in `allowed` takes.
+ * qsv_plan_improve_tile: local search over the tile's high positions (exchange one position at a time while the pass
+ * absorbs more of the first `window` ops); seed 0 = deterministic candidate order, seed > 0 = shuffled orders (the
+ * randomised schedule search).  hi_out must hold n_free_slots ints.  Returns 0, or -1 / non-zero on bad arguments. */
+int qsv_plan_absorbed(const uint64_t *nd, const uint64_t *dg, const uint8_t *never, int n_ops, uint64_t allowed);
+int qsv_plan_improve_tile(const uint64_t *nd, const uint64_t *dg, const uint8_t *never, int n_ops, int window,
+                          uint64_t low_mask, const int *hi_in, int n_hi_in, int n_free_slots, int n_local,
+                          int low_bits, int max_rounds, uint64_t seed, int *hi_out, int *n_hi_out, int *absorbed_out);
+
 /* Single-gate conveniences (host arguments only; each is one pass with a one-op program built by
  * the library).  `targets[0]` is the gate's port 0 = most-significant bit of the matrix index
  * (main/circuit.py:305-313).  Controls are physical positions that must be 1. */

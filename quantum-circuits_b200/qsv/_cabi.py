@@ -56,6 +56,8 @@ SYMBOLS = {
                                              C.POINTER(C.c_uint64), _I, _I, _IP, _IP, _I, _I, _U64, _U64, _U64, _P]),
     "qsv_jit_disk_hits": (C.c_uint64, []),
     "qsv_jit_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_D)]),
+    "qsv_plan_absorbed": (C.c_int, [_P, _P, _P, _I, _U64]),
+    "qsv_plan_improve_tile": (C.c_int, [_P, _P, _P, _I, _I, _U64, _IP, _I, _I, _I, _I, _I, _U64, _IP, _IP, _IP]),
     "qsv_apply_dense": (C.c_int, [_P, _I, _I, _IP, _I, _IP, C.POINTER(_D), _U64, _P]),
     "qsv_apply_diag": (C.c_int, [_P, _I, _I, _IP, C.POINTER(_D), _U64, _P]),
     "qsv_apply_phase": (C.c_int, [_P, _I, _I, _IP, _D, _D, _U64, _P]),

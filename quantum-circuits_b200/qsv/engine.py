@@ -29,7 +29,8 @@ def _ops_fingerprint(ops, geometry):
                    os.environ.get("QSV_REG_BITS"), os.environ.get("QSV_REG_MIN_OPS"), os.environ.get("QSV_JIT"),
                    os.environ.get("QSV_JIT_MIN_QUBITS"), os.environ.get("QSV_TILE_BITS"),
                    os.environ.get("QSV_LOW_BITS"), os.environ.get("QSV_DEBUG_DROP"), os.environ.get("QSV_FILL"), os.environ.get("QSV_FUSE_SWAP"),
-                   os.environ.get("QSV_TRIM_ROUNDS"))).encode())
+                   os.environ.get("QSV_TRIM_ROUNDS"), os.environ.get("QSV_PLAN_RESTARTS"),
+                   os.environ.get("QSV_PLAN_NATIVE"), os.environ.get("QSV_SPARSE_START"))).encode())
     cached = getattr(ops, "digest", None)       # lowering.OpList: the digest the list was cached under
     if cached is not None:
         h.update(cached)
@@ -275,11 +276,11 @@ class StateVector:
         key = _ops_fingerprint(ops, (self.n_local, self.tile_bits, self.low_bits, self.fuse_swaps(), self.g))
         host_plan = _PLAN_CACHE.get(key)
         if host_plan is None:
-            from .schedule import plan_schedule
+            from .schedule import plan_schedule_search
             host_plan = []
             batch = []
-            for kind, item in plan_schedule(ops, self.n_local, self.tile_bits, self.low_bits,
-                                            fuse_swaps=self.fuse_swaps()):
+            for kind, item in plan_schedule_search(ops, self.n_local, self.tile_bits, self.low_bits,
+                                                   fuse_swaps=self.fuse_swaps(), n_global=self.g):
                 if kind == "pass":
                     batch.append(item)
                     continue

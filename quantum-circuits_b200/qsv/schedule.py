@@ -621,6 +621,36 @@ def _improve_tile(masks, hi, low_mask, n_free_slots, n_local, L):
 
 
 _NOT_TILED = 1 << 200     # sentinel bit: an op that can never join a pass
+_M64 = (1 << 64) - 1
+_plan_seed = 0            # > 0: the tile search shuffles its candidate orders (plan_schedule_search sets it per restart)
+_plan_round_cap = None    # not None: overrides QSV_MAX_ROUNDS (plan_schedule_search tries capped and uncapped passes)
+
+
+def _native_planner():
+    return os.environ.get("QSV_PLAN_NATIVE", "1") != "0"
+
+
+def _improve_tile_native(masks, hi, low_mask, n_free_slots, n_local, L, seed=0):
+    """_improve_tile in native code (csrc/qsv_plan.cu: ~1 us per evaluation of a candidate tile instead of ~40 us).
+    seed 0 visits the candidates in ascending order and returns exactly what _improve_tile returns; seed > 0 shuffles
+    the orders (one member of the randomised schedule search)."""
+    import ctypes as C
+    n = len(masks)
+    nd = np.fromiter((m[0] & _M64 for m in masks), dtype=np.uint64, count=n)
+    dg = np.fromiter((m[1] & _M64 for m in masks), dtype=np.uint64, count=n)
+    never = np.fromiter((1 if (m[0] >> 200) else 0 for m in masks), dtype=np.uint8, count=n)
+    hi = sorted(hi)
+    out = (C.c_int * 16)()
+    n_out, got = C.c_int(0), C.c_int(0)
+    lib = _cabi.load()
+    rc = lib.qsv_plan_improve_tile(C.c_void_p(nd.ctypes.data), C.c_void_p(dg.ctypes.data),
+                                   C.c_void_p(never.ctypes.data), n, PLAN_WINDOW, low_mask & _M64,
+                                   _cabi.int_array(hi), len(hi), n_free_slots, n_local, L, PLAN_MAX_ROUNDS,
+                                   int(seed), out, C.byref(n_out), C.byref(got))
+    _cabi.check(rc, "qsv_plan_improve_tile")
+    return set(out[i] for i in range(n_out.value))
+
+
 
 
 def swap_fields(op, n_local):
@@ -683,7 +713,10 @@ def _plan_one_pass(remaining, masks_of, n_local, T, L, search, forbidden=0, allo
         blocked_nd |= nd_m
         blocked_d |= dg_m
     if search:
-        hi = sorted(_improve_tile(masks, hi, low_mask, T - L, n_local, L))
+        if _native_planner() and n_local <= 63:
+            hi = sorted(_improve_tile_native(masks, hi, low_mask, T - L, n_local, L, _plan_seed))
+        else:
+            hi = sorted(_improve_tile(masks, hi, low_mask, T - L, n_local, L))
     free = T - L - len(hi)
     # ---- selection with the tile fixed
     allowed = low_mask | _mask(hi)
@@ -772,12 +805,180 @@ def plan_schedule(ops, n_local, tile_bits=None, low_bits=None, fuse_swaps=False)
     return out
 
 
+# ---- randomised schedule search ---------------------------------------------------------------------------------
+# The greedy planner maximises what the CURRENT pass absorbs; which of several equally greedy tiles it takes decides
+# how the rest of the circuit cuts.  plan_schedule_search runs the same planner with shuffled candidate orders
+# (native tile search, csrc/qsv_plan.cu) and keeps the schedule that is cheapest under the measured model below.
+# Deterministic (fixed seeds): every rank of a sharded register derives the same schedule.
+
+SWEEP_MS = 5.3            # full sweep of 2^30 amplitudes, 1-2 rounds (HBM-bound: 34.4 GB at ~6.5 TB/s)
+SWAP_SHARD_MS = 26.4      # moving a WHOLE 2^30-amplitude shard over NVLink at ~650 GB/s
+
+
+def sweep_ms(n_rounds, n_low=0, n_ops=0):
+    """One full sweep of 2^30 amplitudes by the pass-specialised kernel, fitted to the per-pass CUDA-event times of
+    round 2 (B200, profiles/r02_planner_search.md): HBM-bound (5.3 ms) up to two rounds; three rounds 5.8 ms, then
+    1.3 ms per round (the shared-memory exchanges bound the SM); 0.5 ms per register bit on tile bits 0..2 (the
+    quarter-warps then differ in run bits only and permuted exchanges conflict); 15 us per gate beyond 30 (FP64)."""
+    if n_rounds <= 2:
+        return SWEEP_MS
+    return 5.8 + 1.3 * (n_rounds - 3) + 0.5 * n_low + 0.015 * max(0, n_ops - 30)
+
+
+def _pass_sweep_ms(ps):
+    ms = getattr(ps, "_sweep_ms", None)
+    if ms is None:
+        rounds = plan_rounds(ps, reg_mcx=True, padded_layout=True) if ps.tile_bits == 12 else None
+        if rounds:
+            n_low = sum(1 for R in rounds for b in R.rb if b < 3)
+            ms = sweep_ms(len(rounds), n_low, len(ps.ops))
+        else:           # shared-memory kernel: one tile round trip per op
+            ms = 5.0 + 1.3 * max(0, len(ps.ops) - 1)
+        ps._sweep_ms = ms
+    return ms
+
+
+def schedule_ms(items, n, n_global, sparse=True):
+    """Modelled device time (ms at 2^30 amplitudes per GPU) of a schedule as plan_schedule returns it - plan_cost with
+    the per-round sweep model instead of the per-gate one.  Passes the round planner cannot take run on the
+    shared-memory kernel (one tile round trip per op)."""
+    n_local = n - n_global
+    local = (1 << n_local) - 1
+    sup = Support(n, 0 if sparse else None)
+    if not sparse:
+        sup.dense()
+    total = 0.0
+
+    one_pass = _pass_sweep_ms
+
+    for kind, it in items:
+        if kind == "pass":
+            fixed, _ = sup.pass_mask(it)
+            total += 0.1 + one_pass(it) * Support.fraction(fixed & local)
+            sup.after_ops(it.ops)
+        elif kind == "swap_pass":
+            sw, ps, first = it[0], it[1], it[2]
+            if first:
+                sup.after_ops(ps.ops)
+            j = int(sw.params["n_swap"])
+            frac = min(1.0, 2.0 * Support.fraction(sup.fixed()[0] & local))
+            swap = SWAP_SHARD_MS * (1.0 - 2.0 ** -j)
+            total += 0.2 + max(swap, one_pass(ps)) * frac          # the pass hides under the transfer
+            sup.swap_op(sw, n_local)
+            if not first:
+                sup.after_ops(ps.ops)
+        elif it.kind == "global_swap":
+            j = int(it.params["n_swap"])
+            total += 0.2 + SWAP_SHARD_MS * (1.0 - 2.0 ** -j) * min(1.0, 2.0 * Support.fraction(sup.fixed()[0] & local))
+            sup.swap_op(it, n_local)
+        else:
+            total += 8.0
+            sup.dense()
+    return total
+
+
+def plan_restarts():
+    return max(1, int(os.environ.get("QSV_PLAN_RESTARTS", "32")))
+
+
+def plan_schedule_search(ops, n_local, tile_bits=None, low_bits=None, fuse_swaps=False, n_global=0, restarts=None,
+                         sparse=None):
+    """plan_schedule, `restarts` times with differently shuffled tile searches; the schedule with the smallest
+    schedule_ms wins (restart 0 is the deterministic greedy schedule, so the result is never worse than it under
+    the model).  Small registers (interpreter kernels, latency-bound) keep the greedy schedule."""
+    global _plan_seed, _plan_round_cap
+    if restarts is None:
+        # a restart costs ~12 ms of host time; a sweep of 2^n_local amplitudes 5 ms at n_local = 30: search harder
+        # the bigger the shard (32 restarts from 30 qubits per shard, 8 at 28, 2 at 26)
+        restarts = plan_restarts() if os.environ.get("QSV_PLAN_RESTARTS") else \
+            max(1, min(plan_restarts(), 1 << max(0, n_local - 25)))
+    T, L = _geometry(n_local, tile_bits, low_bits)
+    if restarts <= 1 or not _native_planner() or T != 12 or n_local > 63 or n_local < PLAN_SEARCH_MIN_QUBITS:
+        return plan_schedule(ops, n_local, tile_bits, low_bits, fuse_swaps)
+    if sparse is None:
+        sparse = sparse_start_enabled()
+    n = n_local + n_global
+    best, best_ms = None, float("inf")
+    key = None
+    if _cache_mod().enabled():
+        digest = getattr(ops, "digest", None) or ops_digest(ops)
+        key = "plan-" + _cache_mod().digest(repr((PLAN_MODEL_VERSION, digest, n_local, T, L, bool(fuse_swaps), n_global,
+                                                   restarts, bool(sparse), SWAP_MIN_POS,
+                                                   tuple(os.environ.get(k) for k in _PLAN_ENV))).encode())
+        hit = _cache_mod().load_pickle(key)
+        items = _schedule_from_indices(hit, ops, n_local, T, L) if hit is not None else None
+        if items is not None:
+            return items
+    caps = (None,) if os.environ.get("QSV_MAX_ROUNDS") else (None, 3)     # passes of any depth / of at most 3 rounds
+    try:
+        for seed in range(restarts):
+            for cap in caps:
+                _plan_seed, _plan_round_cap = seed, cap
+                items = plan_schedule(ops, n_local, tile_bits, low_bits, fuse_swaps)
+                ms = schedule_ms(items, n, n_global, sparse)
+                if ms < best_ms - 1e-9:
+                    best, best_ms = items, ms
+    finally:
+        _plan_seed, _plan_round_cap = 0, None
+    if key is not None:
+        _cache_mod().store_pickle(key, _schedule_to_indices(best, ops))
+    return best
+
+
+PLAN_MODEL_VERSION = 2           # bump when sweep_ms / the search changes: cached schedules are keyed by it
+_PLAN_ENV = ("QSV_PLAN_SEARCH", "QSV_TRIM_ROUNDS", "QSV_MAX_ROUNDS", "QSV_TILE_BITS", "QSV_LOW_BITS", "QSV_REG_BITS",
+             "QSV_REG_MCX", "QSV_FILL", "QSV_JIT_PAD")
+
+
+def _cache_mod():
+    from . import cache
+    return cache
+
+
+def _schedule_to_indices(items, ops):
+    """A schedule as plain data (op indices instead of op objects): what the on-disk plan cache stores.  A fresh
+    process re-running a circuit it has seen (Shor's loop over bases, a restarted service) skips the search."""
+    index = {id(op): i for i, op in enumerate(ops)}
+    out = []
+    for kind, it in items:
+        if kind == "pass":
+            out.append(("pass", tuple(it.hi_pos), [index[id(o)] for o in it.ops]))
+        elif kind == "swap_pass":
+            out.append(("swap_pass", index[id(it[0])], tuple(it[1].hi_pos), [index[id(o)] for o in it[1].ops], int(it[2])))
+        else:
+            out.append(("op", index[id(it)]))
+    return out
+
+
+def _schedule_from_indices(data, ops, n_local, T, L):
+    try:
+        items, seen = [], 0
+        for rec in data:
+            if rec[0] == "pass":
+                items.append(("pass", Pass(n_local, T, L, tuple(rec[1]), [ops[i] for i in rec[2]])))
+                seen += len(rec[2])
+            elif rec[0] == "swap_pass":
+                items.append(("swap_pass", (ops[rec[1]], Pass(n_local, T, L, tuple(rec[2]), [ops[i] for i in rec[3]]),
+                                            rec[4])))
+                seen += len(rec[3]) + 1
+            else:
+                items.append(("op", ops[rec[1]]))
+                seen += 1
+        return items if seen == len(ops) else None
+    except (IndexError, TypeError, ValueError):
+        return None
+
+
+PLAN_SEARCH_MIN_QUBITS = 26      # below this a sweep costs microseconds: host time matters more than a pass
+
+
 def _trim_tail_rounds(ps, rest, masks_of):
     """Rounds cost shared-memory round trips (~0.5 ms per round beyond the second at 2^30 amplitudes); a trailing
     round that holds only a couple of ops is handed back to the planner - its ops run first in the next pass,
     whose tile the first-come choice builds around them.  QSV_TRIM_ROUNDS = largest tail round given back (0: off)."""
     limit = int(os.environ.get("QSV_TRIM_ROUNDS", "1"))
-    cap = int(os.environ.get("QSV_MAX_ROUNDS", "0"))        # > 0: rounds beyond the cap go back whatever they hold
+    cap = _plan_round_cap if _plan_round_cap is not None else int(os.environ.get("QSV_MAX_ROUNDS", "0"))
+    # cap > 0: rounds beyond the cap go back whatever they hold
     if (limit <= 0 and cap <= 0) or ps.tile_bits != 12 or not rest:
         return ps, rest
     rounds = plan_rounds(ps, reg_mcx=True, padded_layout=True)

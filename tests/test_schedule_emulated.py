@@ -1,5 +1,7 @@
 """Lowering + pass planning + program packing, executed by a numpy emulation of the tile kernel that
 decodes the packed device image (tests/helpers.py).  Checks all index arithmetic on the CPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -285,3 +287,99 @@ def test_lowering_cache_is_keyed_by_matrix_entries_not_object_identity():
     ops3, _ = lowering.lower(c)
     assert ops_digest(ops3) != ops_digest(ops1)
     assert not any(op.kind == "dense" for op in ops3)
+
+
+# ------------------------------------------------------------------------------------------------
+# native tile search (csrc/qsv_plan.cu) and the randomised schedule search
+# ------------------------------------------------------------------------------------------------
+
+def _layered_ops(n, depth, seed, g=0):
+    from qsv import workloads
+    c = workloads.random_layered_circuit(n, depth, seed=seed)
+    c.sort()
+    ops, src_pos, flip = lower(c, False, True, n_global=g, in_flip=True, free_swap=bool(g), fuse_swaps=bool(g))
+    return ops, src_pos, flip
+
+
+def _schedule_signature(items):
+    out = []
+    for kind, it in items:
+        if kind == "pass":
+            out.append(("pass", tuple(it.hi_pos), tuple(id(o) for o in it.ops)))
+        elif kind == "swap_pass":
+            out.append(("swap_pass", id(it[0]), tuple(it[1].hi_pos), tuple(id(o) for o in it[1].ops), it[2]))
+        else:
+            out.append(("op", id(it)))
+    return out
+
+
+def test_native_tile_search_reproduces_the_python_planner(monkeypatch):
+    """qsv_plan_improve_tile with seed 0 visits the candidates in the same order as schedule._improve_tile: the
+    schedules are identical, unsharded and sharded (joint placement + fused swaps)."""
+    monkeypatch.setenv("QSV_DISK_CACHE", "0")
+    monkeypatch.setenv("QSV_JIT", "force")
+    for n, g, seed in ((18, 0, 5), (22, 0, 6), (24, 2, 7)):
+        sigs = []
+        for native in ("1", "0"):
+            monkeypatch.setenv("QSV_PLAN_NATIVE", native)
+            schedule._PLACE_CACHE.clear()
+            from qsv import lowering
+            lowering._LOWER_CACHE.clear()
+            ops, _, _ = _layered_ops(n, 10, seed, g)
+            items = schedule.plan_schedule(ops, n - g, fuse_swaps=bool(g))
+            sigs.append([(k, tuple(it.hi_pos), len(it.ops)) if k == "pass" else (k,) for k, it in items])
+        assert sigs[0] == sigs[1]
+
+
+def test_native_absorbed_counts_match_python():
+    import ctypes as C
+    from qsv import _cabi
+    rng = np.random.default_rng(3)
+    lib = _cabi.load()
+    for _ in range(50):
+        n_ops = int(rng.integers(1, 80))
+        masks = []
+        for _ in range(n_ops):
+            nd = int(rng.integers(0, 1 << 16)) & int(rng.integers(0, 1 << 16)) & int(rng.integers(0, 1 << 16))
+            dg = int(rng.integers(0, 1 << 16)) & int(rng.integers(0, 1 << 16)) & ~nd
+            if rng.random() < 0.05:
+                nd |= schedule._NOT_TILED
+            masks.append((nd, dg))
+        allowed = int(rng.integers(0, 1 << 16))
+        nd = np.array([m[0] & schedule._M64 for m in masks], dtype=np.uint64)
+        dg = np.array([m[1] & schedule._M64 for m in masks], dtype=np.uint64)
+        nv = np.array([1 if m[0] >> 200 else 0 for m in masks], dtype=np.uint8)
+        got = lib.qsv_plan_absorbed(C.c_void_p(nd.ctypes.data), C.c_void_p(dg.ctypes.data), C.c_void_p(nv.ctypes.data),
+                                    n_ops, allowed)
+        assert got == schedule._absorbed(masks, allowed, n_ops)
+
+
+def test_schedule_search_is_valid_deterministic_and_never_worse_than_greedy(monkeypatch, tmp_path):
+    """The randomised search returns a schedule that (a) holds every op exactly once in an order the emulation
+    accepts (same final state as the greedy schedule), (b) is the same on every call (fixed seeds: the ranks of a
+    sharded register must agree), (c) costs no more than the greedy schedule under the model, (d) survives the
+    on-disk plan cache unchanged."""
+    monkeypatch.setenv("QSV_JIT", "force")
+    monkeypatch.setenv("QSV_CACHE_DIR", str(tmp_path))
+    n = 14
+    ops, src_pos, flip = _layered_ops(n, 8, 11)
+    monkeypatch.setattr(schedule, "PLAN_SEARCH_MIN_QUBITS", 0)
+    greedy = schedule.plan_schedule(ops, n)
+    monkeypatch.setenv("QSV_DISK_CACHE", "0")
+    a = schedule.plan_schedule_search(ops, n, restarts=6)
+    b = schedule.plan_schedule_search(ops, n, restarts=6)
+    assert _schedule_signature(a) == _schedule_signature(b)
+    assert sorted(id(o) for k, it in a for o in it.ops) == sorted(id(o) for o in ops)
+    assert schedule.schedule_ms(a, n, 0) <= schedule.schedule_ms(greedy, n, 0) + 1e-9
+    monkeypatch.setenv("QSV_DISK_CACHE", "1")
+    c1 = schedule.plan_schedule_search(ops, n, restarts=6)          # stores
+    c2 = schedule.plan_schedule_search(ops, n, restarts=6)          # loads
+    assert _schedule_signature(c1) == _schedule_signature(a) == _schedule_signature(c2)
+    assert any(f.startswith("plan-") for f in os.listdir(tmp_path))
+    # both schedules give the same state on the emulated kernels
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[flip] = 1
+    ref = emulate_ops(ops, psi0.copy(), n)
+    reordered = [o for k, it in a for o in it.ops]
+    got = emulate_ops(reordered, psi0.copy(), n)
+    assert np.max(np.abs(got - ref)) <= TOL
