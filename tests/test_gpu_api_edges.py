@@ -204,4 +204,5 @@ def test_get_subcircuit_batched_10_qubits():
         assert np.max(np.abs(U[:, col] - ref)) <= TOL
     assert np.max(np.abs(U.conj().T @ U - np.eye(1 << n))) <= 1e-12
     g = c.get_subcircuit("layered")
-    assert len(g) == n and g.matrix.rows[3][5] == complex(U[3, 5])
+    # (a second sort() of the already sorted circuit may order commuting gates differently: last-bit differences)
+    assert len(g) == n and abs(g.matrix.rows[3][5] - complex(U[3, 5])) <= 1e-14
