@@ -162,6 +162,12 @@ void        qsv_reset_launch_count(void);
  * == rank) writes the 1. */
 int qsv_init_basis(void *state_dev, int n_local, uint64_t index, uint64_t rank, void *stream);
 
+/* |index> WITHOUT the 16 * 2^n_local byte clear (the reference builds its initial column entry by entry,
+ * main/circuit.py:290-301; here the clear alone is 2.6 ms at 30 qubits): only the basis amplitude is written, every other
+ * amplitude of the register stays UNINITIALISED.  Valid only as the start of a sequence of qsv_run_pass_rounds_fresh
+ * passes that ends with one touching every tile; the engine (qsv.engine.StateVector.run_from_basis) checks that. */
+int qsv_init_basis_sparse(void *state_dev, int n_local, uint64_t index, uint64_t rank, void *stream);
+
 /* All basis inputs of an n-qubit circuit in ONE register of 2n qubits (Circuit.get_subcircuit,
  * main/circuit.py:122-157: the whole-circuit unitary column by column): amplitude 1 at index (c << n) | (c ^ flip)
  * for every column c, 0 elsewhere.  The circuit's ops act on positions < n; afterwards state[(c << n) | y] is
@@ -197,6 +203,15 @@ int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *pass, const void *pro
  * read nor written.  The result is identical to qsv_run_pass_rounds; kernels without the skip ignore the hint. */
 int qsv_run_pass_rounds_sparse(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
                                const void *tables_dev, uint64_t fixed_mask, uint64_t fixed_val, void *stream);
+
+/* qsv_run_pass_rounds_sparse on a register that was started with qsv_init_basis_sparse and has not been swept in full
+ * yet: memory outside the support is uninitialised.  The pass loads the tiles of the support and takes every amplitude
+ * whose TILE-LOCAL index (bit t = position t for t < low_bits, else pass->hi_pos[t - low_bits]) differs from zf_val on
+ * the bits of zf_mask - the support's fixed bits inside the tile - as zero, whatever was loaded; every tile it touches
+ * is written in full.  Only the pass-specialised kernel implements this form (error otherwise; no fallback). */
+int qsv_run_pass_rounds_fresh(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                              const void *tables_dev, uint64_t fixed_mask, uint64_t fixed_val, uint32_t zf_mask,
+                              uint32_t zf_val, void *stream);
 
 /* Pass-specialised form of qsv_run_pass_rounds.  For large states (n_local >= 28 by default; environment
  * QSV_JIT=0 never, QSV_JIT=force always, QSV_JIT_MIN_QUBITS=n) qsv_run_pass_rounds does not interpret the

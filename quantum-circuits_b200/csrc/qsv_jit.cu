@@ -627,12 +627,16 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     o.f("}");
     }
 
+    // round 0 reads the tile as it came from global memory: in a FRESH state (no memset behind qsv_init_basis_sparse)
+    // everything outside the support is uninitialised, and the amplitudes whose tile-local index disagrees with the
+    // support's fixed bits (zf_mask / zf_val, tile-local) are taken as zero instead of what was loaded
+    const char *zf_params = k == 0 ? ", const u32 zf_mask, const u32 zf_val" : "";
     if (direct)
         o.f("QSV_FN void qsv_round%d%s(const double2 *tin, double2 *gout, const u64 tile_base, const u32 tid, const u64 gbase,"
-            " const qsv_H%d &H, const double2 *tables, const qsv_ctx &ctx) {", k, suffix, k);
+            " const qsv_H%d &H, const double2 *tables, const qsv_ctx &ctx%s) {", k, suffix, k, zf_params);
     else
         o.f("QSV_FN void qsv_round%d%s(const double2 *tin, double2 *tout, const u32 tid, const u64 gbase, const qsv_H%d &H,"
-            " const double2 *tables) {", k, suffix, k);
+            " const double2 *tables%s) {", k, suffix, k, zf_params);
     reset_slot_vars();
     emit_tb(o, R);
     o.f("    double x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i, x4r, x4i, x5r, x5i, x6r, x6i, x7r, x7i;");
@@ -643,9 +647,22 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
         o.f("    const u32 pa = QP(tb);");
         for (int r = 0; r < 16; ++r)
             o.f("    { const double2 v = tin[pa + %uu]; x%dr = v.x; x%di = v.y; }", pad_slot(slot_offset(R, r)), r, r);
+        if (k == 0) {
+            o.f("    if (zf_mask) {");
+            o.f("        const u32 zt = (tb ^ zf_val) & zf_mask;");
+            for (int r = 0; r < 16; ++r)
+                o.f("        if (zt ^ (0x%xu & zf_mask)) { x%dr = 0.0; x%di = 0.0; }", slot_offset(R, r), r, r);
+            o.f("    }");
+        }
     } else {
         emit_addresses(o, R, ops, f_pre, n_pre, /*reverse=*/true, gen_pre, "a");
         for (int r = 0; r < 16; ++r) o.f("    { const double2 v = tin[QP(a%d)]; x%dr = v.x; x%di = v.y; }", r, r, r);
+        if (k == 0) {
+            o.f("    if (zf_mask) {");
+            for (int r = 0; r < 16; ++r)
+                o.f("        if ((a%d ^ zf_val) & zf_mask) { x%dr = 0.0; x%di = 0.0; }", r, r, r);
+            o.f("    }");
+        }
     }
     o.f("    (void)H; (void)tables; (void)gbase;");
     if (direct) o.f("    QSV_TILE_CONSUMED(ctx);");
@@ -1085,8 +1102,10 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     // sp_mask / sp_val: index bits known to be FIXED in the state's support (a register that started in a basis state
     // and has not been touched non-diagonally on those positions): a tile that disagrees holds only zeros and, the
     // pass being linear, stays zero - it is skipped like a tile whose ops are all switched off
-    o.f("QSV_FN bool qsv_active(const u64 gbase, const u64 sp_mask, const u64 sp_val) {");
-    o.f("    return ((gbase & sp_mask) == sp_val) && (%s);", active.c_str());
+    // zf_mask != 0 (zero-fill form): a tile of the support holds uninitialised memory next to its amplitudes and must
+    // be written in full even if no op acts on it
+    o.f("QSV_FN bool qsv_active(const u64 gbase, const u64 sp_mask, const u64 sp_val, const u32 zf_mask) {");
+    o.f("    return ((gbase & sp_mask) == sp_val) && (zf_mask != 0u || (%s));", active.c_str());
     o.f("}");
 
     // ---- tile base: insert a zero bit at every hi position (ascending)
@@ -1103,23 +1122,24 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     auto rounds_body = [&](Out &w, int mode) {
         for (uint32_t k = 0; k < nr; ++k) {
             const bool last = k + 1 == nr;
+            const char *zf = k == 0 ? ", zf_mask, zf_val" : "";
             if (mode == 0) {
                 if (k > 0) w.f("        __syncthreads();");
                 if (last && direct)
-                    w.f("        qsv_round%u(tile, state, base, tid, gbase, H%u, tables, ctx);", k, k);
+                    w.f("        qsv_round%u(tile, state, base, tid, gbase, H%u, tables, ctx%s);", k, k, zf);
                 else
-                    w.f("        qsv_round%u(tile, tile, tid, gbase, H%u, tables);", k, k);
+                    w.f("        qsv_round%u(tile, tile, tid, gbase, H%u, tables%s);", k, k, zf);
                 continue;
             }
             const char *src_buf = (k & 1) ? "B" : "A", *dst_buf = (k & 1) ? "A" : "B";
             w.f("        for (u32 tid = 0; tid < 256u; ++tid) {");
             w.f("            const qsv_H%u H = qsv_hoist%u(tid);", k, k);
             if (last && direct && mode == 1)
-                w.f("            qsv_round%u(%s, state, base, tid, gbase, H, tables, ctx);", k, src_buf);
+                w.f("            qsv_round%u(%s, state, base, tid, gbase, H, tables, ctx%s);", k, src_buf, zf);
             else if (last && direct)
-                w.f("            qsv_round%u_local(%s, %s, tid, gbase, H, tables);", k, src_buf, dst_buf);
+                w.f("            qsv_round%u_local(%s, %s, tid, gbase, H, tables%s);", k, src_buf, dst_buf, zf);
             else
-                w.f("            qsv_round%u(%s, %s, tid, gbase, H, tables);", k, src_buf, dst_buf);
+                w.f("            qsv_round%u(%s, %s, tid, gbase, H, tables%s);", k, src_buf, dst_buf, zf);
             w.f("        }");
         }
     };
@@ -1167,12 +1187,14 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     if (sw) o.f("struct qsv_peers { double2 *state[16]; u64 *flags[16]; };");
     const bool two_buf = sw && fuse_two_buffers();
     o.f("extern \"C\" __global__ void __launch_bounds__(256, %d)", two_buf ? 1 : 2);
-    if (sw)
+    if (sw) {
         o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
             " const __grid_constant__ qsv_peers peers, const u32 rank, const u64 epoch, const u64 sp_mask, const u64 sp_val) {");
-    else
+        o.f("    const u32 zf_mask = 0u, zf_val = 0u;      // sharded registers are always initialised in full");
+    } else {
     o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
-        " const u64 sp_mask, const u64 sp_val) {");
+        " const u64 sp_mask, const u64 sp_val, const u32 zf_mask, const u32 zf_val) {");
+    }
     o.f("    extern __shared__ __align__(128) unsigned char smem_raw[];");
     o.f("    double2 *tile = reinterpret_cast<double2 *>(smem_raw);");
     o.f("    __shared__ __align__(8) u64 mbar;");
@@ -1274,7 +1296,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    ctx.state = state; ctx.tile = tile; ctx.mbar = &mbar; ctx.s_off = s_off; ctx.warp = warp;");
         o.f("    ctx.flags = (tid == 0 ? 2u : 0u) | 4u;");
         o.f("    u64 t = blockIdx.x;");
-        o.f("    while (t < n_tiles && !qsv_active(qsv_tile_base(t) | rank_bits, sp_mask, sp_val)) t += gridDim.x;");
+        o.f("    while (t < n_tiles && !qsv_active(qsv_tile_base(t) | rank_bits, sp_mask, sp_val, zf_mask)) t += gridDim.x;");
         o.f("    if (t >= n_tiles) return;");
         o.f("    ctx.next_base = qsv_tile_base(t);");
         o.f("    qsv_issue_load(ctx);");
@@ -1282,7 +1304,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("        const u64 base = qsv_tile_base(t);");
         o.f("        const u64 gbase = base | rank_bits;");
         o.f("        u64 tn = t + gridDim.x;");
-        o.f("        while (tn < n_tiles && !qsv_active(qsv_tile_base(tn) | rank_bits, sp_mask, sp_val)) tn += gridDim.x;");
+        o.f("        while (tn < n_tiles && !qsv_active(qsv_tile_base(tn) | rank_bits, sp_mask, sp_val, zf_mask)) tn += gridDim.x;");
         o.f("        ctx.next_base = tn < n_tiles ? qsv_tile_base(tn) : 0ULL;");
         o.f("        ctx.flags = (ctx.flags & 3u) | (tn < n_tiles ? 4u : 0u);");
         o.f("        mbar_wait(&mbar, parity);");
@@ -1301,7 +1323,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {");
         o.f("        const u64 base = qsv_tile_base(t);");
         o.f("        const u64 gbase = base | rank_bits;");
-        o.f("        if (!qsv_active(gbase, sp_mask, sp_val)) continue;");
+        o.f("        if (!qsv_active(gbase, sp_mask, sp_val, zf_mask)) continue;");
         o.f("        if (tid == 0) mbar_expect_tx(&mbar, %uu);", 16u << 12);
         o.f("        if (issuer)");
         o.f("            for (u32 r = warp; r < %du; r += 8u)", n_runs);
@@ -1330,13 +1352,13 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("#else");
     // ---- host emulation driver (tests only): same round functions, threads run sequentially
     o.f("extern \"C\" void qsv_jit_host_run(double2 *state, const u64 rank_bits, const u64 n_tiles, const double2 *tables,"
-        " const u64 sp_mask, const u64 sp_val) {");
+        " const u64 sp_mask, const u64 sp_val, const u32 zf_mask, const u32 zf_val) {");
     o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
     o.f("    qsv_ctx ctx; (void)ctx;");
     o.f("    for (u64 t = 0; t < n_tiles; ++t) {");
     o.f("        const u64 base = qsv_tile_base(t);");
     o.f("        const u64 gbase = base | rank_bits;");
-    o.f("        if (!qsv_active(gbase, sp_mask, sp_val)) continue;");
+    o.f("        if (!qsv_active(gbase, sp_mask, sp_val, zf_mask)) continue;");
     o.f("        for (u32 r = 0; r < %du; ++r)", n_runs);
     o.f("            memcpy(A + (u64)QP(r << %d), state + base + qsv_scatter(r << %d), %uu);", L, L, 16u << L);
     rounds_body(o, 1);
@@ -1354,6 +1376,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
             " const u64 rank_bits, const u64 n_tiles, const double2 *tables, const u64 sp_mask, const u64 sp_val) {");
         o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
         o.f("    qsv_ctx ctx; (void)ctx;");
+        o.f("    const u32 zf_mask = 0u, zf_val = 0u;");
         o.f("    for (u64 u = 0; u < n_tiles; ++u) {");
         o.f("        u64 base, src_base; u32 peer;");
         o.f("        qsv_fused_tile(u, rank, base, src_base, peer);");
@@ -1371,6 +1394,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     // one tile with a caller-chosen global base index (programs of states too large for a host array)
     o.f("extern \"C\" void qsv_jit_host_tile(double2 *tile, const u64 gbase, const double2 *tables) {");
     o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
+    o.f("    const u32 zf_mask = 0u, zf_val = 0u;");
     o.f("    for (u32 r = 0; r < %du; ++r) memcpy(A + (u64)QP(r << %d), tile + ((u64)r << %d), %uu);", n_runs, L, L,
         16u << L);
     o.f("    {");
@@ -1687,14 +1711,16 @@ bool wanted(const qsv_pass_t *P, const void *prog_host) {
 static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out);
 
 int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
-           cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val) {
+           cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask,
+           unsigned zf_val) {
     void *fn = nullptr;
     if (int rc = get_function(P, prog_host, prog_bytes, nullptr, &fn)) return rc;
     std::string err;
     Driver *d = driver(err);
     QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
     unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
-    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &sp_mask, &sp_val};
+    void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &sp_mask, &sp_val, &zf_mask,
+                    &zf_val};
     const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u * tile_slots(P->n_hi), (void *)st, args, nullptr);
     if (rc) {
         const char *es = nullptr;

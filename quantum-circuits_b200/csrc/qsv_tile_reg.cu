@@ -377,7 +377,8 @@ using namespace qsv;
 namespace qsv { namespace jit {
 bool wanted(const qsv_pass_t *P, const void *prog_host);
 int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
-           cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val);
+           cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask,
+           unsigned zf_val);
 } }
 
 static_assert(sizeof(qsv_rop_t) == 128, "qsv_rop_t must be 128 bytes");
@@ -396,7 +397,8 @@ static int sm_count() {
 }
 
 static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
-                           const void *tables_dev, void *stream, uint64_t sp_mask, uint64_t sp_val);
+                           const void *tables_dev, void *stream, uint64_t sp_mask, uint64_t sp_val,
+                           uint32_t zf_mask = 0, uint32_t zf_val = 0);
 
 extern "C" int qsv_run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
                                    const void *tables_dev, void *stream) {
@@ -410,8 +412,31 @@ extern "C" int qsv_run_pass_rounds_sparse(void *state_dev, const qsv_pass_t *P, 
     return run_pass_rounds(state_dev, P, prog_host, prog_bytes, tables_dev, stream, fixed_mask, fixed_val);
 }
 
+// Zero-fill form (qsv_init_basis_sparse): the register was NOT cleared, only the basis amplitude was written.  Memory
+// outside the support of the state is uninitialised; the pass reads the tiles of the support (fixed_mask / fixed_val over
+// the positions outside the tile, as in the sparse form) and takes every amplitude whose TILE-LOCAL index disagrees with
+// (zf_mask, zf_val) - the support's fixed bits inside the tile - as zero.  Every tile it touches is written in full,
+// so after the first pass that touches all tiles the register is an ordinary dense state.  Replaces the 16 * 2^n byte
+// memset of main/circuit.py:290-301's initial vector (17 GB = 2.6 ms of a 63 ms step at 30 qubits).  Only the
+// pass-specialised kernel implements it.
+extern "C" int qsv_run_pass_rounds_fresh(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
+                                         const void *tables_dev, uint64_t fixed_mask, uint64_t fixed_val,
+                                         uint32_t zf_mask, uint32_t zf_val, void *stream) {
+    QSV_CHECK_ARG((fixed_val & ~fixed_mask) == 0, "qsv_run_pass_rounds_fresh: fixed_val has bits outside fixed_mask");
+    QSV_CHECK_ARG((zf_val & ~zf_mask) == 0 && P && zf_mask < (1u << P->tile_bits),
+                  "qsv_run_pass_rounds_fresh: zf_val / zf_mask must be tile-local bit masks");
+    QSV_CHECK_ARG(P->reserved == 0 || P->reserved == 4, "qsv_run_pass_rounds_fresh: needs 4 register bits per round");
+    QSV_CHECK_ARG(prog_host && jit::wanted(P, prog_host),
+                  "qsv_run_pass_rounds_fresh: only the pass-specialised kernel zero-fills (QSV_JIT / register size)");
+    return run_pass_rounds(state_dev, P, prog_host, prog_bytes, tables_dev, stream, fixed_mask, fixed_val, zf_mask | 0x80000000u,
+                           zf_val);
+}
+
 static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
-                           const void *tables_dev, void *stream, uint64_t sp_mask, uint64_t sp_val) {
+                           const void *tables_dev, void *stream, uint64_t sp_mask, uint64_t sp_val, uint32_t zf_mask,
+                           uint32_t zf_val) {
+    const bool fresh = (zf_mask & 0x80000000u) != 0;      // no fallback to the interpreter, which cannot zero-fill
+    zf_mask &= 0x7fffffffu;
     QSV_CHECK_ARG(state_dev && P && prog_host, "qsv_run_pass_rounds: NULL pointer");
     QSV_CHECK_ARG(P->n_local >= 1 && P->n_local <= 40, "qsv_run_pass_rounds: n_local=%d out of range", P->n_local);
     const int RB = P->reserved ? P->reserved : 4;             // register bits per round (3 or 4)
@@ -442,9 +467,9 @@ static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *pro
         const uint64_t resident_j = (uint64_t)sm_count() * 2ull * waves;
         const unsigned grid_j = (unsigned)(n_tiles_j < resident_j ? n_tiles_j : resident_j);
         const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid_j,
-                                   sp_mask, sp_val);
+                                   sp_mask, sp_val, zf_mask, zf_val);
         const char *mode = getenv("QSV_JIT");
-        if (rc == 0 || (mode && !strcmp(mode, "force"))) return rc;
+        if (rc == 0 || fresh || (mode && !strcmp(mode, "force"))) return rc;
         static bool warned = false;
         if (!warned) {
             warned = true;

@@ -112,6 +112,18 @@ extern "C" int qsv_init_basis(void *state_dev, int n_local, uint64_t index, uint
     return 0;
 }
 
+// |index> WITHOUT clearing the register: only the basis amplitude is written.  The passes that follow must run in the
+// zero-fill form (qsv_run_pass_rounds_fresh) until one of them has touched every tile.
+extern "C" int qsv_init_basis_sparse(void *state_dev, int n_local, uint64_t index, uint64_t rank, void *stream) {
+    QSV_CHECK_ARG(state_dev, "qsv_init_basis_sparse: NULL state");
+    QSV_CHECK_ARG(n_local >= 0 && n_local <= 40, "qsv_init_basis_sparse: n_local=%d out of range", n_local);
+    if ((index >> n_local) == rank) {
+        k_set_one<<<1, 1, 0, (cudaStream_t)stream>>>((double2 *)state_dev, index & ((1ull << n_local) - 1ull));
+        QSV_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 extern "C" int qsv_init_columns(void *state_dev, int n, uint64_t flip, void *stream) {
     QSV_CHECK_ARG(state_dev, "qsv_init_columns: NULL state");
     QSV_CHECK_ARG(n >= 1 && n <= 15, "qsv_init_columns: n=%d out of range (the batch register has 2n qubits)", n);

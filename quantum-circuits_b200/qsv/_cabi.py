@@ -35,11 +35,14 @@ SYMBOLS = {
     "qsv_launch_count": (C.c_uint64, []),
     "qsv_reset_launch_count": (None, []),
     "qsv_init_basis": (C.c_int, [_P, _I, _U64, _U64, _P]),
+    "qsv_init_basis_sparse": (C.c_int, [_P, _I, _U64, _U64, _P]),
     "qsv_init_columns": (C.c_int, [_P, _I, _U64, _P]),
     "qsv_run_pass": (C.c_int, [_P, C.POINTER(QsvPass), _P, _P, _I, _P]),
     "qsv_run_pass_sparse": (C.c_int, [_P, C.POINTER(QsvPass), _P, _P, _I, _U64, _U64, _P]),
     "qsv_run_pass_rounds": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _P]),
     "qsv_run_pass_rounds_sparse": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _U64, _U64, _P]),
+    "qsv_run_pass_rounds_fresh": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _U64, _U64, C.c_uint32,
+                                           C.c_uint32, _P]),
     "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_compile": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_wanted": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32]),

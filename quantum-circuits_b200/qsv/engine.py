@@ -340,10 +340,16 @@ class StateVector:
         """Run a prepared plan on the current state.  Right after init_basis the support of the state is known and
         the passes skip the tiles that are still zero (schedule.Support); any other state is treated as dense."""
         basis, self._basis = self._basis, None
-        for kind, seg, sp in self._walk(plan, basis):
+        self._run_segments(plan, basis, 0)
+
+    def _run_segments(self, plan, basis, n_fresh):
+        """The launches of a plan; the first n_fresh passes in the zero-fill form (run_from_basis)."""
+        done = 0
+        for kind, seg, sp, zf in self._walk(plan, basis):
             if kind == "pass":
                 meta, dev = seg
-                self._launch_pass(meta, dev, sp)
+                self._launch_pass(meta, dev, sp, zf if done < n_fresh else None)
+                done += 1
                 self.passes_run += 1
                 self._keep.append(dev)
             elif kind == "swap_pass":
@@ -352,20 +358,64 @@ class StateVector:
                 self._run_whole_state_op(seg, sp if sp is not None else (0, 0))
         self._basis = None
 
+    def run_from_basis(self, index, plan):
+        """init_basis(index) + execute(plan), without clearing the register where the plan allows it.
+
+        The reference builds |in_v> entry by entry (main/circuit.py:290-301); init_basis clears 16 * 2^n bytes for it
+        (17 GB = 2.6 ms of a 63 ms step at 30 qubits).  A plan that starts with pass-specialised kernels and reaches a
+        pass touching every tile does not need the clear: only the basis amplitude is written (qsv_init_basis_sparse),
+        the passes up to and including the first full sweep run in the zero-fill form (qsv_run_pass_rounds_fresh: what
+        lies outside the support of the state is taken as zero, never read as data) and write every tile they touch
+        in full; from then on the register is an ordinary dense state.  Everything else - sharded registers, plans
+        with whole-state ops or interpreter passes before the first full sweep, QSV_SPARSE_START=0, QSV_LAZY_INIT=0 -
+        takes init_basis + execute."""
+        n_fresh = self._fresh_prefix(plan)
+        if not n_fresh:
+            self.init_basis(index)
+            self.execute(plan)
+            return
+        _cabi.check(self.lib.qsv_init_basis_sparse(self._ptr(self.state), self.n_local, int(index), self.rank,
+                                                   self._stream()), "qsv_init_basis_sparse")
+        self._run_segments(plan, int(index), n_fresh)
+
+    def _fresh_prefix(self, plan):
+        """Number of leading passes that must run in the zero-fill form when the register is NOT cleared: up to and
+        including the first pass that touches every tile; 0 if the plan does not qualify (see run_from_basis)."""
+        import os
+        from .schedule import sparse_start_enabled
+        if os.environ.get("QSV_LAZY_INIT", "1") == "0" or not sparse_start_enabled():
+            return 0
+        if self.comm is not None and self.comm.world > 1:
+            return 0
+        key = ("_fresh", os.environ.get("QSV_JIT"), os.environ.get("QSV_JIT_MIN_QUBITS"))
+        if key in plan:
+            return plan[key]
+        count, ok = 0, False
+        for kind, seg, sp, zf in self._walk(plan, 0):
+            if kind != "pass" or not self._jit_runs(seg[0]):
+                break
+            count += 1
+            if not sp[0]:
+                ok = True               # this pass touches every tile: the register is fully written after it
+                break
+        plan[key] = count if ok else 0
+        return plan[key]
+
     def _walk(self, plan, basis):
         """Segments of a plan in execution order with the support hint of every launch:
-        ("pass", (meta, dev), (fixed_mask, fixed_val)) | ("swap_pass", seg, (mask, val) before the swap, the pass's
-        tile bits excluded) | ("op", op, (mask, val) before a global_swap, else None)."""
+        ("pass", (meta, dev), (fixed_mask, fixed_val), (zf_mask, zf_val)) | ("swap_pass", seg, (mask, val) before the
+        swap, the pass's tile bits excluded, None) | ("op", op, (mask, val) before a global_swap else None, None).
+        (zf_mask, zf_val): the support's fixed bits INSIDE the pass's tile, tile-local (zero-fill form)."""
         sup = Support(self.n, basis)
         for kind, seg in plan["segments"]:
             if kind == "program":
                 packed, dev = seg
                 for meta in packed.passes:
-                    yield "pass", (meta, dev), sup.pass_mask(meta[0])
+                    yield "pass", (meta, dev), sup.pass_mask(meta[0]), sup.tile_mask(meta[0])
                     sup.after_ops(meta[0].ops)
             elif kind == "swap_pass":
                 swap_op, packed, dev, pass_first = seg
-                yield "swap_pass", seg, sup.pass_mask(packed.passes[0][0])
+                yield "swap_pass", seg, sup.pass_mask(packed.passes[0][0]), None
                 if pass_first:
                     sup.after_ops(packed.passes[0][0].ops)
                     sup.swap_op(swap_op, self.n_local)
@@ -373,10 +423,10 @@ class StateVector:
                     sup.swap_op(swap_op, self.n_local)
                     sup.after_ops(packed.passes[0][0].ops)
             elif seg.kind == "global_swap":
-                yield "op", seg, sup.fixed()
+                yield "op", seg, sup.fixed(), None
                 sup.swap_op(seg, self.n_local)
             else:
-                yield "op", seg, None
+                yield "op", seg, None, None
                 sup.dense()
 
     def fuse_swaps(self):
@@ -435,14 +485,24 @@ class StateVector:
         return plan
 
     # ------------------------------------------------------------------ instrumentation (bench.py)
-    def _launch_pass(self, packed_meta, dev, support=None):
+    def _launch_pass(self, packed_meta, dev, support=None, fresh=None):
         ps, table_off, n_ops, maxk = packed_meta
         base = dev.data_ptr()
         cp = self._cpass(ps)
+        if fresh is not None and n_ops >= 0:
+            raise RuntimeError("qsv: zero-fill pass requested for a program the pass-specialised kernel does not run")
         if n_ops < 0:       # register-resident round program (host image, passed to the kernel by value)
             prog = maxk[0]
             cp.max_dense_k = 1
             cp.reserved = int(prog[12])          # register bits per round (program header word 3)
+            if fresh is not None:
+                sp = support if support is not None else (0, 0)
+                _cabi.check(self.lib.qsv_run_pass_rounds_fresh(self._ptr(self.state), C.byref(cp),
+                                                               C.c_void_p(prog.ctypes.data), int(prog.size),
+                                                               C.c_void_p(base + table_off), int(sp[0]), int(sp[1]),
+                                                               int(fresh[0]), int(fresh[1]), self._stream()),
+                            "qsv_run_pass_rounds_fresh")
+                return
             if support is not None and support[0]:
                 _cabi.check(self.lib.qsv_run_pass_rounds_sparse(self._ptr(self.state), C.byref(cp),
                                                                 C.c_void_p(prog.ctypes.data), int(prog.size),
@@ -500,14 +560,17 @@ class StateVector:
         out = []
         fr = iter(self.pass_active_fractions(plan))
         local_mask = (1 << self.n_local) - 1
-        for kind, seg, sp in self._walk(plan, basis):
+        n_fresh = self._fresh_prefix(plan) if basis is not None else 0
+        done = 0
+        for kind, seg, sp, zf in self._walk(plan, basis):
             if kind == "pass":
                 meta, dev = seg
                 ms = []
+                done += 1
                 for _ in range(repeats):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(stream)
-                    self._launch_pass(meta, dev, sp)
+                    self._launch_pass(meta, dev, sp, zf if done <= n_fresh else None)
                     e1.record(stream)
                     e1.synchronize()
                     ms.append(e0.elapsed_time(e1))

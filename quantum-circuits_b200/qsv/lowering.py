@@ -281,8 +281,8 @@ def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=Tru
         sv.d2h_bytes = 0
         ops, src_pos, flip = lower(circuit, transposed, presorted, n_global=comm.global_bits, in_flip=True,
                                    free_swap=bool(comm.peer_swap), fuse_swaps=sv.fuse_swaps())
-    sv.init_basis(basis_index(in_v) ^ flip)
-    plan = sv.run_ops(ops)
+    plan = sv.prepare(ops)
+    sv.run_from_basis(basis_index(in_v) ^ flip, plan)      # init_basis + execute, without the clear where possible
     _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=0, passes=sv.passes_run)
     return sv, src_pos
 

@@ -1369,6 +1369,16 @@ class Support:
         fixed = self.all & ~self.free & ~tile
         return fixed, self.vals & fixed
 
+    def tile_mask(self, ps):
+        """(zf_mask, zf_val) in TILE-LOCAL bits: the positions inside the tile of ps that are still fixed, with their
+        values - what the zero-fill form of a pass keeps of a tile read from uninitialised memory."""
+        m = v = 0
+        for t, p in enumerate(list(range(ps.low_bits)) + list(ps.hi_pos)):
+            if not (self.free >> p) & 1:
+                m |= 1 << t
+                v |= ((self.vals >> p) & 1) << t
+        return m, v
+
     def after_ops(self, ops):
         for op in ops:
             if op.kind in TILED_KINDS:

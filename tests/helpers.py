@@ -407,7 +407,8 @@ def jit_source(ps, prog):
     return buf.raw.decode()
 
 
-def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=None, fixed_mask=0, fixed_val=0):
+def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=None, fixed_mask=0, fixed_val=0,
+                 zf_mask=0, zf_val=0):
     """Compile the generated source of one pass as host C++ and run it on psi (numpy complex128).  With
     single_tile_gbase, psi is one tile and only the rounds run (state sizes no host array can hold)."""
     import ctypes as C
@@ -430,7 +431,8 @@ def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=No
         h.qsv_jit_host_tile(C.c_void_p(out.ctypes.data), C.c_uint64(single_tile_gbase), C.c_void_p(tabs.ctypes.data))
         return out
     h.qsv_jit_host_run(C.c_void_p(out.ctypes.data), C.c_uint64(rank_bits), C.c_uint64(1 << (ps.n_local - ps.tile_bits)),
-                       C.c_void_p(tabs.ctypes.data), C.c_uint64(fixed_mask), C.c_uint64(fixed_val))
+                       C.c_void_p(tabs.ctypes.data), C.c_uint64(fixed_mask), C.c_uint64(fixed_val),
+                       C.c_uint32(zf_mask), C.c_uint32(zf_val))
     return out
 
 

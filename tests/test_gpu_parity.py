@@ -549,7 +549,7 @@ def test_support_hint_gives_the_same_state_as_full_sweeps(qsv_gpu, monkeypatch):
     idx = 0b1011 ^ flip
     sv = engine.StateVector(n)
     plan = sv.prepare(ops)
-    hints = [sp for kind, seg, sp in sv._walk(plan, idx) if kind == "pass"]
+    hints = [sp for kind, seg, sp, zf in sv._walk(plan, idx) if kind == "pass"]
     assert sum(1 for sp in hints if sp[0]) >= 2, "expected the first passes to carry a support hint"
     monkeypatch.setenv("QSV_SPARSE_START", "0")
     sv.init_basis(idx)
@@ -565,3 +565,50 @@ def test_support_hint_gives_the_same_state_as_full_sweeps(qsv_gpu, monkeypatch):
     # a state of unknown support (no init_basis before execute) is swept completely
     sv.execute(plan)
     assert sv._basis is None
+
+
+def test_run_from_basis_without_the_clear_is_bit_identical(qsv_gpu, monkeypatch):
+    """StateVector.run_from_basis skips the 16 * 2^n byte clear when the plan's leading passes can zero-fill
+    (qsv_init_basis_sparse + qsv_run_pass_rounds_fresh).  On a register deliberately filled with NaN the final state
+    must equal init_basis + execute bit for bit; with QSV_LAZY_INIT=0, and for plans that do not qualify, it IS
+    init_basis + execute."""
+    lib, engine, lowering, torch = qsv_gpu
+    from qsv import workloads
+    monkeypatch.setenv("QSV_JIT", "force")
+    for n, depth, seed in ((20, 10, 41), (24, 8, 31)):
+        c = workloads.random_layered_circuit(n, depth, seed=seed)
+        c.sort()
+        ops, _, flip = lowering.lower(c, in_flip=True)
+        idx = 0b1101 ^ flip
+        sv = engine.StateVector(n)
+        plan = sv.prepare(ops)
+        sv.init_basis(idx)
+        sv.execute(plan)
+        sv.synchronize()
+        ref = sv.state.clone()
+        n_fresh = sv._fresh_prefix(plan)
+        assert n_fresh >= 2, "expected the plan to start with zero-fill passes"
+        launches = lib.qsv_launch_count()
+        torch.view_as_real(sv.state).fill_(float("nan"))
+        sv.run_from_basis(idx, plan)
+        sv.synchronize()
+        assert torch.equal(torch.view_as_real(sv.state), torch.view_as_real(ref))
+        assert not torch.isnan(torch.view_as_real(sv.state)).any()
+        monkeypatch.setenv("QSV_LAZY_INIT", "0")
+        assert sv._fresh_prefix(plan) == 0
+        torch.view_as_real(sv.state).fill_(float("nan"))
+        sv.run_from_basis(idx, plan)
+        sv.synchronize()
+        assert torch.equal(torch.view_as_real(sv.state), torch.view_as_real(ref))
+        monkeypatch.delenv("QSV_LAZY_INIT")
+    # a shallow circuit never sweeps the whole register: the plan does not qualify and the register is cleared
+    c = workloads.random_layered_circuit(20, 1, seed=3)
+    c.sort()
+    ops, _, flip = lowering.lower(c, in_flip=True)
+    sv = engine.StateVector(20)
+    plan = sv.prepare(ops)
+    torch.view_as_real(sv.state).fill_(float("nan"))
+    sv.run_from_basis(flip, plan)
+    sv.synchronize()
+    assert not torch.isnan(torch.view_as_real(sv.state)).any()
+    assert abs(float(sv.block_sums(None, 12).sum()) - 1.0) < 1e-10

@@ -372,6 +372,84 @@ def test_support_hint_skips_only_zero_tiles(tmp_path):
     assert np.all(dense[~inside] == 0)
 
 
+def test_zero_fill_form_never_reads_outside_the_support(tmp_path):
+    """qsv_run_pass_rounds_fresh on the host: the register holds NaN everywhere except on the support of the state
+    (index bits fixed outside AND inside the tile).  With (zf_mask, zf_val) = the fixed bits inside the tile the pass
+    gives, on every tile it touches, exactly the result of the dense run on the zero-padded state - whatever the
+    uninitialised memory held - and writes those tiles in full; tiles outside the support keep their poison.
+    Plain loads and loads that carry address permutations (X / CNot riding on round 0) are both covered."""
+    from qsv import workloads, lowering, schedule
+    n = 15
+    seen_permuted = seen_plain = 0
+    for seed, which in ((5, 0), (5, 1), (6, 1), (7, 0), (8, 1)):
+        c = workloads.random_layered_circuit(n, 3, seed=seed)
+        c.sort()
+        ops, _ = lowering.lower(c)
+        ps, prog, tables = _round_programs(ops, n)[which]
+        rounds0_pre = int(np.frombuffer(prog.tobytes()[16 + 12:16 + 14], dtype=np.uint16)[0]) & 0x7fff
+        seen_permuted += rounds0_pre > 0
+        seen_plain += rounds0_pre == 0
+        outside = [p for p in range(ps.low_bits, n) if p not in ps.hi_pos]
+        tile_pos = list(range(ps.low_bits)) + list(ps.hi_pos)
+        rng = np.random.default_rng(seed)
+        fixed_out = [outside[0], outside[2]]
+        fixed_in = [int(t) for t in rng.choice(12, size=5, replace=False)]           # tile-local bits still fixed
+        vals = {p: int(rng.integers(0, 2)) for p in fixed_out + [tile_pos[t] for t in fixed_in]}
+        fixed_mask = sum(1 << p for p in fixed_out)
+        fixed_val = sum(vals[p] << p for p in fixed_out)
+        zf_mask = sum(1 << t for t in fixed_in)
+        zf_val = sum(vals[tile_pos[t]] << t for t in fixed_in)
+        idx = np.arange(1 << n)
+        in_tiles = (idx & fixed_mask) == fixed_val
+        in_support = in_tiles.copy()
+        for t in fixed_in:
+            in_support &= ((idx >> tile_pos[t]) & 1) == vals[tile_pos[t]]
+        psi = _rand_state(n, seed)
+        psi[~in_support] = 0
+        dense = jit_host_run(ps, prog, tables, psi, 0, str(tmp_path))
+        poisoned = psi.copy()
+        poisoned[~in_support] = np.nan
+        fresh = jit_host_run(ps, prog, tables, poisoned, 0, str(tmp_path), fixed_mask=fixed_mask, fixed_val=fixed_val,
+                             zf_mask=zf_mask, zf_val=zf_val)
+        assert np.all(np.isnan(fresh[~in_tiles])) and not np.any(np.isnan(fresh[in_tiles]))
+        assert np.array_equal(fresh[in_tiles], dense[in_tiles])
+    assert seen_plain and seen_permuted
+
+
+def test_zero_fill_form_writes_tiles_no_op_acts_on(tmp_path):
+    """A pass whose ops all hang on a control OUTSIDE the tile skips the tiles where that control is 0 - unless it runs
+    in the zero-fill form with fixed bits inside the tile: such a tile holds uninitialised memory next to its
+    amplitudes, so it must be loaded, masked and written in full even though no op acts on it."""
+    from qsv.schedule import Op
+    n = 15
+    s = 2 ** -0.5
+    H = np.array([[s, s], [s, -s]], dtype=np.complex128)
+    ops = [Op("dense", (3,), (14,), matrix=H), Op("mcx", (2,), (14,)), Op("dense", (7,), (14,), matrix=H),
+           Op("phase", (), (14, 9), scalar=1j), Op("dense", (1,), (14,), matrix=H)]
+    progs = _round_programs(ops, n)
+    assert len(progs) == 1
+    ps, prog, tables = progs[0]
+    assert ps.loc(14) < 0
+    tile_pos = list(range(ps.low_bits)) + list(ps.hi_pos)
+    fixed_in = [t for t in range(12) if tile_pos[t] not in (1, 2, 3, 7)][:6]
+    zf_mask = sum(1 << t for t in fixed_in)
+    zf_val = sum(1 << t for t in fixed_in[::2])
+    idx = np.arange(1 << n)
+    in_support = np.ones(1 << n, dtype=bool)
+    for k, t in enumerate(fixed_in):
+        in_support &= ((idx >> tile_pos[t]) & 1) == (1 if k % 2 == 0 else 0)
+    psi = _rand_state(n, 4)
+    psi[~in_support] = 0
+    dense = jit_host_run(ps, prog, tables, psi, 0, str(tmp_path))
+    poisoned = psi.copy()
+    poisoned[~in_support] = np.nan
+    fresh = jit_host_run(ps, prog, tables, poisoned, 0, str(tmp_path), zf_mask=zf_mask, zf_val=zf_val)
+    assert not np.any(np.isnan(fresh)) and np.array_equal(fresh, dense)
+    # without the zero-fill form the tiles with control 14 = 0 are skipped (and keep the poison)
+    plain = jit_host_run(ps, prog, tables, poisoned, 0, str(tmp_path))
+    assert np.any(np.isnan(plain[(idx >> 14) & 1 == 0]))
+
+
 def test_every_kernel_of_the_8_gpu_bench_plan_compiles_for_sm100a():
     """The schedule bench.py runs at --gpus 8 (33 qubits, joint placement, fused swaps): every pass program - the
     plain ones and the fused swap+pass forms - must be accepted by NVRTC for sm_100a.  No GPU needed."""
