@@ -175,7 +175,7 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
         sig = _circuit_signature(gates, table, out_qubits, (
             n, bool(transposed), int(n_global), bool(in_flip), bool(free_swap), bool(fuse_swaps), _sched.SWAP_MIN_POS,
             QFT_DENSE_MAX, tuple(os.environ.get(k) for k in ("QSV_PROPAGATE_X", "QSV_FUSE_1Q", "QSV_PLACE",
-                                                             "QSV_PLACE_THIN", "QSV_PLACE_REPLAN", "QSV_TILE_BITS",
+                                                             "QSV_PLACE_THIN", "QSV_PLACE_REPLAN", "QSV_PLACE_SEEDS", "QSV_TILE_BITS",
                                                              "QSV_LOW_BITS", "QSV_PLAN_SEARCH"))))
         hit = _LOWER_CACHE.get(sig) if sig is not None else None
         if hit is not None:

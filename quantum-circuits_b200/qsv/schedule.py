@@ -1268,7 +1268,8 @@ def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
     key = (ops_digest(ops), n, n_global, tuple(src_pos) if src_pos is not None else None, fuse_swaps, SWAP_MIN_POS,
            os.environ.get("QSV_PLACE_THIN"), os.environ.get("QSV_TILE_BITS"), os.environ.get("QSV_LOW_BITS"),
            os.environ.get("QSV_PLAN_SEARCH"), sparse, os.environ.get("QSV_EARLY_SWAP"),
-           os.environ.get("QSV_PARTIAL_SWAP"), os.environ.get("QSV_PLACE_REPLAN"))
+           os.environ.get("QSV_PARTIAL_SWAP"), os.environ.get("QSV_PLACE_REPLAN"), os.environ.get("QSV_PLACE_SEEDS"),
+           os.environ.get("QSV_PLAN_NATIVE"), PLAN_MODEL_VERSION)
     hit = _PLACE_CACHE.get(key)
     if hit is None:
         hit = _place_disk_cache(key)
@@ -1276,17 +1277,26 @@ def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
             _PLACE_CACHE[key] = hit
     if hit is not None:
         return list(hit[0]), (list(hit[1]) if hit[1] is not None else None)
-    thins = [int(v) for v in os.environ.get("QSV_PLACE_THIN", "1,8,14,20").split(",")]
+    global _plan_seed
+    # thresholds up to a full pass: a swap taken while the pass before it is still fat hides that pass under the
+    # transfer (fused swap+pass), and swaps taken while the state is sparse cost next to nothing
+    thins = [int(v) for v in os.environ.get("QSV_PLACE_THIN", "1,8,14,20,28,36,44").split(",")]
     earlies = (False, True) if (sparse and os.environ.get("QSV_EARLY_SWAP", "1") != "0") else (False,)
+    seeds = range(max(1, int(os.environ.get("QSV_PLACE_SEEDS", "4")))) if _native_planner() else (0,)
     cands, floor = [], float("inf")
-    for early in earlies:
-        for thin in thins:
-            for pen in ((0, 2, 6) if fuse_swaps else (0,)):
-                res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floor + 0.5,
-                                        tile_penalty=pen, early=early, sparse=sparse)
-                if res[1] is not None:
-                    cands.append(res)
-                    floor = min(floor, res[0])
+    try:
+        for seed in seeds:              # seed > 0: the tile searches inside the planner visit their candidates shuffled
+            _plan_seed = seed
+            for early in earlies:
+                for thin in thins:
+                    for pen in ((0, 2, 6) if fuse_swaps else (0,)):
+                        res = _place_joint_once(ops, n, n_global, src_pos, thin, fuse_swaps, cost_cap=floor + 0.5,
+                                                tile_penalty=pen, early=early, sparse=sparse)
+                        if res[1] is not None:
+                            cands.append(res)
+                            floor = min(floor, res[0])
+    finally:
+        _plan_seed = 0
     # The estimate above is the planner's own pass sequence; plan_schedule re-derives the passes from the op list
     # and may cut them differently.  Re-plan the few cheapest distinct candidates and keep the one whose REAL
     # schedule is cheapest (fused passes ride on their swap for free).
@@ -1298,9 +1308,9 @@ def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
         if sig in seen:
             continue
         seen.add(sig)
-        if len(seen) > int(os.environ.get("QSV_PLACE_REPLAN", "2")):
+        if len(seen) > int(os.environ.get("QSV_PLACE_REPLAN", "6")):
             break
-        real = plan_cost(plan_schedule(res[1], n - n_global, fuse_swaps=fuse_swaps), n, n_global, sparse)
+        real = schedule_ms(plan_schedule(res[1], n - n_global, fuse_swaps=fuse_swaps), n, n_global, sparse)
         if real < best_cost:
             best, best_cost = res, real
     if len(_PLACE_CACHE) >= 8:

@@ -318,6 +318,7 @@ def test_native_tile_search_reproduces_the_python_planner(monkeypatch):
     schedules are identical, unsharded and sharded (joint placement + fused swaps)."""
     monkeypatch.setenv("QSV_DISK_CACHE", "0")
     monkeypatch.setenv("QSV_JIT", "force")
+    monkeypatch.setenv("QSV_PLACE_SEEDS", "1")      # the shuffled placement candidates exist in the native search only
     for n, g, seed in ((18, 0, 5), (22, 0, 6), (24, 2, 7)):
         sigs = []
         for native in ("1", "0"):
