@@ -43,6 +43,8 @@ def parse():
                     help="layered = BASELINE config 3 (headline); qft = config 4 (H + controlled-phase ladder); "
                          "grover = config 5 (oracle + diffusion kernels)")
     ap.add_argument("--iterations", type=int, default=32, help="Grover iterations (config 5)")
+    ap.add_argument("--no-cold", action="store_true", help="skip e2e_cold (fresh-process first call) and the "
+                    "reference Grover-7 leg")
     ap.add_argument("--no-check", action="store_true", help="skip the in-run correctness check (norm, hint on/off, "
                                                             "circuit^-1 o circuit round trip)")
     ap.add_argument("--no-big", action="store_true",
@@ -366,6 +368,81 @@ def run_big_shard(args, comm, g, world, rank, barrier):
     return out
 
 # ------------------------------------------------------------------------------------------------
+# cold start of the public API, and the unmodified reference on its own Grover script
+# ------------------------------------------------------------------------------------------------
+
+def _run_json(cmd, env=None, timeout=900):
+    import subprocess
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    if r.returncode != 0:
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")]
+    return json.loads(lines[-1][6:]) if lines else {"error": "no RESULT line"}
+
+
+def cold_start(n, depth, e2e_ms):
+    """`e2e_cold`: the first Circuit.run(in_v, 2) of a FRESH process on the same circuit (tools/cold_run.py), with the
+    on-disk caches this process has just filled (cubins, schedule) and with an empty cache directory (NVRTC and the
+    schedule search included).  The steady-state `e2e` excludes all of this."""
+    import tempfile
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "cold_run.py"), str(n), str(depth), str(SEED)]
+    warm = _run_json(cmd)
+    env = dict(os.environ, QSV_CACHE_DIR=tempfile.mkdtemp(prefix="qsv-cold-"))
+    cold = _run_json(cmd, env=env)
+    out = {"unit": "ms per Circuit.run(in_v, 2), first call of a fresh process (CUDA context already created)",
+           "disk_cache_warm": warm, "disk_cache_empty": cold, "steady_state_e2e_ms": e2e_ms}
+    if "first_call_ms" in warm:
+        out["value"] = warm["first_call_ms"]
+        out["ratio_to_e2e"] = warm["first_call_ms"] / e2e_ms
+    return out
+
+
+def reference_grover7():
+    """The unmodified reference on its own script (main/Grover.py + Circuit.run_method2: 7 qubits, 25 dense gates)
+    against the same circuit through the mirror API on the GPU.  The reference runs live when a checkout is present
+    (QSV_REFERENCE_ROOT / /root/reference - the build container); on the GPU box the committed measurement of
+    tools/time_reference_grover7.py (profiles/r02_reference_grover7.json) is quoted and labelled as such."""
+    import numpy as np
+    import torch
+    from qsv import workloads
+    ref_root = os.environ.get("QSV_REFERENCE_ROOT", "/root/reference")
+    ref, src = None, None
+    if os.path.isdir(os.path.join(ref_root, "main")):
+        import subprocess
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_reference_grover7.py")],
+                           capture_output=True, text=True, timeout=1800)
+        src = "live run of the checkout at %s" % ref_root
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_grover7.json")) as f:
+            ref = json.load(f)
+        src = src or "profiles/r02_reference_grover7.json (measured in the build container; no checkout on this box)"
+    except (OSError, ValueError):
+        return None
+    g = workloads.grover_circuit_dense(6, 13)
+    in_v = [0] * 6 + [1]
+    t0 = time.perf_counter()
+    w = g.run_method2(in_v)
+    torch.cuda.synchronize()
+    first = time.perf_counter() - t0
+    k = 20
+    t0 = time.perf_counter()
+    for _ in range(k):
+        w = g.run_method2(in_v)
+    torch.cuda.synchronize()
+    steady = (time.perf_counter() - t0) / k
+    p = w[2 * 13] + w[2 * 13 + 1]
+    return {"circuit": "main/Grover.py:10-48 (n = 6 search qubits + ancilla, x = 13, 6 iterations, 25 dense gates)",
+            "reference": {"run_method2_s": ref["run_method2_s"], "gates_per_sec": ref["gates_per_sec"],
+                          "p_marked_pair": ref["p_marked_pair"], "source": src, "what": ref["what"]},
+            "gpu": {"api": "Circuit.run_method2 through the mirror (workloads.grover_circuit_dense)",
+                    "first_call_s": first, "steady_s": steady, "gates_per_sec": len(g.gates) / steady,
+                    "p_marked_pair": p},
+            "p_marked_pair_abs_diff": abs(p - ref["p_marked_pair"]), "tolerance": 1e-12,
+            "ok": bool(abs(p - ref["p_marked_pair"]) <= 1e-12),
+            "speedup_steady": ref["run_method2_s"] / steady, "argmax_equal": bool(int(np.argmax(w)) == ref["argmax"])}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 
@@ -627,6 +704,11 @@ def main():
                "d2h_bytes_per_step": st["d2h_bytes"], "ms_per_step": dt * 1e3,
                "api": "main.circuit.Circuit.run(in_v, 2)"}
 
+    e2e_cold = ref_grover = None
+    if world == 1 and e2e is not None and args.workload == "layered" and not args.no_cold:
+        e2e_cold = cold_start(n, args.depth, e2e["ms_per_step"])
+        ref_grover = reference_grover7()
+
     if world > 1 and (16 << n_local) * 2 < 170e9 and args.workload == "layered":
         # the same public call under the one-process-per-GPU launch: Circuit.run shards the register over the
         # ranks by itself (qsv.dist.default_comm); every rank makes the call, the slowest rank's time counts
@@ -696,6 +778,10 @@ def main():
             "value = gates x GPUs / s: units all ranks processed (a gate of the %d-qubit circuit updates all %d "
             "shards of 2^%d amplitudes); circuit_gates_per_sec = %d gates / step time is the raw rate of the "
             "sharded circuit" % (n, world, n_local, n_gates))
+    if e2e_cold is not None:
+        line["e2e_cold"] = e2e_cold
+    if ref_grover is not None:
+        line["reference_grover7"] = ref_grover
     if gate_pass is not None:
         line["gate_pass"] = gate_pass
     if swap is not None:

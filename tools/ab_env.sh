@@ -5,7 +5,7 @@ tag=$1; shift
 i=0
 for envs in "$@"; do
   i=$((i+1))
-  env $envs timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gate-pass --no-big \
+  env $envs timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gate-pass --no-big --no-cold \
      > $out/${tag}_$i.json 2> $out/${tag}_$i.err
   echo "[$envs] rc=$?"
   python - $out/${tag}_$i.json <<'P'
