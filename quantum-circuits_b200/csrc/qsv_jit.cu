@@ -303,7 +303,9 @@ static void thread_bit_order(const qsv_round_t &R, int pos[8]) {
     for (int b = 0; b < 12 && n < 8; ++b)
         if (!is_rb[b] && !used[b]) { pos[n++] = b; used[b] = true; }
 }
-// ---- optional search (QSV_JIT_BANKSEARCH=1, off by default): score the ACTUAL slot addresses -----------------------
+// ---- search over the thread-bit mapping (on by default since round 2; QSV_JIT_BANKSEARCH=0 keeps the static rule):
+// score the ACTUAL slot addresses.  ncu, 30 qubits (profiles/r02_ncu_jit_kernel.md): store conflicts of two passes
+// 160-165 M -> 26-35 M, load conflicts of a third 141 M -> 8 M, 5.78 / 5.84 / 5.42 -> 5.60 / 5.56 / 5.33 ms. ---------
 // The class argument above is static: it ignores X / CNot / Toffoli that ride on a round's loads or stores and XOR
 // thread-dependent bits into the slot index (ncu after the padded layout: 140 M load conflicts per pass are left in
 // such rounds).  With the search on, every triple of non-register tile bits is tried as the low thread-index bits: the
@@ -313,7 +315,7 @@ static thread_local const int *t_tb_override = nullptr;     // mapping chosen fo
 
 static bool bank_search_enabled() {
     const char *e = getenv("QSV_JIT_BANKSEARCH");
-    return e && !strcmp(e, "1");
+    return !(e && !strcmp(e, "0"));
 }
 
 static uint32_t pad_slot(uint32_t a);

@@ -85,7 +85,7 @@ def test_qft_ladder_controlled_phases(tmp_path):
 
 @pytest.mark.parametrize("workload", ["layered", "toffoli"])
 def test_bank_search_mapping_keeps_results_identical(tmp_path, monkeypatch, workload):
-    """QSV_JIT_BANKSEARCH=1 (opt-in): the low thread-index bits of every round are chosen by scoring the actual slot
+    """QSV_JIT_BANKSEARCH (default on, 0 = static rule): the low thread-index bits of every round are chosen by scoring the actual slot
     addresses, permutations included.  Any choice is a relabelling of the threads: the state must come out exactly
     as with the default mapping, and the generated source must differ (the search did pick other bits)."""
     from qsv import workloads, lowering
@@ -109,7 +109,7 @@ def test_bank_search_mapping_keeps_results_identical(tmp_path, monkeypatch, work
     psi = _rand_state(n, 9)
     differs = False
     for ps, prog, tables in progs:
-        monkeypatch.delenv("QSV_JIT_BANKSEARCH", raising=False)
+        monkeypatch.setenv("QSV_JIT_BANKSEARCH", "0")
         src0 = jit_source(ps, prog)
         ref = jit_host_run(ps, prog, tables, psi, 0, str(tmp_path))
         monkeypatch.setenv("QSV_JIT_BANKSEARCH", "1")
