@@ -310,7 +310,7 @@ def run_big_shard(args, comm, g, world, rank, barrier):
     in_index = 0 ^ flip
 
     def step():
-        sv.run_from_basis(in_index, plan)
+        sv.run_from_basis(in_index, plan, sample_src_pos=src_pos)
         return sv.sample(0.37, src_pos)
 
     def timed(k):
@@ -505,8 +505,10 @@ def main():
     in_index = lowering.basis_index(in_bits) ^ flip
 
     def step(u=0.37):
-        sv.run_from_basis(in_index, plan)       # = init_basis + execute (the 16 * 2^n byte clear is skipped where
-        return sv.sample(u, src_pos)            #   the leading passes can zero-fill: StateVector.run_from_basis)
+        # = init_basis + execute + sample, as Circuit.run does it: the 16 * 2^n byte clear is skipped where the leading
+        # passes can zero-fill, and the last pass adds up the weights the sampler's first level needs
+        sv.run_from_basis(in_index, plan, sample_src_pos=src_pos)
+        return sv.sample(u, src_pos)
 
     def barrier():
         if world > 1:

@@ -213,6 +213,17 @@ int qsv_run_pass_rounds_fresh(void *state_dev, const qsv_pass_t *pass, const voi
                               const void *tables_dev, uint64_t fixed_mask, uint64_t fixed_val, uint32_t zf_mask,
                               uint32_t zf_val, void *stream);
 
+/* The LAST pass of a run that ends in a sample (main/circuit.py:360-364): qsv_run_pass_rounds_sparse / _fresh
+ * (zf_mask = 0: nothing to zero-fill) that also adds up, tile by tile while the final amplitudes sit in registers,
+ * the weights re^2 + im^2 in the sampler's exact fixed point and leaves them in `buckets_dev` (4 << n_bits uint64 limbs,
+ * cleared by this call): bucket = the index bits at bucket_pos[0..n_bits) (physical positions OUTSIDE the pass's tile,
+ * bucket_pos[0] = least significant; global positions are read from pass->rank_bits).  With bucket_pos = the positions of
+ * the top output bits this is the first level of the radix descent of qsv_sample_level - without its read of the whole
+ * state (17 GB = 2.6 ms at 30 qubits); continue with qsv_sample_select.  Pass-specialised kernel only. */
+int qsv_run_pass_rounds_sums(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                             const void *tables_dev, uint64_t fixed_mask, uint64_t fixed_val, uint32_t zf_mask,
+                             uint32_t zf_val, int n_bits, const int *bucket_pos, void *buckets_dev, void *stream);
+
 /* Pass-specialised form of qsv_run_pass_rounds.  For large states (n_local >= 28 by default; environment
  * QSV_JIT=0 never, QSV_JIT=force always, QSV_JIT_MIN_QUBITS=n) qsv_run_pass_rounds does not interpret the
  * round program: libqsv generates straight-line sm_100a CUDA for exactly this program (same tile geometry,
@@ -233,6 +244,12 @@ void qsv_jit_stats(uint64_t *kernels_compiled, uint64_t *cache_hits, double *com
 /* Kernels served from the on-disk cubin cache instead of NVRTC since the library was loaded (QSV_CACHE_DIR, default
  * ~/.cache/qsv; keyed by the generated source + compiler version; QSV_DISK_CACHE=0 disables). */
 uint64_t qsv_jit_disk_hits(void);
+/* Source / cubin of the sums variant of a pass kernel (see qsv_run_pass_rounds_sums; tests compile the source as host
+ * C++, where qsv_jit_host_set_buckets(uint64_t*) names the bucket array before qsv_jit_host_run). */
+int  qsv_jit_source_sums(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_bits,
+                         const int *bucket_pos, char *buf, size_t buf_len, size_t *needed);
+int  qsv_jit_compile_sums(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_bits,
+                          const int *bucket_pos, char *cubin_buf, size_t buf_len, size_t *needed);
 /* Modelled shared-memory bank-group collisions of one pass program (sampled quarter-warps x slots x rounds; 0 = none):
  * with the default thread-index mapping, and with the per-round mapping the opt-in search (QSV_JIT_BANKSEARCH=1) picks.
  * A planning aid that needs no GPU (tools/plan_report.py --banks). */

@@ -47,7 +47,9 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) {
     return make_double2(a.x + b.x, a.y + b.y);
 }
-__device__ __forceinline__ double cnorm2(double2 a) { return a.x * a.x + a.y * a.y; }
+// |a|^2 with ONE fixed evaluation order (re * re + round(im * im), fused): the generated pass kernels compute the same
+// weights in their sums epilogue (csrc/qsv_jit.cu, qsv_weight) and must agree with the sampler to the last bit
+__device__ __forceinline__ double cnorm2(double2 a) { return __fma_rn(a.x, a.x, __dmul_rn(a.y, a.y)); }
 
 // Insert a zero bit at position p of v (bits >= p move up by one).
 __device__ __forceinline__ uint64_t insert_zero(uint64_t v, unsigned p) {

@@ -288,6 +288,17 @@ static void apply_multipliers(Out &o, const SlotMul (&m)[16], const std::vector<
 // thread-index bits 0..2 are given to one tile bit of each class {j, L+j, L+3+j} that is not a register bit: all 8
 // combinations then fall into different groups (qsv.schedule.plan_rounds keeps one bit per class out of the registers).
 static thread_local int t_pad_L = -1;       // >= 0: padded layout with runs of 2^L amplitudes; -1: linear layout
+
+// Sums variant (the LAST pass of a run that ends in a sample): while a tile's final amplitudes sit in registers, their
+// weights re^2 + im^2 are added up in the sampler's exact fixed point (csrc/qsv_sample.cu: units of 2^-96, 128-bit) and
+// the tile's total goes to bucket hb = the index bits at pos[0..n_bits) (physical positions OUTSIDE the tile, pos[0] =
+// least significant bucket bit) of a 4-limb bucket array - exactly what the first level of the sampler's radix descent
+// (qsv_sample_level over the top output bits) would compute with another full read of the state.
+struct SumSpec { int n_bits; int pos[12]; };
+constexpr int kSumMaxInside = 3;              // bucket positions that may lie INSIDE the tile (2^3 partial sums per tile)
+static thread_local const SumSpec *t_sums = nullptr;     // sums variant being generated (read by gen_round)
+static thread_local int t_tile_phys[12];                 // physical position of tile-local bit t
+
 static void thread_bit_order(const qsv_round_t &R, int pos[8]) {
     bool is_rb[12] = {false};
     for (int q = 0; q < 4; ++q) is_rb[R.rb[q]] = true;
@@ -629,6 +640,81 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     o.f("}");
     }
 
+    if (direct && t_sums) {
+        // Tile sums of the sums variant.  Bucket bits on positions outside the tile are the same for the whole tile; a
+        // bucket bit INSIDE the tile is held either by a register bit of this (last) round - then every thread keeps one
+        // partial sum per value (acc[]) - or by a thread bit: lanes that agree on those bits form a group
+        // (__reduce_add_sync over the group's mask, 16-bit limbs so that 32 lanes cannot overflow a word), the group
+        // leaders add to a small shared-memory table with one entry per combination of the inside bits, and after the
+        // barrier one thread per entry adds its 128-bit total to the bucket array in global memory.
+        int pos8[8];
+        if (t_tb_override) memcpy(pos8, t_tb_override, sizeof(pos8));
+        else thread_bit_order(R, pos8);
+        int thr_tid[4], thr_kb[4], reg_kb[4], n_thr = 0, n_reg_in = 0;
+        for (int kb = 0; kb < t_sums->n_bits; ++kb) {
+            for (int q = 0; q < 4; ++q)
+                if (t_tile_phys[R.rb[q]] == t_sums->pos[kb]) reg_kb[n_reg_in++] = kb;
+            for (int i = 0; i < 8; ++i)
+                if (t_tile_phys[pos8[i]] == t_sums->pos[kb]) { thr_tid[n_thr] = i; thr_kb[n_thr++] = kb; }
+        }
+        uint32_t ilm = 0;
+        for (int j = 0; j < n_thr; ++j) if (thr_tid[j] < 5) ilm |= 1u << thr_tid[j];
+        uint32_t base_mask = 0;
+        for (uint32_t m = 0; m < 32; ++m) if (!(m & ilm)) base_mask |= 1u << m;
+        const int n_ent = 1 << (n_thr + n_reg_in);
+        o.f("#ifndef QSV_JIT_HOST");
+        o.f("__device__ __forceinline__ void qsv_tile_sum(const qsv_ctx &c, const u64 gbase, const u32 tid, const qsv_u128 *acc) {");
+        o.f("    const u32 lane = tid & 31u;");
+        o.f("    const u32 gm = 0x%xu << (lane & 0x%xu);", base_mask, ilm);
+        o.f("    const bool leader = (lane & 0x%xu) == 0u;", (~ilm) & 31u);
+        {
+            std::string e = "0u";
+            for (int j = 0; j < n_thr; ++j)
+                e += " | (((tid >> " + std::to_string(thr_tid[j]) + ") & 1u) << " + std::to_string(j) + ")";
+            o.f("    const u32 vthr = %s;", e.c_str());
+        }
+        o.f("    u32 *tab = c.s_tab + c.par * %du;", n_ent * 8);
+        o.f("    #pragma unroll");
+        o.f("    for (int a_ = 0; a_ < %d; ++a_) {", 1 << n_reg_in);
+        o.f("        #pragma unroll");
+        o.f("        for (int i_ = 0; i_ < 8; ++i_) {");
+        o.f("            const u32 limb = (u32)(((i_ < 4 ? acc[a_].lo : acc[a_].hi) >> (16 * (i_ & 3))) & 0xffffULL);");
+        o.f("            const u32 s_ = __reduce_add_sync(gm, limb);");
+        o.f("            if (leader && s_) atomicAdd(tab + (vthr | ((u32)a_ << %d)) * 8u + (u32)i_, s_);", n_thr);
+        o.f("        }");
+        o.f("    }");
+        o.f("    __syncthreads();");
+        o.f("    if (tid < %du) {", n_ent);
+        o.f("        u32 *t_ = tab + tid * 8u;");
+        o.f("        qsv_u128 v = {0ULL, 0ULL};");
+        o.f("        #pragma unroll");
+        o.f("        for (int i_ = 0; i_ < 8; ++i_) {");
+        o.f("            const u64 s_ = t_[i_];");
+        o.f("            t_[i_] = 0u;");
+        o.f("            if (i_ < 4) {");
+        o.f("                const u64 add = s_ << (16 * i_);");
+        o.f("                v.lo += add;");
+        o.f("                v.hi += (v.lo < add ? 1ULL : 0ULL) + (i_ ? (s_ >> (64 - 16 * (i_ ? i_ : 1))) : 0ULL);");
+        o.f("            } else {");
+        o.f("                v.hi += s_ << (16 * (i_ - 4));");
+        o.f("            }");
+        o.f("        }");
+        {
+            std::string e = "qsv_bucket_ext(gbase)";
+            for (int j = 0; j < n_thr; ++j)
+                e += " | (((tid >> " + std::to_string(j) + ") & 1u) << " + std::to_string(thr_kb[j]) + ")";
+            for (int j = 0; j < n_reg_in; ++j)
+                e += " | (((tid >> " + std::to_string(n_thr + j) + ") & 1u) << " + std::to_string(reg_kb[j]) + ")";
+            o.f("        if (v.lo | v.hi) {");
+            o.f("            u64 *b = c.bk + 4ULL * (%s);", e.c_str());
+        }
+        o.f("            atomicAdd(b + 0, v.lo & 0xffffffffULL); atomicAdd(b + 1, v.lo >> 32);");
+        o.f("            atomicAdd(b + 2, v.hi & 0xffffffffULL); atomicAdd(b + 3, v.hi >> 32);");
+        o.f("        }");
+        o.f("    }");
+        o.f("}");
+        o.f("#endif");
+    }
     // round 0 reads the tile as it came from global memory: in a FRESH state (no memset behind qsv_init_basis_sparse)
     // everything outside the support is uninitialised, and the amplitudes whose tile-local index disagrees with the
     // support's fixed bits (zf_mask / zf_val, tile-local) are taken as zero instead of what was loaded
@@ -843,6 +929,25 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
         }
         o.f("    QSV_WAIT_PEER(ctx);");
         for (int r = 0; r < 16; ++r) o.f("    QSV_STG(gout + g%d, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
+        if (t_sums) {
+            o.f("#ifdef QSV_JIT_HOST");
+            for (int r = 0; r < 16; ++r) o.f("    qsv_host_add(g%d | gbase, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
+            o.f("#else");
+            // per-thread partial sums, one per combination of the bucket bits this round holds in REGISTERS
+            int reg_q[4], n_reg_in = 0;
+            for (int kb = 0; kb < t_sums->n_bits; ++kb)
+                for (int q = 0; q < 4; ++q)
+                    if (t_tile_phys[R.rb[q]] == t_sums->pos[kb]) reg_q[n_reg_in++] = q;
+            o.f("    { qsv_u128 acc[%d];", 1 << n_reg_in);
+            o.f("      for (int a_ = 0; a_ < %d; ++a_) acc[a_].lo = acc[a_].hi = 0ULL;", 1 << n_reg_in);
+            for (int r = 0; r < 16; ++r) {
+                int sel = 0;
+                for (int j = 0; j < n_reg_in; ++j) sel |= ((r >> reg_q[j]) & 1) << j;
+                o.f("      qsv_wacc(acc[%d], %s, %s);", sel, xr(r).c_str(), xi(r).c_str());
+            }
+            o.f("      qsv_tile_sum(ctx, gbase, tid, acc); }");
+            o.f("#endif");
+        }
         o.f("}");
         return 0;
     }
@@ -921,6 +1026,33 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes) 
 #endif
 )SRC";
 
+// exact weight sums of the sums variant: the arithmetic of csrc/qsv_sample.cu (weight_fix, u128_add, 4 x 32-bit limbs)
+static const char *kSumHelpers = R"SRC(
+struct qsv_u128 { u64 lo, hi; };
+#ifdef QSV_JIT_HOST
+static inline u64 qsv_dbits(double w) { u64 b; memcpy(&b, &w, 8); return b; }
+static inline double qsv_weight(double re, double im) { return __builtin_fma(re, re, im * im); }
+#else
+#define qsv_dbits(w) ((u64)__double_as_longlong(w))
+#define qsv_weight(re, im) __fma_rn(re, re, __dmul_rn(im, im))
+#endif
+QSV_FN void qsv_wacc(qsv_u128 &a, const double re, const double im) {
+    const u64 b = qsv_dbits(qsv_weight(re, im));
+    const int e = (int)((b >> 52) & 0x7ffULL);
+    if (e == 0) return;
+    const u64 m = (b & ((1ULL << 52) - 1ULL)) | (1ULL << 52);
+    const int sh = e - 1075 + 96;
+    u64 lo = 0ULL, hi = 0ULL;
+    if (sh >= 75) { hi = ~0ULL; lo = ~0ULL; }
+    else if (sh >= 64) hi = m << (sh - 64);
+    else if (sh > 0) { lo = m << sh; hi = m >> (64 - sh); }
+    else if (sh == 0) lo = m;
+    else if (sh > -64) lo = m >> (-sh);
+    a.lo += lo;
+    a.hi += hi + (a.lo < lo ? 1ULL : 0ULL);
+}
+)SRC";
+
 // fused swap + pass: two tile buffers and one CTA per SM (QSV_FUSE_BUFFERS=2), or the single buffer and two CTAs per SM
 static bool fuse_two_buffers() {
     const char *e = getenv("QSV_FUSE_BUFFERS");
@@ -947,7 +1079,7 @@ struct SwapSpec { int g; int q[4]; int gb[4]; int pre; int n_local; };
 constexpr unsigned kFlagCtas = 1024;      // flag slots per source rank in the peers' flag arrays
 
 int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, std::string &src, std::string &err,
-             const SwapSpec *sw = nullptr) {
+             const SwapSpec *sw = nullptr, const SumSpec *sums = nullptr) {
     const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
     const uint8_t *body = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);
     std::vector<qsv_round_t> rounds(hdr->n_rounds);
@@ -994,8 +1126,50 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
 
     Out o;
     if (sw) { o.f("#define QSV_FUSED_SWAP 1"); o.f("#define QSV_NLOCAL %d", P.n_local); }
+    if (sums) {
+        if (sw) { err = "sums variant of a fused swap kernel is not supported"; return 1; }
+        if (!direct) { err = "sums variant needs the direct-store kernel"; return 1; }
+        if (sums->n_bits < 1 || sums->n_bits > 12) { err = "sums: n_bits out of range"; return 1; }
+        int n_inside = 0;
+        for (int k = 0; k < sums->n_bits; ++k) {
+            if (sums->pos[k] < 0 || sums->pos[k] >= 48) { err = "sums: bucket position out of range"; return 1; }
+            bool inside = sums->pos[k] < L;
+            for (int j = 0; j < n_hi; ++j) inside = inside || P.hi_pos[j] == sums->pos[k];
+            n_inside += inside;
+        }
+        if (n_inside > kSumMaxInside) { err = "sums: more than 3 bucket positions inside the tile"; return 1; }
+        o.f("#define QSV_SUMS 1");
+    }
     o.s += kPrelude;
     o.s += kDeviceHelpers;
+    if (sums) {
+        o.s += kSumHelpers;
+        // bucket of a FULL global index (host form: every amplitude finds its own bucket)
+        std::string e = "0u";
+        for (int k = 0; k < sums->n_bits; ++k)
+            e += " | ((u32)((full >> " + std::to_string(sums->pos[k]) + ") & 1ULL) << " + std::to_string(k) + ")";
+        o.f("QSV_FN u32 qsv_bucket_of(const u64 full) { return %s; }", e.c_str());
+        {
+            std::string x = "0u";       // the bucket bits on positions OUTSIDE the tile (the same for a whole tile)
+            for (int k = 0; k < sums->n_bits; ++k) {
+                bool inside = sums->pos[k] < L;
+                for (int j = 0; j < n_hi; ++j) inside = inside || P.hi_pos[j] == sums->pos[k];
+                if (!inside)
+                    x += " | ((u32)((gbase >> " + std::to_string(sums->pos[k]) + ") & 1ULL) << " + std::to_string(k) + ")";
+            }
+            o.f("QSV_FN u32 qsv_bucket_ext(const u64 gbase) { return %s; }", x.c_str());
+        }
+        o.f("#ifdef QSV_JIT_HOST");
+        o.f("static u64 *qsv_host_bk = 0;");
+        o.f("extern \"C\" void qsv_jit_host_set_buckets(u64 *bk) { qsv_host_bk = bk; }");
+        o.f("static inline void qsv_host_add(const u64 full, const double re, const double im) {");
+        o.f("    qsv_u128 v = {0ULL, 0ULL};");
+        o.f("    qsv_wacc(v, re, im);");
+        o.f("    u64 *b = qsv_host_bk + 4ULL * qsv_bucket_of(full);");
+        o.f("    b[0] += v.lo & 0xffffffffULL; b[1] += v.lo >> 32; b[2] += v.hi & 0xffffffffULL; b[3] += v.hi >> 32;");
+        o.f("}");
+        o.f("#endif");
+    }
     if (pad)
         o.f("#define QP(a) ((a) + ((a) >> %d) + ((a) >> %d))", L, L + 3);
     else
@@ -1018,7 +1192,8 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
             o.f("struct qsv_ctx { const double2 *next_src; double2 *tile; u64 *mbar; const u64 *s_off; const u64 *wait_flag;"
                 " u64 wait_val; u32 warp; u32 flags; };");
         else
-        o.f("struct qsv_ctx { double2 *state; double2 *tile; u64 *mbar; const u64 *s_off; u64 next_base; u32 warp; u32 flags; };");
+        o.f("struct qsv_ctx { double2 *state; double2 *tile; u64 *mbar; const u64 *s_off; u64 next_base; u32 warp; u32 flags;"
+            " u64 *bk; u32 *s_tab; u32 par; };");
         o.f("__device__ __forceinline__ void qsv_issue_load(const qsv_ctx &c) {");
         o.f("    if (c.flags & 2u) mbar_expect_tx(c.mbar, %uu);", 16u << 12);
         o.f("    u32 elected;");
@@ -1067,6 +1242,8 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     }
     std::vector<RoundInfo> info(nr);
     double scale = 1.0;
+    t_sums = sums;
+    for (int t = 0; t < 12; ++t) t_tile_phys[t] = t < L ? t : (int)P.hi_pos[t - L];
     for (uint32_t k = 0; k < nr; ++k) {
         const bool last = k + 1 == nr;
         const double scale_before = scale;
@@ -1084,6 +1261,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         }
     }
     t_tb_override = nullptr;
+    t_sums = nullptr;
 
     // is a tile ever skipped?  (every op has an external condition)
     bool always_active = false;
@@ -1101,6 +1279,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         active = "true";
     }
     if (sw) active = "true";       // every tile moves, whatever its ops' conditions say
+    if (sums) active = "true";     // every tile of the support is weighed, whether an op acts on it or not
     // sp_mask / sp_val: index bits known to be FIXED in the state's support (a register that started in a basis state
     // and has not been touched non-diagonally on those positions): a tile that disagrees holds only zeros and, the
     // pass being linear, stays zero - it is skipped like a tile whose ops are all switched off
@@ -1195,7 +1374,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    const u32 zf_mask = 0u, zf_val = 0u;      // sharded registers are always initialised in full");
     } else {
     o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
-        " const u64 sp_mask, const u64 sp_val, const u32 zf_mask, const u32 zf_val) {");
+        " const u64 sp_mask, const u64 sp_val, const u32 zf_mask, const u32 zf_val%s) {", sums ? ", u64 *__restrict__ bk" : "");
     }
     o.f("    extern __shared__ __align__(128) unsigned char smem_raw[];");
     o.f("    double2 *tile = reinterpret_cast<double2 *>(smem_raw);");
@@ -1297,6 +1476,14 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("    qsv_ctx ctx;");
         o.f("    ctx.state = state; ctx.tile = tile; ctx.mbar = &mbar; ctx.s_off = s_off; ctx.warp = warp;");
         o.f("    ctx.flags = (tid == 0 ? 2u : 0u) | 4u;");
+        if (sums) {
+            o.f("    __shared__ u32 s_tab[2 * 8 * 8];");
+            o.f("    if (tid < 128u) s_tab[tid] = 0u;");
+            o.f("    __syncthreads();");
+            o.f("    ctx.bk = bk; ctx.s_tab = s_tab; ctx.par = 0u;");
+        } else {
+            o.f("    ctx.bk = nullptr; ctx.s_tab = nullptr; ctx.par = 0u;");
+        }
         o.f("    u64 t = blockIdx.x;");
         o.f("    while (t < n_tiles && !qsv_active(qsv_tile_base(t) | rank_bits, sp_mask, sp_val, zf_mask)) t += gridDim.x;");
         o.f("    if (t >= n_tiles) return;");
@@ -1311,6 +1498,7 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("        ctx.flags = (ctx.flags & 3u) | (tn < n_tiles ? 4u : 0u);");
         o.f("        mbar_wait(&mbar, parity);");
         o.f("        parity ^= 1u;");
+        o.f("        ctx.par ^= 1u;");
         rounds_body(o, 0);
         o.f("        if (tn >= n_tiles) break;");
         o.f("        t = tn;");
@@ -1539,8 +1727,13 @@ static std::mutex g_mu;
 static std::unordered_map<std::string, Entry *> g_cache;
 static std::atomic<uint64_t> g_compiles{0}, g_hits{0}, g_compile_us{0};
 
-static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr) {
+static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr,
+                             const SumSpec *sums = nullptr) {
     std::string k;
+    if (sums) {
+        k.append("SUM");
+        k.append(reinterpret_cast<const char *>(sums), sizeof(*sums));
+    }
     if (sw) {
         k.append(fuse_two_buffers() ? "F2" : "F1");
         k.append(reinterpret_cast<const char *>(sw), sizeof(*sw));
@@ -1557,8 +1750,9 @@ static std::string cache_key(const qsv_pass_t &P, const void *prog, uint32_t byt
     return k;
 }
 
-static Entry *lookup(const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr) {
-    const std::string k = cache_key(P, prog, bytes, sw);
+static Entry *lookup(const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr,
+                     const SumSpec *sums = nullptr) {
+    const std::string k = cache_key(P, prog, bytes, sw, sums);
     std::lock_guard<std::mutex> g(g_mu);
     auto it = g_cache.find(k);
     if (it != g_cache.end()) return it->second;
@@ -1644,13 +1838,14 @@ static void disk_cache_store(const std::string &path, const std::string &cubin) 
 
 static std::atomic<uint64_t> g_disk_hits{0};
 
-static int ensure_compiled(Entry *e, const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr) {
+static int ensure_compiled(Entry *e, const qsv_pass_t &P, const void *prog, uint32_t bytes, const SwapSpec *sw = nullptr,
+                           const SumSpec *sums = nullptr) {
     std::lock_guard<std::mutex> g(e->mu);
     if (e->compiled) { g_hits.fetch_add(1); return 0; }
     if (e->failed) { set_error("qsv jit: %s", e->err.c_str()); return 1; }
     const auto t0 = std::chrono::steady_clock::now();
     std::string src;
-    if (generate(P, prog, bytes, src, e->err, sw)) {
+    if (generate(P, prog, bytes, src, e->err, sw, sums)) {
         e->failed = true;
         set_error("qsv jit: %s", e->err.c_str());
         return 1;
@@ -1710,19 +1905,38 @@ bool wanted(const qsv_pass_t *P, const void *prog_host) {
     return P->n_local >= minq;
 }
 
-static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out);
+static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out,
+                        const SumSpec *sums = nullptr);
+
+static int launch_any(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
+                      const void *tables_dev, cudaStream_t st, unsigned grid, unsigned long long sp_mask,
+                      unsigned long long sp_val, unsigned zf_mask, unsigned zf_val, const SumSpec *sums, void *bk_dev);
 
 int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
            cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask,
            unsigned zf_val) {
+    return launch_any(state_dev, P, prog_host, prog_bytes, tables_dev, st, grid, sp_mask, sp_val, zf_mask, zf_val, nullptr,
+                      nullptr);
+}
+
+int launch_sums(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
+                cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask,
+                unsigned zf_val, const SumSpec &sums, void *bk_dev) {
+    return launch_any(state_dev, P, prog_host, prog_bytes, tables_dev, st, grid, sp_mask, sp_val, zf_mask, zf_val, &sums,
+                      bk_dev);
+}
+
+static int launch_any(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
+                      const void *tables_dev, cudaStream_t st, unsigned grid, unsigned long long sp_mask,
+                      unsigned long long sp_val, unsigned zf_mask, unsigned zf_val, const SumSpec *sums, void *bk_dev) {
     void *fn = nullptr;
-    if (int rc = get_function(P, prog_host, prog_bytes, nullptr, &fn)) return rc;
+    if (int rc = get_function(P, prog_host, prog_bytes, nullptr, &fn, sums)) return rc;
     std::string err;
     Driver *d = driver(err);
     QSV_CHECK_ARG(d, "qsv jit: %s", err.c_str());
     unsigned long long rank_bits = P->rank_bits, n_tiles = 1ull << (P->n_local - P->tile_bits);
     void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &sp_mask, &sp_val, &zf_mask,
-                    &zf_val};
+                    &zf_val, &bk_dev};      // the sums variant takes the bucket array as its ninth parameter
     const int rc = d->LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 16u * tile_slots(P->n_hi), (void *)st, args, nullptr);
     if (rc) {
         const char *es = nullptr;
@@ -1793,10 +2007,11 @@ int launch_swap(void *state_dev, const qsv_pass_t *P, const void *prog_host, uin
     return 0;
 }
 
-static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out) {
+static int get_function(const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const SwapSpec *sw, void **fn_out,
+                        const SumSpec *sums) {
     if (validate(P, prog_host, prog_bytes)) return 1;
-    Entry *e = lookup(*P, prog_host, prog_bytes, sw);
-    if (ensure_compiled(e, *P, prog_host, prog_bytes, sw)) return 1;
+    Entry *e = lookup(*P, prog_host, prog_bytes, sw, sums);
+    if (ensure_compiled(e, *P, prog_host, prog_bytes, sw, sums)) return 1;
     int dev = 0;
     QSV_CUDA(cudaGetDevice(&dev));
     void *fn = nullptr;
@@ -1854,6 +2069,48 @@ extern "C" int qsv_jit_compile(const qsv_pass_t *pass, const void *prog_host, ui
     if (jit::ensure_compiled(e, *pass, prog_host, prog_bytes)) return 1;
     return copy_out(e->cubin, cubin_buf, buf_len, needed);
 }
+
+static int make_sum_spec(jit::SumSpec &sm, int n_bits, const int *positions) {
+    QSV_CHECK_ARG(n_bits >= 1 && n_bits <= 12 && positions, "qsv sums: n_bits=%d out of range or NULL positions", n_bits);
+    memset(&sm, 0, sizeof(sm));
+    sm.n_bits = n_bits;
+    for (int k = 0; k < n_bits; ++k) {
+        QSV_CHECK_ARG(positions[k] >= 0 && positions[k] < 48, "qsv sums: position %d out of range", positions[k]);
+        for (int j = 0; j < k; ++j) QSV_CHECK_ARG(positions[j] != positions[k], "qsv sums: duplicate position %d", positions[k]);
+        sm.pos[k] = positions[k];
+    }
+    return 0;
+}
+
+extern "C" int qsv_jit_source_sums(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_bits,
+                                   const int *positions, char *buf, size_t buf_len, size_t *needed) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return 1;
+    jit::SumSpec sm;
+    if (make_sum_spec(sm, n_bits, positions)) return 1;
+    std::string src, err;
+    if (jit::generate(*pass, prog_host, prog_bytes, src, err, nullptr, &sm)) { set_error("qsv jit: %s", err.c_str()); return 1; }
+    return copy_out(src, buf, buf_len, needed);
+}
+
+extern "C" int qsv_jit_compile_sums(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_bits,
+                                    const int *positions, char *cubin_buf, size_t buf_len, size_t *needed) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return 1;
+    jit::SumSpec sm;
+    if (make_sum_spec(sm, n_bits, positions)) return 1;
+    jit::Entry *e = jit::lookup(*pass, prog_host, prog_bytes, nullptr, &sm);
+    if (jit::ensure_compiled(e, *pass, prog_host, prog_bytes, nullptr, &sm)) return 1;
+    return copy_out(e->cubin, cubin_buf, buf_len, needed);
+}
+
+namespace qsv { namespace jit {
+int run_sums(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
+             cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask,
+             unsigned zf_val, int n_bits, const int *positions, void *bk_dev) {
+    SumSpec sm;
+    if (make_sum_spec(sm, n_bits, positions)) return 1;
+    return launch_sums(state_dev, P, prog_host, prog_bytes, tables_dev, st, grid, sp_mask, sp_val, zf_mask, zf_val, sm, bk_dev);
+}
+} }
 
 static int make_swap_spec(jit::SwapSpec &sw, int j, const int *positions, const int *gbits, int pass_first,
                           const qsv_pass_t *pass) {

@@ -379,6 +379,9 @@ bool wanted(const qsv_pass_t *P, const void *prog_host);
 int launch(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
            cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask,
            unsigned zf_val);
+int run_sums(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
+             cudaStream_t st, unsigned grid, unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask,
+             unsigned zf_val, int n_bits, const int *positions, void *bk_dev);
 } }
 
 static_assert(sizeof(qsv_rop_t) == 128, "qsv_rop_t must be 128 bytes");
@@ -432,6 +435,39 @@ extern "C" int qsv_run_pass_rounds_fresh(void *state_dev, const qsv_pass_t *P, c
                            zf_val);
 }
 
+static unsigned jit_grid(const qsv_pass_t *P) {
+    const uint64_t n_tiles_j = 1ull << (P->n_local - P->tile_bits);
+    // persistent CTAs, 2 resident per SM; the grid holds QSV_JIT_WAVES (default 16; measured 4 -> 16: single-gate sweep 5.45 -> 5.2 ms) times as many, so that the
+    // hardware scheduler evens out SMs that run at different speeds (the tail of a static split is one CTA long)
+    static const unsigned waves = [] {
+        const char *e = getenv("QSV_JIT_WAVES");
+        const int v = e ? atoi(e) : 16;
+        return (unsigned)(v >= 1 && v <= 4096 ? v : 16);
+    }();
+    const uint64_t resident_j = (uint64_t)sm_count() * 2ull * waves;
+    return (unsigned)(n_tiles_j < resident_j ? n_tiles_j : resident_j);
+}
+
+// The LAST pass of a run that ends in a sample: qsv_run_pass_rounds_sparse / _fresh (zf_mask = 0: plain sparse form) that
+// also adds every tile's total weight - exact 2^-96 fixed point, the sampler's arithmetic - to bucket
+// hb = index bits at bucket_pos[0..n_bits) of `buckets_dev` (4 << n_bits uint64 limbs, zeroed by this call): the first
+// level of qsv_sample_level's radix descent without its read of the whole state.  bucket_pos are physical positions
+// outside the pass's tile (global positions allowed: they come from pass->rank_bits).  Pass-specialised kernel only.
+extern "C" int qsv_run_pass_rounds_sums(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
+                                        const void *tables_dev, uint64_t fixed_mask, uint64_t fixed_val, uint32_t zf_mask,
+                                        uint32_t zf_val, int n_bits, const int *bucket_pos, void *buckets_dev,
+                                        void *stream) {
+    QSV_CHECK_ARG(state_dev && P && prog_host && buckets_dev && bucket_pos, "qsv_run_pass_rounds_sums: NULL pointer");
+    QSV_CHECK_ARG((fixed_val & ~fixed_mask) == 0 && (zf_val & ~zf_mask) == 0, "qsv_run_pass_rounds_sums: value bits outside mask");
+    QSV_CHECK_ARG(P->n_local >= 12 && P->n_local <= 40 && P->tile_bits == 12, "qsv_run_pass_rounds_sums: needs 12-bit tiles");
+    QSV_CHECK_ARG((P->reserved == 0 || P->reserved == 4) && prog_bytes >= sizeof(qsv_rprog_hdr_t) && jit::wanted(P, prog_host),
+                  "qsv_run_pass_rounds_sums: only the pass-specialised kernel sums (QSV_JIT / register size)");
+    QSV_CHECK_ARG(n_bits >= 1 && n_bits <= 12, "qsv_run_pass_rounds_sums: n_bits=%d out of range", n_bits);
+    QSV_CUDA(cudaMemsetAsync(buckets_dev, 0, (size_t)32 << n_bits, (cudaStream_t)stream));
+    return jit::run_sums(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, jit_grid(P), fixed_mask,
+                         fixed_val, zf_mask, zf_val, n_bits, bucket_pos, buckets_dev);
+}
+
 static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes,
                            const void *tables_dev, void *stream, uint64_t sp_mask, uint64_t sp_val, uint32_t zf_mask,
                            uint32_t zf_val) {
@@ -456,16 +492,7 @@ static int run_pass_rounds(void *state_dev, const qsv_pass_t *P, const void *pro
     // generated as straight-line code for this program and cached by its bytes.  It has its own (much
     // larger) program capacity, so it is tried before the interpreter's kernel-parameter limits apply.
     if (RB == 4 && jit::wanted(P, prog_host)) {
-        const uint64_t n_tiles_j = 1ull << (P->n_local - P->tile_bits);
-        // persistent CTAs, 2 resident per SM; the grid holds QSV_JIT_WAVES (default 16; measured 4 -> 16: single-gate sweep 5.45 -> 5.2 ms) times as many, so that the
-        // hardware scheduler evens out SMs that run at different speeds (the tail of a static split is one CTA long)
-        static const unsigned waves = [] {
-            const char *e = getenv("QSV_JIT_WAVES");
-            const int v = e ? atoi(e) : 16;
-            return (unsigned)(v >= 1 && v <= 4096 ? v : 16);
-        }();
-        const uint64_t resident_j = (uint64_t)sm_count() * 2ull * waves;
-        const unsigned grid_j = (unsigned)(n_tiles_j < resident_j ? n_tiles_j : resident_j);
+        const unsigned grid_j = jit_grid(P);
         const int rc = jit::launch(state_dev, P, prog_host, prog_bytes, tables_dev, (cudaStream_t)stream, grid_j,
                                    sp_mask, sp_val, zf_mask, zf_val);
         const char *mode = getenv("QSV_JIT");

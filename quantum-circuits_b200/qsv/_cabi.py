@@ -43,6 +43,10 @@ SYMBOLS = {
     "qsv_run_pass_rounds_sparse": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _U64, _U64, _P]),
     "qsv_run_pass_rounds_fresh": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _U64, _U64, C.c_uint32,
                                            C.c_uint32, _P]),
+    "qsv_run_pass_rounds_sums": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, _U64, _U64, C.c_uint32,
+                                          C.c_uint32, _I, _IP, _P, _P]),
+    "qsv_jit_source_sums": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "qsv_jit_compile_sums": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _I, _IP, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_source": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_compile": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "qsv_jit_wanted": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32]),

@@ -15,6 +15,9 @@ SCAN_BITS_EXACT = 20     # up to 2^20 outcomes: one fully sequential scan (bit-e
 SAMPLE_BLOCK_BITS = 12   # larger states: block sums of 2^12 outcomes, then a sequential scan inside one block
 
 
+PRESUM_MIN_BITS = 3      # the last pass weighs the state for the sampler if it can fix at least this many top output bits
+_NO_SAMPLE = object()    # "no sample follows" (None is a valid src_pos: the identity map)
+
 _PLAN_CACHE = {}      # op-list fingerprint -> [("program", PackedProgram) | ("op", Op)] (host objects only)
 _KERNELS_READY = set()   # fingerprints whose specialised kernels are already in libqsv's cache (skip the compile pool)
 
@@ -78,6 +81,7 @@ class StateVector:
         self._keep = []       # host/device buffers that must outlive the async launches
         self.passes_run = 0
         self._basis = None
+        self._presum = None       # (k, src_pos tuple): the sampler's buckets hold the sums of the top k output bits
         self._sampler = None
         self.d2h_bytes = 0
         self.tile_bits = None
@@ -103,6 +107,7 @@ class StateVector:
         """|index>: main/circuit.py:290-301."""
         _cabi.check(self.lib.qsv_init_basis(self._ptr(self.state), self.n_local, int(index), self.rank,
                                             self._stream()), "qsv_init_basis")
+        self._presum = None
         self._basis = int(index)         # the next execute() knows the support of the state (schedule.Support)
 
     def init_columns(self, n, flip=0):
@@ -113,6 +118,7 @@ class StateVector:
         _cabi.check(self.lib.qsv_init_columns(self._ptr(self.state), int(n), int(flip), self._stream()),
                     "qsv_init_columns")
         self._basis = None               # 2^n non-zero amplitudes: not a basis state, no support hint
+        self._presum = None
 
     # ------------------------------------------------------------------ gate application
     def upload_program(self, ops):
@@ -173,6 +179,7 @@ class StateVector:
         """Make `out` the state after an out-of-place op.  A symmetric-memory state keeps its buffer
         (peers hold its address): the result is copied back instead of swapping references."""
         self._basis = None
+        self._presum = None
         if self._owns_symm():
             self.state.copy_(out)
         else:
@@ -191,6 +198,7 @@ class StateVector:
         return self._scratch
 
     def _run_whole_state_op(self, op, support=None):
+        self._presum = None
         if support is None:
             self._basis = None      # called outside execute(): nothing is known about the support any more
         st = self._stream()
@@ -336,19 +344,28 @@ class StateVector:
         _KERNELS_READY.add(key)
         return {"segments": segments, "h2d_bytes": h2d}
 
-    def execute(self, plan):
+    def execute(self, plan, sample_src_pos=_NO_SAMPLE):
         """Run a prepared plan on the current state.  Right after init_basis the support of the state is known and
-        the passes skip the tiles that are still zero (schedule.Support); any other state is treated as dense."""
+        the passes skip the tiles that are still zero (schedule.Support); any other state is treated as dense.
+        sample_src_pos (a src_pos list or None for the identity map): a sample(u, src_pos) with that output wiring
+        follows - if the plan ends in a pass-specialised kernel, that pass also adds up the weights the sampler's
+        first level needs (qsv_run_pass_rounds_sums), saving its read of the whole state."""
         basis, self._basis = self._basis, None
-        self._run_segments(plan, basis, 0)
+        self._run_segments(plan, basis, 0, sample_src_pos)
 
-    def _run_segments(self, plan, basis, n_fresh):
+    def _run_segments(self, plan, basis, n_fresh, sample_src_pos=_NO_SAMPLE):
         """The launches of a plan; the first n_fresh passes in the zero-fill form (run_from_basis)."""
+        items = list(self._walk(plan, basis))
+        presum = self._presum_plan(items, sample_src_pos)
         done = 0
-        for kind, seg, sp, zf in self._walk(plan, basis):
+        for i, (kind, seg, sp, zf) in enumerate(items):
             if kind == "pass":
                 meta, dev = seg
-                self._launch_pass(meta, dev, sp, zf if done < n_fresh else None)
+                fresh = zf if done < n_fresh else None
+                if presum is not None and i == len(items) - 1:
+                    self._launch_pass_sums(meta, dev, sp, fresh, presum)
+                else:
+                    self._launch_pass(meta, dev, sp, fresh)
                 done += 1
                 self.passes_run += 1
                 self._keep.append(dev)
@@ -357,8 +374,51 @@ class StateVector:
             else:
                 self._run_whole_state_op(seg, sp if sp is not None else (0, 0))
         self._basis = None
+        self._presum = (presum[0], presum[2]) if presum is not None else None
 
-    def run_from_basis(self, index, plan):
+    def _presum_plan(self, items, sample_src_pos):
+        """(k, positions, src tuple) if the plan's last launch can weigh the state for a sample in output wiring
+        sample_src_pos: the top k output bits sit on positions outside that pass's tile; None otherwise."""
+        import os
+        if sample_src_pos is _NO_SAMPLE or not items or os.environ.get("QSV_PRESUM", "1") == "0":
+            return None
+        sharded = self.comm is not None and self.comm.world > 1
+        if not sharded and self.n_local <= SCAN_BITS_EXACT:
+            return None                         # small registers sample with the sequential float scan
+        kind, seg, sp, zf = items[-1]
+        if kind != "pass" or not self._jit_runs(seg[0]):
+            return None
+        from .sampling import presum_bits
+        ps = seg[0][0]
+        if ps.tile_bits != 12:
+            return None
+        src = tuple(sample_src_pos) if sample_src_pos is not None else tuple(range(self.n))
+        k = presum_bits(src, self.n, list(range(ps.low_bits)) + list(ps.hi_pos))
+        if k < min(PRESUM_MIN_BITS, self.n):
+            return None
+        positions = [src[b] for b in range(self.n - k, self.n)]          # least significant bucket bit first
+        return k, positions, src
+
+    def _launch_pass_sums(self, packed_meta, dev, support, fresh, presum):
+        ps, table_off, n_ops, extra = packed_meta
+        prog = extra[0]
+        cp = self._cpass(ps)
+        cp.max_dense_k = 1
+        cp.reserved = int(prog[12])
+        if self._sampler is None:
+            from .sampling import ExactSampler
+            self._sampler = ExactSampler(self.lib, self.device)
+        sp = support if support is not None else (0, 0)
+        zf = fresh if fresh is not None else (0, 0)
+        k, positions, _ = presum
+        _cabi.check(self.lib.qsv_run_pass_rounds_sums(self._ptr(self.state), C.byref(cp), C.c_void_p(prog.ctypes.data),
+                                                      int(prog.size), C.c_void_p(dev.data_ptr() + table_off),
+                                                      int(sp[0]), int(sp[1]), int(zf[0]), int(zf[1]), k,
+                                                      _cabi.int_array(positions),
+                                                      C.c_void_p(self._sampler.buckets.data_ptr()), self._stream()),
+                    "qsv_run_pass_rounds_sums")
+
+    def run_from_basis(self, index, plan, sample_src_pos=_NO_SAMPLE):
         """init_basis(index) + execute(plan), without clearing the register where the plan allows it.
 
         The reference builds |in_v> entry by entry (main/circuit.py:290-301); init_basis clears 16 * 2^n bytes for it
@@ -372,11 +432,11 @@ class StateVector:
         n_fresh = self._fresh_prefix(plan)
         if not n_fresh:
             self.init_basis(index)
-            self.execute(plan)
+            self.execute(plan, sample_src_pos)
             return
         _cabi.check(self.lib.qsv_init_basis_sparse(self._ptr(self.state), self.n_local, int(index), self.rank,
                                                    self._stream()), "qsv_init_basis_sparse")
-        self._run_segments(plan, int(index), n_fresh)
+        self._run_segments(plan, int(index), n_fresh, sample_src_pos)
 
     def _fresh_prefix(self, plan):
         """Number of leading passes that must run in the zero-fill form when the register is NOT cleared: up to and
@@ -466,6 +526,7 @@ class StateVector:
         return bool(self.lib.qsv_jit_wanted(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size)))
 
     def _run_swap_pass(self, seg, support=None):
+        self._presum = None
         swap_op, packed, dev, pass_first = seg
         ps, table_off, n_ops, extra = packed.passes[0]
         prog = extra[0]
@@ -486,6 +547,7 @@ class StateVector:
 
     # ------------------------------------------------------------------ instrumentation (bench.py)
     def _launch_pass(self, packed_meta, dev, support=None, fresh=None):
+        self._presum = None
         ps, table_off, n_ops, maxk = packed_meta
         base = dev.data_ptr()
         cp = self._cpass(ps)
@@ -648,9 +710,15 @@ class StateVector:
         if self._sampler is None:
             from .sampling import ExactSampler
             self._sampler = ExactSampler(self.lib, self.device)
+        presummed = 0
+        if self._presum is not None:
+            src = tuple(src_pos) if src_pos is not None else tuple(range(self.n))
+            if self._presum[1] == src:
+                presummed = self._presum[0]      # the last pass left the first level's bucket sums in the sampler
+            self._presum = None                  # (consumed: the descent overwrites the bucket array)
         z, nbytes = self._sampler.draw(self.state, self.n, self.n_local, self.rank, src_pos, u,
                                        torch.cuda.current_stream(self.device).cuda_stream,
-                                       self.comm.all_reduce_int64 if sharded else None)
+                                       self.comm.all_reduce_int64 if sharded else None, presummed=presummed)
         self.d2h_bytes += nbytes
         return z
 

@@ -262,7 +262,7 @@ def release_sharded_states():
             sv.comm.release_state()
 
 
-def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=True):
+def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=True, for_sample=False):
     """Run the circuit on |in_v>: (StateVector, src_pos).  Under one-process-per-GPU launches (torchrun, NCCL)
     the register is sharded over the ranks by its top qubits (qsv.dist.default_comm) unless it is small or
     shard=False; every rank then holds one shard and must make the same calls."""
@@ -282,7 +282,11 @@ def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=Tru
         ops, src_pos, flip = lower(circuit, transposed, presorted, n_global=comm.global_bits, in_flip=True,
                                    free_swap=bool(comm.peer_swap), fuse_swaps=sv.fuse_swaps())
     plan = sv.prepare(ops)
-    sv.run_from_basis(basis_index(in_v) ^ flip, plan)      # init_basis + execute, without the clear where possible
+    # init_basis + execute, without the clear where possible; when a sample follows, the last pass weighs the state for it
+    if for_sample:
+        sv.run_from_basis(basis_index(in_v) ^ flip, plan, sample_src_pos=src_pos)
+    else:
+        sv.run_from_basis(basis_index(in_v) ^ flip, plan)
     _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=0, passes=sv.passes_run)
     return sv, src_pos
 
@@ -336,7 +340,7 @@ def simulate_weights(circuit, in_v, transposed=False, presorted=True):
 
 
 def simulate_sample(circuit, in_v, rand_fn, transposed=False, presorted=True):
-    sv, src_pos = evolve(circuit, in_v, transposed, presorted)
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted, for_sample=True)
     u = rand_fn()                       # exactly one uniform draw per run, after the weights exist
     if sv.comm is not None and sv.comm.world > 1:
         u = sv.comm.broadcast_float(u)  # every rank drew once from its own generator; rank 0's value is used

@@ -407,15 +407,32 @@ def jit_source(ps, prog):
     return buf.raw.decode()
 
 
+def jit_source_sums(ps, prog, positions):
+    import ctypes as C
+    from qsv import _cabi
+    lib = _cabi.load()
+    cp = jit_cpass(ps)
+    need = C.c_size_t(0)
+    pos = _cabi.int_array(positions)
+    _cabi.check(lib.qsv_jit_source_sums(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), len(positions), pos,
+                                        None, 0, C.byref(need)), "qsv_jit_source_sums")
+    buf = C.create_string_buffer(need.value)
+    _cabi.check(lib.qsv_jit_source_sums(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), len(positions), pos,
+                                        buf, need.value, C.byref(need)), "qsv_jit_source_sums")
+    return buf.raw.decode()
+
+
 def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=None, fixed_mask=0, fixed_val=0,
-                 zf_mask=0, zf_val=0):
+                 zf_mask=0, zf_val=0, sums=None):
     """Compile the generated source of one pass as host C++ and run it on psi (numpy complex128).  With
-    single_tile_gbase, psi is one tile and only the rounds run (state sizes no host array can hold)."""
+    single_tile_gbase, psi is one tile and only the rounds run (state sizes no host array can hold).
+    sums = (bucket positions, uint64 array of 4 << len(positions) limbs): the sums variant of the kernel, which adds
+    the weights of every tile it writes to the bucket array."""
     import ctypes as C
     import hashlib
     import os
     import subprocess
-    src = jit_source(ps, prog)
+    src = jit_source(ps, prog) if sums is None else jit_source_sums(ps, prog, sums[0])
     tag = hashlib.sha1(src.encode()).hexdigest()[:16]
     cu, so = os.path.join(workdir, tag + ".cu"), os.path.join(workdir, tag + ".so")
     if not os.path.exists(so):
@@ -430,6 +447,8 @@ def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=No
     if single_tile_gbase is not None:
         h.qsv_jit_host_tile(C.c_void_p(out.ctypes.data), C.c_uint64(single_tile_gbase), C.c_void_p(tabs.ctypes.data))
         return out
+    if sums is not None:
+        h.qsv_jit_host_set_buckets(C.c_void_p(sums[1].ctypes.data))
     h.qsv_jit_host_run(C.c_void_p(out.ctypes.data), C.c_uint64(rank_bits), C.c_uint64(1 << (ps.n_local - ps.tile_bits)),
                        C.c_void_p(tabs.ctypes.data), C.c_uint64(fixed_mask), C.c_uint64(fixed_val),
                        C.c_uint32(zf_mask), C.c_uint32(zf_val))
@@ -511,7 +530,7 @@ def exact_draw_bruteforce(weights_phys, n, src_pos, u):
     return (1 << n) - 1
 
 
-def exact_draw_emulated(weights_phys, n, g, src_pos, u):
+def exact_draw_emulated(weights_phys, n, g, src_pos, u, first_bits=0):
     """The radix descent of qsv.sampling.level_plan over 2^g virtual ranks, kernel by kernel (level / leaf bucket sums,
     integer all-reduce, select) with Python integers."""
     from qsv.sampling import level_plan, u_fixed
@@ -521,10 +540,12 @@ def exact_draw_emulated(weights_phys, n, g, src_pos, u):
     mant, shift = u_fixed(u)
     fixed_val = z = 0
     target = None
-    for kind, out_bits, positions, fixed in level_plan(src_pos, n, n_local):
+    for step, (kind, out_bits, positions, fixed) in enumerate(level_plan(src_pos, n, n_local, first_bits=first_bits)):
         nb = len(out_bits)
         buckets = [0] * (1 << nb)
-        if kind == "leaf":
+        if step == 0 and first_bits:
+            assert nb == first_bits and fixed == 0      # bucket sums of the last gate pass: any positions, no run rule
+        elif kind == "leaf":
             assert sorted(p for p in positions if p < n_local) == [p for p in range(n_local) if not (fixed >> p) & 1]
         else:
             run = [p for p in range(n_local) if not (fixed >> p) & 1][:10]

@@ -612,3 +612,59 @@ def test_run_from_basis_without_the_clear_is_bit_identical(qsv_gpu, monkeypatch)
     sv.synchronize()
     assert not torch.isnan(torch.view_as_real(sv.state)).any()
     assert abs(float(sv.block_sums(None, 12).sum()) - 1.0) < 1e-10
+
+
+def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch):
+    """execute(plan, sample_src_pos=...) lets the last pass add up the sampler's first-level bucket sums
+    (qsv_run_pass_rounds_sums).  The draws must equal the ones of the plain path (qsv_sample_level over the whole state)
+    for every u, with identity and permuted output wiring; the state itself is bit-identical; a sample with another
+    wiring, or after the state changed, does not use the stale sums."""
+    lib, engine, lowering, torch = qsv_gpu
+    from qsv import workloads
+    monkeypatch.setenv("QSV_JIT", "force")
+    us = [0.0, 0.123, 0.5, 0.87654321, 1.0 - 2.0 ** -53]
+    inside_seen = set()
+    for n, seed in ((23, 17), (23, 18), (23, 19), (24, 31), (22, 5)):
+        c = workloads.random_layered_circuit(n, 8, seed=seed)
+        c.sort()
+        ops, src_pos, flip = lowering.lower(c, in_flip=True)
+        sv = engine.StateVector(n)
+        plan = sv.prepare(ops)
+        sv.run_from_basis(flip, plan)
+        sv.synchronize()
+        ref_state = sv.state.clone()
+        plain, totals = [], []
+        for u in us:
+            plain.append(sv.sample(u, src_pos))
+            totals.append(sv._sampler.sel.cpu().tolist()[4:6])
+        used = 0
+        for u, want, tot in zip(us, plain, totals):
+            sv.run_from_basis(flip, plan, sample_src_pos=src_pos)
+            used += sv._presum is not None
+            k = sv._presum[0] if sv._presum is not None else 0
+            assert sv.sample(u, src_pos) == want
+            assert sv._sampler.sel.cpu().tolist()[4:6] == tot          # the exact 128-bit total weight
+            assert sv._presum is None
+        assert used == len(us), "the plan's last pass was expected to carry the sums"
+        assert torch.equal(torch.view_as_real(sv.state), torch.view_as_real(ref_state))
+        last = [seg for kind, seg, sp, zf in sv._walk(plan, flip) if kind == "pass"][-1][0][0]
+        tile = set(range(last.low_bits)) | set(last.hi_pos)
+        inside_seen.add(sum(1 for b in range(n - k, n) if src_pos[b] in tile))
+    assert max(inside_seen) >= 1, "no case with a bucket bit inside the last pass's tile"
+    n, seed = 23, 17
+    c = workloads.random_layered_circuit(n, 8, seed=seed)
+    c.sort()
+    ops, src_pos, flip = lowering.lower(c, in_flip=True)
+    sv = engine.StateVector(n)
+    plan = sv.prepare(ops)
+    # a different output wiring: the sums on the device do not apply, the sampler sweeps the state itself
+    other = list(src_pos)
+    other[0], other[n - 1] = other[n - 1], other[0]
+    sv.run_from_basis(flip, plan, sample_src_pos=src_pos)
+    z_other = sv.sample(0.5, other)
+    sv.run_from_basis(flip, plan)
+    assert sv.sample(0.5, other) == z_other
+    # state changed after the sums were taken: they are dropped
+    sv.run_from_basis(flip, plan, sample_src_pos=src_pos)
+    sv.execute(plan)
+    assert sv._presum is None

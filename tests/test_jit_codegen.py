@@ -450,6 +450,55 @@ def test_zero_fill_form_writes_tiles_no_op_acts_on(tmp_path):
     assert np.any(np.isnan(plain[(idx >> 14) & 1 == 0]))
 
 
+def test_sums_variant_adds_exact_tile_weights_to_the_sampler_buckets(tmp_path):
+    """qsv_run_pass_rounds_sums on the host: the state comes out exactly as from the plain kernel, and the bucket array
+    holds, per bucket (index bits at the given positions outside the tile, rank bits included), the EXACT sum of
+    floor(w * 2^96) over its amplitudes with w = fma(re, re, round(im * im)) - big-integer arithmetic here, four 32-bit
+    limbs there.  Tiles no op acts on are weighed too; the sums kernel also compiles for sm_100a."""
+    import ctypes as C
+    from fractions import Fraction
+    from qsv import workloads, lowering, _cabi
+    from helpers import jit_cpass
+    n = 15
+    c = workloads.random_layered_circuit(n, 3, seed=8)
+    c.sort()
+    ops, _ = lowering.lower(c)
+    ps, prog, tables = _round_programs(ops, n)[-1]
+    outside = [p for p in range(ps.low_bits, n) if p not in ps.hi_pos]
+    # two local positions outside the tile, one global (from rank_bits), and three INSIDE the tile (a low bit and two
+    # of the tile's high positions: register- or thread-held in the last round, whatever the round planner chose)
+    positions = [outside[2], ps.hi_pos[1], outside[0], 3, n + 1, ps.hi_pos[4]]
+    rank_bits = 0b10 << n
+    psi = _rand_state(n, 12)
+    psi[::7] = 0
+    psi[5] = 3e-20 + 1e-25j                              # below the 2^-96 resolution after squaring: contributes 0
+    ref = jit_host_run(ps, prog, tables, psi, rank_bits, str(tmp_path))
+    bk = np.zeros(4 << len(positions), dtype=np.uint64)
+    got = jit_host_run(ps, prog, tables, psi, rank_bits, str(tmp_path), sums=(positions, bk))
+    assert np.array_equal(got, ref)
+    expect = [0] * (1 << len(positions))
+    for i, a in enumerate(got):
+        im2 = float(a.imag) * float(a.imag)
+        w = float(Fraction(float(a.real)) * Fraction(float(a.real)) + Fraction(im2))      # correctly rounded = fma
+        g = i | rank_bits
+        b = sum(((g >> p) & 1) << k for k, p in enumerate(positions))
+        expect[b] += int(Fraction(w) * (1 << 96)) if w >= 2.0 ** -1022 else 0
+    have = [int(bk[4 * b]) + (int(bk[4 * b + 1]) << 32) + (int(bk[4 * b + 2]) << 64) + (int(bk[4 * b + 3]) << 96)
+            for b in range(1 << len(positions))]
+    assert have == expect
+    assert sum(1 for v in expect if v) == 32            # the global position pins one half of the bucket index
+    lib = _cabi.load()
+    cp = jit_cpass(ps)
+    need = C.c_size_t(0)
+    rc = lib.qsv_jit_compile_sums(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), len(positions),
+                                  _cabi.int_array(positions), None, 0, C.byref(need))
+    assert rc == 0 and need.value > 1000, lib.qsv_last_error()
+    # more than three bucket positions inside the tile are refused
+    rc = lib.qsv_jit_compile_sums(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size), 4,
+                                  _cabi.int_array([0, 1, ps.hi_pos[0], ps.hi_pos[2]]), None, 0, C.byref(need))
+    assert rc != 0 and b"inside the tile" in lib.qsv_last_error()
+
+
 def test_every_kernel_of_the_8_gpu_bench_plan_compiles_for_sm100a():
     """The schedule bench.py runs at --gpus 8 (33 qubits, joint placement, fused swaps): every pass program - the
     plain ones and the fused swap+pass forms - must be accepted by NVRTC for sm_100a.  No GPU needed."""

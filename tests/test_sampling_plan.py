@@ -40,6 +40,28 @@ def test_descent_matches_bruteforce_in_output_order(n, g):
             assert got == want, (n, g, trial, u, got, want)
 
 
+@pytest.mark.parametrize("n,g,k", [(13, 0, 3), (15, 2, 5), (16, 1, 12), (17, 0, 7)])
+def test_descent_with_a_presummed_first_level(n, g, k):
+    """The first level forced to the top k output bits (their bucket sums come from the last gate pass,
+    qsv_run_pass_rounds_sums): the descent below them finds the same outcome as the plain plan and as brute force."""
+    rng = np.random.default_rng(7 * n + k)
+    pyr = random.Random(n + k)
+    for trial in range(3):
+        src = list(range(n))
+        if trial:
+            pyr.shuffle(src)
+        w = _random_weights(rng, n, ("dense", "sparse", "spiky")[trial])
+        steps = sampling.level_plan(src, n, n - g, first_bits=k)
+        assert steps[0][1] == list(range(n - k, n)) and sum(len(s_[1]) for s_ in steps) == n
+        for u in (0.0, pyr.random(), 1.0 - 2.0 ** -53):
+            want = helpers.exact_draw_bruteforce(w, n, src, u)
+            assert helpers.exact_draw_emulated(w, n, g, src, u, first_bits=k) == want
+    tile = [0, 1, 2, 3, 4, 5, 9, 11, 12]
+    assert sampling.presum_bits(None, 16, tile) == 10                      # 12, 11, 9 inside; stops at bit 5 (the fourth)
+    assert sampling.presum_bits(list(range(15, -1, -1)), 16, tile) == 3     # the top output bits sit on positions 0, 1, 2
+    assert sampling.presum_bits(None, 30, list(range(12))) == 12           # never more than one level's worth
+
+
 def test_plan_shapes():
     # identity wiring at 30 qubits: 12 + (8 high + 2 low) bits, then levels of two low bits until <= 12 bits are left
     steps = sampling.level_plan(None, 30, 30)
