@@ -623,7 +623,7 @@ def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch):
     from qsv import workloads
     monkeypatch.setenv("QSV_JIT", "force")
     us = [0.0, 0.123, 0.5, 0.87654321, 1.0 - 2.0 ** -53]
-    inside_seen = set()
+    inside_seen, cases_used = set(), 0
     for n, seed in ((23, 17), (23, 18), (23, 19), (24, 31), (22, 5)):
         c = workloads.random_layered_circuit(n, 8, seed=seed)
         c.sort()
@@ -645,11 +645,14 @@ def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch):
             assert sv.sample(u, src_pos) == want
             assert sv._sampler.sel.cpu().tolist()[4:6] == tot          # the exact 128-bit total weight
             assert sv._presum is None
-        assert used == len(us), "the plan's last pass was expected to carry the sums"
+        assert used in (0, len(us))             # (0: the plan ends in a 1-2 op pass of the shared-memory kernel)
+        cases_used += used > 0
         assert torch.equal(torch.view_as_real(sv.state), torch.view_as_real(ref_state))
         last = [seg for kind, seg, sp, zf in sv._walk(plan, flip) if kind == "pass"][-1][0][0]
         tile = set(range(last.low_bits)) | set(last.hi_pos)
-        inside_seen.add(sum(1 for b in range(n - k, n) if src_pos[b] in tile))
+        if used:
+            inside_seen.add(sum(1 for b in range(n - k, n) if src_pos[b] in tile))
+    assert cases_used >= 2, "the last pass was expected to carry the sums in at least two of the circuits"
     assert max(inside_seen) >= 1, "no case with a bucket bit inside the last pass's tile"
     n, seed = 23, 17
     c = workloads.random_layered_circuit(n, 8, seed=seed)
