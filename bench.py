@@ -254,9 +254,21 @@ def layered_check(sv, comm, n, depth, plan, in_index, src_pos, g, roundtrip=True
     else:
         os.environ["QSV_SPARSE_START"] = old
     identical = bool(allmin(int(torch.equal(sums_hint, sums_dense))))
+    # the sample of the timed step (first level of the sampler's descent summed by the last gate pass) against the
+    # sample the sampler finds on its own, for three draws
+    same = True
+    presummed = 0
+    for u in (0.37, 0.0, 0.93):
+        sv.run_from_basis(in_index, plan, sample_src_pos=src_pos)
+        presummed = max(presummed, sv._presum[0] if sv._presum is not None else 0)
+        z_fused = sv.sample(u, src_pos)
+        sv.run_from_basis(in_index, plan)
+        same = same and (z_fused == sv.sample(u, src_pos))
+    same = bool(allmin(int(same)))
     out = {"norm_error": abs(norm - 1.0), "hint_on_off_block_sums_bit_identical": identical, "tolerance": 1e-10,
-           "zero_fill_passes_on_nan_poisoned_register": int(n_fresh)}
-    ok = abs(norm - 1.0) <= 1e-10 and identical
+           "zero_fill_passes_on_nan_poisoned_register": int(n_fresh),
+           "sample_with_sums_of_the_last_pass_equals_plain_sampler": same, "output_bits_summed_by_the_last_pass": presummed}
+    ok = abs(norm - 1.0) <= 1e-10 and identical and same
     if roundtrip:
         rt = workloads.random_layered_roundtrip_circuit(n, depth, seed=SEED)
         rt.sort()
