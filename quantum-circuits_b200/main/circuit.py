@@ -339,7 +339,8 @@ class Gate(object):
 
     def __init__(self, mtrx, name, bypass_error_check=False):
         if not bypass_error_check:
-            if len(mtrx) != len(mtrx.rows[0]):
+            symbolic = getattr(mtrx, "structure", None) is not None and mtrx.structure() is not None
+            if not symbolic and len(mtrx) != len(mtrx.rows[0]):          # (symbolic matrices are square by construction)
                 raise RuntimeError("Gates should be represented by square matrices.")
             if not mtrx.isUnitary():
                 raise RuntimeError("Gates should be represented by unitary matrices.")

@@ -75,7 +75,8 @@ class Matrix(object):
         self.__dict__.pop('_spec', None)   # once written, the matrix is whatever the caller made it
 
     def structure(self):
-        """('power', base_rows, size) / ('qft', size) while the matrix is still symbolic, else None."""
+        """('power', base_rows, size) / ('qft', size) / ('kron', A, B) / ('id', size) while the matrix is still
+        symbolic, else None."""
         d = self.__dict__
         return d.get('_spec') if 'rows' not in d else None
 
@@ -94,6 +95,13 @@ class Matrix(object):
             return acc.rows
         if spec[0] == 'qft':
             return _qft_rows(spec[1])
+        if spec[0] == 'kron':
+            return _kron_rows(spec[1].rows, spec[2].rows)
+        if spec[0] == 'id':
+            rows = [[0] * dim for _ in range(dim)]
+            for i in range(dim):
+                rows[i][i] = 1
+            return rows
         if spec[0] == 'rows_fn':
             return spec[1]()
         raise MatrixError('unknown symbolic matrix')
@@ -167,21 +175,45 @@ class Matrix(object):
         The reference evaluates the O(n^3) product entry by entry in Python - 80 % of its run time at 8 qubits
         (SURVEY 8a-4).  Numeric matrices take the same test through one BLAS product; the entries differ from the
         reference's sums by rounding (1e-16), far inside the 12-decimal comparison."""
+        spec = self.structure()
+        if spec is not None and spec[0] in ('kron', 'power', 'qft', 'id'):
+            # decided on the structure: a Kronecker product / tensor power is unitary iff its factors are (up to
+            # scalars, which the reference's test would reject in either factor just the same for |c| != 1)
+            if spec[0] == 'kron':
+                return spec[1].isUnitary() and spec[2].isUnitary()
+            if spec[0] == 'power':
+                return Matrix([list(r) for r in spec[1]]).isUnitary()
+            return True
         fast = _is_unitary_fast(self.rows)
         if fast is not None:
             return fast
         return (self * (self.getConjugate())).Round(12) == Matrix.Id(len(self))
 
     def bintensor(self, M):
-        """self (x) M  (reference main/matrix.py:98-112); entry = self[a][b] * M[k][l]."""
-        out = []
-        for arow in self.rows:
-            for mrow in M.rows:
-                line = []
-                for a in arow:
-                    line.extend([a * m for m in mrow])
-                out.append(line)
-        return Matrix(out)
+        """self (x) M  (reference main/matrix.py:98-112); entry = self[a][b] * M[k][l].
+        A product with a symbolic factor, or one of 2^12 rows and more, stays symbolic (('kron', A, B)): the lowering
+        takes it factor by factor and nobody pays for 4^q entries (`tensor([Matrix.H(n), Matrix.Id(2)])` of
+        main/Grover.py:42-44 at n = 20 would be 4 * 10^12 of them).  Reading or writing `.rows` expands it, with
+        the reference's entry order and arithmetic."""
+        if isinstance(M, Matrix) and (self.structure() is not None or M.structure() is not None
+                                      or len(self) * len(M) >= LAZY_KRON_DIM) \
+                and _is_square(self) and _is_square(M):
+            return Matrix._symbolic(('kron', self, M), len(self) * len(M))
+        return Matrix(_kron_rows(self.rows, M.rows))
+
+    def signature(self):
+        """Hashable description of the matrix without expanding symbolic ones (the lowering cache keys on it)."""
+        d = self.__dict__
+        if 'rows' in d:
+            return tuple(map(tuple, d['rows']))
+        spec = d.get('_spec')
+        if spec[0] == 'kron':
+            return ('kron', spec[1].signature(), spec[2].signature())
+        if spec[0] == 'power':
+            return ('power', tuple(map(tuple, spec[1])), spec[2])
+        if spec[0] == 'rows_fn':
+            raise TypeError('structured gate: not describable by content')
+        return tuple(spec)
 
     def apply(self, matrices):
         if len(self.rows[0]) > 1:
@@ -204,6 +236,8 @@ class Matrix(object):
 
     @classmethod
     def Id(cls, size):
+        if size >= LAZY_KRON_DIM:
+            return cls._symbolic(('id', size), size)      # expanded when somebody reads or writes .rows
         rows = [[0] * size for _ in range(size)]
         for i in range(size):
             rows[i][i] = 1
@@ -272,6 +306,28 @@ class Matrix(object):
         m.rows[6] = [0, 0, 0, 0, 0, 0, 0, 1]
         m.rows[7] = [0, 0, 0, 0, 0, 0, 1, 0]
         return m
+
+
+LAZY_KRON_DIM = 1 << 12      # Kronecker products of this many rows and more are kept as a pair of factors
+
+
+def _is_square(m):
+    d = m.__dict__
+    if 'rows' not in d:
+        return True                  # symbolic matrices are square by construction
+    rows = d['rows']
+    return len(rows) > 0 and all(len(r) == len(rows) for r in rows)
+
+
+def _kron_rows(arows, mrows):
+    out = []
+    for arow in arows:
+        for mrow in mrows:
+            line = []
+            for a in arow:
+                line.extend([a * m for m in mrow])
+            out.append(line)
+    return out
 
 
 def _is_unitary_fast(rows):

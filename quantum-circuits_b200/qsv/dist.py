@@ -161,6 +161,9 @@ class Comm:
         """Global<->local swap of `positions` + the gate pass that follows it as ONE kernel over peer memory
         (qsv_run_pass_rounds_swap): tiles are pulled from the peers, transformed and stored locally; a per-tile flag
         handshake keeps the exchange in place.  One barrier before (earlier kernels of all ranks are done), none after."""
+        if support is None:
+            sv._basis = None
+            sv._presum = None
         self._check_owner(sv)
         raw, hdl, ptrs = self._symm
         fraw, fhdl, fptrs = self._flag_arrays(sv.state.device)
@@ -284,6 +287,10 @@ class Comm:
         """Engine hook for a 'global_swap' op: the peer-memory kernel (any local positions, any subset of the global
         bits, support hint), or the chunked NCCL all-to-all with the CUDA pack/unpack kernels of libqsv (all global
         qubits against the top local positions only)."""
+        if support is None:
+            # called outside StateVector.execute(): whatever was known about the support / weights of the state is void
+            sv._basis = None
+            sv._presum = None
         if self.peer_swap and self._symm is not None and sv.state.data_ptr() == self._symm[2][self.rank]:
             return self._swap_peer(sv, n_swap, positions, gbits, support)
         if n_swap != self.global_bits or (gbits is not None and list(gbits) != list(range(n_swap))):

@@ -96,9 +96,24 @@ def lower_gate(gate, wires, layout, transposed=False):
     hook = getattr(gate, "_qsv_lower", None)
     if hook is not None:
         return hook(wires, layout, transposed)
-    m = gate.matrix
+    return lower_matrix(gate.matrix, wires, layout, transposed, getattr(gate, "name", ""))
+
+
+def lower_matrix(m, wires, layout, transposed=False, name=""):
+    """Ops for the matrix m acting on logical qubits `wires`.  Symbolic matrices are lowered from their structure:
+    tensor powers qubit by qubit, Kronecker products factor by factor (the first factor owns the first wires, as in
+    main/matrix.py:98-112), large QFTs as a ladder, the identity as nothing - never through their entries."""
     spec = m.structure() if hasattr(m, "structure") else None
-    name = getattr(gate, "name", "")
+    if spec is not None and spec[0] == "kron":
+        ka = len(spec[1]).bit_length() - 1
+        if (1 << ka) != len(spec[1]) or ka > len(wires):
+            raise RuntimeError("Gates should be represented by square matrices.")
+        return (lower_matrix(spec[1], wires[:ka], layout, transposed, name)
+                + lower_matrix(spec[2], wires[ka:], layout, transposed, name))
+    if spec is not None and spec[0] == "id":
+        if len(m) != 1 << len(wires):
+            raise RuntimeError("Gates should be represented by square matrices.")
+        return []
     if spec is not None and spec[0] == "power":
         base = np.array(spec[1], dtype=np.complex128)
         if transposed:
@@ -145,7 +160,7 @@ def _circuit_signature(gates, table, out_qubits, extra):
             if rows is not None:
                 sig.append((tuple(wires), tuple(map(tuple, rows))))
             else:
-                sig.append((tuple(wires), "spec", repr(d.get("_spec")), d.get("_dim")))
+                sig.append((tuple(wires), "spec", g.matrix.signature(), d.get("_dim")))
         key = (extra, tuple(out_qubits), tuple(sig))
         hash(key)
         return key

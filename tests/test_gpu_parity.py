@@ -671,3 +671,35 @@ def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch):
     sv.run_from_basis(flip, plan, sample_src_pos=src_pos)
     sv.execute(plan)
     assert sv._presum is None
+
+
+def test_support_hint_is_dropped_when_the_state_changes_outside_execute(qsv_gpu, monkeypatch):
+    """init_basis -> run_program(H) -> run_ops(ops): the register is no longer the basis state when execute() runs,
+    so the passes must sweep everything (a stale hint would skip non-zero tiles silently)."""
+    lib, engine, lowering, torch = qsv_gpu
+    import numpy as np
+    from qsv import workloads
+    from qsv.schedule import Op
+    monkeypatch.setenv("QSV_JIT", "force")
+    n = 20
+    c = workloads.random_layered_circuit(n, 6, seed=9)
+    c.sort()
+    ops, _, flip = lowering.lower(c, in_flip=True)
+    s_ = 2 ** -0.5
+    pre = [Op("dense", (n - 1,), (), matrix=np.array([[s_, s_], [s_, -s_]], dtype=np.complex128)),
+           Op("dense", (n - 3,), (), matrix=np.array([[s_, s_], [s_, -s_]], dtype=np.complex128))]
+    sv = engine.StateVector(n)
+    h = sv.upload_program(pre)
+    sv.init_basis(flip)
+    sv.run_program(h)
+    assert sv._basis is None
+    sv.run_ops(ops)
+    sv.synchronize()
+    got = sv.state.clone()
+    monkeypatch.setenv("QSV_SPARSE_START", "0")
+    sv.init_basis(flip)
+    sv.run_program(h)
+    sv.run_ops(ops)
+    sv.synchronize()
+    assert torch.equal(torch.view_as_real(got), torch.view_as_real(sv.state))
+    assert abs(float(sv.block_sums(None, 12).sum()) - 1.0) < 1e-10

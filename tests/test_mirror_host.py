@@ -211,3 +211,36 @@ def test_reference_saved_circuits_unpickle_with_the_mirror(golden):
     g.sort()
     ops, src = lower(g)
     assert {o.kind for o in ops} <= {"dense", "mcx", "diag", "phase"}
+
+
+def test_lazy_kronecker_products_and_identities():
+    """(f-2) Matrix.bintensor with a symbolic factor / a large result and Matrix.Id(2^12+) stay symbolic: building
+    `tensor([Matrix.H(n), Matrix.Id(2)])` (main/Grover.py:42-44) at n = 24 costs nothing, the lowering takes the factors
+    one by one, and `.rows` - when somebody does ask - holds exactly the reference's entries."""
+    import time
+    from main.matrix import Matrix, tensor
+    import main.circuit as mc
+    from qsv import lowering
+    t0 = time.perf_counter()
+    big = tensor([Matrix.H(24), Matrix.Id(2)])
+    gate = mc.Gate(big, "h", False)                      # error checks on: unitarity is decided on the structure
+    assert time.perf_counter() - t0 < 0.5 and len(gate) == 25 and big.structure()[0] == "kron"
+    c = mc.Circuit(25)
+    g = c.add(gate)
+    c.add_wires(c, (), g, ())
+    c.add_wires(g, (), c, ())
+    c.sort()
+    ops, src = lowering.lower(c)
+    assert len(ops) == 24 and all(o.kind == "dense" and len(o.targets) == 1 for o in ops)
+    assert sorted(o.targets[0] for o in ops) == list(range(1, 25))        # wire 24 (position 0) carries the identity
+    # small products with a symbolic factor: the expansion equals the eager product entry by entry
+    lazy = tensor([Matrix.H(3), Matrix.Id(2), Matrix.PhaseShift(0.3)])
+    assert lazy.structure()[0] == "kron"
+    eager = Matrix(Matrix.H(3).rows).bintensor(Matrix.Id(2)).bintensor(Matrix.PhaseShift(0.3))
+    assert eager.structure() is None and lazy.rows == eager.rows and lazy.structure() is None
+    assert Matrix.Id(1 << 12).structure() == ("id", 1 << 12) and Matrix.Id(1 << 12).isUnitary()
+    m = Matrix.Id(1 << 12)
+    m[5][5] = 0                                          # a write expands it, like the reference's list of lists
+    m[5][6] = 1
+    assert m.structure() is None and m.rows[5][6] == 1 and m.rows[7][7] == 1
+    assert not tensor([Matrix([[1, 0], [0, 2]]), Matrix.H(2)]).isUnitary()
