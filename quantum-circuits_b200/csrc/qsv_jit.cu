@@ -641,46 +641,27 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
     }
 
     if (direct && t_sums) {
-        // Tile sums of the sums variant.  Bucket bits on positions outside the tile are the same for the whole tile; a
-        // bucket bit INSIDE the tile is held either by a register bit of this (last) round - then every thread keeps one
-        // partial sum per value (acc[]) - or by a thread bit: lanes that agree on those bits form a group
-        // (__reduce_add_sync over the group's mask, 16-bit limbs so that 32 lanes cannot overflow a word), the group
-        // leaders add to a small shared-memory table with one entry per combination of the inside bits, and after the
-        // barrier one thread per entry adds its 128-bit total to the bucket array in global memory.
-        int pos8[8];
-        if (t_tb_override) memcpy(pos8, t_tb_override, sizeof(pos8));
-        else thread_bit_order(R, pos8);
-        int thr_tid[4], thr_kb[4], reg_kb[4], n_thr = 0, n_reg_in = 0;
-        for (int kb = 0; kb < t_sums->n_bits; ++kb) {
-            for (int q = 0; q < 4; ++q)
-                if (t_tile_phys[R.rb[q]] == t_sums->pos[kb]) reg_kb[n_reg_in++] = kb;
-            for (int i = 0; i < 8; ++i)
-                if (t_tile_phys[pos8[i]] == t_sums->pos[kb]) { thr_tid[n_thr] = i; thr_kb[n_thr++] = kb; }
-        }
-        uint32_t ilm = 0;
-        for (int j = 0; j < n_thr; ++j) if (thr_tid[j] < 5) ilm |= 1u << thr_tid[j];
-        uint32_t base_mask = 0;
-        for (uint32_t m = 0; m < 32; ++m) if (!(m & ilm)) base_mask |= 1u << m;
-        const int n_ent = 1 << (n_thr + n_reg_in);
+        // Tile sums of the sums variant.  Bucket bits on positions outside the tile are the same for the whole tile.  A
+        // bucket bit INSIDE the tile is read from the amplitude's FINAL global index (the address it is stored to:
+        // X / CNot riding on the stores move amplitudes between register slots and threads), so every thread keeps one
+        // partial sum per combination of the inside bits (acc[]); the warps reduce them with __reduce_add_sync (16-bit
+        // limbs: 32 lanes cannot overflow a word), lane 0 adds to a small shared-memory table, and after the barrier one
+        // thread per combination adds its 128-bit total to the bucket array in global memory.
+        int in_kb[4], n_in = 0;
+        for (int kb = 0; kb < t_sums->n_bits; ++kb)
+            for (int t = 0; t < 12; ++t)
+                if (t_tile_phys[t] == t_sums->pos[kb]) in_kb[n_in++] = kb;
+        const int n_ent = 1 << n_in;
         o.f("#ifndef QSV_JIT_HOST");
         o.f("__device__ __forceinline__ void qsv_tile_sum(const qsv_ctx &c, const u64 gbase, const u32 tid, const qsv_u128 *acc) {");
-        o.f("    const u32 lane = tid & 31u;");
-        o.f("    const u32 gm = 0x%xu << (lane & 0x%xu);", base_mask, ilm);
-        o.f("    const bool leader = (lane & 0x%xu) == 0u;", (~ilm) & 31u);
-        {
-            std::string e = "0u";
-            for (int j = 0; j < n_thr; ++j)
-                e += " | (((tid >> " + std::to_string(thr_tid[j]) + ") & 1u) << " + std::to_string(j) + ")";
-            o.f("    const u32 vthr = %s;", e.c_str());
-        }
         o.f("    u32 *tab = c.s_tab + c.par * %du;", n_ent * 8);
         o.f("    #pragma unroll");
-        o.f("    for (int a_ = 0; a_ < %d; ++a_) {", 1 << n_reg_in);
+        o.f("    for (int a_ = 0; a_ < %d; ++a_) {", n_ent);
         o.f("        #pragma unroll");
         o.f("        for (int i_ = 0; i_ < 8; ++i_) {");
         o.f("            const u32 limb = (u32)(((i_ < 4 ? acc[a_].lo : acc[a_].hi) >> (16 * (i_ & 3))) & 0xffffULL);");
-        o.f("            const u32 s_ = __reduce_add_sync(gm, limb);");
-        o.f("            if (leader && s_) atomicAdd(tab + (vthr | ((u32)a_ << %d)) * 8u + (u32)i_, s_);", n_thr);
+        o.f("            const u32 s_ = __reduce_add_sync(0xffffffffu, limb);");
+        o.f("            if ((tid & 31u) == 0u && s_) atomicAdd(tab + (u32)a_ * 8u + (u32)i_, s_);");
         o.f("        }");
         o.f("    }");
         o.f("    __syncthreads();");
@@ -701,10 +682,8 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
         o.f("        }");
         {
             std::string e = "qsv_bucket_ext(gbase)";
-            for (int j = 0; j < n_thr; ++j)
-                e += " | (((tid >> " + std::to_string(j) + ") & 1u) << " + std::to_string(thr_kb[j]) + ")";
-            for (int j = 0; j < n_reg_in; ++j)
-                e += " | (((tid >> " + std::to_string(n_thr + j) + ") & 1u) << " + std::to_string(reg_kb[j]) + ")";
+            for (int j = 0; j < n_in; ++j)
+                e += " | (((tid >> " + std::to_string(j) + ") & 1u) << " + std::to_string(in_kb[j]) + ")";
             o.f("        if (v.lo | v.hi) {");
             o.f("            u64 *b = c.bk + 4ULL * (%s);", e.c_str());
         }
@@ -933,17 +912,29 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             o.f("#ifdef QSV_JIT_HOST");
             for (int r = 0; r < 16; ++r) o.f("    qsv_host_add(g%d | gbase, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
             o.f("#else");
-            // per-thread partial sums, one per combination of the bucket bits this round holds in REGISTERS
-            int reg_q[4], n_reg_in = 0;
+            // per-thread partial sums, one per combination of the bucket bits INSIDE the tile, selected by the final
+            // global index g<r> of every amplitude
+            int in_pos[4], n_in = 0;
             for (int kb = 0; kb < t_sums->n_bits; ++kb)
-                for (int q = 0; q < 4; ++q)
-                    if (t_tile_phys[R.rb[q]] == t_sums->pos[kb]) reg_q[n_reg_in++] = q;
-            o.f("    { qsv_u128 acc[%d];", 1 << n_reg_in);
-            o.f("      for (int a_ = 0; a_ < %d; ++a_) acc[a_].lo = acc[a_].hi = 0ULL;", 1 << n_reg_in);
+                for (int t = 0; t < 12; ++t)
+                    if (t_tile_phys[t] == t_sums->pos[kb]) in_pos[n_in++] = t_sums->pos[kb];
+            o.f("    { qsv_u128 acc[%d];", 1 << n_in);
+            o.f("      for (int a_ = 0; a_ < %d; ++a_) acc[a_].lo = acc[a_].hi = 0ULL;", 1 << n_in);
             for (int r = 0; r < 16; ++r) {
-                int sel = 0;
-                for (int j = 0; j < n_reg_in; ++j) sel |= ((r >> reg_q[j]) & 1) << j;
-                o.f("      qsv_wacc(acc[%d], %s, %s);", sel, xr(r).c_str(), xi(r).c_str());
+                if (n_in == 0) {
+                    o.f("      qsv_wacc(acc[0], %s, %s);", xr(r).c_str(), xi(r).c_str());
+                    continue;
+                }
+                std::string sel = "0u";
+                for (int j = 0; j < n_in; ++j)
+                    sel += " | ((u32)((g" + std::to_string(r) + " >> " + std::to_string(in_pos[j]) + ") & 1ULL) << " +
+                           std::to_string(j) + ")";
+                o.f("      { qsv_u128 q_ = {0ULL, 0ULL}; qsv_wacc(q_, %s, %s); const u32 sel_ = %s;", xr(r).c_str(),
+                    xi(r).c_str(), sel.c_str());
+                o.f("        #pragma unroll");
+                o.f("        for (int a_ = 0; a_ < %d; ++a_) {", 1 << n_in);
+                o.f("          const u64 l_ = sel_ == (u32)a_ ? q_.lo : 0ULL, h_ = sel_ == (u32)a_ ? q_.hi : 0ULL;");
+                o.f("          acc[a_].lo += l_; acc[a_].hi += h_ + (acc[a_].lo < l_ ? 1ULL : 0ULL); } }");
             }
             o.f("      qsv_tile_sum(ctx, gbase, tid, acc); }");
             o.f("#endif");
