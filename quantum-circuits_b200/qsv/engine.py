@@ -310,7 +310,9 @@ class StateVector:
                     continue
                 host_plan.append(("op", item))
             if batch:
-                host_plan.append(("program", pack_passes(batch)))
+                # the plan ends in a pass: a round program whatever its size, so that it can weigh the state for the
+                # sampler (a lone one- or two-op pass stays on the shared-memory kernel, which is faster for it)
+                host_plan.append(("program", pack_passes(batch, last_as_rounds=bool(host_plan) or len(batch) > 1)))
             if len(_PLAN_CACHE) >= 16:
                 _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
             _PLAN_CACHE[key] = host_plan

@@ -1541,7 +1541,7 @@ def common_external_controls(ps):
     return mask, val
 
 
-def pack_passes(passes, register_kernel=None, min_ops=None):
+def pack_passes(passes, register_kernel=None, min_ops=None, last_as_rounds=False):
     """Device image [offset tables | ops] for the passes that run on the shared-memory kernel (op
     offsets relative to the start of the buffer).  Passes the register-resident kernel can run carry a
     HOST round program instead (it is passed to the kernel by value) plus, if they use diagonal tables,
@@ -1559,8 +1559,15 @@ def pack_passes(passes, register_kernel=None, min_ops=None):
             max_rounds, max_ops = program_capacity(ps)
             mode = os.environ.get("QSV_REG_MCX", "1")
             specialised = False if (max_ops <= RPROG_MAX_OPS or mode == "0") else ("all" if mode == "all" else True)
+            # last_as_rounds: the LAST pass of a run becomes a round program whatever its size when the
+            # pass-specialised kernel will run it - only that kernel can weigh the state for the sampler on its way
+            # out (qsv_run_pass_rounds_sums: saves the sampler's sweep of the whole state, 2.6 ms at 2^30 amplitudes,
+            # for ~0.3 ms of round overhead)
+            threshold = (int(os.environ.get("QSV_REG_MIN_OPS", "2")) if min_ops is None else min_ops)
+            if last_as_rounds and i == len(passes) - 1 and max_ops > RPROG_MAX_OPS:
+                threshold = 0
             rounds = plan_rounds(ps, reg_mcx=specialised, padded_layout=max_ops > RPROG_MAX_OPS) \
-                if len(ps.ops) > (int(os.environ.get("QSV_REG_MIN_OPS", "2")) if min_ops is None else min_ops) else None
+                if len(ps.ops) > threshold else None
             if rounds is not None:
                 enc = encode_rounds(ps, rounds, max_rounds, max_ops)
                 if enc is None and len(ps.ops) >= 8:
