@@ -882,7 +882,7 @@ def plan_restarts():
 
 
 def plan_schedule_search(ops, n_local, tile_bits=None, low_bits=None, fuse_swaps=False, n_global=0, restarts=None,
-                         sparse=None):
+                         sparse=None, use_disk_cache=True):
     """plan_schedule, `restarts` times with differently shuffled tile searches; the schedule with the smallest
     schedule_ms wins (restart 0 is the deterministic greedy schedule, so the result is never worse than it under
     the model).  Small registers (interpreter kernels, latency-bound) keep the greedy schedule."""
@@ -900,7 +900,7 @@ def plan_schedule_search(ops, n_local, tile_bits=None, low_bits=None, fuse_swaps
     n = n_local + n_global
     best, best_ms = None, float("inf")
     key = None
-    if _cache_mod().enabled():
+    if use_disk_cache and _cache_mod().enabled():
         digest = getattr(ops, "digest", None) or ops_digest(ops)
         key = "plan-" + _cache_mod().digest(repr((PLAN_MODEL_VERSION, digest, n_local, T, L, bool(fuse_swaps), n_global,
                                                    restarts, bool(sparse), SWAP_MIN_POS,
@@ -1308,9 +1308,12 @@ def place_joint(ops, n, n_global, src_pos=None, fuse_swaps=False):
         if sig in seen:
             continue
         seen.add(sig)
-        if len(seen) > int(os.environ.get("QSV_PLACE_REPLAN", "6")):
+        if len(seen) > int(os.environ.get("QSV_PLACE_REPLAN", "10")):
             break
-        real = schedule_ms(plan_schedule(res[1], n - n_global, fuse_swaps=fuse_swaps), n, n_global, sparse)
+        # judged the way the engine will schedule it (a short version of the same search), not by the greedy schedule
+        real = schedule_ms(plan_schedule_search(res[1], n - n_global, fuse_swaps=fuse_swaps, n_global=n_global,
+                                                restarts=int(os.environ.get("QSV_PLACE_REPLAN_RESTARTS", "4")),
+                                                sparse=sparse, use_disk_cache=False), n, n_global, sparse)
         if real < best_cost:
             best, best_cost = res, real
     if len(_PLACE_CACHE) >= 8:
