@@ -652,6 +652,16 @@ def main():
         k["ms"] += t["ms"]; k["bytes"] += t["bytes"]; k["launch_groups"] += 1; k["ops"] += t["ops"]
     dom = max(by_kind, key=lambda k: by_kind[k]["ms"]) if by_kind else "pass"
     d = by_kind.get(dom, {"ms": 0.0, "bytes": 0.0, "launch_groups": 0, "ops": 0})
+    # load balance of the stand-alone passes: every rank's sum of pass times for one step (with the support hint some
+    # ranks hold nothing of the state before the first swaps); idle share = (slowest - fastest rank) / step time
+    balance = None
+    if world > 1:
+        mine = torch.tensor([sum(t["ms"] for t in timed if t["kind"] == "pass")], device="cuda", dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [float(x.item()) for x in allr]
+        balance = {"pass_ms_per_rank": [round(v, 3) for v in per_rank], "max_ms": max(per_rank), "min_ms": min(per_rank),
+                   "idle_share_of_step": (max(per_rank) - min(per_rank)) / ms_per_step if ms_per_step else None}
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
     import ctypes
     jc, jh, js = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_double(0)
@@ -800,6 +810,8 @@ def main():
         line["gate_pass"] = gate_pass
     if swap is not None:
         line["swap"] = swap
+    if balance is not None:
+        line["rank_balance"] = balance
     if check is not None:
         line["check"] = check
     if big is not None:
