@@ -256,6 +256,19 @@ int  qsv_jit_compile_sums(const qsv_pass_t *pass, const void *prog_host, uint32_
 int  qsv_jit_bank_score(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
                         uint64_t *default_score, uint64_t *searched_score);
 
+/* ---- Feynman path sum: Circuit.run_method1, main/circuit.py:221-276 ------------------------------------------
+ * weights[out] = | sum over the 2^n_internal assignments of the internal wires of prod over the gates of
+ * matrix_g[i][j] |^2, i / j = the values of the gate's in- / out-wires (first wire most significant), for every
+ * assignment `out` of the n_outputs output wires (index bit n_outputs-1-i = output wire i).  Device arrays:
+ * wires [n_wires][2] uint8 = (kind, idx): kind 0 constant bit idx (fed by a circuit input), 1 bit idx of `out`,
+ * 2 bit idx of the internal assignment; gate_hdr [n_gates][3] uint32 = (k, offset of the row-major 2^k x 2^k complex128
+ * matrix in mats, offset of the gate's 2k wire ids in ports: k in-wires then k out-wires); direct [n_direct][2] uint32 =
+ * (input bit, bit position of `out`) for wires that run from a circuit input straight to an output.  The reference's
+ * own algorithm and cost (2^(n + internal) * gates), one CTA per output assignment. */
+int qsv_path_sum(const void *wires_dev, int n_wires, const void *gate_hdr_dev, const void *ports_dev,
+                 const void *mats_dev, int n_gates, int n_outputs, int n_internal, const void *direct_dev,
+                 int n_direct, void *weights_dev, void *stream);
+
 /* ---- host-side pass planning (no device work; qsv.schedule) ---------------------------------------------------
  * The reference applies one gate per full-state product (main/circuit.py:315-327); here a PASS (one read+write of the
  * state) applies every op whose non-diagonal targets lie inside its tile and that commutes past what stays behind.

@@ -138,6 +138,49 @@ def run_method1(circuit, in_v):
     return weights(evolve(steps, sq, in_v, transposed=True))
 
 
+def run_method1_path_sum(circuit, in_v):
+    """Circuit.run_method1 as the reference writes it (main/circuit.py:221-276), loop for loop: every output
+    assignment, every assignment of the internal wires, the product over circuit.gates of matrix[i][j] with i / j read
+    from the in- / out-wire values (first wire most significant), |Sum|^2.  Pure Python: small circuits only."""
+    validate_input(circuit, in_v)
+    n = len(circuit)
+    value = {}
+    for i in range(n):
+        value[id(circuit.input[i])] = in_v[i]
+    int_wires = circuit.get_internal_wires()
+    mats = [gate_matrix(g) for g in circuit.gates]
+    w = np.zeros(1 << n)
+    for index, out in enumerate(itertools.product(range(2), repeat=n)):
+        clash = False
+        for i in range(n):                                   # a wire from an input straight to output i
+            if circuit.output[i].left is circuit and value[id(circuit.output[i])] != out[i]:
+                clash = True
+                break
+            value[id(circuit.output[i])] = out[i]
+        if clash:
+            for i in range(n):                               # (the reference keeps input wires' values: restore)
+                value[id(circuit.input[i])] = in_v[i]
+            continue
+        total = 0
+        for assign in itertools.product(range(2), repeat=len(int_wires)):
+            for wire, v in zip(int_wires, assign):
+                value[id(wire)] = v
+            prod = 1
+            for g, M in zip(circuit.gates, mats):
+                i = j = 0
+                for wire in g.in_wires:
+                    i = (i << 1) | value[id(wire)]
+                for wire in g.out_wires:
+                    j = (j << 1) | value[id(wire)]
+                if M[i][j] == 0:
+                    prod = 0
+                    break
+                prod = prod * M[i][j]
+            total += prod
+        w[index] = abs(total) ** 2
+    return w
+
+
 def validate_input(circuit, in_v):
     """main/circuit.py:282-288."""
     if len(in_v) != len(circuit):

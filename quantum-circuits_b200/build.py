@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "qsv", "libqsv.so")
-SOURCES = ["qsv_api.cu", "qsv_tile.cu", "qsv_tile_reg.cu", "qsv_jit.cu", "qsv_wide.cu", "qsv_measure.cu", "qsv_sample.cu", "qsv_algos.cu", "qsv_peer.cu", "qsv_plan.cu"]
+SOURCES = ["qsv_api.cu", "qsv_tile.cu", "qsv_tile_reg.cu", "qsv_jit.cu", "qsv_wide.cu", "qsv_measure.cu", "qsv_sample.cu", "qsv_algos.cu", "qsv_peer.cu", "qsv_plan.cu", "qsv_pathsum.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas=-v",

@@ -217,13 +217,17 @@ class Circuit(object):
                 raise RuntimeError("Invalid input - values must be 0 or 1.")
 
     def run_method1(self, in_v):
-        """Reference: Feynman path sum (main/circuit.py:221-276).  Here the same weights come from the
-        state-vector engine; the path sum indexes gate.matrix[in][out], i.e. applies the TRANSPOSED
-        gate matrices, which is reproduced."""
+        """Reference: Feynman path sum (main/circuit.py:221-276).  Circuits with few paths (qsv.pathsum.wanted:
+        2^(n + internal wires) within the limit, QSV_METHOD1=pathsum|engine overrides) are summed path by path on
+        the device, as the reference defines the method; the rest get the same weights from the state-vector
+        engine - the path sum indexes gate.matrix[in][out], i.e. applies the TRANSPOSED gate matrices, which is
+        reproduced."""
         self._validate_input(in_v)
         for i in range(len(self)):
             (self.input[i]).value = in_v[i]
-        from qsv import lowering
+        from qsv import lowering, pathsum
+        if pathsum.wanted(self):
+            return pathsum.weights(self, in_v).tolist()
         return lowering.simulate_weights(self, in_v, transposed=True, presorted=False)
 
     def run_method2(self, in_v):
