@@ -662,6 +662,22 @@ def main():
         per_rank = [float(x.item()) for x in allr]
         balance = {"pass_ms_per_rank": [round(v, 3) for v in per_rank], "max_ms": max(per_rank), "min_ms": min(per_rank),
                    "idle_share_of_step": (max(per_rank) - min(per_rank)) / ms_per_step if ms_per_step else None}
+    # timeline of ONE step as every rank saw it: events between the launch groups of a real step (waits at the swaps'
+    # barriers land in the group that follows them); "init" = clear / basis store, "sample" = the draw
+    step()
+    barrier()
+    sv.trace = []
+    sv.mark("start")
+    step()
+    sv.mark("sample")
+    torch.cuda.synchronize()
+    tr, sv.trace = sv.trace, None
+    mine = [(b[0], round(a[1].elapsed_time(b[1]), 3)) for a, b in zip(tr, tr[1:])]
+    allt = [mine]
+    if world > 1:
+        allt = [None] * world
+        dist.all_gather_object(allt, mine)
+    timeline = {"labels": [x[0] for x in mine], "ms_per_rank": [[x[1] for x in r] for r in allt]}
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
     import ctypes
     jc, jh, js = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_double(0)
@@ -812,6 +828,7 @@ def main():
         line["swap"] = swap
     if balance is not None:
         line["rank_balance"] = balance
+    line["step_timeline"] = timeline
     if check is not None:
         line["check"] = check
     if big is not None:

@@ -253,6 +253,11 @@ int  qsv_jit_compile_sums(const qsv_pass_t *pass, const void *prog_host, uint32_
 /* Modelled shared-memory bank-group collisions of one pass program (sampled quarter-warps x slots x rounds; 0 = none):
  * with the default thread-index mapping, and with the per-round mapping the opt-in search (QSV_JIT_BANKSEARCH=1) picks.
  * A planning aid that needs no GPU (tools/plan_report.py --banks). */
+/* 1 if the sums variant of this pass classifies amplitudes into buckets with constants fixed at generation time (nothing
+ * that depends on the thread or the tile permutes the last round's stores: any number of bucket bits inside the tile is
+ * then as cheap as none), 0 if it reads every amplitude's bucket from its final index (~2.4 ms per 2^30 amplitudes for two
+ * inside bits, ~6 ms for three: the host then settles for fewer bits), -1 on an invalid program. */
+int  qsv_jit_sums_static(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes);
 int  qsv_jit_bank_score(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
                         uint64_t *default_score, uint64_t *searched_score);
 

@@ -299,6 +299,26 @@ constexpr int kSumMaxInside = 3;              // bucket positions that may lie I
 static thread_local const SumSpec *t_sums = nullptr;     // sums variant being generated (read by gen_round)
 static thread_local int t_tile_phys[12];                 // physical position of tile-local bit t
 
+// sums variant, STATIC form.  Register slot r of a thread is stored to the tile-local address b0 ^ XOR_{q in r} d_q
+// (linear form of the store permutation).  When no op makes a delta d_q depend on the thread or on external bits -
+// plain X / CNot riding on the stores, or no permutation at all - the d_q are known when the code is generated: the
+// bucket bits INSIDE the tile then split into a per-thread part (read once from the address of slot 0) and a per-slot
+// constant.  Returns false when the general form is needed; d[q] = tile-local delta of register bit q.
+// (QSV_SUM_STATIC=0: always the general form, for A/B runs)
+static bool sum_static(const qsv_round_t &R, const qsv_rop_t *ops, int f_post, int n_post, bool gen_post, uint32_t d[4]) {
+    const char *e = getenv("QSV_SUM_STATIC");
+    if (gen_post || (e && !strcmp(e, "0"))) return false;
+    for (int q = 0; q < 4; ++q) d[q] = 1u << R.rb[q];
+    for (int i = 0; i < n_post; ++i) {          // mirrors the linear branch of emit_addresses
+        const qsv_rop_t &p = ops[f_post + i];
+        const uint32_t xm = p.table_off, q = p.j, pbit = p.flags, cmu = p.tmask & ~pbit;
+        if (q == 0xffu || pbit == 0u) continue;                 // moves the base only
+        if (cmu || p.ext_mask) return false;                    // the delta would depend on the thread / the tile
+        if (d[q] & pbit) d[q] ^= xm;
+    }
+    return true;
+}
+
 static void thread_bit_order(const qsv_round_t &R, int pos[8]) {
     bool is_rb[12] = {false};
     for (int q = 0; q < 4; ++q) is_rb[R.rb[q]] = true;
@@ -692,6 +712,81 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
         o.f("        }");
         o.f("    }");
         o.f("}");
+        uint32_t sd[4];
+        if (sum_static(R, ops, f_post, n_post, gen_post, sd)) {
+            // per-slot constants c_r (inside bucket bits of XOR_{q in r} d_q) -> one partial sum per distinct value;
+            // the per-thread part s0 comes in as an argument.  Lanes of a warp that differ in s0 reduce in separate
+            // groups (__match_any_sync), the first lane of a group adds to the shared-memory table.
+            int tl_j[4];
+            for (int j = 0; j < n_in; ++j)
+                for (int t = 0; t < 12; ++t) if (t_tile_phys[t] == t_sums->pos[in_kb[j]]) tl_j[j] = t;
+            std::vector<uint32_t> cs;
+            for (int r = 0; r < 16; ++r) {
+                uint32_t x = 0, c = 0;
+                for (int q = 0; q < 4; ++q) if ((r >> q) & 1) x ^= sd[q];
+                for (int j = 0; j < n_in; ++j) c |= ((x >> tl_j[j]) & 1u) << j;
+                if (std::find(cs.begin(), cs.end(), c) == cs.end()) cs.push_back(c);
+            }
+            o.f("__device__ __forceinline__ void qsv_sum_one(u32 *tab, const u32 ent, const bool lane0, const qsv_u128 &a) {");
+            o.f("    #pragma unroll");
+            o.f("    for (int i_ = 0; i_ < 8; ++i_) {");
+            o.f("        const u32 limb = (u32)(((i_ < 4 ? a.lo : a.hi) >> (16 * (i_ & 3))) & 0xffffULL);");
+            o.f("        const u32 s_ = __reduce_add_sync(0xffffffffu, limb);");
+            o.f("        if (lane0 && s_) atomicAdd(tab + ent * 8u + (u32)i_, s_);");
+            o.f("    }");
+            o.f("}");
+            o.f("__device__ __forceinline__ void qsv_tile_sum_s(const qsv_ctx &c, const u64 gbase, const u32 tid, const qsv_u128 *acc,"
+                " const u32 s0) {");
+            o.f("    u32 *tab = c.s_tab + c.par * %du;", n_ent * 8);
+            o.f("    const bool lane0 = (tid & 31u) == 0u;");
+            if (n_in == 0) {
+                o.f("    qsv_sum_one(tab, 0u, lane0, acc[0]); (void)s0;");
+            } else {
+                // REDUX needs one mask for the whole warp.  Warps whose lanes agree on s0 (the inside bucket bits are held
+                // by warp-index bits of the thread number) reduce every partial sum once; the others offer every table
+                // entry the partial sum that belongs to it (or zero).  The thread mapping is fixed per kernel: a warp
+                // always takes the same side of this warp-uniform branch.
+                o.f("    if (__all_sync(0xffffffffu, s0 == __shfl_sync(0xffffffffu, s0, 0))) {");
+                for (size_t ci = 0; ci < cs.size(); ++ci)
+                    o.f("        qsv_sum_one(tab, s0 ^ 0x%xu, lane0, acc[%d]);", cs[ci], (int)ci);
+                o.f("    } else {");
+                for (int e_ = 0; e_ < n_ent; ++e_) {
+                    o.f("        { qsv_u128 v_ = {0ULL, 0ULL};");
+                    for (size_t ci = 0; ci < cs.size(); ++ci)
+                        o.f("          if ((s0 ^ 0x%xu) == %du) v_ = acc[%d];", cs[ci], e_, (int)ci);
+                    o.f("          qsv_sum_one(tab, %du, lane0, v_); }", e_);
+                }
+                o.f("    }");
+            }
+        o.f("    __syncthreads();");
+        o.f("    if (tid < %du) {", n_ent);
+        o.f("        u32 *t_ = tab + tid * 8u;");
+        o.f("        qsv_u128 v = {0ULL, 0ULL};");
+        o.f("        #pragma unroll");
+        o.f("        for (int i_ = 0; i_ < 8; ++i_) {");
+        o.f("            const u64 s_ = t_[i_];");
+        o.f("            t_[i_] = 0u;");
+        o.f("            if (i_ < 4) {");
+        o.f("                const u64 add = s_ << (16 * i_);");
+        o.f("                v.lo += add;");
+        o.f("                v.hi += (v.lo < add ? 1ULL : 0ULL) + (i_ ? (s_ >> (64 - 16 * (i_ ? i_ : 1))) : 0ULL);");
+        o.f("            } else {");
+        o.f("                v.hi += s_ << (16 * (i_ - 4));");
+        o.f("            }");
+        o.f("        }");
+        {
+            std::string e = "qsv_bucket_ext(gbase)";
+            for (int j = 0; j < n_in; ++j)
+                e += " | (((tid >> " + std::to_string(j) + ") & 1u) << " + std::to_string(in_kb[j]) + ")";
+            o.f("        if (v.lo | v.hi) {");
+            o.f("            u64 *b = c.bk + 4ULL * (%s);", e.c_str());
+        }
+        o.f("            atomicAdd(b + 0, v.lo & 0xffffffffULL); atomicAdd(b + 1, v.lo >> 32);");
+        o.f("            atomicAdd(b + 2, v.hi & 0xffffffffULL); atomicAdd(b + 3, v.hi >> 32);");
+        o.f("        }");
+        o.f("    }");
+        o.f("}");
+        }
         o.f("#endif");
     }
     // round 0 reads the tile as it came from global memory: in a FRESH state (no memset behind qsv_init_basis_sparse)
@@ -910,7 +1005,27 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
         for (int r = 0; r < 16; ++r) o.f("    QSV_STG(gout + g%d, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
         if (t_sums) {
             o.f("#ifdef QSV_JIT_HOST");
-            for (int r = 0; r < 16; ++r) o.f("    qsv_host_add(g%d | gbase, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
+            uint32_t hd[4];
+            if (sum_static(R, ops, f_post, n_post, gen_post, hd)) {
+                // host form of the STATIC classification: the bucket is composed the way the device code composes it
+                // (bits outside the tile from gbase, the per-thread part from slot 0's final address, the per-slot
+                // constant from the deltas known at generation time), not read from the amplitude's full index - the
+                // CPU tests check the classification itself
+                for (int r = 0; r < 16; ++r) {
+                    uint32_t x = 0;
+                    for (int q = 0; q < 4; ++q) if ((r >> q) & 1) x ^= hd[q];
+                    std::string e = "qsv_bucket_ext(gbase)";
+                    for (int kb = 0; kb < t_sums->n_bits; ++kb)
+                        for (int t = 0; t < 12; ++t) {
+                            if (t_tile_phys[t] != t_sums->pos[kb]) continue;
+                            e += " | ((((u32)(g0 >> " + std::to_string(t_sums->pos[kb]) + ") & 1u) ^ " +
+                                 std::to_string((x >> t) & 1u) + "u) << " + std::to_string(kb) + ")";
+                        }
+                    o.f("    qsv_host_add_b(%s, %s, %s);", e.c_str(), xr(r).c_str(), xi(r).c_str());
+                }
+            } else {
+                for (int r = 0; r < 16; ++r) o.f("    qsv_host_add(g%d | gbase, %s, %s);", r, xr(r).c_str(), xi(r).c_str());
+            }
             o.f("#else");
             // per-thread partial sums, one per combination of the bucket bits INSIDE the tile, selected by the final
             // global index g<r> of every amplitude
@@ -918,6 +1033,32 @@ static int gen_round(Out &o, int k, const qsv_round_t &R, const qsv_rop_t *ops, 
             for (int kb = 0; kb < t_sums->n_bits; ++kb)
                 for (int t = 0; t < 12; ++t)
                     if (t_tile_phys[t] == t_sums->pos[kb]) in_pos[n_in++] = t_sums->pos[kb];
+            uint32_t sd[4];
+            if (sum_static(R, ops, f_post, n_post, gen_post, sd)) {
+                int tl_j[4];
+                for (int j = 0; j < n_in; ++j)
+                    for (int t = 0; t < 12; ++t) if (t_tile_phys[t] == in_pos[j]) tl_j[j] = t;
+                std::vector<uint32_t> cs;
+                int cidx[16];
+                for (int r = 0; r < 16; ++r) {
+                    uint32_t x = 0, c = 0;
+                    for (int q = 0; q < 4; ++q) if ((r >> q) & 1) x ^= sd[q];
+                    for (int j = 0; j < n_in; ++j) c |= ((x >> tl_j[j]) & 1u) << j;
+                    auto it = std::find(cs.begin(), cs.end(), c);
+                    if (it == cs.end()) { cs.push_back(c); cidx[r] = (int)cs.size() - 1; }
+                    else cidx[r] = (int)(it - cs.begin());
+                }
+                std::string s0 = "0u";          // inside bucket bits of slot 0's final address
+                for (int j = 0; j < n_in; ++j)
+                    s0 += " | ((u32)((g0 >> " + std::to_string(in_pos[j]) + ") & 1ULL) << " + std::to_string(j) + ")";
+                o.f("    { qsv_u128 acc[%d];", (int)cs.size());
+                o.f("      for (int a_ = 0; a_ < %d; ++a_) acc[a_].lo = acc[a_].hi = 0ULL;", (int)cs.size());
+                for (int r = 0; r < 16; ++r) o.f("      qsv_wacc(acc[%d], %s, %s);", cidx[r], xr(r).c_str(), xi(r).c_str());
+                o.f("      qsv_tile_sum_s(ctx, gbase, tid, acc, %s); }", s0.c_str());
+                o.f("#endif");
+                o.f("}");
+                return 0;
+            }
             o.f("    { qsv_u128 acc[%d];", 1 << n_in);
             o.f("      for (int a_ = 0; a_ < %d; ++a_) acc[a_].lo = acc[a_].hi = 0ULL;", 1 << n_in);
             for (int r = 0; r < 16; ++r) {
@@ -1153,6 +1294,12 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         o.f("#ifdef QSV_JIT_HOST");
         o.f("static u64 *qsv_host_bk = 0;");
         o.f("extern \"C\" void qsv_jit_host_set_buckets(u64 *bk) { qsv_host_bk = bk; }");
+        o.f("static inline void qsv_host_add_b(const u32 bucket, const double re, const double im) {");
+        o.f("    qsv_u128 v = {0ULL, 0ULL};");
+        o.f("    qsv_wacc(v, re, im);");
+        o.f("    u64 *b = qsv_host_bk + 4ULL * bucket;");
+        o.f("    b[0] += v.lo & 0xffffffffULL; b[1] += v.lo >> 32; b[2] += v.hi & 0xffffffffULL; b[3] += v.hi >> 32;");
+        o.f("}");
         o.f("static inline void qsv_host_add(const u64 full, const double re, const double im) {");
         o.f("    qsv_u128 v = {0ULL, 0ULL};");
         o.f("    qsv_wacc(v, re, im);");
@@ -2180,6 +2327,22 @@ extern "C" int qsv_run_pass_rounds_swap(void *state_dev, const qsv_pass_t *pass,
                                         int rank, uint64_t epoch, void *stream) {
     return qsv_run_pass_rounds_swap_ex(state_dev, pass, prog_host, prog_bytes, tables_dev, peer_state_ptrs, peer_flag_ptrs,
                                        1 << g, g, positions, nullptr, pass_first, rank, epoch, 0, 0, stream);
+}
+
+extern "C" int qsv_jit_sums_static(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes) {
+    if (jit::validate(pass, prog_host, prog_bytes)) return -1;
+    const qsv_rprog_hdr_t *hdr = static_cast<const qsv_rprog_hdr_t *>(prog_host);
+    const uint8_t *body = static_cast<const uint8_t *>(prog_host) + sizeof(qsv_rprog_hdr_t);
+    if (hdr->n_rounds == 0) return 0;
+    std::vector<qsv_round_t> rounds(hdr->n_rounds);
+    std::vector<qsv_rop_t> ops(hdr->n_ops);
+    memcpy(rounds.data(), body, sizeof(qsv_round_t) * hdr->n_rounds);
+    memcpy(ops.data(), body + sizeof(qsv_round_t) * hdr->n_rounds, sizeof(qsv_rop_t) * hdr->n_ops);
+    const qsv_round_t &R = rounds.back();
+    const int n_pre = R.n_pre & 0x7fff, n_post = R.n_post & 0x7fff;
+    const int n_reg = (int)(R.n_ops & 0xffffu), n_pt = (int)((R.n_ops >> 16) & 0x3fffu);
+    uint32_t d[4];
+    return jit::sum_static(R, ops.data(), (int)R.first_op + n_pre + n_pt + n_reg, n_post, (R.n_post & 0x8000) != 0, d) ? 1 : 0;
 }
 
 extern "C" int qsv_jit_bank_score(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,

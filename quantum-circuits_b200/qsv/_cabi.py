@@ -63,6 +63,7 @@ SYMBOLS = {
                                              C.POINTER(C.c_uint64), _I, _I, _IP, _IP, _I, _I, _U64, _U64, _U64, _P]),
     "qsv_jit_disk_hits": (C.c_uint64, []),
     "qsv_jit_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_D)]),
+    "qsv_jit_sums_static": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32]),
     "qsv_path_sum": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P]),
     "qsv_plan_absorbed": (C.c_int, [_P, _P, _P, _I, _U64]),
     "qsv_plan_improve_tile": (C.c_int, [_P, _P, _P, _I, _I, _U64, _IP, _I, _I, _I, _I, _I, _U64, _IP, _IP, _IP]),

@@ -16,6 +16,9 @@ SAMPLE_BLOCK_BITS = 12   # larger states: block sums of 2^12 outcomes, then a se
 
 
 PRESUM_MIN_BITS = 3      # the last pass weighs the state for the sampler if it can fix at least this many top output bits
+PRESUM_SWEEP_MS = 4.7                        # the sampler's own first-level sweep of 2^30 amplitudes
+PRESUM_STATIC_MS = (0.5, 0.6, 1.2, 2.0)      # sums variant over the plain pass, by bucket bits inside the tile (static form)
+PRESUM_GENERAL_MS = (0.5, 0.7, 2.4, 6.3)     # ... general form
 _NO_SAMPLE = object()    # "no sample follows" (None is a valid src_pos: the identity map)
 
 _PLAN_CACHE = {}      # op-list fingerprint -> [("program", PackedProgram) | ("op", Op)] (host objects only)
@@ -360,7 +363,10 @@ class StateVector:
         items = list(self._walk(plan, basis))
         presum = self._presum_plan(items, sample_src_pos)
         done = 0
+        self.mark("init")
         for i, (kind, seg, sp, zf) in enumerate(items):
+            if i:
+                self.mark(items[i - 1][0] if items[i - 1][0] != "op" else items[i - 1][1].kind)
             if kind == "pass":
                 meta, dev = seg
                 fresh = zf if done < n_fresh else None
@@ -375,8 +381,20 @@ class StateVector:
                 self._run_swap_pass(seg, sp)
             else:
                 self._run_whole_state_op(seg, sp if sp is not None else (0, 0))
+        if items:
+            self.mark(items[-1][0] if items[-1][0] != "op" else items[-1][1].kind)
         self._basis = None
         self._presum = (presum[0], presum[2]) if presum is not None else None
+
+    def mark(self, label):
+        """Step timeline (bench.py, N > 1): with `trace` set to a list, an event is recorded on the stream after every
+        launch group of a run - the gaps between consecutive events are what each group cost THIS rank, waits at the
+        swaps' barriers included.  Off (None) by default: nothing is recorded."""
+        tr = getattr(self, "trace", None)
+        if tr is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            tr.append((label, ev))
 
     def _presum_plan(self, items, sample_src_pos):
         """(k, positions, src tuple) if the plan's last launch can weigh the state for a sample in output wiring
@@ -395,8 +413,31 @@ class StateVector:
         if ps.tile_bits != 12:
             return None
         src = tuple(sample_src_pos) if sample_src_pos is not None else tuple(range(self.n))
-        k = presum_bits(src, self.n, list(range(ps.low_bits)) + list(ps.hi_pos))
-        if k < min(PRESUM_MIN_BITS, self.n):
+        # What the sums cost on top of the plain pass (ms per 2^30 amplitudes, B200, bench.py step_timeline): the weights
+        # themselves ~0.5, every bucket bit INSIDE the tile more - little when the kernel classifies with
+        # generation-time constants (qsv_jit_sums_static), a lot when it reads every amplitude's bucket from its final
+        # index.  What they save: the sampler's first sweep (4.7 ms); the next level still reads 2^-k of the state.
+        # The cheapest of the four limits wins; none may beat the sampler's own sweep.
+        prog = seg[0][3][0]
+        cp = self._cpass(ps)
+        cp.reserved = int(prog[12])
+        static = self.lib.qsv_jit_sums_static(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size)) == 1
+        inside_ms = PRESUM_STATIC_MS if static else PRESUM_GENERAL_MS
+        tile = list(range(ps.low_bits)) + list(ps.hi_pos)
+        tile_set = set(tile)
+        best, k = PRESUM_SWEEP_MS, 0
+        if os.environ.get("QSV_PRESUM_COST", "1") == "0":       # tests / A-B runs: as many bits as the kernel can take
+            best = float("inf")
+            inside_ms = (3.0, 2.0, 1.0, 0.0)
+        for limit in range(4):
+            kk = presum_bits(src, self.n, tile, max_inside=limit)
+            if kk < min(PRESUM_MIN_BITS, self.n):
+                continue
+            n_in = sum(1 for b in range(self.n - kk, self.n) if src[b] in tile_set)
+            ms = inside_ms[n_in] + PRESUM_SWEEP_MS * 2.0 ** -kk
+            if ms < best - 1e-9:
+                best, k = ms, kk
+        if not k:
             return None
         positions = [src[b] for b in range(self.n - k, self.n)]          # least significant bucket bit first
         return k, positions, src

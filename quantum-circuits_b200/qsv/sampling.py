@@ -9,6 +9,7 @@ geometry, never on the data; the chosen bits stay in device memory between the k
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -22,16 +23,18 @@ MAX_LOW = 2            # ... and keeps per-thread accumulators for at most two b
 PRESUM_MAX_INSIDE = 3   # kSumMaxInside of csrc/qsv_jit.cu
 
 
-def presum_bits(src_pos, n, tile_positions):
+def presum_bits(src_pos, n, tile_positions, max_inside=PRESUM_MAX_INSIDE):
     """How many of the TOP output bits the last pass of a run can weigh for the sampler (qsv_run_pass_rounds_sums):
     the longest prefix, at most 12 bits, of which at most three sit on positions INSIDE that pass's tile (a bucket
-    bit outside the tile is the same for a whole tile; every bit inside doubles the partial sums a tile keeps)."""
+    bit outside the tile is the same for a whole tile; every bit inside doubles the partial sums a tile keeps).
+    max_inside / QSV_PRESUM_MAX_INSIDE lower the three."""
     src = list(src_pos) if src_pos is not None else list(range(n))
     tile = set(tile_positions)
     k = inside = 0
+    max_inside = min(PRESUM_MAX_INSIDE, max_inside, int(os.environ.get("QSV_PRESUM_MAX_INSIDE", PRESUM_MAX_INSIDE)))
     while k < min(LEVEL_BITS, n):
         if src[n - 1 - k] in tile:
-            if inside == PRESUM_MAX_INSIDE:
+            if inside == max_inside:
                 break
             inside += 1
         k += 1

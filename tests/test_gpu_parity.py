@@ -614,7 +614,8 @@ def test_run_from_basis_without_the_clear_is_bit_identical(qsv_gpu, monkeypatch)
     assert abs(float(sv.block_sums(None, 12).sum()) - 1.0) < 1e-10
 
 
-def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch):
+@pytest.mark.parametrize("static_form,by_cost", [("1", "1"), ("1", "0"), ("0", "0")])
+def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch, static_form, by_cost):
     """execute(plan, sample_src_pos=...) lets the last pass add up the sampler's first-level bucket sums
     (qsv_run_pass_rounds_sums).  The draws must equal the ones of the plain path (qsv_sample_level over the whole state)
     for every u, with identity and permuted output wiring; the state itself is bit-identical; a sample with another
@@ -622,6 +623,12 @@ def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch):
     lib, engine, lowering, torch = qsv_gpu
     from qsv import workloads
     monkeypatch.setenv("QSV_JIT", "force")
+    # "1": buckets from generation-time constants where the last round's stores allow it (qsv_tile_sum_s, up to three
+    # bucket bits inside the tile); "0": every amplitude's bucket from its final index (at most two inside)
+    monkeypatch.setenv("QSV_SUM_STATIC", static_form)
+    # by_cost "1": the engine weighs the cost of bucket bits inside the tile against the sweep they save (default);
+    # "0": as many top output bits as the kernel can take (up to three inside the tile)
+    monkeypatch.setenv("QSV_PRESUM_COST", by_cost)
     us = [0.0, 0.123, 0.5, 0.87654321, 1.0 - 2.0 ** -53]
     inside_seen, cases_used = set(), 0
     for n, seed in ((23, 17), (23, 18), (23, 19), (24, 31), (22, 5)) + tuple((22, s_) for s_ in range(40, 52)):
@@ -653,7 +660,7 @@ def test_last_pass_weighs_the_state_for_the_sampler(qsv_gpu, monkeypatch):
         if used:
             inside_seen.add(sum(1 for b in range(n - k, n) if src_pos[b] in tile))
     assert cases_used >= 6, "the last pass was expected to carry the sums in at least six of the circuits"
-    assert max(inside_seen) >= 1, "no case with a bucket bit inside the last pass's tile"
+    assert max(inside_seen) >= (2 if by_cost == "0" else 1), "no case with bucket bits inside the last pass's tile"
     n, seed = 23, 17
     c = workloads.random_layered_circuit(n, 8, seed=seed)
     c.sort()

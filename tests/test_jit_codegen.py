@@ -617,3 +617,55 @@ def test_fused_partial_swaps_and_support_hint(tmp_path, world_bits, positions, g
     ref = swap_positions(run_pass(full), swap, n_local) if pass_first else run_pass(swap_positions(full, swap, n_local))
     got = np.concatenate(got)
     assert np.max(np.abs(got - ref)) == 0.0
+
+
+def test_sums_static_and_general_classification_agree(tmp_path, monkeypatch):
+    """The sums variant classifies an amplitude into its bucket either from the final global index (general form) or,
+    when nothing permutes the last round's stores, from (bits outside the tile | thread bits | register-slot bits) fixed
+    at generation time (static form, qsv_tile_sum_s).  Both host forms must fill the bucket array identically, for
+    bucket positions on register bits, thread bits and outside the tile, over several pass programs."""
+    import ctypes as C
+    from qsv import workloads, lowering, _cabi
+    from helpers import jit_source_sums, jit_cpass
+    lib = _cabi.load()
+    n = 15
+    static_seen = general_seen = 0
+    kinds = set()
+    for seed in (8, 9, 11, 12, 14):
+        c = workloads.random_layered_circuit(n, 3, seed=seed)
+        c.sort()
+        ops, _ = lowering.lower(c)
+        for ps, prog, tables in _round_programs(ops, n)[-2:]:
+            outside = [p for p in range(ps.low_bits, n) if p not in ps.hi_pos]
+            tile_phys = list(range(ps.low_bits)) + list(ps.hi_pos)
+            hdr = prog[:16].view(np.uint32)
+            rb = [int(b) for b in prog[16 + 16 * (int(hdr[0]) - 1):][:4]]          # register bits of the LAST round
+            reg_pos = [tile_phys[b] for b in rb]
+            thr_pos = [p for p in tile_phys if p not in reg_pos]
+            for positions in ([outside[0], reg_pos[0], reg_pos[3], outside[1], reg_pos[1]],
+                              [thr_pos[0], outside[1], thr_pos[5], thr_pos[7]],
+                              [reg_pos[2], thr_pos[1], n + 1, thr_pos[6], outside[0]],
+                              [outside[2], outside[0], n]):
+                psi = _rand_state(n, seed)
+                psi[::5] = 0
+                res = {}
+                for mode in ("1", "0"):
+                    monkeypatch.setenv("QSV_SUM_STATIC", mode)
+                    src = jit_source_sums(ps, prog, positions)
+                    is_static = "qsv_tile_sum_s" in src
+                    assert mode == "1" or not is_static
+                    cp = jit_cpass(ps)
+                    assert lib.qsv_jit_sums_static(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size)) == int(is_static)
+                    bk = np.zeros(4 << len(positions), dtype=np.uint64)
+                    out = jit_host_run(ps, prog, tables, psi, 0b01 << n, str(tmp_path), sums=(positions, bk))
+                    res[mode] = (out, bk, is_static)
+                assert np.array_equal(res["1"][0], res["0"][0])
+                assert np.array_equal(res["1"][1], res["0"][1]), (seed, positions)
+                assert res["0"][1].any()
+                if res["1"][2]:
+                    static_seen += 1
+                    kinds.add((sum(p in reg_pos for p in positions), sum(p in thr_pos for p in positions)))
+                else:
+                    general_seen += 1
+    assert static_seen >= 8, "the static form was expected for most last rounds (no permutation on the stores)"
+    assert {(3, 0), (0, 3), (1, 2), (0, 0)} <= kinds
