@@ -455,6 +455,17 @@ int qsv_run_pass_rounds_swap_ex(void *state_dev, const qsv_pass_t *pass, const v
                                 const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
                                 const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
                                 uint64_t sp_val, void *stream);
+/* Zero-fill form (sharded counterpart of qsv_run_pass_rounds_fresh): the register was NOT cleared before the run
+ * (qsv_init_basis_sparse wrote the basis amplitude only), so whatever lies outside the support of the state is
+ * uninitialised.  A tile pulled from outside the support (sp_mask / sp_val) counts as zeros, a tile inside it keeps only
+ * the amplitudes whose tile-local index agrees with the fixed bits inside the tile (`zf_mask` / `zf_val`, 12 tile-local
+ * bits); every tile of an active pair is written in full.  The host form's qsv_jit_host_run_swap takes
+ * (..., sp_mask, sp_val, zf_mask, zf_val, zf_on). */
+int qsv_run_pass_rounds_swap_fresh(void *state_dev, const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes,
+                                   const void *tables_dev, const uint64_t *peer_state_ptrs,
+                                   const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
+                                   const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
+                                   uint64_t sp_val, uint32_t zf_mask, uint32_t zf_val, void *stream);
 int qsv_jit_source_swap_ex(const qsv_pass_t *pass, const void *prog_host, uint32_t prog_bytes, int n_swap,
                            const int *positions, const int *gbits, int pass_first, char *buf, size_t buf_len,
                            size_t *needed);

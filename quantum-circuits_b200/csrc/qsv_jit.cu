@@ -1508,8 +1508,8 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
     o.f("extern \"C\" __global__ void __launch_bounds__(256, %d)", two_buf ? 1 : 2);
     if (sw) {
         o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
-            " const __grid_constant__ qsv_peers peers, const u32 rank, const u64 epoch, const u64 sp_mask, const u64 sp_val) {");
-        o.f("    const u32 zf_mask = 0u, zf_val = 0u;      // sharded registers are always initialised in full");
+            " const __grid_constant__ qsv_peers peers, const u32 rank, const u64 epoch, const u64 sp_mask, const u64 sp_val,"
+            " const u32 zf_mask_in, const u32 zf_val_in, const u32 zf_on) {");
     } else {
     o.f("qsv_jit_pass(double2 *__restrict__ state, const u64 rank_bits, const u64 n_tiles, const double2 *__restrict__ tables,"
         " const u64 sp_mask, const u64 sp_val, const u32 zf_mask, const u32 zf_val%s) {", sums ? ", u64 *__restrict__ bk" : "");
@@ -1562,6 +1562,13 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
             o.f("        const u64 gbase = src_base | ((u64)peer << %d);", sw->n_local);
         else
             o.f("        const u64 gbase = base | rank_bits;");
+        // zero-fill form (zf_on: the register was NOT cleared before the run): a tile pulled from outside the support
+        // of the state holds garbage and counts as zeros; inside the support only the amplitudes that agree with the
+        // fixed bits of the tile (zf_mask_in / zf_val_in, tile-local) are data.  Bit 31 is set in no tile-local
+        // address: (mask, val) = (2^31, 2^31) zeroes every amplitude of the tile in round 0.
+        o.f("        const bool src_in = (((src_base | ((u64)peer << %d)) & sp_mask) == sp_val);", sw->n_local);
+        o.f("        const u32 zf_mask = zf_on ? (src_in ? zf_mask_in : 0x80000000u) : 0u;");
+        o.f("        const u32 zf_val = src_in ? zf_val_in : 0x80000000u;");
         o.f("        const u32 cur_peer = peer;");
         o.f("        const u64 cur_base = base;");
         o.f("        u64 un = u + gridDim.x;");
@@ -1701,14 +1708,17 @@ int generate(const qsv_pass_t &P, const void *prog_host, uint32_t prog_bytes, st
         // fused variant on the host: `state` is this rank's shard AFTER the swap (output), src_states[j] the shards
         // BEFORE the swap (inputs, never written)
         o.f("extern \"C\" void qsv_jit_host_run_swap(double2 *state, const double2 *const *src_states, const u32 rank,"
-            " const u64 rank_bits, const u64 n_tiles, const double2 *tables, const u64 sp_mask, const u64 sp_val) {");
+            " const u64 rank_bits, const u64 n_tiles, const double2 *tables, const u64 sp_mask, const u64 sp_val,"
+            " const u32 zf_mask_in, const u32 zf_val_in, const u32 zf_on) {");
         o.f("    static double2 A[QSV_TILE_SLOTS], B[QSV_TILE_SLOTS];");
         o.f("    qsv_ctx ctx; (void)ctx;");
-        o.f("    const u32 zf_mask = 0u, zf_val = 0u;");
         o.f("    for (u64 u = 0; u < n_tiles; ++u) {");
         o.f("        u64 base, src_base; u32 peer;");
         o.f("        qsv_fused_tile(u, rank, base, src_base, peer);");
         o.f("        if (!qsv_pair_active(base, src_base, peer, rank, sp_mask, sp_val)) continue;");
+        o.f("        const bool src_in = (((src_base | ((u64)peer << %d)) & sp_mask) == sp_val);", sw->n_local);
+        o.f("        const u32 zf_mask = zf_on ? (src_in ? zf_mask_in : 0x80000000u) : 0u;");
+        o.f("        const u32 zf_val = src_in ? zf_val_in : 0x80000000u;");
         if (sw->pre)
             o.f("        const u64 gbase = src_base | ((u64)peer << %d); (void)rank_bits;", sw->n_local);
         else
@@ -2107,7 +2117,8 @@ static int sm_count() {
 // grid that never could), whatever else is resident; the flag spin inside is bounded by a watchdog.
 int launch_swap(void *state_dev, const qsv_pass_t *P, const void *prog_host, uint32_t prog_bytes, const void *tables_dev,
                 const SwapSpec &sw, const PeerTable &peers, unsigned rank, unsigned long long epoch,
-                unsigned long long sp_mask, unsigned long long sp_val, cudaStream_t st) {
+                unsigned long long sp_mask, unsigned long long sp_val, unsigned zf_mask, unsigned zf_val, unsigned zf_on,
+                cudaStream_t st) {
     void *fn = nullptr;
     if (int rc = get_function(P, prog_host, prog_bytes, &sw, &fn)) return rc;
     std::string err;
@@ -2129,7 +2140,7 @@ int launch_swap(void *state_dev, const qsv_pass_t *P, const void *prog_host, uin
     if (grid > n_tiles) grid = n_tiles;
     PeerTable pt = peers;
     void *args[] = {&state_dev, &rank_bits, &n_tiles, const_cast<void **>(&tables_dev), &pt, &rank, &epoch, &sp_mask,
-                    &sp_val};
+                    &sp_val, &zf_mask, &zf_val, &zf_on};
     const char *coop = getenv("QSV_FUSE_COOPERATIVE");
     if (coop && !strcmp(coop, "0"))
         rc = d->LaunchKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, smem, (void *)st, args, nullptr);
@@ -2298,11 +2309,11 @@ extern "C" int qsv_jit_compile_swap(const qsv_pass_t *pass, const void *prog_hos
     return qsv_jit_compile_swap_ex(pass, prog_host, prog_bytes, g, positions, nullptr, pass_first, cubin_buf, buf_len, needed);
 }
 
-extern "C" int qsv_run_pass_rounds_swap_ex(void *state_dev, const qsv_pass_t *pass, const void *prog_host,
-                                           uint32_t prog_bytes, const void *tables_dev, const uint64_t *peer_state_ptrs,
-                                           const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
-                                           const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
-                                           uint64_t sp_val, void *stream) {
+static int run_swap(void *state_dev, const qsv_pass_t *pass, const void *prog_host,
+                    uint32_t prog_bytes, const void *tables_dev, const uint64_t *peer_state_ptrs,
+                    const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
+                    const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
+                    uint64_t sp_val, uint32_t zf_mask, uint32_t zf_val, uint32_t zf_on, void *stream) {
     QSV_CHECK_ARG(state_dev && pass && prog_host && peer_state_ptrs && peer_flag_ptrs, "qsv_run_pass_rounds_swap: NULL pointer");
     jit::SwapSpec sw;
     if (make_swap_spec(sw, n_swap, positions, gbits, pass_first, pass)) return 1;
@@ -2318,7 +2329,26 @@ extern "C" int qsv_run_pass_rounds_swap_ex(void *state_dev, const qsv_pass_t *pa
         QSV_CHECK_ARG(pt.state[j] && pt.flags[j], "qsv_run_pass_rounds_swap: peer %d has no mapped pointer", j);
     }
     return jit::launch_swap(state_dev, pass, prog_host, prog_bytes, tables_dev, sw, pt, (unsigned)rank, epoch, sp_mask,
-                            sp_val, (cudaStream_t)stream);
+                            sp_val, zf_mask, zf_val, zf_on, (cudaStream_t)stream);
+}
+
+extern "C" int qsv_run_pass_rounds_swap_ex(void *state_dev, const qsv_pass_t *pass, const void *prog_host,
+                                           uint32_t prog_bytes, const void *tables_dev, const uint64_t *peer_state_ptrs,
+                                           const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
+                                           const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
+                                           uint64_t sp_val, void *stream) {
+    return run_swap(state_dev, pass, prog_host, prog_bytes, tables_dev, peer_state_ptrs, peer_flag_ptrs, n_ranks, n_swap,
+                    positions, gbits, pass_first, rank, epoch, sp_mask, sp_val, 0, 0, 0, stream);
+}
+
+extern "C" int qsv_run_pass_rounds_swap_fresh(void *state_dev, const qsv_pass_t *pass, const void *prog_host,
+                                              uint32_t prog_bytes, const void *tables_dev, const uint64_t *peer_state_ptrs,
+                                              const uint64_t *peer_flag_ptrs, int n_ranks, int n_swap, const int *positions,
+                                              const int *gbits, int pass_first, int rank, uint64_t epoch, uint64_t sp_mask,
+                                              uint64_t sp_val, uint32_t zf_mask, uint32_t zf_val, void *stream) {
+    QSV_CHECK_ARG(!((zf_mask | zf_val) >> 12), "qsv_run_pass_rounds_swap_fresh: zf_mask / zf_val are tile-local (12 bits)");
+    return run_swap(state_dev, pass, prog_host, prog_bytes, tables_dev, peer_state_ptrs, peer_flag_ptrs, n_ranks, n_swap,
+                    positions, gbits, pass_first, rank, epoch, sp_mask, sp_val, zf_mask, zf_val, 1, stream);
 }
 
 extern "C" int qsv_run_pass_rounds_swap(void *state_dev, const qsv_pass_t *pass, const void *prog_host,

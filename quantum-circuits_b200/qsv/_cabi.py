@@ -61,6 +61,9 @@ SYMBOLS = {
                                          C.POINTER(C.c_size_t)]),
     "qsv_run_pass_rounds_swap_ex": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, C.POINTER(C.c_uint64),
                                              C.POINTER(C.c_uint64), _I, _I, _IP, _IP, _I, _I, _U64, _U64, _U64, _P]),
+    "qsv_run_pass_rounds_swap_fresh": (C.c_int, [_P, C.POINTER(QsvPass), _P, C.c_uint32, _P, C.POINTER(C.c_uint64),
+                                                C.POINTER(C.c_uint64), _I, _I, _IP, _IP, _I, _I, _U64, _U64, _U64,
+                                                C.c_uint32, C.c_uint32, _P]),
     "qsv_jit_disk_hits": (C.c_uint64, []),
     "qsv_jit_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_D)]),
     "qsv_jit_sums_static": (C.c_int, [C.POINTER(QsvPass), _P, C.c_uint32]),

@@ -157,7 +157,7 @@ class Comm:
             self._epoch = 0
         return self._flags
 
-    def swap_pass(self, sv, positions, cpass, prog, tables_ptr, pass_first=0, gbits=None, support=None):
+    def swap_pass(self, sv, positions, cpass, prog, tables_ptr, pass_first=0, gbits=None, support=None, fresh=None):
         """Global<->local swap of `positions` + the gate pass that follows it as ONE kernel over peer memory
         (qsv_run_pass_rounds_swap): tiles are pulled from the peers, transformed and stored locally; a per-tile flag
         handshake keeps the exchange in place.  One barrier before (earlier kernels of all ranks are done), none after."""
@@ -175,11 +175,18 @@ class Comm:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         hdl.barrier()
         ev[0].record()
-        _cabi.check(sv.lib.qsv_run_pass_rounds_swap_ex(sv._ptr(sv.state), C.byref(cpass), C.c_void_p(prog.ctypes.data),
-                                                       int(prog.size), tables_ptr, arr, farr, self.world,
-                                                       len(positions), _cabi.int_array(positions), _cabi.int_array(gb),
-                                                       int(pass_first), self.rank, self._epoch << 32, int(sp_mask),
-                                                       int(sp_val), sv._stream()), "qsv_run_pass_rounds_swap_ex")
+        if fresh is not None:       # the register was not cleared before the run: zero-fill form (fresh = zf_mask, zf_val)
+            _cabi.check(sv.lib.qsv_run_pass_rounds_swap_fresh(
+                sv._ptr(sv.state), C.byref(cpass), C.c_void_p(prog.ctypes.data), int(prog.size), tables_ptr, arr, farr,
+                self.world, len(positions), _cabi.int_array(positions), _cabi.int_array(gb), int(pass_first), self.rank,
+                self._epoch << 32, int(sp_mask), int(sp_val), int(fresh[0]), int(fresh[1]), sv._stream()),
+                "qsv_run_pass_rounds_swap_fresh")
+        else:
+            _cabi.check(sv.lib.qsv_run_pass_rounds_swap_ex(sv._ptr(sv.state), C.byref(cpass), C.c_void_p(prog.ctypes.data),
+                                                           int(prog.size), tables_ptr, arr, farr, self.world,
+                                                           len(positions), _cabi.int_array(positions), _cabi.int_array(gb),
+                                                           int(pass_first), self.rank, self._epoch << 32, int(sp_mask),
+                                                           int(sp_val), sv._stream()), "qsv_run_pass_rounds_swap_ex")
         ev[1].record()
         self.swap_events.append(ev)
         self.fused_swaps = getattr(self, "fused_swaps", 0) + 1

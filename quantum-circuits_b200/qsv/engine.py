@@ -359,7 +359,8 @@ class StateVector:
         self._run_segments(plan, basis, 0, sample_src_pos)
 
     def _run_segments(self, plan, basis, n_fresh, sample_src_pos=_NO_SAMPLE):
-        """The launches of a plan; the first n_fresh passes in the zero-fill form (run_from_basis)."""
+        """The launches of a plan; the first n_fresh launch groups (passes, swaps, fused swap+pass kernels) run in
+        the zero-fill form (run_from_basis: the register was not cleared)."""
         items = list(self._walk(plan, basis))
         presum = self._presum_plan(items, sample_src_pos)
         done = 0
@@ -369,7 +370,7 @@ class StateVector:
                 self.mark(items[i - 1][0] if items[i - 1][0] != "op" else items[i - 1][1].kind)
             if kind == "pass":
                 meta, dev = seg
-                fresh = zf if done < n_fresh else None
+                fresh = zf if i < n_fresh else None
                 if presum is not None and i == len(items) - 1:
                     self._launch_pass_sums(meta, dev, sp, fresh, presum)
                 else:
@@ -378,7 +379,7 @@ class StateVector:
                 self.passes_run += 1
                 self._keep.append(dev)
             elif kind == "swap_pass":
-                self._run_swap_pass(seg, sp)
+                self._run_swap_pass(seg, sp, zf if i < n_fresh else None)
             else:
                 self._run_whole_state_op(seg, sp if sp is not None else (0, 0))
         if items:
@@ -469,7 +470,9 @@ class StateVector:
         pass touching every tile does not need the clear: only the basis amplitude is written (qsv_init_basis_sparse),
         the passes up to and including the first full sweep run in the zero-fill form (qsv_run_pass_rounds_fresh: what
         lies outside the support of the state is taken as zero, never read as data) and write every tile they touch
-        in full; from then on the register is an ordinary dense state.  Everything else - sharded registers, plans
+        in full; from then on the register is an ordinary dense state.  Sharded registers (peer-memory state) do the
+        same: support-aware swaps move what lies outside the support around untouched, fused swap+pass kernels take
+        tiles pulled from outside the support as zeros (qsv_run_pass_rounds_swap_fresh).  Everything else - plans
         with whole-state ops or interpreter passes before the first full sweep, QSV_SPARSE_START=0, QSV_LAZY_INIT=0 -
         takes init_basis + execute."""
         n_fresh = self._fresh_prefix(plan)
@@ -482,24 +485,34 @@ class StateVector:
         self._run_segments(plan, int(index), n_fresh, sample_src_pos)
 
     def _fresh_prefix(self, plan):
-        """Number of leading passes that must run in the zero-fill form when the register is NOT cleared: up to and
-        including the first pass that touches every tile; 0 if the plan does not qualify (see run_from_basis)."""
+        """Number of leading launch groups that must run in the zero-fill form when the register is NOT cleared: up to
+        and including the first pass (or fused swap+pass) that touches every tile of every shard; 0 if the plan does
+        not qualify (see run_from_basis).  On a sharded register the groups before it may also be support-aware swaps
+        (they move whatever lies outside the support around as it is: it stays outside) and fused swap+pass kernels
+        (qsv_run_pass_rounds_swap_fresh); QSV_LAZY_INIT_SHARDED=0 keeps the clear there."""
         import os
         from .schedule import sparse_start_enabled
         if os.environ.get("QSV_LAZY_INIT", "1") == "0" or not sparse_start_enabled():
             return 0
-        if self.comm is not None and self.comm.world > 1:
+        sharded = self.comm is not None and self.comm.world > 1
+        if sharded and (os.environ.get("QSV_LAZY_INIT_SHARDED", "1") == "0" or not self._owns_symm()):
             return 0
-        key = ("_fresh", os.environ.get("QSV_JIT"), os.environ.get("QSV_JIT_MIN_QUBITS"))
+        key = ("_fresh", os.environ.get("QSV_JIT"), os.environ.get("QSV_JIT_MIN_QUBITS"), sharded)
         if key in plan:
             return plan[key]
         count, ok = 0, False
         for kind, seg, sp, zf in self._walk(plan, 0):
-            if kind != "pass" or not self._jit_runs(seg[0]):
+            if kind == "pass":
+                if not self._jit_runs(seg[0]):
+                    break
+            elif kind == "swap_pass":
+                if not sharded:
+                    break
+            elif not (sharded and kind == "op" and seg.kind == "global_swap"):
                 break
             count += 1
-            if not sp[0]:
-                ok = True               # this pass touches every tile: the register is fully written after it
+            if kind != "op" and not sp[0]:
+                ok = True               # this launch touches every tile: the register is fully written after it
                 break
         plan[key] = count if ok else 0
         return plan[key]
@@ -507,7 +520,8 @@ class StateVector:
     def _walk(self, plan, basis):
         """Segments of a plan in execution order with the support hint of every launch:
         ("pass", (meta, dev), (fixed_mask, fixed_val), (zf_mask, zf_val)) | ("swap_pass", seg, (mask, val) before the
-        swap, the pass's tile bits excluded, None) | ("op", op, (mask, val) before a global_swap else None, None).
+        swap, the pass's tile bits excluded, (zf_mask, zf_val)) | ("op", op, (mask, val) before a global_swap else None,
+        None).
         (zf_mask, zf_val): the support's fixed bits INSIDE the pass's tile, tile-local (zero-fill form)."""
         sup = Support(self.n, basis)
         for kind, seg in plan["segments"]:
@@ -518,7 +532,7 @@ class StateVector:
                     sup.after_ops(meta[0].ops)
             elif kind == "swap_pass":
                 swap_op, packed, dev, pass_first = seg
-                yield "swap_pass", seg, sup.pass_mask(packed.passes[0][0]), None
+                yield "swap_pass", seg, sup.pass_mask(packed.passes[0][0]), sup.tile_mask(packed.passes[0][0])
                 if pass_first:
                     sup.after_ops(packed.passes[0][0].ops)
                     sup.swap_op(swap_op, self.n_local)
@@ -568,7 +582,7 @@ class StateVector:
         cp.reserved = int(prog[12])
         return bool(self.lib.qsv_jit_wanted(C.byref(cp), C.c_void_p(prog.ctypes.data), int(prog.size)))
 
-    def _run_swap_pass(self, seg, support=None):
+    def _run_swap_pass(self, seg, support=None, fresh=None):
         self._presum = None
         swap_op, packed, dev, pass_first = seg
         ps, table_off, n_ops, extra = packed.passes[0]
@@ -578,7 +592,7 @@ class StateVector:
         cp.reserved = int(prog[12])
         pos, gb = swap_fields(swap_op, self.n_local)
         self.comm.swap_pass(self, pos, cp, prog, C.c_void_p(dev.data_ptr() + table_off), pass_first, gbits=gb,
-                            support=support)
+                            support=support, fresh=fresh)
         self.passes_run += 1
         self._keep.append(dev)
 
@@ -666,16 +680,14 @@ class StateVector:
         fr = iter(self.pass_active_fractions(plan))
         local_mask = (1 << self.n_local) - 1
         n_fresh = self._fresh_prefix(plan) if basis is not None else 0
-        done = 0
-        for kind, seg, sp, zf in self._walk(plan, basis):
+        for i, (kind, seg, sp, zf) in enumerate(self._walk(plan, basis)):
             if kind == "pass":
                 meta, dev = seg
                 ms = []
-                done += 1
                 for _ in range(repeats):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(stream)
-                    self._launch_pass(meta, dev, sp, zf if done <= n_fresh else None)
+                    self._launch_pass(meta, dev, sp, zf if i < n_fresh else None)
                     e1.record(stream)
                     e1.synchronize()
                     ms.append(e0.elapsed_time(e1))

@@ -124,6 +124,37 @@ def main():
         # whether a given swap can carry a pass is the planner's call (victims outside the pass's tile); across the two
         # circuits at least one fused kernel must have run, or this section tested nothing
         check("fused swap+pass kernels executed: %d" % fused_total, fused_total > 0)
+        # 1b'. the same circuits WITHOUT the clear of the register (run_from_basis on a sharded register): the shards
+        #      are filled with NaN first; passes, support-aware swaps and fused swap+pass kernels up to the first full
+        #      sweep run in the zero-fill form - any read from outside the support would poison the result
+        fresh_groups = fresh_fused = 0
+        for n, depth, seed in ((16 + g, 16, 12), (17 + g, 24, 13), (17 + g, 20, 21)):
+            c = workloads.random_layered_circuit(n, depth, seed=seed)
+            c.sort()
+            sv = engine.StateVector(n, comm=comm)
+            ref = np.zeros(1 << n, dtype=np.complex128)
+            ref[0] = 1
+            for M, wires, _ in so.random_layered_steps(n, depth, seed=seed):
+                ref = so.apply_gate(ref, n, wires, M)
+            ops, src_pos, flip = lowering.lower(c, n_global=g, in_flip=True, free_swap=True, fuse_swaps=sv.fuse_swaps())
+            plan = sv.prepare(ops)
+            n_fresh = sv._fresh_prefix(plan)
+            kinds = [k for k, _, _, _ in sv._walk(plan, flip)][:n_fresh]
+            fresh_groups += n_fresh
+            fresh_fused += kinds.count("swap_pass")
+            for rep in range(2):
+                torch.view_as_real(sv.state).fill_(float("nan"))
+                torch.cuda.synchronize()
+                dist.barrier()
+                sv.run_from_basis(flip, plan)
+                sv.synchronize()
+            full = gather_full(sv, comm)
+            err = np.max(np.abs(to_output_order(full, src_pos) - ref)) if not np.any(np.isnan(full)) else float("nan")
+            check("no clear, NaN-poisoned shards n=%d depth=%d zero-fill groups=%d %s err=%.2e"
+                  % (n, depth, n_fresh, kinds, err), err <= 1e-12)
+            del sv
+        check("zero-fill launch groups executed: %d (fused swap+pass among them: %d)" % (fresh_groups, fresh_fused),
+              fresh_groups > 0)
         os.environ.pop("QSV_JIT")
 
     # 1c. QFT as H + controlled-phase ladder on a sharded register (config 4): every wire gets one H, so every global

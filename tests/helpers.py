@@ -456,11 +456,12 @@ def jit_host_run(ps, prog, tables, psi, rank_bits, workdir, single_tile_gbase=No
 
 
 def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pass_first=0, gbits=None, support=(0, 0),
-                      ):
+                      fresh=None):
     """Fused swap + pass on the host: `shards` = the shards BEFORE the swap (numpy complex128 arrays, one per rank).
     Returns the list of shards after swap + pass, one call of the generated qsv_jit_host_run_swap per rank.
     gbits: positions[k] trades places with global bit gbits[k] (partial swaps); support = (fixed_mask, fixed_val) of the
-    state before the swap."""
+    state before the swap.  fresh = (zf_mask, zf_val): zero-fill form (qsv_run_pass_rounds_swap_fresh) - what lies outside
+    the support in `shards` is never used as data."""
     import ctypes as C
     import hashlib
     import os
@@ -496,7 +497,9 @@ def jit_host_run_swap(ps, prog, tables, shards, positions, n_local, workdir, pas
         dst = before[rank].copy() if support[0] else np.zeros(1 << n_local, dtype=np.complex128)
         h.qsv_jit_host_run_swap(C.c_void_p(dst.ctypes.data), ptrs, C.c_uint32(rank), C.c_uint64(rank << n_local),
                                 C.c_uint64(1 << (n_local - ps.tile_bits)), C.c_void_p(tabs.ctypes.data),
-                                C.c_uint64(support[0]), C.c_uint64(support[1]))
+                                C.c_uint64(support[0]), C.c_uint64(support[1]),
+                                C.c_uint32(fresh[0] if fresh else 0), C.c_uint32(fresh[1] if fresh else 0),
+                                C.c_uint32(1 if fresh is not None else 0))
         out.append(dst)
     return out
 

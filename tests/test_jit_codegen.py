@@ -619,6 +619,72 @@ def test_fused_partial_swaps_and_support_hint(tmp_path, world_bits, positions, g
     assert np.max(np.abs(got - ref)) == 0.0
 
 
+@pytest.mark.parametrize("world_bits,positions,gbits,pass_first", [
+    (1, [13], [0], 0), (1, [13], [0], 1), (2, [9, 14], [0, 1], 0), (2, [13], [1], 1), (3, [10, 14], [0, 2], 0)])
+def test_fused_swap_zero_fill_form_on_poisoned_shards(tmp_path, world_bits, positions, gbits, pass_first):
+    """qsv_run_pass_rounds_swap_fresh on the host: the register was not cleared, everything outside the support of the
+    state is NaN.  Tiles pulled from outside the support count as zeros, tiles inside it keep only the amplitudes that
+    agree with the fixed bits inside the tile; every tile of an active pair is written in full (no NaN survives there)
+    and equals swap + pass of the clean state; pairs outside the support on both sides are left alone."""
+    from helpers import jit_host_run_swap, swap_positions
+    from qsv.schedule import Op, plan_schedule, pack_passes
+    n_local = 15
+    n = n_local + world_bits
+    P = 1 << world_bits
+    H = np.array([[1, 1], [1, -1]], dtype=np.complex128) * 2 ** -0.5
+    S = np.array([[0.5 + 0.5j, 0.5 - 0.5j], [0.5 - 0.5j, 0.5 + 0.5j]], dtype=np.complex128)
+    ph = complex(math.cos(0.7), math.sin(0.7))
+    free = [p for p in range(6, n_local) if p not in positions]
+    swap = Op("global_swap", (), (), params={"n_swap": len(positions), "positions": positions, "gbits": gbits})
+    gates = [Op("dense", (0,), (), matrix=H), Op("dense", (free[0],), (), matrix=S), Op("mcx", (free[1],), (positions[0],)),
+             Op("phase", (), (positions[-1], 3), scalar=ph), Op("phase", (), (n_local, free[2]), scalar=-1.0 + 0j),
+             Op("dense", (free[2],), (n - 1,), matrix=H), Op("mcx", (2,), (free[0], positions[0])),
+             Op("dense", (free[3],), (), matrix=H), Op("dense", (1,), (), matrix=S), Op("dense", (4,), (), matrix=H)]
+    ops = gates + [swap] if pass_first else [swap] + gates
+    sched = plan_schedule(ops, n_local, 12, 6, fuse_swaps=True)
+    assert sched[0][0] == "swap_pass" and sched[0][1][2] == pass_first
+    ps = sched[0][1][1]
+    packed = pack_passes([ps])
+    ps_, off, n_ops, extra = packed.passes[0]
+    prog, tables = extra[0], packed.blob.tobytes()[off:]
+    tile_phys = list(range(ps.low_bits)) + list(ps.hi_pos)
+    outside = [p for p in range(6, n_local) if p not in ps.hi_pos and p not in positions]
+    # support: the first swapped position = 0, one global bit = 1, a local position outside the tile = 1 (-> sp_mask),
+    # and INSIDE the tile position 5 = 1, position 0 = 0 and the tile's highest position = 0 (-> zf_mask, tile-local)
+    sp_mask = (1 << positions[0]) | (1 << (n_local + gbits[-1])) | (1 << outside[0])
+    sp_val = (1 << (n_local + gbits[-1])) | (1 << outside[0])
+    in_tile = {5: 1, 0: 0, ps.hi_pos[-1]: 0}
+    zf_mask = sum(1 << tile_phys.index(p) for p in in_tile)
+    zf_val = sum(v << tile_phys.index(p) for p, v in in_tile.items())
+    full_mask = sp_mask | sum(1 << p for p in in_tile)
+    full_val = sp_val | sum(v << p for p, v in in_tile.items())
+    clean = np.concatenate([_rand_state(n_local, 90 + r) for r in range(P)])
+    idx = np.arange(1 << n)
+    inside = (idx & full_mask) == full_val
+    clean[~inside] = 0
+    poisoned = clean.copy()
+    poisoned[~inside] = complex(np.nan, np.nan)
+    shards = [poisoned[r << n_local: (r + 1) << n_local].copy() for r in range(P)]
+    got = np.concatenate(jit_host_run_swap(ps_, prog, tables, shards, positions, n_local, str(tmp_path),
+                                           pass_first=pass_first, gbits=gbits, support=(sp_mask, sp_val),
+                                           fresh=(zf_mask, zf_val)))
+
+    def run_pass(state):
+        return np.concatenate([jit_host_run(ps_, prog, tables, state[r << n_local: (r + 1) << n_local], r << n_local,
+                                            str(tmp_path)) for r in range(P)])
+    ref = swap_positions(run_pass(clean), swap, n_local) if pass_first else run_pass(swap_positions(clean, swap, n_local))
+    bad = np.isnan(got.real) | np.isnan(got.imag)
+    assert np.count_nonzero(ref) > 0 and not np.any(bad & (ref != 0))
+    assert np.array_equal(got[~bad], ref[~bad])
+    # what was left alone is exactly the set of tile pairs outside the support on both sides: after the swap the support
+    # has the swapped position's and the global bit's roles exchanged where they were part of it
+    assert np.count_nonzero(~bad) >= 2 * np.count_nonzero(ref) // 8
+    # the plain form of the same kernel would have used the poison as data
+    plain = np.concatenate(jit_host_run_swap(ps_, prog, tables, shards, positions, n_local, str(tmp_path),
+                                             pass_first=pass_first, gbits=gbits, support=(sp_mask, sp_val)))
+    assert np.any(np.isnan(plain[ref != 0].real))
+
+
 def test_sums_static_and_general_classification_agree(tmp_path, monkeypatch):
     """The sums variant classifies an amplitude into its bucket either from the final global index (general form) or,
     when nothing permutes the last round's stores, from (bits outside the tile | thread bits | register-slot bits) fixed
