@@ -763,6 +763,20 @@ def main():
             with contextlib.redirect_stdout(io.StringIO()):
                 circ.run(in_v, 2)
         k_e2e = max(2, min(args.steps, 5))
+        if os.environ.get("QSV_BENCH_PROFILE_E2E") and rank == 0:      # where the host time of a sharded run() goes
+            import cProfile
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(k_e2e):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    circ.run(in_v, 2)
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
+        elif os.environ.get("QSV_BENCH_PROFILE_E2E"):
+            for _ in range(k_e2e):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    circ.run(in_v, 2)
         barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):

@@ -38,6 +38,10 @@ class Wire(object):
         return isinstance(self.left, Gate) and isinstance(self.right, Gate)
 
 
+import weakref as _weakref
+_SORT_CACHE = _weakref.WeakKeyDictionary()      # Circuit -> [(structure before, sorted gates, structure after)]
+
+
 class Circuit(object):
     """Reference: main/circuit.py:27-445."""
 
@@ -156,6 +160,46 @@ class Circuit(object):
                 self.ordered_gates.insert(0, g)
 
     def sort(self):
+        self._sort_structure()
+
+    def _structure(self):
+        """Everything check() / sort() / the lowering read of the GRAPH (not of the gate matrices) as one flat tuple:
+        the gate order, per gate where its in-wires come from and where its out-wires lead, the output wiring.  None
+        while the circuit is unfinished (a missing wire).  run() is called over and over on one circuit (Shor's
+        sampling loop, benchmarks): an unchanged tuple means the previous sort's result still holds."""
+        fp = [len(self.gates)]
+        app = fp.append
+        try:
+            fp.extend(map(id, self.gates))
+            for g in self.gates:
+                for w in g.in_wires:
+                    app(id(w.left))
+                    app(w.lind)
+                app(-1)
+                for w in g.out_wires:
+                    app(id(w.right))
+                app(-2)
+            for w in self.output:
+                app(id(w.left))
+                app(w.lind)
+            for w in self.input:
+                app(id(w.right))
+        except AttributeError:          # a port without a wire (None): let check() report it
+            return None
+        return tuple(fp)
+
+    def _sort_structure(self):
+        """sort() of the reference (main/circuit.py:173-184: check, depth-first post-order, gates re-ordered), returning
+        the structure tuple of the SORTED circuit (None if it cannot be described).  The result is remembered per
+        structure (a few entries per circuit, module-level and weakly keyed: nothing is added to the instance, its
+        pickles stay what the reference writes): the same graph sorts to the same order without walking it again."""
+        before = self._structure()
+        cache = _SORT_CACHE.get(self)
+        if before is not None and cache is not None:
+            for fp, ordered, after in cache:
+                if fp == before:
+                    self.gates = list(ordered)
+                    return after
         if not self.check():
             raise RuntimeError("Cannot sort - please finish building the circuit first.")
         for gate in self.gates:
@@ -166,6 +210,14 @@ class Circuit(object):
         for gate in self.gates:
             gate.marked = False
             gate.tempmarked = False
+        after = self._structure()
+        if before is not None and after is not None:
+            if cache is None:
+                cache = _SORT_CACHE[self] = []
+            if len(cache) >= 4:
+                cache.pop(0)
+            cache.append((before, list(self.gates), after))
+        return after
 
     def check(self):
         return (
@@ -179,11 +231,11 @@ class Circuit(object):
     def contains_cycle(self):
         """True iff the gate graph has a directed cycle (reference main/circuit.py:199-217)."""
         WHITE, GREY, BLACK = 0, 1, 2
-        colour = {}
+        colour = {}                     # keyed by id(): Gate.__hash__ goes through the uuid (three Python calls)
         for root in self.gates:
-            if colour.get(root, WHITE) != WHITE:
+            if colour.get(id(root), WHITE) != WHITE:
                 continue
-            colour[root] = GREY
+            colour[id(root)] = GREY
             stack = [(root, 0)]
             while stack:
                 g, port = stack.pop()
@@ -193,17 +245,17 @@ class Circuit(object):
                     port += 1
                     if w is None or w.right is self:
                         continue
-                    c = colour.get(w.right, WHITE)
+                    c = colour.get(id(w.right), WHITE)
                     if c == GREY:
                         return True
                     if c == WHITE:
                         stack.append((g, port))
-                        colour[w.right] = GREY
+                        colour[id(w.right)] = GREY
                         stack.append((w.right, 0))
                         descended = True
                         break
                 if not descended:
-                    colour[g] = BLACK
+                    colour[id(g)] = BLACK
         return False
 
     # ---------------------------------------------------------------- simulation (the hot path)
@@ -232,10 +284,18 @@ class Circuit(object):
 
     def run_method2(self, in_v):
         """State-vector evolution (reference main/circuit.py:279-337) on the GPU engine."""
-        self.sort()
+        structure = self._sorted()
         self._validate_input(in_v)
         from qsv import lowering
-        return lowering.simulate_weights(self, in_v, transposed=False, presorted=True)
+        return lowering.simulate_weights(self, in_v, transposed=False, presorted=True, structure=structure)
+
+    def _sorted(self):
+        """self.sort(); the structure tuple of the sorted circuit when our own sort() did it (the lowering then skips
+        re-deriving what every gate acts on for a graph it has seen), None for a subclass's sort()."""
+        if type(self).sort is Circuit.sort:
+            return self._sort_structure()
+        self.sort()
+        return None
 
     def run(self, in_v, method=None):
         """One measurement outcome as a list of bits, wire 0 first (reference main/circuit.py:341-366).
@@ -252,20 +312,22 @@ class Circuit(object):
                 print("Running method 2...")
                 method = 2
 
+        structure = None
         if method == 1:
             self._validate_input(in_v)
             for i in range(len(self)):
                 (self.input[i]).value = in_v[i]
             transposed, presorted = True, False
         elif method == 2:
-            self.sort()
+            structure = self._sorted()
             self._validate_input(in_v)
             transposed, presorted = False, True
         else:
             raise RuntimeError("Please choose one of the avalible methods: 1 or 2")
 
         from qsv import lowering
-        index = lowering.simulate_sample(self, in_v, _random.random, transposed=transposed, presorted=presorted)
+        index = lowering.simulate_sample(self, in_v, _random.random, transposed=transposed, presorted=presorted,
+                                         structure=structure)
         n = len(self)
         return [(index >> (n - 1 - i)) & 1 for i in range(n)]
 

@@ -45,15 +45,16 @@ def gate_targets(circuit, gates):
     table = []
     for g in gates:
         tg = []
+        gid = id(g)                     # (Gate.__hash__ goes through the uuid: three Python calls per lookup)
         for j, w in enumerate(g.in_wires):
-            q = w.lind if w.left is circuit else qubit_of[(w.left, w.lind)]
-            qubit_of[(g, j)] = q
+            q = w.lind if w.left is circuit else qubit_of[(id(w.left), w.lind)]
+            qubit_of[(gid, j)] = q
             tg.append(q)
         table.append(tg)
     out = []
     for i in range(len(circuit)):
         w = circuit.output[i]
-        out.append(w.lind if w.left is circuit else qubit_of[(w.left, w.lind)])
+        out.append(w.lind if w.left is circuit else qubit_of[(id(w.left), w.lind)])
     return table, out
 
 
@@ -142,6 +143,7 @@ class OpList(list):
     digest = None
 
 
+_TARGETS_CACHE = {}     # structure tuple of a sorted circuit -> (circuit, gate_targets table, output qubits)
 _LOWER_CACHE = {}       # circuit signature -> (ops, src_pos, flip); Shor's sampling loop and benchmarks re-run one circuit
 
 
@@ -168,7 +170,8 @@ def _circuit_signature(gates, table, out_qubits, extra):
         return None
 
 
-def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, free_swap=False, fuse_swaps=False):
+def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, free_swap=False, fuse_swaps=False,
+          structure=None):
     """(ops, src_pos): ops in application order; src_pos[b] = physical position feeding bit b of the
     OUTPUT index (bit n-1-i <-> output wire i), i.e. main/circuit.py:329-332 as a bit map.  With
     n_global > 0 the ops are placed on a register sharded by its top n_global positions
@@ -183,7 +186,17 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
     stay above the tile's low positions and the planner accounts for the pass that avoids them."""
     n = len(circuit)
     gates = circuit.gates if presorted else topological_gates(circuit)
-    table, out_qubits = gate_targets(circuit, gates)
+    # structure (Circuit._structure() of the sorted circuit, taken by run() right after its sort): the wires every gate
+    # acts on depend on the graph only - the same graph gives the same table
+    hit = _TARGETS_CACHE.get(structure) if (structure is not None and presorted) else None
+    if hit is not None and hit[0] is circuit:
+        table, out_qubits = hit[1], hit[2]
+    else:
+        table, out_qubits = gate_targets(circuit, gates)
+        if structure is not None and presorted:
+            if len(_TARGETS_CACHE) >= 8:
+                _TARGETS_CACHE.pop(next(iter(_TARGETS_CACHE)))
+            _TARGETS_CACHE[structure] = (circuit, table, out_qubits)
     from . import schedule as _sched
     sig = None
     if os.environ.get("QSV_LOWER_CACHE", "1") != "0":
@@ -277,7 +290,7 @@ def release_sharded_states():
             sv.comm.release_state()
 
 
-def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=True, for_sample=False):
+def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=True, for_sample=False, structure=None):
     """Run the circuit on |in_v>: (StateVector, src_pos).  Under one-process-per-GPU launches (torchrun, NCCL)
     the register is sharded over the ranks by its top qubits (qsv.dist.default_comm) unless it is small or
     shard=False; every rank then holds one shard and must make the same calls."""
@@ -289,13 +302,13 @@ def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=Tru
         if comm is not None and n - comm.global_bits < min_local:
             comm = None
     if comm is None or comm.world < 2:
-        ops, src_pos, flip = lower(circuit, transposed, presorted, in_flip=True)
+        ops, src_pos, flip = lower(circuit, transposed, presorted, in_flip=True, structure=structure)
         sv = _engine.StateVector(n, comm=comm)
     else:
         sv = _sharded_state(n, comm)
         sv.d2h_bytes = 0
         ops, src_pos, flip = lower(circuit, transposed, presorted, n_global=comm.global_bits, in_flip=True,
-                                   free_swap=bool(comm.peer_swap), fuse_swaps=sv.fuse_swaps())
+                                   free_swap=bool(comm.peer_swap), fuse_swaps=sv.fuse_swaps(), structure=structure)
     plan = sv.prepare(ops)
     # init_basis + execute, without the clear where possible; when a sample follows, the last pass weighs the state for it
     if for_sample:
@@ -344,8 +357,8 @@ def _gathered_weights(sv, src_pos):
     return full[y]
 
 
-def simulate_weights(circuit, in_v, transposed=False, presorted=True):
-    sv, src_pos = evolve(circuit, in_v, transposed, presorted)
+def simulate_weights(circuit, in_v, transposed=False, presorted=True, structure=None):
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted, structure=structure)
     w = _gathered_weights(sv, src_pos) if (sv.comm is not None and sv.comm.world > 1) else sv.probs(src_pos)
     sv.synchronize()
     if len(circuit) <= LIST_WEIGHTS_MAX_QUBITS:
@@ -354,8 +367,8 @@ def simulate_weights(circuit, in_v, transposed=False, presorted=True):
     return LazyWeights(w)
 
 
-def simulate_sample(circuit, in_v, rand_fn, transposed=False, presorted=True):
-    sv, src_pos = evolve(circuit, in_v, transposed, presorted, for_sample=True)
+def simulate_sample(circuit, in_v, rand_fn, transposed=False, presorted=True, structure=None):
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted, for_sample=True, structure=structure)
     u = rand_fn()                       # exactly one uniform draw per run, after the weights exist
     if sv.comm is not None and sv.comm.world > 1:
         u = sv.comm.broadcast_float(u)  # every rank drew once from its own generator; rank 0's value is used

@@ -244,3 +244,58 @@ def test_lazy_kronecker_products_and_identities():
     m[5][6] = 1
     assert m.structure() is None and m.rows[5][6] == 1 and m.rows[7][7] == 1
     assert not tensor([Matrix([[1, 0], [0, 2]]), Matrix.H(2)]).isUnitary()
+
+
+def test_sort_is_remembered_per_graph_and_forgets_on_any_change():
+    """Circuit.sort() (reference main/circuit.py:173-184) walks the whole graph; run() calls it every time.  The mirror
+    remembers the result per graph structure: the remembered order must be the order an uncached sort produces, any
+    change of the graph (new gate, re-wired port, re-ordered gate list) must be seen, an unfinished circuit must raise
+    as before, and nothing is stored on the instance (pickles stay what the reference writes)."""
+    import pickle
+    import random
+    import main.circuit as mc
+    random.seed(11)
+    c = mc.Circuit.random_circuit(6, 9)
+    names0 = [id(g) for g in c.gates]
+    orders = []
+    for _ in range(4):
+        c.sort()
+        orders.append([id(g) for g in c.gates])
+    # the same sequence with the memory wiped before every call
+    c.gates = [g for i in names0 for g in c.gates if id(g) == i]
+    plain = []
+    for _ in range(4):
+        mc._SORT_CACHE.clear()
+        c.sort()
+        plain.append([id(g) for g in c.gates])
+    assert orders == plain
+    assert c in mc._SORT_CACHE and "_SORT_CACHE" not in c.__dict__ and not any(k.startswith("_qsv") for k in c.__dict__)
+    blob = pickle.dumps(c)
+    assert b"SORT_CACHE" not in blob
+    # a structure tuple is returned for the lowering; it changes with the graph
+    s1 = c._sorted()
+    assert s1 is not None and s1 == c._structure()         # (a re-sort may order commuting gates differently again)
+    h = c.gates[-1]
+    c.gates.reverse()                                   # same gates, another order
+    assert c._structure() != s1
+    c.sort()
+    # re-wire: cut an output wire of the last gate -> unfinished circuit, same error as the reference
+    w = h.out_wires[0]
+    c.remove_wire(w)
+    with pytest.raises(RuntimeError, match="finish building"):
+        c.sort()
+    c.add_wire(h, w.lind, w.right, w.rind)
+    c.sort()
+    before = len(mc._SORT_CACHE[c])
+    g = c.add(mc.H(1, "late"))                          # a new gate on output 0's wire
+    wo = c.output[0]
+    src, sp = wo.left, wo.lind
+    c.remove_wire(wo)
+    c.add_wire(src, sp, g, 0)
+    c.add_wire(g, 0, c, 0)
+    c.sort()
+    assert g in c.gates and len(mc._SORT_CACHE[c]) >= min(before + 1, 4) - 1
+    pos = {id(x): i for i, x in enumerate(c.gates)}
+    for x in c.gates:                                   # a topological order: every gate after its producers
+        for wv in x.in_wires:
+            assert wv.left is c or pos[id(wv.left)] < pos[id(x)]
