@@ -31,8 +31,8 @@ SEED = 20261019
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--qubits", type=int, default=0, help="total qubits (default 30 + log2(gpus))")
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -81,7 +81,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi has been streaming since before the warm-up (its start-up takes longer
+        than a short timed region), only the samples from here on count."""
+        self.t0 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -94,7 +99,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        inside = [ln for t, ln in self.lines if t >= t0]
+        if not inside and self.lines:
+            inside = [self.lines[-1][1]]            # region shorter than one sampling interval: the sample next to it
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -527,14 +536,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
 
     # ---- timed region: K steps, CUDA events, max over ranks
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     lib.qsv_reset_launch_count()
     passes0 = sv.passes_run
     if comm is not None:

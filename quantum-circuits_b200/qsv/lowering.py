@@ -290,7 +290,8 @@ def release_sharded_states():
             sv.comm.release_state()
 
 
-def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=True, for_sample=False, structure=None):
+def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=True, for_sample=False, structure=None,
+           rand_fn=None):
     """Run the circuit on |in_v>: (StateVector, src_pos).  Under one-process-per-GPU launches (torchrun, NCCL)
     the register is sharded over the ranks by its top qubits (qsv.dist.default_comm) unless it is small or
     shard=False; every rank then holds one shard and must make the same calls."""
@@ -312,11 +313,20 @@ def evolve(circuit, in_v, transposed=False, presorted=True, comm=None, shard=Tru
     plan = sv.prepare(ops)
     # init_basis + execute, without the clear where possible; when a sample follows, the last pass weighs the state for it
     if for_sample:
+        if rand_fn is not None and sv.comm is not None and sv.comm.world > 1:
+            # sharded: every rank draws once from its own generator and rank 0's value is used.  The broadcast needs a
+            # host round trip; done now, before the gate passes are queued, it costs microseconds - after them it would
+            # wait for the whole evolution and leave the sampler's launches exposed behind it.  (Everything that can
+            # fail - validation, sort, lowering, planning - has run by now: no draw is consumed by a failing call.)
+            _draw[0] = sv.comm.broadcast_float(rand_fn())
         sv.run_from_basis(basis_index(in_v) ^ flip, plan, sample_src_pos=src_pos)
     else:
         sv.run_from_basis(basis_index(in_v) ^ flip, plan)
     _last_stats.update(h2d_bytes=plan["h2d_bytes"], d2h_bytes=0, passes=sv.passes_run)
     return sv, src_pos
+
+
+_draw = [None]      # the uniform draw of a sharded simulate_sample, taken inside evolve (see there)
 
 
 class LazyWeights:
@@ -368,10 +378,12 @@ def simulate_weights(circuit, in_v, transposed=False, presorted=True, structure=
 
 
 def simulate_sample(circuit, in_v, rand_fn, transposed=False, presorted=True, structure=None):
-    sv, src_pos = evolve(circuit, in_v, transposed, presorted, for_sample=True, structure=structure)
-    u = rand_fn()                       # exactly one uniform draw per run, after the weights exist
-    if sv.comm is not None and sv.comm.world > 1:
-        u = sv.comm.broadcast_float(u)  # every rank drew once from its own generator; rank 0's value is used
+    _draw[0] = None
+    sv, src_pos = evolve(circuit, in_v, transposed, presorted, for_sample=True, structure=structure, rand_fn=rand_fn)
+    if _draw[0] is not None:
+        u, _draw[0] = _draw[0], None    # sharded register: drawn and broadcast before the passes were queued
+    else:
+        u = rand_fn()                   # exactly one uniform draw per run, after the weights exist
     z = sv.sample(u, src_pos)
     sv.synchronize()
     _last_stats["d2h_bytes"] = sv.d2h_bytes
