@@ -72,3 +72,39 @@ def test_selector_limits(monkeypatch):
         big.add_wire(g, i, big, i)
     monkeypatch.setenv("QSV_METHOD1", "pathsum")
     assert not pathsum.wanted(big)
+
+
+def _direct_cases():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pathsum_direct.json")
+    with open(path) as f:
+        return json.load(f)["cases"]
+
+
+def _build_direct(case):
+    import main.circuit as mc
+    c = mc.Circuit(case["n"])
+    objs = [c.add(getattr(mc, g["cls"])(*g["args"])) for g in case["gates"]]
+    for s, sp, d, dp in case["wires"]:
+        c.add_wire(c if s < 0 else objs[s], sp, c if d < 0 else objs[d], dp)
+    return c
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_direct_wire_circuits_match_the_reference(idx):
+    """tests/golden/pathsum_direct.json (oracle/gen_pathsum_golden.py: the unmodified reference's run_method1 and
+    run_method2 on circuits whose inputs are wired straight to outputs, every basis input): the oracle's loop-for-loop
+    path sum, its transposed evolution, its run_method2 and the kernel's packed description must all reproduce them."""
+    from qsv import pathsum
+    case = _direct_cases()[idx]
+    c = _build_direct(case)
+    assert any(w.right is c for w in c.input), "fixture without a direct wire"
+    for in_v, w1, w2 in zip(case["inputs"], case["weights_m1"], case["weights_m2"]):
+        w1, w2 = np.array(w1), np.array(w2)
+        assert np.max(np.abs(so.run_method1_path_sum(c, list(in_v)) - w1)) <= TOL
+        assert np.max(np.abs(so.run_method1(c, list(in_v)) - w1)) <= TOL
+        assert np.max(np.abs(so.run_method2(c, list(in_v)) - w2)) <= TOL
+        desc = pathsum.describe(c, list(in_v))
+        assert desc[4].shape[0] == sum(1 for w in c.input if w.right is c)
+        assert np.max(np.abs(pathsum.emulate(desc, len(c)) - w1)) <= TOL

@@ -384,3 +384,17 @@ def test_schedule_search_is_valid_deterministic_and_never_worse_than_greedy(monk
     reordered = [o for k, it in a for o in it.ops]
     got = emulate_ops(reordered, psi0.copy(), n)
     assert np.max(np.abs(got - ref)) <= TOL
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_emulated_engine_on_direct_wire_circuits(idx):
+    """Circuits whose inputs are wired straight to outputs (fixtures of oracle/gen_pathsum_golden.py, the reference's own
+    run_method1 / run_method2 weights): lowering + pass schedule, emulated on the CPU, for both methods."""
+    from test_pathsum_host import _direct_cases, _build_direct
+    case = _direct_cases()[idx]
+    c = _build_direct(case)
+    for in_v, w1, w2 in zip(case["inputs"], case["weights_m1"], case["weights_m2"]):
+        psi, _ = _run_emulated(c, in_v)
+        assert np.max(np.abs(np.abs(psi) ** 2 - np.array(w2))) <= TOL
+        psi1, _ = _run_emulated(c, in_v, transposed=True, tile_bits=2, low_bits=1)
+        assert np.max(np.abs(np.abs(psi1) ** 2 - np.array(w1))) <= TOL
