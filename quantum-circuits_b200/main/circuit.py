@@ -39,7 +39,7 @@ class Wire(object):
 
 
 import weakref as _weakref
-_SORT_CACHE = _weakref.WeakKeyDictionary()      # Circuit -> [(structure before, sorted gates, structure after)]
+_SORT_CACHE = _weakref.WeakKeyDictionary()      # Circuit -> [(structure before, sorted order as indices, structure after)]
 
 
 class Circuit(object):
@@ -192,13 +192,15 @@ class Circuit(object):
         """sort() of the reference (main/circuit.py:173-184: check, depth-first post-order, gates re-ordered), returning
         the structure tuple of the SORTED circuit (None if it cannot be described).  The result is remembered per
         structure (a few entries per circuit, module-level and weakly keyed: nothing is added to the instance, its
-        pickles stay what the reference writes): the same graph sorts to the same order without walking it again."""
+        pickles stay what the reference writes; entries hold integers only): the same graph sorts to the same order
+        without walking it again."""
         before = self._structure()
         cache = _SORT_CACHE.get(self)
         if before is not None and cache is not None:
-            for fp, ordered, after in cache:
+            for fp, order, after in cache:
                 if fp == before:
-                    self.gates = list(ordered)
+                    gates = self.gates
+                    self.gates = [gates[i] for i in order]
                     return after
         if not self.check():
             raise RuntimeError("Cannot sort - please finish building the circuit first.")
@@ -216,7 +218,10 @@ class Circuit(object):
                 cache = _SORT_CACHE[self] = []
             if len(cache) >= 4:
                 cache.pop(0)
-            cache.append((before, list(self.gates), after))
+            # the order as a permutation of the gate list it started from: no reference to a gate (a gate points back at
+            # its circuit, and an entry that kept the key alive would never leave the weak table)
+            position = {gid: i for i, gid in enumerate(before[1:1 + before[0]])}
+            cache.append((before, [position[id(g)] for g in self.gates], after))
         return after
 
     def check(self):

@@ -143,7 +143,7 @@ class OpList(list):
     digest = None
 
 
-_TARGETS_CACHE = {}     # structure tuple of a sorted circuit -> (circuit, gate_targets table, output qubits)
+_TARGETS_CACHE = {}     # structure tuple of a sorted circuit -> (gate_targets table, output qubits)
 _LOWER_CACHE = {}       # circuit signature -> (ops, src_pos, flip); Shor's sampling loop and benchmarks re-run one circuit
 
 
@@ -189,14 +189,14 @@ def lower(circuit, transposed=False, presorted=True, n_global=0, in_flip=False, 
     # structure (Circuit._structure() of the sorted circuit, taken by run() right after its sort): the wires every gate
     # acts on depend on the graph only - the same graph gives the same table
     hit = _TARGETS_CACHE.get(structure) if (structure is not None and presorted) else None
-    if hit is not None and hit[0] is circuit:
-        table, out_qubits = hit[1], hit[2]
+    if hit is not None:
+        table, out_qubits = hit
     else:
         table, out_qubits = gate_targets(circuit, gates)
         if structure is not None and presorted:
             if len(_TARGETS_CACHE) >= 8:
                 _TARGETS_CACHE.pop(next(iter(_TARGETS_CACHE)))
-            _TARGETS_CACHE[structure] = (circuit, table, out_qubits)
+            _TARGETS_CACHE[structure] = (table, out_qubits)        # integers only: no circuit is kept alive
     from . import schedule as _sched
     sig = None
     if os.environ.get("QSV_LOWER_CACHE", "1") != "0":

@@ -299,3 +299,22 @@ def test_sort_is_remembered_per_graph_and_forgets_on_any_change():
     for x in c.gates:                                   # a topological order: every gate after its producers
         for wv in x.in_wires:
             assert wv.left is c or pos[id(wv.left)] < pos[id(x)]
+
+
+def test_remembered_sort_does_not_keep_circuits_alive():
+    import gc
+    import random
+    import weakref
+    import main.circuit as mc
+    from qsv import lowering
+    random.seed(3)
+    c = mc.Circuit.random_circuit(5, 6)
+    st = c._sorted()
+    c._sorted()
+    lowering.lower(c, structure=c._sorted())
+    assert c in mc._SORT_CACHE
+    r = weakref.ref(c)
+    del c
+    gc.collect()
+    assert r() is None, "a cache entry holds the circuit (or one of its gates, which point back at it)"
+    assert st is not None
