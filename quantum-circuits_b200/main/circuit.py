@@ -39,6 +39,9 @@ class Wire(object):
 
 
 import weakref as _weakref
+from itertools import chain as _chain
+from operator import attrgetter as _attrgetter
+_W_LEFT, _W_LIND, _W_RIGHT = _attrgetter("left"), _attrgetter("lind"), _attrgetter("right")
 _SORT_CACHE = _weakref.WeakKeyDictionary()      # Circuit -> [(structure before, sorted order as indices, structure after)]
 
 
@@ -163,30 +166,23 @@ class Circuit(object):
         self._sort_structure()
 
     def _structure(self):
-        """Everything check() / sort() / the lowering read of the GRAPH (not of the gate matrices) as one flat tuple:
+        """Everything check() / sort() / the lowering read of the GRAPH (not of the gate matrices) as one tuple of tuples:
         the gate order, per gate where its in-wires come from and where its out-wires lead, the output wiring.  None
         while the circuit is unfinished (a missing wire).  run() is called over and over on one circuit (Shor's
         sampling loop, benchmarks): an unchanged tuple means the previous sort's result still holds."""
-        fp = [len(self.gates)]
-        app = fp.append
+        gates = self.gates
         try:
-            fp.extend(map(id, self.gates))
-            for g in self.gates:
-                for w in g.in_wires:
-                    app(id(w.left))
-                    app(w.lind)
-                app(-1)
-                for w in g.out_wires:
-                    app(id(w.right))
-                app(-2)
-            for w in self.output:
-                app(id(w.left))
-                app(w.lind)
-            for w in self.input:
-                app(id(w.right))
+            ins = [g.in_wires for g in gates]
+            outs = [g.out_wires for g in gates]
+            win = list(_chain.from_iterable(ins))
+            wout = list(_chain.from_iterable(outs))
+            # (C-level loops over the ~3 wires per gate: attrgetter raises AttributeError on a missing wire, None)
+            return (len(gates), tuple(map(id, gates)), tuple(map(len, ins)), tuple(map(len, outs)),
+                    tuple(map(id, map(_W_LEFT, win))), tuple(map(_W_LIND, win)), tuple(map(id, map(_W_RIGHT, wout))),
+                    tuple(map(id, map(_W_LEFT, self.output))), tuple(map(_W_LIND, self.output)),
+                    tuple(map(id, map(_W_RIGHT, self.input))))
         except AttributeError:          # a port without a wire (None): let check() report it
             return None
-        return tuple(fp)
 
     def _sort_structure(self):
         """sort() of the reference (main/circuit.py:173-184: check, depth-first post-order, gates re-ordered), returning
@@ -220,7 +216,7 @@ class Circuit(object):
                 cache.pop(0)
             # the order as a permutation of the gate list it started from: no reference to a gate (a gate points back at
             # its circuit, and an entry that kept the key alive would never leave the weak table)
-            position = {gid: i for i, gid in enumerate(before[1:1 + before[0]])}
+            position = {gid: i for i, gid in enumerate(before[1])}
             cache.append((before, [position[id(g)] for g in self.gates], after))
         return after
 
